@@ -1,0 +1,245 @@
+/* b2rl.h — C ABI of libb2rl.so: the B200-native SAC/TD3 learner update.
+ *
+ * The reference (lionelblonde/sac-td3-cudagraphs-pytorch) has no FFI of its own: its
+ * hot path is the Python object `Agent` (agents/agent.py) driven by orchestrator.py:337-352.
+ * Each entry point below replaces one torch-op sequence of that path; the citation on
+ * every function names the reference lines it stands in for. The host-side mirror
+ * (sac_td3_cudagraphs_pytorch_b200/agents/agent.py) binds these with ctypes.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, POD structs; no torch / C++ types.
+ *  - every pointer marked `dev` is device memory owned by the caller (torch allocator).
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*): no
+ *    allocation, no synchronisation, no host read of device memory => legal inside CUDA
+ *    graph capture (the replacement for tensordict's CudaGraphModule, orchestrator.py:313-315).
+ *  - return value: 0 on success, <0 on error (B2RL_E_*); text via b2rl_last_error().
+ *  - all floating point is fp32; indices are int64 (as torchrl's sampler returns them).
+ */
+#ifndef B2RL_H
+#define B2RL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2RL_VERSION 100 /* 0.1.0 */
+#define B2RL_HID 256     /* hidden width; agents/agent.py:56,101 hard-codes (256, 256) */
+#define B2RL_ROWS 4      /* batch rows per CTA in the fused kernels; batch must be a multiple */
+#define B2RL_MAX_OUT 64  /* max head width (2*A for SAC) */
+#define B2RL_MAX_SEG 8   /* max segments per adam_polyak_multi launch */
+
+#define B2RL_OK 0
+#define B2RL_E_INVALID (-1) /* bad argument (null pointer, unsupported size, misalignment) */
+#define B2RL_E_LAUNCH (-2)  /* CUDA reported an error at launch */
+
+/* ---- parameter arena -------------------------------------------------------------------
+ * One agent owns one flat fp32 ARENA of 5 equally laid out REGIONS:
+ *   0 online params | 1 target params | 2 Adam exp_avg | 3 Adam exp_avg_sq | 4 gradients
+ * A net (actor or one critic) is a contiguous span [begin,end) of a region; b2rl_net_t gives
+ * the float offsets of its tensors inside a region. Layouts:
+ *   w1t [in_dim][256], w2t [256][256]  "forward layout": w?t[k*256+j] == fc.weight[j][k]
+ *       (exposed to torch as a transposed view, so state_dict keys/shapes stay those of
+ *        agents/nets.py:66-84);
+ *   w3  [out_dim][256]                 natural torch layout (head.weight);
+ *   w2n [256][256]                     natural-layout SHADOW of fc_block_2.fc.weight used by the
+ *        backward dX pass; it is a parameter in its own right (own grad, exp_avg, exp_avg_sq,
+ *        updated by the same Adam arithmetic), hence bit-identical to w2t transposed. -1 if absent.
+ */
+typedef struct b2rl_net {
+  int32_t in_dim;     /* O (actor) or O+A (critic)            agents/nets.py:63-67,106-110 */
+  int32_t out_dim;    /* 1 (critic), A (TD3 actor), 2A (SAC)  agents/nets.py:84,127,192   */
+  int32_t layer_norm; /* hps.layer_norm                        agents/nets.py:69,75        */
+  int32_t reserved;
+  int64_t w1t, b1, g1, be1;
+  int64_t w2t, b2, g2, be2;
+  int64_t w3, b3;
+  int64_t w2n;
+  int64_t begin, end;
+} b2rl_net_t;
+
+/* ---- transition rows -------------------------------------------------------------------
+ * Replay storage AND sampled batches use one padded array-of-structs row per transition:
+ *   [ obs(O) | act(A) | reward | done(0/1) | next_obs(O) | pad ]   row_stride % 4 == 0 floats
+ * so a row is a whole number of 128-bit words and [obs|act] (the critic input, agents/nets.py:89)
+ * is already contiguous. The reference stores six separate [cap,d] tensors (main.py:167-171,
+ * orchestrator.py:100-113). */
+typedef struct b2rl_rowfmt {
+  int32_t ob_dim, ac_dim;
+  int32_t row_stride; /* floats, multiple of 4, >= 2*ob_dim + ac_dim + 2 */
+  int32_t reserved;
+} b2rl_rowfmt_t;
+
+/* ---- device-side counters ----------------------------------------------------------------
+ * uint64[8] in device memory, owned by the caller, zero-initialised:
+ *   [0] critic Adam steps done  [1] actor Adam steps done  [2] alpha Adam steps done
+ *   [3] replay samples drawn    [4] ticket (self-resetting)   [5] replay size   [6..7] spare
+ * They advance on the device so that a captured graph can be replayed without host patches. */
+#define B2RL_CTR_Q 0
+#define B2RL_CTR_PI 1
+#define B2RL_CTR_ALPHA 2
+#define B2RL_CTR_SAMPLE 3
+#define B2RL_CTR_TICKET 4 /* alpha_update's last-CTA ticket */
+#define B2RL_CTR_SIZE 5   /* replay rows filled, written by the host side of the replay buffer */
+
+typedef struct b2rl_hyper {
+  int32_t td3;                 /* hps.prefer_td3_over_sac */
+  int32_t bcq_mix;             /* hps.bcq_style_targ_mix        agents/agent.py:213-219 */
+  int32_t targ_smoothing;      /* hps.targ_actor_smoothing      agents/agent.py:197-202 */
+  int32_t autotune;            /* hps.autotune                  agents/agent.py:130-139 */
+  float gamma;                 /* agents/agent.py:228 */
+  float td3_std, td3_c;        /* agents/agent.py:198-199 */
+  float targ_ent;              /* -A                            agents/agent.py:134 */
+  uint64_t seed;               /* Philox key when noise/indices are drawn on the device */
+} b2rl_hyper_t;
+
+/* Everything a fused update needs. Pointers are `dev`. Population stacking: agent g uses
+ * base + g*<x>_agent_stride for every per-agent buffer (n_agents == 1 for a single learner). */
+typedef struct b2rl_update_args {
+  b2rl_hyper_t hp;
+  b2rl_rowfmt_t fmt;
+  b2rl_net_t actor;            /* online actor                                         */
+  b2rl_net_t critic[2];        /* twin critics (reference stacks them on dim 0, agent.py:106) */
+  int32_t batch;               /* B, multiple of B2RL_ROWS */
+  int32_t n_agents;
+  int64_t region_stride;       /* floats between regions of the arena */
+  int64_t arena_agent_stride;  /* floats between agents' arenas */
+  float* arena;                /* dev */
+  const float* rows;           /* dev: the sampled batch, [n_agents][B][row_stride] */
+  int64_t rows_agent_stride;
+  const float* min_ac;         /* dev [A] */
+  const float* max_ac;         /* dev [A] */
+  float* log_alpha;            /* dev: 5 floats per agent {log_alpha, grad, exp_avg, exp_avg_sq, spare}; SAC only */
+  const float* eps;            /* dev [n_agents][B][A] N(0,1) noise, or NULL => Philox on device */
+  const float* eps2;           /* dev: second noise tensor (SAC alpha step), or NULL */
+  float* eps_out;              /* dev or NULL: noise actually used (parity tests) */
+  float* eps2_out;             /* dev or NULL */
+  uint64_t* counters;          /* dev uint64[8] per agent */
+  float* workspace;            /* dev, b2rl_workspace_floats() per agent */
+  int64_t workspace_agent_stride;
+  float* out;                  /* dev float[8] per agent: {qf_loss, actor_loss, alpha_loss, alpha, ...} */
+  float* dbg_targ_q;           /* dev [n_agents][B] or NULL   (TD target y, agent.py:226-228) */
+  float* dbg_q;                /* dev [n_agents][2][B] or NULL (online Q values) */
+} b2rl_update_args_t;
+
+#define B2RL_OUT_QF_LOSS 0
+#define B2RL_OUT_ACTOR_LOSS 1
+#define B2RL_OUT_ALPHA_LOSS 2
+#define B2RL_OUT_ALPHA 3
+#define B2RL_OUT_LOGPI_MEAN 4
+
+/* segment of the arena handled by one adam_polyak_multi launch */
+typedef struct b2rl_seg {
+  int64_t begin, end;  /* float offsets inside a region */
+  float lr;
+  int32_t do_adam;     /* p,m,v <- Adam(p, g, m, v)           torch/optim/adam.py:347-551 */
+  int32_t do_polyak;   /* target <- lerp(target, p, polyak)   agents/agent.py:328-331 */
+  int32_t counter;     /* B2RL_CTR_* holding this optimizer's step count (read, not bumped) */
+  float grad_scale;    /* multiplies g first (1/world for data parallel; 1 otherwise) */
+  int32_t clip;        /* 1: scale g by min(1, clip_norm/(norm+1e-6)), norm from b2rl_grad_norm */
+} b2rl_seg_t;
+
+typedef struct b2rl_adam_args {
+  b2rl_seg_t seg[B2RL_MAX_SEG];
+  int32_t n_seg;
+  int32_t n_agents;
+  float polyak;
+  float clip_norm;             /* hps.clip_norm (agents/agent.py:284-285), used when seg.clip */
+  float beta1, beta2, eps;     /* 0.9, 0.999, 1e-8 (torch defaults, agents/agent.py:115-124) */
+  int32_t reserved;
+  int64_t region_stride, arena_agent_stride;
+  float* arena;                /* dev */
+  const uint64_t* counters;    /* dev uint64[8] per agent */
+  const float* grad_sumsq;     /* dev float per agent (from b2rl_grad_sumsq) or NULL */
+} b2rl_adam_args_t;
+
+/* ---- entry points ---------------------------------------------------------------------- */
+
+int b2rl_version(void);
+const char* b2rl_last_error(void);
+
+/* Load every kernel and opt in to large dynamic shared memory. Call once per process and device,
+ * after the CUDA context exists and BEFORE any stream capture (CUDA loads kernels lazily and a
+ * first launch inside a capture is illegal). The only entry point that is not capture-safe. */
+int b2rl_init(void);
+
+/* floats of workspace one agent needs for a batch of B rows */
+int64_t b2rl_workspace_floats(int32_t batch);
+
+/* Replaces `agent.rb.sample(B)` (orchestrator.py:338): torchrl RandomSampler
+ * `randint(0, len, (B,))` + one advanced-index gather per key + the 7 copies CudaGraphModule makes
+ * into its static inputs (orchestrator.py:313-315). Uniform with replacement.
+ *   storage [n_agents][capacity][row_stride], size = filled rows (same for all agents), or 0 to
+ *           read it from counters[B2RL_CTR_SIZE] on the device (a captured graph then follows a
+ *           buffer that is still filling)
+ *   idx_in  int64 [n_agents][B] or NULL => idx = (philox(seed, step, row) * size) >> 32 with
+ *           step = counters[step_counter] (B2RL_CTR_SAMPLE when the sampler runs on its own with
+ *           bump = 1; B2RL_CTR_Q with bump = 0 inside a fused iteration, where the critic step
+ *           advances that counter)
+ *   idx_out int64 [n_agents][B] or NULL;  rows_out [n_agents][B][row_stride] */
+int b2rl_replay_sample_gather(const float* storage, int64_t storage_agent_stride, int64_t size,
+                              b2rl_rowfmt_t fmt, int32_t batch, int32_t n_agents,
+                              const int64_t* idx_in, int64_t* idx_out, float* rows_out,
+                              uint64_t seed, uint64_t* counters, int32_t step_counter, int32_t bump,
+                              void* stream);
+
+/* Replaces `rb.extend(td)` (orchestrator.py:100-113; torchrl round-robin writer): scatter n
+ * freshly packed rows [n][row_stride] to storage rows (cursor + i) % capacity. */
+int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_rowfmt_t fmt,
+                       const float* new_rows, int32_t n, void* stream);
+
+/* Replaces Agent.update_qnets up to and including `qf_loss.backward()` (agents/agent.py:186-235);
+ * advances counters[Q] (the optimizer's step_t += 1) so that the Adam launch that follows sees t:
+ * next action (SAC: online tanh-Gaussian sample + log-prob, nets.py:222-234; TD3: target actor +
+ * clipped noise, agent.py:194-202), twin target Q (agent.py:208-210), min / BCQ mix (:212-219),
+ * entropy term (:221-223), TD target (:226-228), twin online Q + per-critic MSE + sum (:230-233),
+ * full backward into region 4 (gradients of both critics). Writes out[QF_LOSS]. Two launches. */
+int b2rl_critic_update_sac(const b2rl_update_args_t* a, void* stream);
+int b2rl_critic_update_td3(const b2rl_update_args_t* a, void* stream);
+
+/* Replaces Agent.update_actor up to `actor_loss.backward()` (agents/agent.py:247-283): actor
+ * forward (+ reparameterised sample and log-prob for SAC), twin Q with constant critic params
+ * (:272-278), loss `alpha*logpi - min Q` (SAC) or `-Q_0` (TD3), backward through the critics'
+ * inputs into the actor; gradients of the actor into region 4. Writes out[ACTOR_LOSS]; advances
+ * counters[PI]. Two launches. */
+int b2rl_actor_update_sac(const b2rl_update_args_t* a, void* stream);
+int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream);
+
+/* Replaces the autotune tail of update_actor (agents/agent.py:295-303): second no-grad
+ * get_action with the UPDATED actor and fresh noise (a->eps2), alpha_loss, its gradient, and the
+ * scalar Adam step on log_alpha (lr = log_alpha_lr). Writes out[ALPHA_LOSS], out[ALPHA];
+ * bumps counters[ALPHA]. One launch. */
+int b2rl_alpha_update(const b2rl_update_args_t* a, float log_alpha_lr, void* stream);
+
+/* Sum of squares of the gradient span [begin,end) of region 4, per agent, into sumsq[agent]
+ * (first half of clip_grad_norm_, agents/agent.py:284-285). Deterministic two-stage reduction. */
+int b2rl_grad_sumsq(const float* arena, int64_t region_stride, int64_t arena_agent_stride,
+                    int64_t begin, int64_t end, int32_t n_agents, float* sumsq, float* scratch,
+                    void* stream);
+
+/* Replaces `optimizer.step()` (agents/agent.py:236,286; torch _multi_tensor_adam, ~16 foreach
+ * launches per step) and `update_targ_nets` (agents/agent.py:320-331; foreach lerp_) with ONE
+ * launch over up to B2RL_MAX_SEG spans. Adam follows torch's `capturable` branch
+ * (torch/optim/adam.py:478-527), which is what the reference runs on the GPU (agent.py:118). */
+int b2rl_adam_polyak_multi(const b2rl_adam_args_t* a, void* stream);
+
+/* counters[which] += 1 for every agent (the optimizer's `step_t += 1`, adam.py:413). Runs as a
+ * 1-thread-per-agent kernel so the value the *next* launches see is stream-ordered. */
+int b2rl_bump_counter(uint64_t* counters, int32_t which, int32_t n_agents, void* stream);
+
+/* Replaces the policies behind Agent.predict (agents/agent.py:172-181, nets.py:149-159,222-234):
+ * actor forward on n observation rows [n][ob_dim] -> actions [n][A].
+ *   mode 0: SAC mode / TD3 exploit;  1: SAC sample / TD3 explore (noise from a->eps [n][A], or
+ *   Philox keyed on `draw`, which the caller advances per call) */
+int b2rl_actor_predict(const b2rl_update_args_t* a, const float* obs, int32_t n, int32_t mode,
+                       float explore_std, uint64_t draw, float* actions_out, void* stream);
+
+/* fp32 FFMA peak probe (roofline denominator for the fused MLP kernels): runs `iters` dependent
+ * FFMA chains on every SM; the caller times it. flops = 2 * 148*? is returned through *flops. */
+int b2rl_ffma_probe(float* sink, int32_t iters, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RL_H */

@@ -1,0 +1,322 @@
+// actor.cu — fused actor step (forward, policy loss, backward through the critics' inputs into the
+// actor; agents/agent.py:247-283), the SAC temperature step (agents/agent.py:295-303) and the
+// inference policy (agents/agent.py:172-181), 4 batch rows per CTA.
+#include "mlp_rows.cuh"
+#include "policy.cuh"
+#include "rng.cuh"
+
+namespace b2rl {
+
+struct ActorSmem {
+  float4 x[XMAX];  // [obs | a_pi]
+  Acts pi;         // actor activations (kept for its backward pass)
+  Acts q[2];       // critics' activations
+  Scratch s;
+  float4 da[MAX_OUT];       // dLoss/da accumulated over the critics: [action dim] -> 4 rows
+  float4 qv[2], logpi, dq[2];
+  float eps[ROWS][MAX_OUT / 2], sg[ROWS][MAX_OUT / 2], yy[ROWS][MAX_OUT / 2], th[ROWS][MAX_OUT / 2];
+};
+
+__global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ActorSmem& M = *reinterpret_cast<ActorSmem*>(smem_raw);
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
+  const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const bool td3 = A.hp.td3 != 0;
+  const int nq = td3 ? 1 : 2;  // TD3's loss uses critic 0 only (agent.py:274-275)
+
+  const float* P = A.arena + (size_t)agent * A.arena_agent_stride;
+  const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
+  const uint64_t step = A.counters[(size_t)agent * 8 + B2RL_CTR_PI];
+  float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
+  const Workspace ws = ws_carve(wsb, B, 0);
+  float* part = ws.part + (size_t)rb * PART_LEN;
+  const float alpha = td3 ? 0.f : expf(A.log_alpha[(size_t)agent * 5]);
+  const float invB = 1.0f / (float)B;
+  int tog = 0;
+  float4 pr1, pr2;  // actor rstd
+  float4 qr1[2], qr2[2];
+
+  // ---- actor forward on obs (agent.py:251 / :254-255)
+  load_x(rows, rs, b0, 0, O, M.x, 0);
+  __syncthreads();
+  const Net act = resolve(P, A.actor);
+  trunk_fwd(act, M.x, M.pi, M.s, tog, pr1, pr2, ws.h1, ws.h2, b0);
+  rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
+  __syncthreads();
+  if (w < ROWS) {
+    const int r = w;
+    float lp = 0.f;
+    if (l < AD) {
+      const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+      const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+      float act_v;
+      if (td3) {
+        float th;
+        act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
+        M.th[r][l] = th;
+      } else {
+        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
+        const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_ACTOR_EPS);
+        if (A.eps_out) A.eps_out[e] = z;
+        const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
+        act_v = g.action;
+        lp = g.logp;
+        M.eps[r][l] = z; M.sg[r][l] = g.sigma; M.yy[r][l] = g.y; M.th[r][l] = g.th;
+      }
+      reinterpret_cast<float*>(&M.x[O + l])[r] = act_v;
+    }
+    lp = warp_sum(lp);
+    if (l == 0) reinterpret_cast<float*>(&M.logpi)[r] = lp;
+  }
+  if (t < MAX_OUT) M.da[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+
+  // ---- Q(obs, a_pi) with the critics' parameters held constant (agent.py:272-278)
+  for (int k = 0; k < nq; ++k) {
+    const Net q = resolve(P, A.critic[k]);
+    trunk_fwd(q, M.x, M.q[k], M.s, tog, qr1[k], qr2[k], nullptr, nullptr, b0);
+    rowdot(q.w3, q.b3, 1, M.q[k].h2, &M.qv[k]);
+    __syncthreads();
+  }
+
+  // ---- loss and dLoss/dQ_k per row: SAC  mean(alpha*logpi - min_k Q_k), TD3  mean(-Q_0)
+  if (t < ROWS) {
+    const int r = t;
+    const float q0 = f4get(M.qv[0], r);
+    float lossr, d0 = -invB, d1 = 0.f;
+    if (td3) {
+      lossr = -q0;
+    } else {
+      const float q1 = f4get(M.qv[1], r);
+      const bool first = q0 <= q1;  // torch.min(0) returns the first minimal index on ties
+      d0 = first ? -invB : 0.f;
+      d1 = first ? 0.f : -invB;
+      lossr = __fsub_rn(__fmul_rn(alpha, f4get(M.logpi, r)), first ? q0 : q1);
+    }
+    reinterpret_cast<float*>(&M.dq[0])[r] = d0;
+    reinterpret_cast<float*>(&M.dq[1])[r] = d1;
+    reinterpret_cast<float*>(&M.s.u[0])[r] = lossr;
+  }
+  __syncthreads();
+  if (t == 0) {
+    const float4 lr4 = M.s.u[0], lp4 = M.logpi;
+    part[PART_SCAL] = lr4.x + lr4.y + lr4.z + lr4.w;
+    part[PART_SCAL + 1] = lp4.x + lp4.y + lp4.z + lp4.w;
+  }
+
+  // ---- backward through each critic down to its action inputs
+  for (int k = 0; k < nq; ++k) {
+    const Net q = resolve(P, A.critic[k]);
+    const float w3 = __ldg(q.w3 + t);
+    const float4 dq = M.dq[k];
+    const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
+    trunk_bwd(q, dh2, M.q[k], M.s, tog, qr1[k], qr2[k], nullptr, nullptr, nullptr, b0);
+    rowdot(q.w1t + (size_t)O * HID, nullptr, AD, M.s.d, M.s.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
+    __syncthreads();
+    if (t < AD) {
+      float4 a = M.da[t];
+      const float4 g = M.s.u[t];
+      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+      M.da[t] = a;
+    }
+    __syncthreads();
+  }
+
+  // ---- backward through the action head
+  if (w < ROWS) {
+    const int r = w;
+    float g_a = 0.f, g_b = 0.f;
+    if (l < AD) {
+      const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+      const float scale = (hi - lo) * 0.5f;
+      const float ga = f4get(M.da[l], r);
+      if (td3) {
+        const float th = M.th[r][l];
+        g_a = ga * scale * (1.0f - th * th);
+      } else {
+        GaussSample g;
+        g.y = M.yy[r][l]; g.sigma = M.sg[r][l]; g.th = M.th[r][l];
+        gauss_backward(g, M.eps[r][l], scale, ga, alpha * invB, g_a, g_b);
+      }
+      reinterpret_cast<float*>(&M.s.du[l])[r] = g_a;
+      ws.dz3[(size_t)(b0 + r) * MAX_OUT + l] = g_a;
+      if (!td3) {
+        reinterpret_cast<float*>(&M.s.du[AD + l])[r] = g_b;
+        ws.dz3[(size_t)(b0 + r) * MAX_OUT + AD + l] = g_b;
+      }
+    }
+  }
+  __syncthreads();
+  if (t < act.out_dim) {
+    const float4 d = M.s.du[t];
+    part[PART_DB3 + t] = d.x + d.y + d.z + d.w;
+  }
+  const float4 dh2 = head_bwd(act.w3, act.out_dim, M.s.du);
+  trunk_bwd(act, dh2, M.pi, M.s, tog, pr1, pr2, ws.dz1, ws.dz2, part, b0);
+}
+
+// ---- SAC temperature step -------------------------------------------------------------------
+// Every CTA: log-prob of a fresh sample from the UPDATED actor for its 4 rows; the last CTA to
+// finish (ticket in counters[4]) sums the per-CTA partials in a fixed order, forms
+//   alpha_loss = mean(alpha * (-logpi - targ_ent)),  d/dlog_alpha = same value,
+// and applies torch's capturable Adam step to the scalar.
+struct AlphaSmem {
+  float4 x[XMAX];
+  Acts pi;
+  Scratch s;
+  float4 logpi;
+  int last;
+};
+
+__device__ __forceinline__ void adam_scalar(float* st /*{p,g,m,v}*/, float g, float lr, float t, float b1, float b2,
+                                            float eps) {
+  float p = st[0], m = st[2], v = st[3];
+  m = m + (1.0f - b1) * (g - m);
+  v = v * b2 + (1.0f - b2) * g * g;
+  const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
+  const float ssn = -(lr / bc1);
+  const float denom = sqrtf(v) / (sqrtf(bc2) * ssn) + eps / ssn;
+  p += m / denom;
+  st[0] = p; st[1] = g; st[2] = m; st[3] = v;
+}
+
+__global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2rl_update_args_t A, float lr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AlphaSmem& M = *reinterpret_cast<AlphaSmem*>(smem_raw);
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
+  const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const float* P = A.arena + (size_t)agent * A.arena_agent_stride;
+  const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
+  uint64_t* ctr = A.counters + (size_t)agent * 8;
+  const uint64_t step = ctr[B2RL_CTR_PI];
+  float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
+  float* part = ws_carve(wsb, B, 0).part;
+  int tog = 0;
+  float4 r1, r2;
+
+  load_x(rows, rs, b0, 0, O, M.x, 0);
+  __syncthreads();
+  const Net act = resolve(P, A.actor);
+  trunk_fwd(act, M.x, M.pi, M.s, tog, r1, r2, nullptr, nullptr, b0);
+  rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
+  __syncthreads();
+  if (w < ROWS) {
+    const int r = w;
+    float lp = 0.f;
+    if (l < AD) {
+      const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+      const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
+      const float z = noise_at(A.eps2, e, A.hp.seed, b0 + r, l, step, agent, STREAM_ALPHA_EPS);
+      if (A.eps2_out) A.eps2_out[e] = z;
+      lp = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, (hi - lo) * 0.5f, (hi + lo) * 0.5f).logp;
+    }
+    lp = warp_sum(lp);
+    if (l == 0) reinterpret_cast<float*>(&M.logpi)[r] = lp;
+  }
+  __syncthreads();
+  if (t == 0) {
+    const float4 lp4 = M.logpi;
+    const float te = A.hp.targ_ent;
+    // sum_r (-logpi_r - targ_ent), agent.py:300
+    part[(size_t)rb * PART_LEN + PART_SCAL + 2] = (-lp4.x - te) + (-lp4.y - te) + (-lp4.z - te) + (-lp4.w - te);
+    __threadfence();
+    const unsigned long long ticket = atomicAdd((unsigned long long*)&ctr[B2RL_CTR_TICKET], 1ULL);
+    M.last = (ticket == (unsigned long long)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!M.last) return;
+  if (t == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(&part[(size_t)i * PART_LEN + PART_SCAL + 2]);
+    float* st = A.log_alpha + (size_t)agent * 5;
+    const float alpha = expf(st[0]);
+    const float loss = alpha * (s / (float)B);
+    const uint64_t tstep = ctr[B2RL_CTR_ALPHA] + 1;
+    adam_scalar(st, loss, lr, (float)tstep, 0.9f, 0.999f, 1e-8f);
+    ctr[B2RL_CTR_ALPHA] = tstep;
+    ctr[B2RL_CTR_TICKET] = 0;  // re-arm the ticket for the next launch / graph replay
+    float* out = A.out + (size_t)agent * 8;
+    out[B2RL_OUT_ALPHA_LOSS] = loss;
+    out[B2RL_OUT_ALPHA] = expf(st[0]);
+  }
+}
+
+// ---- inference policy ----------------------------------------------------------------------------
+struct PredictSmem {
+  float4 x[XMAX];
+  Acts pi;
+  Scratch s;
+};
+
+__global__ void __launch_bounds__(NT, 1)
+predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __restrict__ obs, int n, int mode,
+               float explore_std, uint64_t draw, float* __restrict__ actions) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PredictSmem& M = *reinterpret_cast<PredictSmem*>(smem_raw);
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int b0 = blockIdx.x * ROWS;
+  const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim;
+  const bool td3 = A.hp.td3 != 0;
+  const float* P = A.arena;
+  const uint64_t step = draw;
+  int tog = 0;
+  float4 r1, r2;
+  load_x(obs, O, b0, 0, O, M.x, 0, min(ROWS, n - b0));
+  __syncthreads();
+  const Net act = resolve(P, A.actor);
+  trunk_fwd(act, M.x, M.pi, M.s, tog, r1, r2, nullptr, nullptr, b0);
+  rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
+  __syncthreads();
+  if (w < ROWS && l < AD && b0 + w < n) {
+    const int r = w;
+    const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+    const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+    const int64_t e = (int64_t)(b0 + r) * AD + l;
+    float a;
+    if (td3) {  // agents/nets.py:149-159
+      float th;
+      a = td3_action(f4get(M.s.u[l], r), scale, bias, th);
+      if (mode == 1) a += noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS) * (scale * explore_std);
+    } else if (mode == 1) {  // sample
+      const float z = noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS);  // key != learner's
+      a = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias).action;
+    } else {  // mode = tanh(mean)*scale + bias, agents/nets.py:233
+      a = __fadd_rn(__fmul_rn(tanhf(f4get(M.s.u[l], r)), scale), bias);
+    }
+    actions[e] = a;
+  }
+}
+
+cudaError_t init_actor() {
+  cudaError_t e = cudaFuncSetAttribute(actor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ActorSmem));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AlphaSmem));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredictSmem));
+  return e;
+}
+
+cudaError_t launch_actor_fused(const b2rl_update_args_t& a, cudaStream_t st) {
+  dim3 grid(a.batch / ROWS, a.n_agents);
+  actor_fused_kernel<<<grid, NT, sizeof(ActorSmem), st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_alpha(const b2rl_update_args_t& a, float lr, cudaStream_t st) {
+  dim3 grid(a.batch / ROWS, a.n_agents);
+  alpha_kernel<<<grid, NT, sizeof(AlphaSmem), st>>>(a, lr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_predict(const b2rl_update_args_t& a, const float* obs, int n, int mode, float explore_std,
+                           uint64_t draw, float* actions, cudaStream_t st) {
+  predict_kernel<<<(n + ROWS - 1) / ROWS, NT, sizeof(PredictSmem), st>>>(a, obs, n, mode, explore_std, draw, actions);
+  return cudaGetLastError();
+}
+
+}  // namespace b2rl

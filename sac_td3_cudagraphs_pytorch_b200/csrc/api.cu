@@ -1,0 +1,230 @@
+// api.cu — the extern "C" surface declared in include/b2rl.h: argument validation, error text,
+// kernel launches. No allocation, no synchronisation, no host read of device memory.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace b2rl {
+cudaError_t launch_critic_fused(const b2rl_update_args_t&, cudaStream_t);
+cudaError_t launch_actor_fused(const b2rl_update_args_t&, cudaStream_t);
+cudaError_t launch_alpha(const b2rl_update_args_t&, float, cudaStream_t);
+cudaError_t launch_predict(const b2rl_update_args_t&, const float*, int, int, float, uint64_t, float*, cudaStream_t);
+cudaError_t launch_wgrad(const b2rl_update_args_t&, int, int, cudaStream_t);
+cudaError_t launch_adam(const b2rl_adam_args_t&, cudaStream_t);
+cudaError_t launch_sumsq(const float*, int64_t, int64_t, int64_t, int64_t, int, float*, float*, cudaStream_t);
+cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
+cudaError_t launch_gather(const float*, int64_t, int64_t, b2rl_rowfmt_t, int, int, const int64_t*, int64_t*, float*,
+                          uint64_t, uint64_t*, int, int, cudaStream_t);
+cudaError_t launch_extend(float*, int64_t, int64_t, b2rl_rowfmt_t, const float*, int, cudaStream_t);
+cudaError_t init_critic();
+cudaError_t init_actor();
+cudaError_t init_wgrad();
+cudaError_t init_adam();
+cudaError_t init_replay();
+}  // namespace b2rl
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int check_launch(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return B2RL_OK;
+  return fail(B2RL_E_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_fmt(const b2rl_rowfmt_t& f) {
+  if (f.ob_dim < 1 || f.ac_dim < 1) return fail(B2RL_E_INVALID, "row format: ob_dim/ac_dim must be >= 1");
+  if (f.ac_dim > B2RL_MAX_OUT / 2) return fail(B2RL_E_INVALID, "ac_dim %d > %d", f.ac_dim, B2RL_MAX_OUT / 2);
+  if (f.ob_dim + f.ac_dim > 1024) return fail(B2RL_E_INVALID, "ob_dim + ac_dim %d > 1024", f.ob_dim + f.ac_dim);
+  if (f.row_stride % 4 != 0 || f.row_stride < 2 * f.ob_dim + f.ac_dim + 2)
+    return fail(B2RL_E_INVALID, "row_stride %d must be a multiple of 4 and >= 2*ob+ac+2", f.row_stride);
+  return B2RL_OK;
+}
+
+static int check_net(const b2rl_net_t& n, const char* name, bool need_w2n) {
+  if (n.in_dim < 1 || n.in_dim > 1024 || n.out_dim < 1 || n.out_dim > B2RL_MAX_OUT)
+    return fail(B2RL_E_INVALID, "%s: in_dim %d / out_dim %d out of range", name, n.in_dim, n.out_dim);
+  const int64_t offs[] = {n.w1t, n.b1, n.w2t, n.b2, n.w3, n.b3, n.begin, n.end};
+  for (int64_t o : offs)
+    if (o < 0 || (o & 3)) return fail(B2RL_E_INVALID, "%s: tensor offsets must be >= 0 and multiples of 4 floats", name);
+  if (n.layer_norm && ((n.g1 | n.be1 | n.g2 | n.be2) < 0 || ((n.g1 | n.be1 | n.g2 | n.be2) & 3)))
+    return fail(B2RL_E_INVALID, "%s: LayerNorm offsets invalid", name);
+  if (need_w2n && (n.w2n < 0 || (n.w2n & 3))) return fail(B2RL_E_INVALID, "%s: needs the w2n shadow", name);
+  return B2RL_OK;
+}
+
+static int check_update(const b2rl_update_args_t* a, bool actor_step) {
+  if (!a) return fail(B2RL_E_INVALID, "null args");
+  if (int rc = check_fmt(a->fmt)) return rc;
+  if (a->batch < B2RL_ROWS || a->batch % B2RL_ROWS) return fail(B2RL_E_INVALID, "batch %d must be a positive multiple of %d", a->batch, B2RL_ROWS);
+  if (a->n_agents < 1 || a->n_agents > 65535) return fail(B2RL_E_INVALID, "n_agents %d out of range", a->n_agents);
+  if (!a->arena || !a->rows || !a->min_ac || !a->max_ac || !a->counters || !a->workspace || !a->out)
+    return fail(B2RL_E_INVALID, "null device pointer in update args");
+  if (!aligned16(a->arena) || !aligned16(a->workspace) || (a->region_stride & 3) || (a->arena_agent_stride & 3) ||
+      (a->workspace_agent_stride & 3))
+    return fail(B2RL_E_INVALID, "arena/workspace must be 16-byte aligned with strides that are multiples of 4 floats");
+  if (!a->hp.td3 && !a->log_alpha) return fail(B2RL_E_INVALID, "SAC needs log_alpha");
+  if (int rc = check_net(a->actor, "actor", actor_step)) return rc;
+  if (int rc = check_net(a->critic[0], "critic[0]", true)) return rc;
+  if (int rc = check_net(a->critic[1], "critic[1]", true)) return rc;
+  const int want_out = a->hp.td3 ? a->fmt.ac_dim : 2 * a->fmt.ac_dim;
+  if (a->actor.in_dim != a->fmt.ob_dim || a->actor.out_dim != want_out)
+    return fail(B2RL_E_INVALID, "actor dims (%d -> %d) do not match the row format / algorithm", a->actor.in_dim, a->actor.out_dim);
+  for (int k = 0; k < 2; ++k)
+    if (a->critic[k].in_dim != a->fmt.ob_dim + a->fmt.ac_dim || a->critic[k].out_dim != 1)
+      return fail(B2RL_E_INVALID, "critic[%d] dims (%d -> %d) do not match the row format", k, a->critic[k].in_dim, a->critic[k].out_dim);
+  return B2RL_OK;
+}
+
+// ---- FFMA probe ----------------------------------------------------------------------------------
+namespace b2rl {
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* sink, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+  const float m = 0.999f, c = 1e-3f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) sink[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace b2rl
+
+extern "C" {
+
+int b2rl_version(void) { return B2RL_VERSION; }
+const char* b2rl_last_error(void) { return g_err; }
+
+int b2rl_init(void) {
+  cudaError_t e = b2rl::init_critic();
+  if (e == cudaSuccess) e = b2rl::init_actor();
+  if (e == cudaSuccess) e = b2rl::init_wgrad();
+  if (e == cudaSuccess) e = b2rl::init_adam();
+  if (e == cudaSuccess) e = b2rl::init_replay();
+  if (e == cudaSuccess) {
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, b2rl::ffma_probe_kernel);
+  }
+  return check_launch(e, "b2rl_init");
+}
+
+int64_t b2rl_workspace_floats(int32_t batch) {
+  if (batch < B2RL_ROWS || batch % B2RL_ROWS) return -1;
+  return b2rl::ws_floats(batch);
+}
+
+int b2rl_replay_sample_gather(const float* storage, int64_t storage_agent_stride, int64_t size, b2rl_rowfmt_t fmt,
+                              int32_t batch, int32_t n_agents, const int64_t* idx_in, int64_t* idx_out,
+                              float* rows_out, uint64_t seed, uint64_t* counters, int32_t step_counter, int32_t bump,
+                              void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
+  if (!storage || !rows_out) return fail(B2RL_E_INVALID, "null storage / rows_out");
+  if (!aligned16(storage) || !aligned16(rows_out)) return fail(B2RL_E_INVALID, "storage and rows_out must be 16-byte aligned");
+  if (batch < 1 || n_agents < 1 || n_agents > 65535) return fail(B2RL_E_INVALID, "bad batch / n_agents");
+  if (size < 0 || size >= (1LL << 32)) return fail(B2RL_E_INVALID, "size %lld must be in [0, 2^32)", (long long)size);
+  if ((!idx_in || size == 0) && !counters) return fail(B2RL_E_INVALID, "device-side sampling needs the counters");
+  if (step_counter < 0 || step_counter > 3) return fail(B2RL_E_INVALID, "bad step_counter");
+  if (storage_agent_stride & 3) return fail(B2RL_E_INVALID, "storage_agent_stride must be a multiple of 4 floats");
+  return check_launch(b2rl::launch_gather(storage, storage_agent_stride, size, fmt, batch, n_agents, idx_in, idx_out,
+                                          rows_out, seed, counters, step_counter, bump, (cudaStream_t)stream),
+                      "replay_sample_gather");
+}
+
+int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_rowfmt_t fmt, const float* new_rows,
+                       int32_t n, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
+  if (!storage || !new_rows || !aligned16(storage) || !aligned16(new_rows))
+    return fail(B2RL_E_INVALID, "storage / new_rows must be non-null and 16-byte aligned");
+  if (capacity < 1 || cursor < 0 || cursor >= capacity || n < 0 || n > capacity)
+    return fail(B2RL_E_INVALID, "bad capacity / cursor / n");
+  if (n == 0) return B2RL_OK;
+  return check_launch(b2rl::launch_extend(storage, capacity, cursor, fmt, new_rows, n, (cudaStream_t)stream), "replay_extend");
+}
+
+static int critic_update(const b2rl_update_args_t* a, int td3, void* stream) {
+  if (int rc = check_update(a, false)) return rc;
+  if ((a->hp.td3 != 0) != (td3 != 0)) return fail(B2RL_E_INVALID, "hp.td3 does not match the entry point");
+  if (int rc = check_launch(b2rl::launch_critic_fused(*a, (cudaStream_t)stream), "critic_fused")) return rc;
+  return check_launch(b2rl::launch_wgrad(*a, 0, B2RL_CTR_Q, (cudaStream_t)stream), "critic wgrad");
+}
+int b2rl_critic_update_sac(const b2rl_update_args_t* a, void* stream) { return critic_update(a, 0, stream); }
+int b2rl_critic_update_td3(const b2rl_update_args_t* a, void* stream) { return critic_update(a, 1, stream); }
+
+static int actor_update(const b2rl_update_args_t* a, int td3, void* stream) {
+  if (int rc = check_update(a, true)) return rc;
+  if ((a->hp.td3 != 0) != (td3 != 0)) return fail(B2RL_E_INVALID, "hp.td3 does not match the entry point");
+  if (int rc = check_launch(b2rl::launch_actor_fused(*a, (cudaStream_t)stream), "actor_fused")) return rc;
+  return check_launch(b2rl::launch_wgrad(*a, 1, B2RL_CTR_PI, (cudaStream_t)stream), "actor wgrad");
+}
+int b2rl_actor_update_sac(const b2rl_update_args_t* a, void* stream) { return actor_update(a, 0, stream); }
+int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream) { return actor_update(a, 1, stream); }
+
+int b2rl_alpha_update(const b2rl_update_args_t* a, float log_alpha_lr, void* stream) {
+  if (int rc = check_update(a, false)) return rc;
+  if (a->hp.td3) return fail(B2RL_E_INVALID, "alpha_update is SAC-only");
+  if (!(log_alpha_lr > 0.f)) return fail(B2RL_E_INVALID, "log_alpha_lr must be > 0");
+  return check_launch(b2rl::launch_alpha(*a, log_alpha_lr, (cudaStream_t)stream), "alpha_update");
+}
+
+int b2rl_grad_sumsq(const float* arena, int64_t region_stride, int64_t arena_agent_stride, int64_t begin, int64_t end,
+                    int32_t n_agents, float* sumsq, float* scratch, void* stream) {
+  if (!arena || !sumsq || !scratch || begin < 0 || end < begin || n_agents < 1)
+    return fail(B2RL_E_INVALID, "grad_sumsq: bad arguments");
+  return check_launch(b2rl::launch_sumsq(arena, region_stride, arena_agent_stride, begin, end, n_agents, sumsq, scratch,
+                                         (cudaStream_t)stream),
+                      "grad_sumsq");
+}
+
+int b2rl_adam_polyak_multi(const b2rl_adam_args_t* a, void* stream) {
+  if (!a || !a->arena || !a->counters) return fail(B2RL_E_INVALID, "adam: null args");
+  if (a->n_seg < 1 || a->n_seg > B2RL_MAX_SEG) return fail(B2RL_E_INVALID, "adam: n_seg %d out of range", a->n_seg);
+  if (a->n_agents < 1 || a->n_agents > 65535) return fail(B2RL_E_INVALID, "adam: bad n_agents");
+  if (!aligned16(a->arena) || (a->region_stride & 3) || (a->arena_agent_stride & 3))
+    return fail(B2RL_E_INVALID, "adam: arena must be 16-byte aligned, strides multiples of 4 floats");
+  for (int i = 0; i < a->n_seg; ++i) {
+    const b2rl_seg_t& s = a->seg[i];
+    if (s.begin < 0 || s.end < s.begin || (s.begin & 3) || (s.end & 3) || s.end > a->region_stride)
+      return fail(B2RL_E_INVALID, "adam: segment %d [%lld,%lld) must be 4-float aligned inside a region", i,
+                  (long long)s.begin, (long long)s.end);
+    if (s.do_adam && (s.counter < 0 || s.counter > 3)) return fail(B2RL_E_INVALID, "adam: segment %d bad counter", i);
+    if (s.do_adam && s.clip && !a->grad_sumsq) return fail(B2RL_E_INVALID, "adam: clip needs grad_sumsq");
+  }
+  return check_launch(b2rl::launch_adam(*a, (cudaStream_t)stream), "adam_polyak_multi");
+}
+
+int b2rl_bump_counter(uint64_t* counters, int32_t which, int32_t n_agents, void* stream) {
+  if (!counters || which < 0 || which > 7 || n_agents < 1) return fail(B2RL_E_INVALID, "bump_counter: bad arguments");
+  return check_launch(b2rl::launch_bump(counters, which, n_agents, (cudaStream_t)stream), "bump_counter");
+}
+
+int b2rl_actor_predict(const b2rl_update_args_t* a, const float* obs, int32_t n, int32_t mode, float explore_std,
+                       uint64_t draw, float* actions_out, void* stream) {
+  if (!a || !obs || !actions_out || n < 1) return fail(B2RL_E_INVALID, "predict: bad arguments");
+  if (int rc = check_fmt(a->fmt)) return rc;
+  if (int rc = check_net(a->actor, "actor", false)) return rc;
+  if (!a->arena || !a->min_ac || !a->max_ac) return fail(B2RL_E_INVALID, "predict: null device pointer");
+  if (mode != 0 && mode != 1) return fail(B2RL_E_INVALID, "predict: mode must be 0 or 1");
+  return check_launch(b2rl::launch_predict(*a, obs, n, mode, explore_std, draw, actions_out, (cudaStream_t)stream), "actor_predict");
+}
+
+int b2rl_ffma_probe(float* sink, int32_t iters, double* flops, void* stream) {
+  if (!sink || iters < 1) return fail(B2RL_E_INVALID, "ffma_probe: bad arguments");
+  const int ctas = 148 * 8;
+  b2rl::ffma_probe_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+  if (flops) *flops = 2.0 * 16.0 * (double)iters * 256.0 * (double)ctas;
+  return check_launch(cudaGetLastError(), "ffma_probe");
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// critic.cu — fused critic step: next action -> twin target Q -> TD target -> twin online Q ->
+// MSE -> backward (dX path), for 4 batch rows per CTA. Replaces agents/agent.py:186-235
+// (Agent.update_qnets up to qf_loss.backward()); the weight-gradient contraction over the batch
+// is wgrad.cu, the optimizer step is adam.cu.
+#include "mlp_rows.cuh"
+#include "policy.cuh"
+#include "rng.cuh"
+
+namespace b2rl {
+
+struct CriticSmem {
+  float4 x[XMAX];  // [next_obs | a'] for the target pass, then [obs | act]
+  Acts a;
+  Scratch s;
+  float4 logpi, qn[2], y;  // per-row scalars
+};
+
+__global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CriticSmem& M = *reinterpret_cast<CriticSmem*>(smem_raw);
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
+  const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const bool td3 = A.hp.td3 != 0;
+
+  const float* P = A.arena + (size_t)agent * A.arena_agent_stride;  // region 0: online
+  const float* T = P + A.region_stride;                             // region 1: target
+  const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
+  const uint64_t step = A.counters[(size_t)agent * 8 + B2RL_CTR_Q];
+  float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
+  int tog = 0;
+  float4 rstd1, rstd2;
+
+  // ---- next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor
+  //      plus clipped noise (agent.py:194-202)
+  load_x(rows, rs, b0, O + AD + 2, O, M.x, 0);
+  __syncthreads();
+  {
+    const Net act = resolve(td3 ? T : P, A.actor);
+    trunk_fwd(act, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0);
+    rowdot(act.w3, act.b3, act.out_dim, M.a.h2, M.s.u);
+    __syncthreads();
+    if (w < ROWS) {  // warp r <-> batch row b0+r, lane <-> action dim
+      const int r = w;
+      float lp = 0.f;
+      if (l < AD) {
+        const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+        const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;  // agents/nets.py:200-204
+        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
+        float act_v;
+        if (td3) {
+          float th;
+          act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
+          if (A.hp.targ_smoothing) {
+            const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_CRITIC_EPS);
+            if (A.eps_out) A.eps_out[e] = z;
+            float n = __fmul_rn(z, A.hp.td3_std);
+            n = fminf(fmaxf(n, -A.hp.td3_c), A.hp.td3_c);
+            act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
+          }
+        } else {
+          const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_CRITIC_EPS);
+          if (A.eps_out) A.eps_out[e] = z;
+          const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
+          act_v = g.action;
+          lp = g.logp;
+        }
+        reinterpret_cast<float*>(&M.x[O + l])[r] = act_v;
+      }
+      lp = warp_sum(lp);
+      if (l == 0) reinterpret_cast<float*>(&M.logpi)[r] = lp;
+    }
+    __syncthreads();
+  }
+
+  // ---- twin target Q on (next_obs, a')  (agent.py:208-210)
+  for (int k = 0; k < 2; ++k) {
+    const Net q = resolve(T, A.critic[k]);
+    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0);
+    rowdot(q.w3, q.b3, 1, M.a.h2, &M.qn[k]);
+    __syncthreads();
+  }
+
+  // ---- TD target (agent.py:212-228)
+  if (t < ROWS) {
+    const int r = t;
+    const float q0 = f4get(M.qn[0], r), q1 = f4get(M.qn[1], r);
+    const float qmin = fminf(q0, q1);
+    float qp = A.hp.bcq_mix ? __fadd_rn(__fmul_rn(0.75f, qmin), __fmul_rn(0.25f, fmaxf(q0, q1))) : qmin;
+    if (!td3) {
+      const float alpha = expf(A.log_alpha[(size_t)agent * 5]);
+      qp = __fsub_rn(qp, __fmul_rn(alpha, f4get(M.logpi, r)));
+    }
+    const float* row = rows + (size_t)(b0 + r) * rs;
+    const float rew = row[O + AD], done = row[O + AD + 1];
+    const float y = __fadd_rn(rew, __fmul_rn(__fmul_rn(1.0f - done, A.hp.gamma), qp));
+    reinterpret_cast<float*>(&M.y)[r] = y;
+    if (A.dbg_targ_q) A.dbg_targ_q[(size_t)agent * B + b0 + r] = y;
+  }
+  load_x(rows, rs, b0, 0, O + AD, M.x, 0);  // [obs | act] is contiguous in the row
+  __syncthreads();
+
+  // ---- twin online Q, loss, backward (agent.py:230-235)
+  for (int k = 0; k < 2; ++k) {
+    const Net q = resolve(P, A.critic[k]);
+    const Workspace ws = ws_carve(wsb, B, k);
+    float* part = ws.part + (size_t)rb * PART_LEN;
+    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, ws.h1, ws.h2, b0);
+    rowdot(q.w3, q.b3, 1, M.a.h2, &M.s.u[0]);
+    __syncthreads();
+    const float4 qv = M.s.u[0], yv = M.y;
+    const float4 dlt = make_float4(qv.x - yv.x, qv.y - yv.y, qv.z - yv.z, qv.w - yv.w);
+    const float sc = 2.0f / (float)B;  // d mean((q-y)^2) / dq
+    const float4 dq = make_float4(dlt.x * sc, dlt.y * sc, dlt.z * sc, dlt.w * sc);
+    if (t < ROWS) {
+      ws.dz3[(size_t)(b0 + t) * MAX_OUT] = f4get(dq, t);
+      if (A.dbg_q) A.dbg_q[((size_t)agent * 2 + k) * B + b0 + t] = f4get(qv, t);
+    }
+    if (t == 0) {
+      part[PART_DB3] = dq.x + dq.y + dq.z + dq.w;
+      part[PART_SCAL] = dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z + dlt.w * dlt.w;
+    }
+    const float w3 = __ldg(q.w3 + t);
+    const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
+    trunk_bwd(q, dh2, M.a, M.s, tog, rstd1, rstd2, ws.dz1, ws.dz2, part, b0);
+  }
+}
+
+size_t critic_smem_bytes() { return sizeof(CriticSmem); }
+
+// loads the kernel (CUDA loads lazily; a first launch inside stream capture would fail) and opts in
+// to > 48 KB of dynamic shared memory
+cudaError_t init_critic() {
+  return cudaFuncSetAttribute(critic_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sizeof(CriticSmem));
+}
+
+cudaError_t launch_critic_fused(const b2rl_update_args_t& a, cudaStream_t st) {
+  dim3 grid(a.batch / ROWS, a.n_agents);
+  critic_fused_kernel<<<grid, NT, sizeof(CriticSmem), st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace b2rl

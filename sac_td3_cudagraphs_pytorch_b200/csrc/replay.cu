@@ -1,0 +1,87 @@
+// replay.cu — GPU-resident replay buffer: uniform index sample + transition gather, and the
+// round-robin write. Replaces torchrl's TensorDictReplayBuffer(LazyTensorStorage) as the reference
+// uses it (main.py:167-171; sample at orchestrator.py:338, extend at orchestrator.py:100-113):
+// there, one randint kernel + one `index` kernel per key (6-7) on SoA tensors whose rows are not
+// 16-byte aligned (11 floats), then 7 more copies into the CUDA graph's static inputs.
+// Here a transition is ONE padded row (row_stride % 4 == 0 floats), so the whole gather is a
+// stream of 128-bit loads/stores: thread i moves float4 chunk (i % chunks) of batch row (i / chunks).
+// HBM-bound: algorithmic bytes per sampled transition = 2 * row_stride * 4 (+ 8 for the index).
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace b2rl {
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const float* __restrict__ storage, int64_t storage_agent_stride, int64_t size, int row_stride,
+              int batch, const int64_t* __restrict__ idx_in, int64_t* __restrict__ idx_out,
+              float* __restrict__ rows_out, uint64_t seed, const uint64_t* __restrict__ counters, int step_counter) {
+  const int agent = blockIdx.y;
+  const int chunks = row_stride >> 2;
+  const int64_t total = (int64_t)batch * chunks;
+  const uint64_t step = counters ? counters[(size_t)agent * 8 + step_counter] : 0;
+  if (size == 0) size = (int64_t)counters[(size_t)agent * 8 + B2RL_CTR_SIZE];  // buffer still filling under a graph
+  const float* src = storage + (size_t)agent * storage_agent_stride;
+  float* dst = rows_out + (size_t)agent * batch * row_stride;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chunks), c = (int)(i - (int64_t)b * chunks);
+    const int64_t r = idx_in ? idx_in[(size_t)agent * batch + b]
+                             : philox_index(seed, (uint32_t)b, step, (uint32_t)agent, (uint64_t)size);
+    if (idx_out && c == 0) idx_out[(size_t)agent * batch + b] = r;
+    st_stream4(dst + ((size_t)b * row_stride + 4 * c), ld_stream4(src + ((size_t)r * row_stride + 4 * c)));
+  }
+}
+
+// a counter must advance only after every CTA of gather_kernel has read it: separate tiny launch,
+// used when the sampler is driven on its own (inside the fused iteration the draw is keyed on the
+// critic step counter, which wgrad.cu advances, so no extra launch is needed there)
+__global__ void bump_sample_kernel(uint64_t* counters, int n_agents, int which) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n_agents) counters[(size_t)a * 8 + which] += 1ULL;
+}
+
+__global__ void __launch_bounds__(256)
+extend_kernel(float* __restrict__ storage, int64_t capacity, int64_t cursor, int row_stride,
+              const float* __restrict__ new_rows, int n) {
+  const int chunks = row_stride >> 2;
+  const int64_t total = (int64_t)n * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chunks), c = (int)(i - (int64_t)b * chunks);
+    const int64_t r = (cursor + b) % capacity;
+    st_stream4(storage + ((size_t)r * row_stride + 4 * c), ld_stream4(new_rows + ((size_t)b * row_stride + 4 * c)));
+  }
+}
+
+cudaError_t init_replay() {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, gather_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, bump_sample_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, extend_kernel);
+  return e;
+}
+
+cudaError_t launch_gather(const float* storage, int64_t storage_agent_stride, int64_t size, b2rl_rowfmt_t fmt,
+                          int batch, int n_agents, const int64_t* idx_in, int64_t* idx_out, float* rows_out,
+                          uint64_t seed, uint64_t* counters, int step_counter, int bump, cudaStream_t st) {
+  const int64_t total = (int64_t)batch * (fmt.row_stride >> 2);
+  int ctas = (int)((total + 255) / 256);
+  if (ctas > 148 * 8) ctas = 148 * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
+  if (ctas < 1) ctas = 1;
+  gather_kernel<<<dim3(ctas, n_agents), 256, 0, st>>>(storage, storage_agent_stride, size, fmt.row_stride, batch,
+                                                    idx_in, idx_out, rows_out, seed, counters, step_counter);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || idx_in || !counters || !bump) return e;
+  bump_sample_kernel<<<(n_agents + 127) / 128, 128, 0, st>>>(counters, n_agents, step_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_rowfmt_t fmt, const float* new_rows,
+                          int n, cudaStream_t st) {
+  const int64_t total = (int64_t)n * (fmt.row_stride >> 2);
+  int ctas = (int)((total + 255) / 256);
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  extend_kernel<<<ctas, 256, 0, st>>>(storage, capacity, cursor, fmt.row_stride, new_rows, n);
+  return cudaGetLastError();
+}
+
+}  // namespace b2rl

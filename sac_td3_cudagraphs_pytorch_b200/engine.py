@@ -1,0 +1,118 @@
+"""Whole learner iterations as CUDA graphs — the replacement for the reference's per-function
+``CudaGraphModule`` wrapping (orchestrator.py:308-315) and its eager sample / Polyak calls
+(orchestrator.py:338, :352).
+
+One iteration of orchestrator.py:337-352 is: sample -> update_qnets -> (every
+``actor_update_delay+1``-th iteration) ``actor_update_delay`` x update_actor on the same batch ->
+update_targ_nets. Here that is ONE graph replay of 4 launches (critic-only iteration) or
+4 + 4*delay launches (SAC; 3*delay for TD3): the sampler writes straight into the batch buffer the
+update kernels read (no static-input copies), indices and noise come from Philox keyed on
+device-side step counters (so replays need no host patching), and the Polyak average rides in the
+Adam launch of the same parameters (legal: nothing reads the targets between the two, and
+``target += polyak*(online_new - target)`` is the same arithmetic either way).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .agents.agent import Agent
+from .replay import Batch, ReplayBuffer
+
+
+class LearnerEngine:
+    def __init__(self, agent: Agent, rb: Optional[ReplayBuffer] = None, batch_size: Optional[int] = None,
+                 use_graphs: Optional[bool] = None, record_noise: bool = False):
+        self.agent = agent
+        self.rb = rb if rb is not None else agent.rb
+        assert self.rb is not None and self.rb.storage is not None, "the replay buffer must hold data"
+        self.B = int(batch_size or agent.hps.batch_size)
+        self.use_graphs = bool(agent.hps.cudagraphs) if use_graphs is None else use_graphs
+        dev = agent.device
+        self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
+        self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        delay = int(agent.hps.actor_update_delay)
+        mk = (lambda: torch.zeros(self.B, agent.ac_dim, device=dev)) if record_noise else (lambda: None)
+        # noise actually drawn by each step (parity tests replay a trajectory through the eager API)
+        self.noise_q, self.noise_pi, self.noise_alpha = mk(), [mk() for _ in range(delay)], [mk() for _ in range(delay)]
+        self.args_q = agent.update_args(self.rows, eps_out=self.noise_q)
+        self.args_pi = [agent.update_args(self.rows, eps_out=self.noise_pi[j], eps2_out=self.noise_alpha[j])
+                        for j in range(delay)]
+        self.graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._size_on_device = -1
+        self.launches_per_variant: dict[tuple, int] = {}
+
+    # -- what one iteration enqueues --------------------------------------------------------------
+    def _enqueue(self, do_actor: bool, do_polyak: bool) -> int:
+        ag, rb = self.agent, self.rb
+        st = ag._stream()
+        n = 0
+        L.check(ag._lib.b2rl_replay_sample_gather(
+            rb.storage.data_ptr(), 0, 0, rb.fmt, self.B, 1, None, self.idx.data_ptr(), self.rows.data_ptr(),
+            C.c_uint64(ag.seed), ag.counters.data_ptr(), L.CTR_Q, 0, st), "replay_sample_gather")
+        n += 1
+        delay = int(ag.hps.actor_update_delay) if do_actor else 0
+        # TD3's target actor is averaged once per iteration, after the last actor update if there is one
+        extra = ag.polyak_segs(critics=False, actor=True) if (ag.td3 and do_polyak and delay == 0) else []
+        ag.enqueue_critic_step(self.args_q, extra_segs=extra, polyak=do_polyak)
+        n += 3
+        for j in range(delay):
+            ag.enqueue_actor_step(self.args_pi[j], polyak=ag.td3 and do_polyak and j == delay - 1)
+            n += 3 + (1 if ag.autotune else 0) + (2 if ag.hps.clip_norm > 0 else 0)
+        return n
+
+    def _polyak_due(self) -> bool:
+        ag = self.agent  # agents/agent.py:323-324, evaluated after the orchestrator bumped the counter
+        return ag.td3 or ((ag.qnet_updates_so_far + 1) % ag.hps.crit_targ_update_freq == 0)
+
+    def _sync_size(self) -> None:
+        if self._size_on_device != len(self.rb):
+            self._size_on_device = len(self.rb)
+            self.agent.counters[L.CTR_SIZE] = self._size_on_device
+
+    def iteration(self, i: int) -> None:
+        """One learner iteration (orchestrator.py:337-352) — enqueue only, nothing is read back."""
+        ag = self.agent
+        do_actor = (i % (ag.hps.actor_update_delay + 1) == 0)
+        key = (do_actor, self._polyak_due())
+        self._sync_size()
+        if not self.use_graphs:
+            self.launches_per_variant[key] = self._enqueue(*key)
+        else:
+            g = self.graphs.get(key)
+            if g is None:
+                g = self._capture(key)
+            g.replay()
+        ag.qnet_updates_so_far += 1
+        if do_actor:
+            ag.actor_updates_so_far += int(ag.hps.actor_update_delay)
+
+    def _capture(self, key) -> torch.cuda.CUDAGraph:
+        """Capture the variant. Capture itself executes nothing, so learner state is untouched."""
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.agent.device)
+        with torch.cuda.graph(g):
+            self.launches_per_variant[key] = self._enqueue(*key)
+        self.graphs[key] = g
+        return g
+
+    def launches(self, i: int) -> int:
+        key = (i % (self.agent.hps.actor_update_delay + 1) == 0, self._polyak_due())
+        return self.launches_per_variant.get(key, 0)
+
+    def logs(self) -> dict[str, torch.Tensor]:
+        """The reference's log keys (agents/agent.py:238-242, :288-318) as views of the device-side
+        output block — no clone, no sync; read them when you log."""
+        ag, o = self.agent, self.agent.out
+        d = {"loss/qf_loss": o[L.OUT_QF_LOSS], "loss/actor_loss": o[L.OUT_ACTOR_LOSS]}
+        if not ag.td3:
+            d["vitals/alpha"] = o[L.OUT_ALPHA]
+            if ag.autotune:
+                d["loss/alpha_loss"] = o[L.OUT_ALPHA_LOSS]
+        return d
+
+    def last_batch(self) -> Batch:
+        return Batch(self.rows, self.agent.fmt, self.idx)

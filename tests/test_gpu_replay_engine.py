@@ -1,0 +1,186 @@
+"""GPU tests for the replay sampler/gather (bit-exact), the whole-iteration engine (graph == eager ==
+step-by-step API, bitwise) and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_synthetic_transitions, philox_randint
+from tests.golden.cases import case_inputs
+from tests.helpers import make_agent
+
+pytestmark = pytest.mark.gpu
+
+
+def _rb(cap, td, seed=0):
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    rb = ReplayBuffer(cap, "cuda", seed=seed)
+    rb.extend({k: v.cuda() for k, v in td.items()})
+    return rb
+
+
+@pytest.mark.parametrize("ob,ac", [(11, 3), (376, 17), (4, 1), (17, 6)])
+def test_gather_is_bit_exact(ob, ac):
+    n, B = 5000, 256
+    td = make_synthetic_transitions(n, ob, ac, [-1.0] * ac, [1.0] * ac, seed=1234)
+    rb = _rb(n, td)
+    assert len(rb) == n
+    idx = torch.randint(0, n, (B,), generator=torch.Generator().manual_seed(4321))
+    batch = rb.sample(B, idx=idx)
+    torch.cuda.synchronize()
+    for k in ("observations", "next_observations", "actions", "rewards", "terminations", "dones"):
+        want = td[k][idx]
+        got = batch[k].cpu()
+        assert got.dtype == want.dtype and got.shape == want.shape, k
+        assert torch.equal(got, want), k  # storage[key][idx], torchrl LazyTensorStorage semantics
+    assert torch.equal(batch["index"].cpu(), idx)
+    again = rb.sample(B, idx=idx).rows.clone()  # idempotent
+    assert torch.equal(again, batch.rows)
+
+
+def test_device_sampler_matches_philox_twin():
+    n, B, seed = 70001, 512, 0xDEADBEEF12345
+    td = make_synthetic_transitions(n, 11, 3, [-1.0] * 3, [1.0] * 3)
+    rb = _rb(n, td, seed=seed)
+    for step in range(3):
+        b = rb.sample(B)
+        idx = b["index"].cpu()
+        want = torch.from_numpy(philox_randint(seed, step, n, B))
+        assert torch.equal(idx, want), f"draw {step}"  # integer Philox: bit-exact with the numpy twin
+        assert torch.equal(b["observations"].cpu(), td["observations"][idx])
+        assert 0 <= int(idx.min()) and int(idx.max()) < n
+    assert int(rb.counters[3]) == 3
+
+
+def test_extend_round_robin_wraps():
+    td = make_synthetic_transitions(13, 5, 2, [-1.0, -1.0], [1.0, 1.0])
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    rb = ReplayBuffer(10, "cuda")
+    first = {k: v[:7].cuda() for k, v in td.items()}
+    second = {k: v[7:13].cuda() for k, v in td.items()}
+    rb.extend(first)
+    assert len(rb) == 7
+    rb.extend(second)  # rows 7,8,9 then wraps onto 0,1,2
+    assert len(rb) == 10
+    got = rb.sample(10, idx=torch.arange(10))["observations"].cpu()
+    want = torch.cat([td["observations"][10:13], td["observations"][3:10]])
+    assert torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        ReplayBuffer(4, "cuda").sample(2)
+
+
+def _arena_equal(a, b):
+    return torch.equal(a.arena.flat, b.arena.flat) and torch.equal(a._alpha_state, b._alpha_state)
+
+
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_clip_targfreq2"])
+def test_engine_graph_equals_eager_equals_api(name):
+    from sac_td3_cudagraphs_pytorch_b200.engine import LearnerEngine
+    inp = case_inputs(name)
+    td = inp["storage"]
+    n_it = 7
+    agents = [make_agent(inp, seed=99) for _ in range(3)]
+    rbs = [_rb(td["observations"].shape[0], td, seed=99) for _ in range(3)]
+    eng_graph = LearnerEngine(agents[0], rbs[0], use_graphs=True)
+    eng_eager = LearnerEngine(agents[1], rbs[1], use_graphs=False, record_noise=True)
+    api = agents[2]
+    for i in range(n_it):
+        eng_graph.iteration(i)
+        eng_eager.iteration(i)
+        # replay the same draws through the reference-shaped API (separate Polyak launch)
+        torch.cuda.synchronize()
+        rows = eng_eager.rows.clone()
+        api.update_qnets(rows, eps=eng_eager.noise_q.clone())
+        api.qnet_updates_so_far += 1
+        if i % (inp["hps"]["actor_update_delay"] + 1) == 0:
+            for j in range(inp["hps"]["actor_update_delay"]):
+                api.update_actor(rows, eps=eng_eager.noise_pi[j].clone(), eps_alpha=eng_eager.noise_alpha[j].clone())
+                api.actor_updates_so_far += 1
+        api.update_targ_nets()
+    torch.cuda.synchronize()
+    assert _arena_equal(agents[0], agents[1]), "graph replay differs from eager launches"
+    assert _arena_equal(agents[1], agents[2]), "fused-Polyak iteration differs from the step-by-step API"
+    assert torch.equal(agents[0].counters[:3], agents[1].counters[:3])
+    assert int(agents[0].counters[0]) == n_it
+    assert agents[0].qnet_updates_so_far == n_it
+    assert torch.isfinite(agents[0].out).all()
+
+
+@pytest.mark.parametrize("algo,ob,ac,bound", [("sac", 11, 3, 1.0), ("td3", 11, 3, 1.0), ("sac", 376, 17, 0.4)])
+def test_full_size_properties(algo, ob, ac, bound):
+    """BASELINE.json sizes: batch 256, replay 1e6 (Hopper) / 2e5 (Humanoid, 618 MB), graphs on."""
+    from sac_td3_cudagraphs_pytorch_b200 import sac_hps, td3_hps
+    from sac_td3_cudagraphs_pytorch_b200.agents.agent import Agent
+    from sac_td3_cudagraphs_pytorch_b200.engine import LearnerEngine
+    hps = sac_hps() if algo == "sac" else td3_hps()
+    cap = 1_000_000 if ob < 100 else 200_000
+    td = make_synthetic_transitions(cap, ob, ac, [-bound] * ac, [bound] * ac, seed=1234)
+    rb = _rb(cap, td, seed=5)
+    torch.manual_seed(0)
+    ag = Agent({"ob_shape": (4, ob), "ac_shape": (4, ac)}, np.full(ac, -bound, np.float32),
+               np.full(ac, bound, np.float32), torch.device("cuda"), hps, rb=rb, seed=5)
+    p0 = ag.arena.region(0).clone()
+    eng = LearnerEngine(ag)
+    n_it = 60
+    qf = []
+    for i in range(n_it):
+        eng.iteration(i)
+        if i % 10 == 9:
+            qf.append(float(eng.logs()["loss/qf_loss"]))
+    torch.cuda.synchronize()
+    assert all(np.isfinite(qf)), qf
+    assert torch.isfinite(ag.arena.flat).all()
+    n_pi = 2 * ((n_it + 2) // 3)
+    assert ag.counters[:3].tolist() == [n_it, n_pi, n_pi if algo == "sac" else 0]
+    assert ag.qnet_updates_so_far == n_it and ag.actor_updates_so_far == n_pi
+    # every online tensor moved; targets trail the online nets (Polyak) but moved too
+    moved = (ag.arena.region(0) != p0)
+    lay = ag.layout
+    for net in (*lay.critic, lay.actor):
+        for f in ("w1t", "w2t", "w3", "b1", "b2", "b3"):
+            o = net.off[f]
+            assert moved[o:o + net.numel(f)].any(), f
+    t_gap = (ag.arena.region(1) - ag.arena.region(0))[lay.critic[0].begin:lay.critic[1].end].abs().max()
+    assert 0 < float(t_gap) < 1.0
+    # sampled indices stay inside the buffer and the gathered rows are the stored rows
+    idx = eng.idx.cpu()
+    assert 0 <= int(idx.min()) and int(idx.max()) < cap
+    assert torch.equal(eng.last_batch()["observations"].cpu(), td["observations"][idx])
+    # the fc2 shadow copies never drift from the primary weights
+    for net, mod in ((lay.critic[0], ag.qnet1), (lay.critic[1], ag.qnet2), (lay.actor, ag.actor)):
+        assert torch.equal(ag.arena.tensor(net, "w2n"), mod.fc_stack.fc_block_2.fc.weight.detach().contiguous())
+    if algo == "sac":
+        assert float(ag.alpha) > 0
+    # drop-in inference policy: deterministic action within bounds
+    a = ag.predict({"observations": td["observations"][:4]}, explore=False)
+    assert a.shape == (4, ac) and np.all(np.abs(a) <= bound + 1e-6)
+
+
+def test_predict_matches_torch_forward():
+    for name in ("sac_hopper", "td3_hopper", "sac_humanoid"):
+        inp = case_inputs(name)
+        ag = make_agent(inp)
+        obs = inp["storage"]["observations"][:7].cuda()
+        eps = inp["eps_q"][0][:7].cuda()
+        with torch.no_grad():
+            if ag.td3:
+                want0 = ag.actor_detach(obs)
+                want1 = want0 + eps * (ag.actor_detach.action_scale * ag.actor_detach.exploration_noise)
+            else:
+                r = ag.actor_detach.get_action(obs, eps)
+                want0, want1 = r["mode"], r["sample"]
+        got0 = ag.predict_device(obs, explore=False)
+        got1 = ag.predict_device(obs, explore=True, eps=eps)
+        assert torch.allclose(got0, want0, rtol=1e-5, atol=2e-6), name
+        assert torch.allclose(got1, want1, rtol=1e-5, atol=2e-6), name
+
+
+def test_errors_are_loud():
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L, sac_hps
+    from sac_td3_cudagraphs_pytorch_b200.agents.agent import Agent
+    with pytest.raises(L.B2rlError):
+        Agent({"ob_shape": (11,), "ac_shape": (3,)}, np.full(3, -1.0, np.float32), np.full(3, 1.0, np.float32),
+              torch.device("cpu"), sac_hps())
+    inp = case_inputs("sac_hopper")
+    ag = make_agent(inp)
+    with pytest.raises(L.B2rlError, match="multiple of 4"):
+        ag.update_qnets(torch.zeros(6, ag.fmt.row_stride, device="cuda"))
