@@ -235,6 +235,11 @@ int b2rl_bump_counter(uint64_t* counters, int32_t which, int32_t n_agents, void*
 int b2rl_actor_predict(const b2rl_update_args_t* a, const float* obs, int32_t n, int32_t mode,
                        float explore_std, uint64_t draw, float* actions_out, void* stream);
 
+/* Measurement hook: enqueue exactly ONE kernel of the update so that bench.py / ncu can time it in
+ * isolation. which: 0 critic_fused, 1 critic wgrad, 2 actor_fused, 3 actor wgrad, 4 alpha (SAC).
+ * Step counters are NOT advanced (wgrad's bump is disabled), otherwise same work as in the update. */
+int b2rl_launch_single(const b2rl_update_args_t* a, int32_t which, void* stream);
+
 /* fp32 FFMA peak probe (roofline denominator for the fused MLP kernels): runs `iters` dependent
  * FFMA chains on every SM; the caller times it. flops = 2 * 148*? is returned through *flops. */
 int b2rl_ffma_probe(float* sink, int32_t iters, double* flops, void* stream);

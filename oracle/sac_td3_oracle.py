@@ -288,7 +288,8 @@ class OracleAgent:
 
     def __init__(self, ob_dim: int, ac_dim: int, min_ac, max_ac, hps: OracleHps,
                  device="cpu", dtype=torch.float32, seed: int = 0,
-                 actor_init: Optional[dict] = None, qnet_init: Optional[list[dict]] = None):
+                 actor_init: Optional[dict] = None, qnet_init: Optional[list[dict]] = None,
+                 torch_adam: bool = False):
         self.ob_dim, self.ac_dim, self.hps = ob_dim, ac_dim, hps
         self.device, self.dtype = torch.device(device), dtype
         self.td3 = bool(hps.prefer_td3_over_sac)
@@ -315,14 +316,18 @@ class OracleAgent:
         self.qnet_target = {k: v.detach().clone() for k, v in self.qnet.items()}
 
         cap = hps.adam_capturable
-        self.q_optimizer = _Adam(self.qnet.values(), hps.qnets_lr, cap)
-        self.actor_optimizer = _Adam(self.actor.values(), hps.actor_lr, cap)
+        if torch_adam:  # the real torch.optim.Adam, as agents/agent.py:115-139 (capturable on the GPU)
+            _mk = lambda ps, lr: torch.optim.Adam(list(ps), lr=lr, capturable=self.device.type == "cuda")
+        else:
+            _mk = lambda ps, lr: _Adam(ps, lr, cap)
+        self.q_optimizer = _mk(self.qnet.values(), hps.qnets_lr)
+        self.actor_optimizer = _mk(self.actor.values(), hps.actor_lr)
         if not self.td3:
             self.log_alpha = torch.tensor(hps.alpha_init, dtype=dtype, device=self.device).log()
             if hps.autotune:
                 self.log_alpha.requires_grad_(True)
                 self.targ_ent = -ac_dim  # agents/agent.py:134
-                self.alpha_optimizer = _Adam([self.log_alpha], hps.log_alpha_lr, cap)
+                self.alpha_optimizer = _mk([self.log_alpha], hps.log_alpha_lr)
         self.qnet_updates_so_far = 0
         self.actor_updates_so_far = 0
 

@@ -77,6 +77,7 @@ SYMBOLS = {
     "b2rl_bump_counter": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_actor_predict": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                      C.c_uint64, C.c_void_p, C.c_void_p]),
+    "b2rl_launch_single": (C.c_int, [C.POINTER(UpdateArgs), C.c_int32, C.c_void_p]),
     "b2rl_ffma_probe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),
 }
 

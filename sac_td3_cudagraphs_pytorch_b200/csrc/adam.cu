@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   float* T = P + A.region_stride;
   float* M1 = P + 2 * A.region_stride;
   float* V = P + 3 * A.region_stride;
-  const float* G = P + 4 * A.region_stride;
+  float* G = P + 4 * A.region_stride;
   const uint64_t* ctr = A.counters + (size_t)agent * 8;
 
   __shared__ SegScalars sc[B2RL_MAX_SEG];
@@ -60,11 +60,14 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float gg = gp[c] * k.gscale;
+          gp[c] = gg;
           mp[c] = mp[c] + omb1 * (gg - mp[c]);
           vp[c] = __fmul_rn(vp[c], A.beta2) + omb2 * gg * gg;
           const float denom = sqrtf(vp[c]) / (k.bc2s * k.ssn) + A.eps / k.ssn;
           pp[c] = pp[c] + mp[c] / denom;
         }
+        // clip_grad_norm_ scales .grad in place (agent.py:284-285): keep region 4 what torch would show
+        if (s.clip) *reinterpret_cast<float4*>(G + i) = g;
         *reinterpret_cast<float4*>(P + i) = p;
         *reinterpret_cast<float4*>(M1 + i) = m;
         *reinterpret_cast<float4*>(V + i) = v;

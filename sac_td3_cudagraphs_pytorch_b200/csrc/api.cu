@@ -219,6 +219,21 @@ int b2rl_actor_predict(const b2rl_update_args_t* a, const float* obs, int32_t n,
   return check_launch(b2rl::launch_predict(*a, obs, n, mode, explore_std, draw, actions_out, (cudaStream_t)stream), "actor_predict");
 }
 
+int b2rl_launch_single(const b2rl_update_args_t* a, int32_t which, void* stream) {
+  if (int rc = check_update(a, which >= 2)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (which) {
+    case 0: return check_launch(b2rl::launch_critic_fused(*a, st), "critic_fused");
+    case 1: return check_launch(b2rl::launch_wgrad(*a, 0, -1, st), "critic wgrad");
+    case 2: return check_launch(b2rl::launch_actor_fused(*a, st), "actor_fused");
+    case 3: return check_launch(b2rl::launch_wgrad(*a, 1, -1, st), "actor wgrad");
+    case 4:
+      if (a->hp.td3) return fail(B2RL_E_INVALID, "alpha kernel is SAC-only");
+      return check_launch(b2rl::launch_alpha(*a, 1e-3f, st), "alpha");
+    default: return fail(B2RL_E_INVALID, "launch_single: which must be 0..4");
+  }
+}
+
 int b2rl_ffma_probe(float* sink, int32_t iters, double* flops, void* stream) {
   if (!sink || iters < 1) return fail(B2RL_E_INVALID, "ffma_probe: bad arguments");
   const int ctas = 148 * 8;
