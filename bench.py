@@ -120,17 +120,28 @@ def build_learner(workload, device, seed):
     return ag, rb, eng, fmt
 
 
-def time_kernel(fn, iters=200, warm=20):
-    for _ in range(warm):
+def time_kernel(fn, iters=200, warm=20, per_graph=20):
+    """Seconds per launch of `fn` (which enqueues exactly one kernel on the current stream), timed with
+    CUDA events around replays of a CUDA graph holding `per_graph` back-to-back launches, so that the
+    host's launch cost (several us through ctypes) is not what is measured."""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(per_graph):
+            fn()
+    reps = max(1, iters // per_graph)
+    for _ in range(max(1, warm // per_graph)):
+        g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(reps):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e-3  # seconds per launch
+    return e0.elapsed_time(e1) / (reps * per_graph) * 1e-3
 
 
 def run_b2rl(args, rank, world, device):

@@ -1,6 +1,8 @@
 // actor.cu — fused actor step (forward, policy loss, backward through the critics' inputs into the
 // actor; agents/agent.py:247-283), the SAC temperature step (agents/agent.py:295-303) and the
 // inference policy (agents/agent.py:172-181), 4 batch rows per CTA.
+#include <cooperative_groups.h>
+
 #include "mlp_rows.cuh"
 #include "policy.cuh"
 #include "rng.cuh"
@@ -10,21 +12,29 @@ namespace b2rl {
 struct ActorSmem {
   float4 x[XMAX];  // [obs | a_pi]
   Acts pi;         // actor activations (kept for its backward pass)
-  Acts q[2];       // critics' activations
+  Acts q;          // this CTA's critic activations
   Scratch s;
-  float4 da[MAX_OUT];       // dLoss/da accumulated over the critics: [action dim] -> 4 rows
+  float4 da_peer[MAX_OUT];  // dLoss/da through the peer CTA's critic: [action dim] -> 4 rows
   float4 qv[2], logpi, dq[2];
   float eps[ROWS][MAX_OUT / 2], sg[ROWS][MAX_OUT / 2], yy[ROWS][MAX_OUT / 2], th[ROWS][MAX_OUT / 2];
 };
 
-__global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
+// SAC: the two CTAs of a cluster share 4 batch rows; CTA k evaluates and differentiates critic k
+// (both recompute the identical actor forward), they swap Q_k (one float4) to agree on the arg-min,
+// CTA 1 hands its dQ/da to CTA 0 through distributed shared memory and retires; CTA 0 runs the actor's
+// backward pass. TD3's loss uses critic 0 only (agent.py:274-275): CTA 1 retires at once.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
+actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ActorSmem& M = *reinterpret_cast<ActorSmem*>(smem_raw);
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int k = (int)cluster.block_rank();
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
+  const int agent = blockIdx.y, rb = blockIdx.x >> 1, b0 = rb * ROWS;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
   const bool td3 = A.hp.td3 != 0;
-  const int nq = td3 ? 1 : 2;  // TD3's loss uses critic 0 only (agent.py:274-275)
+  if (td3 && k == 1) return;  // the TD3 path never touches the cluster barrier
 
   const float* P = A.arena + (size_t)agent * A.arena_agent_stride;
   const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
@@ -35,14 +45,13 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   const float alpha = td3 ? 0.f : expf(A.log_alpha[(size_t)agent * 5]);
   const float invB = 1.0f / (float)B;
   int tog = 0;
-  float4 pr1, pr2;  // actor rstd
-  float4 qr1[2], qr2[2];
+  float4 pr1, pr2, qr1, qr2;  // LayerNorm rstd of the actor / of the critic (threads < ET)
 
   // ---- actor forward on obs (agent.py:251 / :254-255)
   load_x(rows, rs, b0, 0, O, M.x, 0);
   __syncthreads();
   const Net act = resolve(P, A.actor);
-  trunk_fwd(act, M.x, M.pi, M.s, tog, pr1, pr2, ws.h1, ws.h2, b0);
+  trunk_fwd(act, M.x, M.pi, M.s, tog, pr1, pr2, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0);
   rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
   __syncthreads();
   if (w < ROWS) {
@@ -59,7 +68,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
       } else {
         const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
         const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_ACTOR_EPS);
-        if (A.eps_out) A.eps_out[e] = z;
+        if (A.eps_out && k == 0) A.eps_out[e] = z;
         const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
         act_v = g.action;
         lp = g.logp;
@@ -70,15 +79,16 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
     lp = warp_sum(lp);
     if (l == 0) reinterpret_cast<float*>(&M.logpi)[r] = lp;
   }
-  if (t < MAX_OUT) M.da[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
-  // ---- Q(obs, a_pi) with the critics' parameters held constant (agent.py:272-278)
-  for (int k = 0; k < nq; ++k) {
-    const Net q = resolve(P, A.critic[k]);
-    trunk_fwd(q, M.x, M.q[k], M.s, tog, qr1[k], qr2[k], nullptr, nullptr, b0);
-    rowdot(q.w3, q.b3, 1, M.q[k].h2, &M.qv[k]);
-    __syncthreads();
+  // ---- Q_k(obs, a_pi) with the critic's parameters held constant (agent.py:272-278)
+  const Net q = resolve(P, A.critic[k]);
+  trunk_fwd(q, M.x, M.q, M.s, tog, qr1, qr2, nullptr, nullptr, b0);
+  rowdot(q.w3, q.b3, 1, M.q.h2, &M.qv[k]);
+  __syncthreads();
+  if (!td3) {
+    if (t == 0) *cluster.map_shared_rank(&M.qv[k], k ^ 1) = M.qv[k];
+    cluster.sync();
   }
 
   // ---- loss and dLoss/dQ_k per row: SAC  mean(alpha*logpi - min_k Q_k), TD3  mean(-Q_0)
@@ -100,38 +110,36 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
     reinterpret_cast<float*>(&M.s.u[0])[r] = lossr;
   }
   __syncthreads();
-  if (t == 0) {
+  if (t == 0 && k == 0) {
     const float4 lr4 = M.s.u[0], lp4 = M.logpi;
     part[PART_SCAL] = lr4.x + lr4.y + lr4.z + lr4.w;
     part[PART_SCAL + 1] = lp4.x + lp4.y + lp4.z + lp4.w;
   }
 
-  // ---- backward through each critic down to its action inputs
-  for (int k = 0; k < nq; ++k) {
-    const Net q = resolve(P, A.critic[k]);
-    const float w3 = __ldg(q.w3 + t);
+  // ---- backward through critic k down to its action inputs
+  {
+    const float w3 = t < ET ? __ldg(q.w3 + t) : 0.f;
     const float4 dq = M.dq[k];
     const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
-    trunk_bwd(q, dh2, M.q[k], M.s, tog, qr1[k], qr2[k], nullptr, nullptr, nullptr, b0);
+    trunk_bwd(q, dh2, M.q, M.s, tog, qr1, qr2, nullptr, nullptr, nullptr, b0);
     rowdot(q.w1t + (size_t)O * HID, nullptr, AD, M.s.d, M.s.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
     __syncthreads();
-    if (t < AD) {
-      float4 a = M.da[t];
-      const float4 g = M.s.u[t];
-      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-      M.da[t] = a;
-    }
-    __syncthreads();
+  }
+  if (!td3) {
+    if (k == 1 && t < AD) *cluster.map_shared_rank(&M.da_peer[t], 0) = M.s.u[t];
+    cluster.sync();
+    if (k == 1) return;
   }
 
-  // ---- backward through the action head
+  // ---- backward through the action head (CTA 0)
   if (w < ROWS) {
     const int r = w;
     float g_a = 0.f, g_b = 0.f;
     if (l < AD) {
       const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
       const float scale = (hi - lo) * 0.5f;
-      const float ga = f4get(M.da[l], r);
+      float ga = f4get(M.s.u[l], r);                    // through critic 0
+      if (!td3) ga += f4get(M.da_peer[l], r);           // + through critic 1
       if (td3) {
         const float th = M.th[r][l];
         g_a = ga * scale * (1.0f - th * th);
@@ -228,20 +236,23 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   }
   __syncthreads();
   if (!M.last) return;
-  if (t == 0) {
+  if (w == 0) {  // the last CTA: lane-strided sum of the per-CTA partials, fixed shuffle tree
     __threadfence();
     float s = 0.f;
-    for (int i = 0; i < (int)gridDim.x; ++i) s += __ldcg(&part[(size_t)i * PART_LEN + PART_SCAL + 2]);
-    float* st = A.log_alpha + (size_t)agent * 5;
-    const float alpha = expf(st[0]);
-    const float loss = alpha * (s / (float)B);
-    const uint64_t tstep = ctr[B2RL_CTR_ALPHA] + 1;
-    adam_scalar(st, loss, lr, (float)tstep, 0.9f, 0.999f, 1e-8f);
-    ctr[B2RL_CTR_ALPHA] = tstep;
-    ctr[B2RL_CTR_TICKET] = 0;  // re-arm the ticket for the next launch / graph replay
-    float* out = A.out + (size_t)agent * 8;
-    out[B2RL_OUT_ALPHA_LOSS] = loss;
-    out[B2RL_OUT_ALPHA] = expf(st[0]);
+    for (int i = l; i < (int)gridDim.x; i += 32) s += __ldcg(&part[(size_t)i * PART_LEN + PART_SCAL + 2]);
+    s = warp_sum(s);
+    if (l == 0) {
+      float* st = A.log_alpha + (size_t)agent * 5;
+      const float alpha = expf(st[0]);
+      const float loss = alpha * (s / (float)B);
+      const uint64_t tstep = ctr[B2RL_CTR_ALPHA] + 1;
+      adam_scalar(st, loss, lr, (float)tstep, 0.9f, 0.999f, 1e-8f);
+      ctr[B2RL_CTR_ALPHA] = tstep;
+      ctr[B2RL_CTR_TICKET] = 0;  // re-arm the ticket for the next launch / graph replay
+      float* out = A.out + (size_t)agent * 8;
+      out[B2RL_OUT_ALPHA_LOSS] = loss;
+      out[B2RL_OUT_ALPHA] = expf(st[0]);
+    }
   }
 }
 
@@ -302,7 +313,7 @@ cudaError_t init_actor() {
 }
 
 cudaError_t launch_actor_fused(const b2rl_update_args_t& a, cudaStream_t st) {
-  dim3 grid(a.batch / ROWS, a.n_agents);
+  dim3 grid(2 * (a.batch / ROWS), a.n_agents);  // clusters of 2 along x: (row block, critic)
   actor_fused_kernel<<<grid, NT, sizeof(ActorSmem), st>>>(a);
   return cudaGetLastError();
 }

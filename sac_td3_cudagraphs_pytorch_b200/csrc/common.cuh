@@ -9,8 +9,11 @@ namespace b2rl {
 
 constexpr int HID = B2RL_HID;    // 256
 constexpr int ROWS = B2RL_ROWS;  // batch rows per CTA
-constexpr int NT = 256;          // threads per CTA in the fused kernels (thread t <-> hidden unit t)
+constexpr int NT = 512;          // threads per CTA in the fused kernels: 16 warps feed the FFMA pipes
 constexpr int NW = NT / 32;
+constexpr int ET = HID;          // "epilogue threads": thread t < ET <-> hidden unit t (warps 0..7)
+constexpr int EW = ET / 32;
+constexpr int KSPLIT = 8;        // GEMM k-slices (x 2 column halves = 16 warps)
 constexpr int MAX_OUT = B2RL_MAX_OUT;
 constexpr float LN_EPS = 1e-5f;  // torch.nn.LayerNorm default (agents/nets.py:70)
 
@@ -64,19 +67,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Sum of v[0..3] over all NT threads, result broadcast to every thread; fixed order => deterministic.
-// `buf` is NW float4 of shared memory; callers alternate between two buffers so that one
-// __syncthreads per call is enough.
+// barrier over the ET epilogue threads only (named barrier 1; barrier 0 is __syncthreads)
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); }
+
+// Sum of v[0..3] over the ET epilogue threads, result broadcast to each of them; fixed order =>
+// deterministic. `buf` is EW float4 of shared memory; callers alternate between two buffers so that
+// one barrier per call is enough. Must be called by exactly the threads t < ET.
 __device__ __forceinline__ float4 block_sum4(float4 v, float4* buf) {
   v.x = warp_sum(v.x);
   v.y = warp_sum(v.y);
   v.z = warp_sum(v.z);
   v.w = warp_sum(v.w);
   if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = v;
-  __syncthreads();
+  epi_sync();
   float4 s = buf[0];
 #pragma unroll
-  for (int w = 1; w < NW; ++w) {
+  for (int w = 1; w < EW; ++w) {
     const float4 t = buf[w];
     s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
   }

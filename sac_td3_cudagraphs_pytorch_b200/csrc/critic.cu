@@ -1,7 +1,15 @@
 // critic.cu — fused critic step: next action -> twin target Q -> TD target -> twin online Q ->
-// MSE -> backward (dX path), for 4 batch rows per CTA. Replaces agents/agent.py:186-235
+// MSE -> backward (dX path), for 4 batch rows per CTA PAIR. Replaces agents/agent.py:186-235
 // (Agent.update_qnets up to qf_loss.backward()); the weight-gradient contraction over the batch
 // is wgrad.cu, the optimizer step is adam.cu.
+//
+// The twin critics are independent except for min(Q'_1, Q'_2) in the TD target, so the two CTAs of a
+// thread-block cluster each take one critic (target pass, online pass, backward) for the same 4 rows
+// and exchange one float4 (their target Q for the 4 rows) through distributed shared memory. Both
+// recompute the (cheap, identical) next-action pass. Critical path: 4 network passes instead of 7,
+// on 2*B/4 = 128 SMs instead of 64.
+#include <cooperative_groups.h>
+
 #include "mlp_rows.cuh"
 #include "policy.cuh"
 #include "rng.cuh"
@@ -15,11 +23,15 @@ struct CriticSmem {
   float4 logpi, qn[2], y;  // per-row scalars
 };
 
-__global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
+critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CriticSmem& M = *reinterpret_cast<CriticSmem*>(smem_raw);
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int k = (int)cluster.block_rank();  // the critic this CTA owns
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
+  const int agent = blockIdx.y, rb = blockIdx.x >> 1, b0 = rb * ROWS;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
   const bool td3 = A.hp.td3 != 0;
 
@@ -53,14 +65,14 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
           act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
           if (A.hp.targ_smoothing) {
             const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_CRITIC_EPS);
-            if (A.eps_out) A.eps_out[e] = z;
+            if (A.eps_out && k == 0) A.eps_out[e] = z;
             float n = __fmul_rn(z, A.hp.td3_std);
             n = fminf(fmaxf(n, -A.hp.td3_c), A.hp.td3_c);
             act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
           }
         } else {
           const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_CRITIC_EPS);
-          if (A.eps_out) A.eps_out[e] = z;
+          if (A.eps_out && k == 0) A.eps_out[e] = z;
           const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
           act_v = g.action;
           lp = g.logp;
@@ -73,12 +85,14 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     __syncthreads();
   }
 
-  // ---- twin target Q on (next_obs, a')  (agent.py:208-210)
-  for (int k = 0; k < 2; ++k) {
+  // ---- target Q_k on (next_obs, a')  (agent.py:208-210), then swap the 4 values with the peer CTA
+  {
     const Net q = resolve(T, A.critic[k]);
     trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0);
     rowdot(q.w3, q.b3, 1, M.a.h2, &M.qn[k]);
     __syncthreads();
+    if (t == 0) *cluster.map_shared_rank(&M.qn[k], k ^ 1) = M.qn[k];
+    cluster.sync();
   }
 
   // ---- TD target (agent.py:212-228)
@@ -95,13 +109,13 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     const float rew = row[O + AD], done = row[O + AD + 1];
     const float y = __fadd_rn(rew, __fmul_rn(__fmul_rn(1.0f - done, A.hp.gamma), qp));
     reinterpret_cast<float*>(&M.y)[r] = y;
-    if (A.dbg_targ_q) A.dbg_targ_q[(size_t)agent * B + b0 + r] = y;
+    if (A.dbg_targ_q && k == 0) A.dbg_targ_q[(size_t)agent * B + b0 + r] = y;
   }
   load_x(rows, rs, b0, 0, O + AD, M.x, 0);  // [obs | act] is contiguous in the row
   __syncthreads();
 
-  // ---- twin online Q, loss, backward (agent.py:230-235)
-  for (int k = 0; k < 2; ++k) {
+  // ---- online Q_k, loss, backward (agent.py:230-235)
+  {
     const Net q = resolve(P, A.critic[k]);
     const Workspace ws = ws_carve(wsb, B, k);
     float* part = ws.part + (size_t)rb * PART_LEN;
@@ -120,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
       part[PART_DB3] = dq.x + dq.y + dq.z + dq.w;
       part[PART_SCAL] = dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z + dlt.w * dlt.w;
     }
-    const float w3 = __ldg(q.w3 + t);
+    const float w3 = t < ET ? __ldg(q.w3 + t) : 0.f;
     const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
     trunk_bwd(q, dh2, M.a, M.s, tog, rstd1, rstd2, ws.dz1, ws.dz2, part, b0);
   }
@@ -136,7 +150,7 @@ cudaError_t init_critic() {
 }
 
 cudaError_t launch_critic_fused(const b2rl_update_args_t& a, cudaStream_t st) {
-  dim3 grid(a.batch / ROWS, a.n_agents);
+  dim3 grid(2 * (a.batch / ROWS), a.n_agents);  // clusters of 2 along x: (row block, critic)
   critic_fused_kernel<<<grid, NT, sizeof(CriticSmem), st>>>(a);
   return cudaGetLastError();
 }

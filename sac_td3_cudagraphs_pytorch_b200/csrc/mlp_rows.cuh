@@ -1,5 +1,5 @@
 // mlp_rows.cuh — building blocks of the fused SAC/TD3 kernels: a 2x256 MLP evaluated (and
-// differentiated) for a tile of ROWS=4 batch rows by one 256-thread CTA.
+// differentiated) for a tile of ROWS=4 batch rows by one 512-thread CTA.
 //
 // Why this shape: at batch 256 the update is a chain of ~20 dependent
 // [256x256]x[256xB] products. Batch rows are independent through the whole forward pass and
@@ -37,8 +37,8 @@ struct Acts {  // what one forward pass leaves behind for its backward pass
 constexpr int XMAX = 1024;  // max input width (O + A)
 
 struct Scratch {
-  float red[NW * ROWS * HID];  // split-K partial sums [warp][row][col]
-  float4 sred[2][NW];          // block_sum4 ping-pong
+  float red[KSPLIT * ROWS * HID];  // split-K partial sums [k-slice][row][col]
+  float4 sred[2][EW];              // block_sum4 ping-pong
   float4 u[MAX_OUT];           // head outputs / small row-dot results: [output] -> 4 rows
   float4 du[MAX_OUT];
   float4 d[HID];               // gradient tile fed to the backward GEMM
@@ -59,64 +59,56 @@ __device__ __forceinline__ void fma16(float (&acc)[4][4], const float4& w, const
   acc[3][2] = fmaf(w.w, x.z, acc[3][2]); acc[3][3] = fmaf(w.w, x.w, acc[3][3]);
 }
 
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ W, int K,
-                                          const float4* __restrict__ x, float* __restrict__ red) {
+// (__noinline__: one copy of the hot loop for all ~20 layer evaluations of a fused kernel.)
+// 16 warps = 8 k-slices x 2 column halves: warp (s, c) accumulates k in slice s for columns
+// [128c, 128c+128), lane l owning columns 128c+4l..+3 for the 4 rows: per k one coalesced LDG.128 of
+// weights, one broadcast LDS.128 of x[k], 16 FFMA. Weight loads are software-pipelined one group of 4 k
+// ahead through two register sets (no register copies).
+#define B2RL_LOADG(buf, kk)                                         \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) buf[u] = ldg4(wp + (size_t)B2RL_K(kk, u) * HID);
+#define B2RL_FMAG(buf, kk)                                          \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) fma16(acc, buf[u], B2RL_X(kk, u));
+
+static __device__ __noinline__ void gemm_rows(const float* __restrict__ W, int K,
+                                              const float4* __restrict__ x, float* __restrict__ red) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  const int ks = (K + NW - 1) / NW;
-  const int k0 = min(K, w * ks), k1 = min(K, k0 + ks);
-  float lo[4][4], hi[4][4];  // [col][row] for the two 128-column halves
+  const int s = w & (KSPLIT - 1), c = w >> 3;
+  const int ks = (K + KSPLIT - 1) / KSPLIT;
+  const int k0 = min(K, s * ks), n = min(K, k0 + ks) - k0;
+  float acc[4][4];  // [col][row]
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) lo[c][r] = hi[c][r] = 0.f;
+    for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
 
-  const float* wp = W + 4 * l;
-  int k = k0;
-  if (k + 4 <= k1) {
-    float4 wa[4], wb[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      wa[u] = ldg4(wp + (size_t)(k + u) * HID);
-      wb[u] = ldg4(wp + (size_t)(k + u) * HID + 128);
-    }
-    for (; k + 8 <= k1; k += 4) {  // steady state: next group's loads are in flight during the FMAs
-      float4 na[4], nb[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        na[u] = ldg4(wp + (size_t)(k + 4 + u) * HID);
-        nb[u] = ldg4(wp + (size_t)(k + 4 + u) * HID + 128);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 xv = x[k + u];
-        fma16(lo, wa[u], xv);
-        fma16(hi, wb[u], xv);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { wa[u] = na[u]; wb[u] = nb[u]; }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4 xv = x[k + u];
-      fma16(lo, wa[u], xv);
-      fma16(hi, wb[u], xv);
-    }
-    k += 4;
+  const float* wp = W + (size_t)k0 * HID + c * 128 + 4 * l;
+  const float4* xp = x + k0;
+  // groups of 4 k; a ragged last group re-reads the slice's last row with x = 0 (no serial tail loop:
+  // for the narrow first layers, K = 11 or 14, a slice IS one ragged group and costs one L2 round trip)
+  const int g = (n + 3) >> 2;
+  float4 A[4], B[4];
+#define B2RL_K(kk, u) min((kk) + (u), n - 1)
+#define B2RL_X(kk, u) (((kk) + (u)) < n ? xp[(kk) + (u)] : make_float4(0.f, 0.f, 0.f, 0.f))
+  if (g > 0) { B2RL_LOADG(A, 0) }
+  int i = 0;
+  for (; i + 2 <= g; i += 2) {
+    B2RL_LOADG(B, 4 * i + 4)
+    B2RL_FMAG(A, 4 * i)
+    if (i + 2 < g) { B2RL_LOADG(A, 4 * i + 8) }
+    B2RL_FMAG(B, 4 * i + 4)
   }
-  for (; k < k1; ++k) {
-    const float4 xv = x[k];
-    fma16(lo, ldg4(wp + (size_t)k * HID), xv);
-    fma16(hi, ldg4(wp + (size_t)k * HID + 128), xv);
-  }
+  if (i < g) { B2RL_FMAG(A, 4 * i) }
+#undef B2RL_K
+#undef B2RL_X
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    float* dst = red + (w * ROWS + r) * HID + 4 * l;
-    *reinterpret_cast<float4*>(dst) = make_float4(lo[0][r], lo[1][r], lo[2][r], lo[3][r]);
-    *reinterpret_cast<float4*>(dst + 128) = make_float4(hi[0][r], hi[1][r], hi[2][r], hi[3][r]);
-  }
+  for (int r = 0; r < 4; ++r)
+    *reinterpret_cast<float4*>(red + (s * ROWS + r) * HID + c * 128 + 4 * l) =
+        make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
 }
+#undef B2RL_LOADG
+#undef B2RL_FMAG
 
-// thread j: sum the NW partials of column j (fixed order)
+// thread j < ET: sum the KSPLIT partials of column j (fixed order)
 __device__ __forceinline__ float4 reduce_partials(const float* __restrict__ red) {
   const int j = threadIdx.x;
   float z[4];
@@ -124,7 +116,7 @@ __device__ __forceinline__ float4 reduce_partials(const float* __restrict__ red)
   for (int r = 0; r < 4; ++r) {
     float s = red[r * HID + j];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) s += red[(w * ROWS + r) * HID + j];
+    for (int w = 1; w < KSPLIT; ++w) s += red[(w * ROWS + r) * HID + j];
     z[r] = s;
   }
   return make_float4(z[0], z[1], z[2], z[3]);
@@ -132,11 +124,8 @@ __device__ __forceinline__ float4 reduce_partials(const float* __restrict__ red)
 
 // ---- forward epilogue: bias, LayerNorm (biased variance, eps 1e-5, affine), ReLU -----------------
 // Returns h for column j = threadIdx.x; xhat/rstd are what the backward pass needs.
-__device__ __forceinline__ float4 fwd_epilogue(float4 z, const float* __restrict__ b, const float* __restrict__ g,
-                                               const float* __restrict__ be, bool ln, float4 (*sred)[NW], int& tog,
-                                               float4& xhat, float4& rstd) {
-  const int j = threadIdx.x;
-  const float bj = __ldg(b + j);
+__device__ __forceinline__ float4 fwd_epilogue(float4 z, float bj, float gj, float bej, bool ln, float4 (*sred)[EW],
+                                               int& tog, float4& xhat, float4& rstd) {
   z.x += bj; z.y += bj; z.z += bj; z.w += bj;
   float4 n;
   if (ln) {
@@ -148,7 +137,6 @@ __device__ __forceinline__ float4 fwd_epilogue(float4 z, const float* __restrict
     rstd = make_float4(1.0f / sqrtf(s.x * inv + LN_EPS), 1.0f / sqrtf(s.y * inv + LN_EPS),
                        1.0f / sqrtf(s.z * inv + LN_EPS), 1.0f / sqrtf(s.w * inv + LN_EPS));
     xhat = make_float4(d.x * rstd.x, d.y * rstd.y, d.z * rstd.z, d.w * rstd.w);
-    const float gj = __ldg(g + j), bej = __ldg(be + j);
     n = make_float4(fmaf(xhat.x, gj, bej), fmaf(xhat.y, gj, bej), fmaf(xhat.z, gj, bej), fmaf(xhat.w, gj, bej));
   } else {
     rstd = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -162,15 +150,12 @@ __device__ __forceinline__ float4 fwd_epilogue(float4 z, const float* __restrict
 // dh: gradient w.r.t. the post-ReLU activation of column j. Returns dz (gradient w.r.t. the Linear
 // output). colsum = {sum_r dz, sum_r dn*xhat, sum_r dn}: this CTA's contribution to d(bias),
 // d(ln.weight), d(ln.bias) for column j.
-__device__ __forceinline__ float4 bwd_epilogue(float4 dh, float4 h, float4 xhat, float4 rstd,
-                                               const float* __restrict__ g, bool ln, float4 (*sred)[NW], int& tog,
-                                               float (&colsum)[3]) {
-  const int j = threadIdx.x;
+__device__ __forceinline__ float4 bwd_epilogue(float4 dh, float4 h, float4 xhat, float4 rstd, float gj, bool ln,
+                                               float4 (*sred)[EW], int& tog, float (&colsum)[3]) {
   const float4 dn = make_float4(h.x > 0.f ? dh.x : 0.f, h.y > 0.f ? dh.y : 0.f, h.z > 0.f ? dh.z : 0.f,
                                 h.w > 0.f ? dh.w : 0.f);
   float4 dz;
   if (ln) {
-    const float gj = __ldg(g + j);
     const float inv = 1.0f / HID;
     const float4 dx = make_float4(dn.x * gj, dn.y * gj, dn.z * gj, dn.w * gj);
     float4 s1 = block_sum4(dx, sred[tog]); tog ^= 1;
@@ -193,7 +178,7 @@ __device__ __forceinline__ float4 bwd_epilogue(float4 dh, float4 h, float4 xhat,
 // ---- small products against [n][256] row-major matrices ----------------------------------------------
 // out[o] (4 rows) = bias[o] + sum_k W[o][k] * x[k]: warp w takes outputs w, w+NW, ...; lanes stride k.
 // Used for the heads (n = 1, A or 2A) and for dQ/da = dz1 . w1t[O+a][:] in the actor step.
-__device__ __forceinline__ void rowdot(const float* __restrict__ W, const float* __restrict__ bias, int n,
+static __device__ __noinline__ void rowdot(const float* __restrict__ W, const float* __restrict__ bias, int n,
                                        const float4* __restrict__ x, float4* __restrict__ out) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int o = w; o < n; o += NW) {
@@ -217,6 +202,7 @@ __device__ __forceinline__ void rowdot(const float* __restrict__ W, const float*
 __device__ __forceinline__ float4 head_bwd(const float* __restrict__ W, int n, const float4* __restrict__ du) {
   const int k = threadIdx.x;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k >= ET) return a;
   for (int o = 0; o < n; ++o) {
     const float wv = __ldg(W + (size_t)o * HID + k);
     const float4 d = du[o];
@@ -249,52 +235,70 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, int b0, floa
 
 // ---- the two hidden layers, forward. Leaves h1/h2/xh1/xh2 in `A`; rstd1/rstd2 in registers. -----------
 // Ends with a __syncthreads: A.h2 is readable by every thread on return.
-__device__ __forceinline__ void trunk_fwd(const Net& n, const float4* __restrict__ x, Acts& A, Scratch& S, int& tog,
-                                          float4& rstd1, float4& rstd2, float* ws_h1, float* ws_h2, int b0) {
+static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __restrict__ x, Acts& A, Scratch& S, int& tog,
+                                              float4& rstd1, float4& rstd2, float* ws_h1, float* ws_h2, int b0) {
   const int j = threadIdx.x;
+  // per-column parameters are fetched before the GEMMs so that their L2 round trip is off the epilogues
+  float b1 = 0.f, g1 = 1.f, be1 = 0.f, b2 = 0.f, g2 = 1.f, be2 = 0.f;
+  if (j < ET) {
+    b1 = __ldg(n.b1 + j); b2 = __ldg(n.b2 + j);
+    if (n.ln) { g1 = __ldg(n.g1 + j); be1 = __ldg(n.be1 + j); g2 = __ldg(n.g2 + j); be2 = __ldg(n.be2 + j); }
+  }
   gemm_rows(n.w1t, n.in_dim, x, S.red);
   __syncthreads();
-  float4 xh;
-  float4 h = fwd_epilogue(reduce_partials(S.red), n.b1, n.g1, n.be1, n.ln, S.sred, tog, xh, rstd1);
-  A.h1[j] = h;
-  A.xh1[j] = xh;
-  if (ws_h1) store_rows(ws_h1, b0, h);
+  if (j < ET) {
+    float4 xh;
+    const float4 h = fwd_epilogue(reduce_partials(S.red), b1, g1, be1, n.ln, S.sred, tog, xh, rstd1);
+    A.h1[j] = h;
+    A.xh1[j] = xh;
+    if (ws_h1) store_rows(ws_h1, b0, h);
+  }
   __syncthreads();
   gemm_rows(n.w2t, HID, A.h1, S.red);
   __syncthreads();
-  h = fwd_epilogue(reduce_partials(S.red), n.b2, n.g2, n.be2, n.ln, S.sred, tog, xh, rstd2);
-  A.h2[j] = h;
-  A.xh2[j] = xh;
-  if (ws_h2) store_rows(ws_h2, b0, h);
+  if (j < ET) {
+    float4 xh;
+    const float4 h = fwd_epilogue(reduce_partials(S.red), b2, g2, be2, n.ln, S.sred, tog, xh, rstd2);
+    A.h2[j] = h;
+    A.xh2[j] = xh;
+    if (ws_h2) store_rows(ws_h2, b0, h);
+  }
   __syncthreads();
 }
 
-// ---- the two hidden layers, backward (dX path). dh2 = gradient w.r.t. h2 for column j. -------------------
+// ---- the two hidden layers, backward (dX path). dh2 = gradient w.r.t. h2 for column j (threads < ET). ------
 // Writes dz2/dz1 to the workspace (for wgrad.cu) and this CTA's column partial sums when `part` != NULL.
 // On return S.d holds dz1 (synchronised).
-__device__ __forceinline__ void trunk_bwd(const Net& n, float4 dh2, const Acts& A, Scratch& S, int& tog, float4 rstd1,
-                                          float4 rstd2, float* ws_dz1, float* ws_dz2, float* part, int b0) {
+static __device__ __noinline__ void trunk_bwd(const Net& n, float4 dh2, const Acts& A, Scratch& S, int& tog, float4 rstd1,
+                                              float4 rstd2, float* ws_dz1, float* ws_dz2, float* part, int b0) {
   const int j = threadIdx.x;
-  float cs[3];
-  float4 dz = bwd_epilogue(dh2, A.h2[j], A.xh2[j], rstd2, n.g2, n.ln, S.sred, tog, cs);
-  S.d[j] = dz;
-  if (ws_dz2) store_rows(ws_dz2, b0, dz);
-  if (part) {
-    part[3 * HID + j] = cs[0];
-    part[4 * HID + j] = cs[1];
-    part[5 * HID + j] = cs[2];
+  float g1 = 1.f, g2 = 1.f;
+  if (j < ET && n.ln) { g1 = __ldg(n.g1 + j); g2 = __ldg(n.g2 + j); }
+  if (j < ET) {
+    float cs[3];
+    const float4 dz = bwd_epilogue(dh2, A.h2[j], A.xh2[j], rstd2, g2, n.ln, S.sred, tog, cs);
+    S.d[j] = dz;
+    if (ws_dz2) store_rows(ws_dz2, b0, dz);
+    if (part) {
+      part[3 * HID + j] = cs[0];
+      part[4 * HID + j] = cs[1];
+      part[5 * HID + j] = cs[2];
+    }
   }
   __syncthreads();
   gemm_rows(n.w2n, HID, S.d, S.red);
   __syncthreads();
-  dz = bwd_epilogue(reduce_partials(S.red), A.h1[j], A.xh1[j], rstd1, n.g1, n.ln, S.sred, tog, cs);
-  if (ws_dz1) store_rows(ws_dz1, b0, dz);
-  if (part) {
-    part[0 * HID + j] = cs[0];
-    part[1 * HID + j] = cs[1];
-    part[2 * HID + j] = cs[2];
+  if (j < ET) {
+    float cs[3];
+    const float4 dz = bwd_epilogue(reduce_partials(S.red), A.h1[j], A.xh1[j], rstd1, g1, n.ln, S.sred, tog, cs);
+    if (ws_dz1) store_rows(ws_dz1, b0, dz);
+    if (part) {
+      part[0 * HID + j] = cs[0];
+      part[1 * HID + j] = cs[1];
+      part[2 * HID + j] = cs[2];
+    }
+    S.d[j] = dz;  // safe: every thread passed the barrier above, i.e. finished reading S.d in gemm_rows
   }
-  S.d[j] = dz;  // safe: every thread passed the barrier above, i.e. finished reading S.d in gemm_rows
   __syncthreads();
 }
 

@@ -12,6 +12,7 @@
 namespace b2rl {
 
 constexpr int TM = 32, TN = 32;  // output tile; N (the 256-wide side) is always a multiple of TN
+constexpr int WT = 256, WW = WT / 32;  // threads / warps per CTA of this kernel
 
 struct GemmJob {
   const float* A;  // [B][lda], M columns used
@@ -21,48 +22,73 @@ struct GemmJob {
   int lda, ldb, M;
 };
 
+constexpr int CHUNK = 32;  // batch rows staged per warp at a time
 struct WgradSmem {
-  float red[NW][TM][TN + 1];
+  union {
+    float stage[WW][2][CHUNK][TM];  // per warp: A rows then B rows of the current chunk (8 KB per warp)
+    float red[WW][TM][TN + 1];      // after the k loop: per-warp partial tiles
+  };
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;  // src-size 0 => the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+
 // C[m0+i][n0+j] = sum_b A[b][m0+i] * Bm[b][n0+j]; warp w sums its slice of b, lanes hold a 4x8 sub-tile.
+// Each warp first fires ALL global->shared copies of its batch slice (cp.async: no register dependency, so
+// the whole slice is one L2 round trip instead of one per row - the first version, with plain loads, was
+// bound by exactly that: 32 dependent round trips, 10 us), then multiplies out of shared memory.
 __device__ void gemm_tile(const GemmJob& J, int B, int m0, int n0, WgradSmem& S) {
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const int mi = (l >> 2) * 4, ni = (l & 3) * 8;
-  const int bs = (B + NW - 1) / NW;
+  const int bs = (B + WW - 1) / WW;
   const int bA = min(B, w * bs), bB = min(B, bA + bs);
   float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  const bool a_ok = (m0 + mi + 3) < J.lda;  // whole float4 inside the row (columns >= M are discarded later)
-  const float* ap = J.A + m0 + mi;
-  const float* bp = J.Bm + n0 + ni;
+  float(*As)[TM] = S.stage[w][0];
+  float(*Bs)[TM] = S.stage[w][1];
+  for (int b0 = bA; b0 < bB; b0 += CHUNK) {
+    const int nb = min(CHUNK, bB - b0);
+    for (int idx = l; idx < nb * 8; idx += 32) {
+      const int row = idx >> 3, seg = (idx & 7) * 4;
+      cp_async16(&As[row][seg], J.A + (size_t)(b0 + row) * J.lda + m0 + seg, m0 + seg + 3 < J.lda);
+      cp_async16(&Bs[row][seg], J.Bm + (size_t)(b0 + row) * J.ldb + n0 + seg, true);
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 #pragma unroll 4
-  for (int b = bA; b < bB; ++b) {
-    const float4 a = a_ok ? ldg4(ap + (size_t)b * J.lda) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 x0 = ldg4(bp + (size_t)b * J.ldb), x1 = ldg4(bp + (size_t)b * J.ldb + 4);
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    for (int row = 0; row < nb; ++row) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[row][mi]);
+      const float4 x0 = *reinterpret_cast<const float4*>(&Bs[row][ni]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&Bs[row][ni + 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], xv[j], acc[i][j]);
+    }
+    __syncwarp();
   }
+  __syncthreads();  // staging area is dead: reuse it for the partial tiles
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) S.red[w][mi + i][ni + j] = acc[i][j];
   __syncthreads();
-  // 1024 outputs / 256 threads: thread -> (row i = t/8 + 0.. , 4 consecutive columns)
+  // 1024 outputs / 256 threads: thread -> (row i = t/8, 4 consecutive columns)
   const int i = t >> 3, j0 = (t & 7) * 4;
   float s[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float v = S.red[0][i][j0 + j];
 #pragma unroll
-    for (int ww = 1; ww < NW; ++ww) v += S.red[ww][i][j0 + j];
+    for (int ww = 1; ww < WW; ++ww) v += S.red[ww][i][j0 + j];
     s[j] = v;
   }
   if (m0 + i < J.M) {
@@ -97,8 +123,9 @@ __host__ __device__ inline int tiles_of_net(const b2rl_net_t& n) {
 }
 constexpr int VEC_CTAS = PART_VEC + 1;  // 6 column vectors + {db3, scalars}
 
-__global__ void __launch_bounds__(NT) wgrad_kernel(const __grid_constant__ WgradArgs W) {
-  __shared__ WgradSmem S;
+__global__ void __launch_bounds__(WT) wgrad_kernel(const __grid_constant__ WgradArgs W) {
+  extern __shared__ __align__(16) unsigned char wsm_raw[];
+  WgradSmem& S = *reinterpret_cast<WgradSmem*>(wsm_raw);
   const b2rl_update_args_t& A = W.u;
   const int agent = blockIdx.y, t = threadIdx.x;
   const int B = A.batch, nblk = B / ROWS;
@@ -135,32 +162,38 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const __grid_constant__ Wgrad
         const int64_t off = id == 0 ? net.b1 : id == 1 ? net.g1 : id == 2 ? net.be1 : id == 3 ? net.b2 : id == 4 ? net.g2 : net.be2;
         const float* p = ws.part + (size_t)id * HID + t;
         float s = 0.f;
-        for (int i = 0; i < nblk; ++i) s += p[(size_t)i * PART_LEN];
+#pragma unroll 16
+        for (int i = 0; i < nblk; ++i) s += p[(size_t)i * PART_LEN];  // loads are independent: 16 in flight
         G[off + t] = s;
       } else {  // head bias gradient and the scalar outputs
         if (t < net.out_dim) {
           float s = 0.f;
+#pragma unroll 16
           for (int i = 0; i < nblk; ++i) s += ws.part[(size_t)i * PART_LEN + PART_DB3 + t];
           G[net.b3 + t] = s;
         }
-        if (t == 32 && n == n_nets - 1) {  // a lane of another warp: the step's scalar outputs
+        if ((t >> 5) == 2 && n == n_nets - 1) {  // warp 2: the step's scalar outputs (lane-strided, fixed tree)
+          const int lane = t & 31;
           float* out = A.out + (size_t)agent * 8;
           float tot = 0.f, lp = 0.f;
           for (int m = 0; m < n_nets; ++m) {  // sum over critics of the per-critic mean (agent.py:233)
             const float* pm = ws_carve(wsb, B, m).part;
-            float s0 = 0.f;
-            for (int i = 0; i < nblk; ++i) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int i = lane; i < nblk; i += 32) {
               s0 += pm[(size_t)i * PART_LEN + PART_SCAL];
-              lp += pm[(size_t)i * PART_LEN + PART_SCAL + 1];
+              s1 += pm[(size_t)i * PART_LEN + PART_SCAL + 1];
             }
-            tot += s0 / (float)B;
+            tot += warp_sum(s0) / (float)B;
+            lp += warp_sum(s1);
           }
-          if (W.actor_step) {
-            out[B2RL_OUT_ACTOR_LOSS] = tot;
-            out[B2RL_OUT_LOGPI_MEAN] = lp / (float)B;
-            if (!A.hp.td3) out[B2RL_OUT_ALPHA] = expf(A.log_alpha[(size_t)agent * 5]);
-          } else {
-            out[B2RL_OUT_QF_LOSS] = tot;
+          if (lane == 0) {
+            if (W.actor_step) {
+              out[B2RL_OUT_ACTOR_LOSS] = tot;
+              out[B2RL_OUT_LOGPI_MEAN] = lp / (float)B;
+              if (!A.hp.td3) out[B2RL_OUT_ALPHA] = expf(A.log_alpha[(size_t)agent * 5]);
+            } else {
+              out[B2RL_OUT_QF_LOSS] = tot;
+            }
           }
         }
       }
@@ -174,8 +207,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const __grid_constant__ Wgrad
 }
 
 cudaError_t init_wgrad() {
-  cudaFuncAttributes fa;
-  return cudaFuncGetAttributes(&fa, wgrad_kernel);
+  return cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WgradSmem));
 }
 
 cudaError_t launch_wgrad(const b2rl_update_args_t& a, int actor_step, int bump_counter, cudaStream_t st) {
@@ -187,7 +219,7 @@ cudaError_t launch_wgrad(const b2rl_update_args_t& a, int actor_step, int bump_c
   const int n_nets = actor_step ? 1 : 2;
   for (int n = 0; n < n_nets; ++n) ctas += tiles_of_net(actor_step ? a.actor : a.critic[n]) + VEC_CTAS;
   dim3 grid(ctas, a.n_agents);
-  wgrad_kernel<<<grid, NT, 0, st>>>(W);
+  wgrad_kernel<<<grid, WT, sizeof(WgradSmem), st>>>(W);
   return cudaGetLastError();
 }
 
