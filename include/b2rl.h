@@ -103,6 +103,9 @@ typedef struct b2rl_update_args {
   b2rl_net_t critic[2];        /* twin critics (reference stacks them on dim 0, agent.py:106) */
   int32_t batch;               /* B, multiple of B2RL_ROWS */
   int32_t n_agents;
+  int32_t agent_base;          /* global id of local agent 0: Philox streams are keyed on the GLOBAL id, so a
+                                  population gives the same results however it is sharded over GPUs */
+  int32_t reserved;
   int64_t region_stride;       /* floats between regions of the arena */
   int64_t arena_agent_stride;  /* floats between agents' arenas */
   float* arena;                /* dev */
@@ -182,7 +185,7 @@ int b2rl_replay_sample_gather(const float* storage, int64_t storage_agent_stride
                               b2rl_rowfmt_t fmt, int32_t batch, int32_t n_agents,
                               const int64_t* idx_in, int64_t* idx_out, float* rows_out,
                               uint64_t seed, uint64_t* counters, int32_t step_counter, int32_t bump,
-                              void* stream);
+                              int32_t agent_base, void* stream);
 
 /* Replaces `rb.extend(td)` (orchestrator.py:100-113; torchrl round-robin writer): scatter n
  * freshly packed rows [n][row_stride] to storage rows (cursor + i) % capacity. */

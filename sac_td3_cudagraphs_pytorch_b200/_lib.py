@@ -34,7 +34,7 @@ class Hyper(C.Structure):
 
 class UpdateArgs(C.Structure):
     _fields_ = [("hp", Hyper), ("fmt", RowFmt), ("actor", Net), ("critic", Net * 2),
-                ("batch", C.c_int32), ("n_agents", C.c_int32),
+                ("batch", C.c_int32), ("n_agents", C.c_int32), ("agent_base", C.c_int32), ("reserved", C.c_int32),
                 ("region_stride", C.c_int64), ("arena_agent_stride", C.c_int64),
                 ("arena", C.c_void_p), ("rows", C.c_void_p), ("rows_agent_stride", C.c_int64),
                 ("min_ac", C.c_void_p), ("max_ac", C.c_void_p), ("log_alpha", C.c_void_p),
@@ -64,7 +64,7 @@ SYMBOLS = {
     "b2rl_workspace_floats": (C.c_int64, [C.c_int32]),
     "b2rl_replay_sample_gather": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, RowFmt, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
-                                            C.c_int32, C.c_int32, C.c_void_p]),
+                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_replay_extend": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, RowFmt, C.c_void_p, C.c_int32, C.c_void_p]),
     "b2rl_critic_update_sac": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_critic_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),

@@ -82,7 +82,7 @@ class ArenaAdam:
 class Agent:
 
     def __init__(self, net_shapes: dict[str, tuple[int, ...]], min_ac: np.ndarray, max_ac: np.ndarray,
-                 device: torch.device, hps: Any, rb: Optional[Any] = None, seed: int = 0):
+                 device: torch.device, hps: Any, rb: Optional[Any] = None, seed: int = 0, agent_id: int = 0):
         ob_shape, ac_shape = net_shapes["ob_shape"], net_shapes["ac_shape"]
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -95,6 +95,7 @@ class Agent:
         self.hps = hps
         self.td3 = bool(hps.prefer_td3_over_sac)
         self.seed = int(seed)
+        self.agent_id = int(agent_id)  # global learner id (Philox key); a Population member g has agent_id base+g
 
         self.timesteps_so_far = 0
         self.actor_updates_so_far = 0
@@ -215,7 +216,7 @@ class Agent:
         a.hp, a.fmt = self._hyper, self.fmt
         a.actor = lay.actor.c_struct()
         a.critic[0], a.critic[1] = lay.critic[0].c_struct(), lay.critic[1].c_struct()
-        a.batch, a.n_agents = B, 1
+        a.batch, a.n_agents, a.agent_base = B, 1, self.agent_id
         a.region_stride, a.arena_agent_stride = lay.region, self.arena.agent_stride
         a.arena, a.rows, a.rows_agent_stride = self.arena.flat.data_ptr(), rows.data_ptr(), rows.numel()
         a.min_ac, a.max_ac = self.min_ac.data_ptr(), self.max_ac.data_ptr()

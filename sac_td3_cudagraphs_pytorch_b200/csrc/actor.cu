@@ -33,6 +33,7 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const int agent = blockIdx.y, rb = blockIdx.x >> 1, b0 = rb * ROWS;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const uint32_t gid = (uint32_t)(A.agent_base + agent);  // global agent id: keys the Philox streams
   const bool td3 = A.hp.td3 != 0;
   if (td3 && k == 1) return;  // the TD3 path never touches the cluster barrier
 
@@ -67,7 +68,7 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
         M.th[r][l] = th;
       } else {
         const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
-        const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_ACTOR_EPS);
+        const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, gid, STREAM_ACTOR_EPS);
         if (A.eps_out && k == 0) A.eps_out[e] = z;
         const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
         act_v = g.action;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const uint32_t gid = (uint32_t)(A.agent_base + agent);
   const float* P = A.arena + (size_t)agent * A.arena_agent_stride;
   const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
   uint64_t* ctr = A.counters + (size_t)agent * 8;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
     if (l < AD) {
       const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
       const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
-      const float z = noise_at(A.eps2, e, A.hp.seed, b0 + r, l, step, agent, STREAM_ALPHA_EPS);
+      const float z = noise_at(A.eps2, e, A.hp.seed, b0 + r, l, step, gid, STREAM_ALPHA_EPS);
       if (A.eps2_out) A.eps2_out[e] = z;
       lp = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, (hi - lo) * 0.5f, (hi + lo) * 0.5f).logp;
     }

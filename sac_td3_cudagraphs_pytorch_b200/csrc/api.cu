@@ -16,7 +16,7 @@ cudaError_t launch_adam(const b2rl_adam_args_t&, cudaStream_t);
 cudaError_t launch_sumsq(const float*, int64_t, int64_t, int64_t, int64_t, int, float*, float*, cudaStream_t);
 cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
 cudaError_t launch_gather(const float*, int64_t, int64_t, b2rl_rowfmt_t, int, int, const int64_t*, int64_t*, float*,
-                          uint64_t, uint64_t*, int, int, cudaStream_t);
+                          uint64_t, uint64_t*, int, int, int, cudaStream_t);
 cudaError_t launch_extend(float*, int64_t, int64_t, b2rl_rowfmt_t, const float*, int, cudaStream_t);
 cudaError_t init_critic();
 cudaError_t init_actor();
@@ -66,6 +66,7 @@ static int check_update(const b2rl_update_args_t* a, bool actor_step) {
   if (int rc = check_fmt(a->fmt)) return rc;
   if (a->batch < B2RL_ROWS || a->batch % B2RL_ROWS) return fail(B2RL_E_INVALID, "batch %d must be a positive multiple of %d", a->batch, B2RL_ROWS);
   if (a->n_agents < 1 || a->n_agents > 65535) return fail(B2RL_E_INVALID, "n_agents %d out of range", a->n_agents);
+  if (a->agent_base < 0 || (int64_t)a->agent_base + a->n_agents > (1 << 30)) return fail(B2RL_E_INVALID, "agent ids must stay below 2^30");
   if (!a->arena || !a->rows || !a->min_ac || !a->max_ac || !a->counters || !a->workspace || !a->out)
     return fail(B2RL_E_INVALID, "null device pointer in update args");
   if (!aligned16(a->arena) || !aligned16(a->workspace) || (a->region_stride & 3) || (a->arena_agent_stride & 3) ||
@@ -128,7 +129,7 @@ int64_t b2rl_workspace_floats(int32_t batch) {
 int b2rl_replay_sample_gather(const float* storage, int64_t storage_agent_stride, int64_t size, b2rl_rowfmt_t fmt,
                               int32_t batch, int32_t n_agents, const int64_t* idx_in, int64_t* idx_out,
                               float* rows_out, uint64_t seed, uint64_t* counters, int32_t step_counter, int32_t bump,
-                              void* stream) {
+                              int32_t agent_base, void* stream) {
   if (int rc = check_fmt(fmt)) return rc;
   if (!storage || !rows_out) return fail(B2RL_E_INVALID, "null storage / rows_out");
   if (!aligned16(storage) || !aligned16(rows_out)) return fail(B2RL_E_INVALID, "storage and rows_out must be 16-byte aligned");
@@ -138,7 +139,7 @@ int b2rl_replay_sample_gather(const float* storage, int64_t storage_agent_stride
   if (step_counter < 0 || step_counter > 3) return fail(B2RL_E_INVALID, "bad step_counter");
   if (storage_agent_stride & 3) return fail(B2RL_E_INVALID, "storage_agent_stride must be a multiple of 4 floats");
   return check_launch(b2rl::launch_gather(storage, storage_agent_stride, size, fmt, batch, n_agents, idx_in, idx_out,
-                                          rows_out, seed, counters, step_counter, bump, (cudaStream_t)stream),
+                                          rows_out, seed, counters, step_counter, bump, agent_base, (cudaStream_t)stream),
                       "replay_sample_gather");
 }
 

@@ -33,6 +33,7 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const int agent = blockIdx.y, rb = blockIdx.x >> 1, b0 = rb * ROWS;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const uint32_t gid = (uint32_t)(A.agent_base + agent);  // global agent id: keys the Philox streams
   const bool td3 = A.hp.td3 != 0;
 
   const float* P = A.arena + (size_t)agent * A.arena_agent_stride;  // region 0: online
@@ -64,14 +65,14 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
           float th;
           act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
           if (A.hp.targ_smoothing) {
-            const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_CRITIC_EPS);
+            const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, gid, STREAM_CRITIC_EPS);
             if (A.eps_out && k == 0) A.eps_out[e] = z;
             float n = __fmul_rn(z, A.hp.td3_std);
             n = fminf(fmaxf(n, -A.hp.td3_c), A.hp.td3_c);
             act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
           }
         } else {
-          const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, agent, STREAM_CRITIC_EPS);
+          const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, gid, STREAM_CRITIC_EPS);
           if (A.eps_out && k == 0) A.eps_out[e] = z;
           const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
           act_v = g.action;

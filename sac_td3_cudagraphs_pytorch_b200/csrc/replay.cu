@@ -14,7 +14,8 @@ namespace b2rl {
 __global__ void __launch_bounds__(256)
 gather_kernel(const float* __restrict__ storage, int64_t storage_agent_stride, int64_t size, int row_stride,
               int batch, const int64_t* __restrict__ idx_in, int64_t* __restrict__ idx_out,
-              float* __restrict__ rows_out, uint64_t seed, const uint64_t* __restrict__ counters, int step_counter) {
+              float* __restrict__ rows_out, uint64_t seed, const uint64_t* __restrict__ counters, int step_counter,
+              int agent_base) {
   const int agent = blockIdx.y;
   const int chunks = row_stride >> 2;
   const int64_t total = (int64_t)batch * chunks;
@@ -25,7 +26,7 @@ gather_kernel(const float* __restrict__ storage, int64_t storage_agent_stride, i
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / chunks), c = (int)(i - (int64_t)b * chunks);
     const int64_t r = idx_in ? idx_in[(size_t)agent * batch + b]
-                             : philox_index(seed, (uint32_t)b, step, (uint32_t)agent, (uint64_t)size);
+                             : philox_index(seed, (uint32_t)b, step, (uint32_t)(agent_base + agent), (uint64_t)size);
     if (idx_out && c == 0) idx_out[(size_t)agent * batch + b] = r;
     st_stream4(dst + ((size_t)b * row_stride + 4 * c), ld_stream4(src + ((size_t)r * row_stride + 4 * c)));
   }
@@ -61,13 +62,13 @@ cudaError_t init_replay() {
 
 cudaError_t launch_gather(const float* storage, int64_t storage_agent_stride, int64_t size, b2rl_rowfmt_t fmt,
                           int batch, int n_agents, const int64_t* idx_in, int64_t* idx_out, float* rows_out,
-                          uint64_t seed, uint64_t* counters, int step_counter, int bump, cudaStream_t st) {
+                          uint64_t seed, uint64_t* counters, int step_counter, int bump, int agent_base, cudaStream_t st) {
   const int64_t total = (int64_t)batch * (fmt.row_stride >> 2);
   int ctas = (int)((total + 255) / 256);
   if (ctas > 148 * 8) ctas = 148 * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
   if (ctas < 1) ctas = 1;
   gather_kernel<<<dim3(ctas, n_agents), 256, 0, st>>>(storage, storage_agent_stride, size, fmt.row_stride, batch,
-                                                    idx_in, idx_out, rows_out, seed, counters, step_counter);
+                                                    idx_in, idx_out, rows_out, seed, counters, step_counter, agent_base);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || idx_in || !counters || !bump) return e;
   bump_sample_kernel<<<(n_agents + 127) / 128, 128, 0, st>>>(counters, n_agents, step_counter);

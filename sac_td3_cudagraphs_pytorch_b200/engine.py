@@ -52,7 +52,7 @@ class LearnerEngine:
         n = 0
         L.check(ag._lib.b2rl_replay_sample_gather(
             rb.storage.data_ptr(), 0, 0, rb.fmt, self.B, 1, None, self.idx.data_ptr(), self.rows.data_ptr(),
-            C.c_uint64(ag.seed), ag.counters.data_ptr(), L.CTR_Q, 0, st), "replay_sample_gather")
+            C.c_uint64(ag.seed), ag.counters.data_ptr(), L.CTR_Q, 0, ag.agent_id, st), "replay_sample_gather")
         n += 1
         delay = int(ag.hps.actor_update_delay) if do_actor else 0
         # TD3's target actor is averaged once per iteration, after the last actor update if there is one

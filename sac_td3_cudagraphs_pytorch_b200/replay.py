@@ -62,8 +62,9 @@ def pack_rows(td: Mapping[str, torch.Tensor], fmt: L.RowFmt, out: Optional[torch
 
 
 class ReplayBuffer:
-    def __init__(self, capacity: int, device, seed: int = 0):
+    def __init__(self, capacity: int, device, seed: int = 0, agent_id: int = 0):
         self.capacity, self.device, self.seed = int(capacity), torch.device(device), int(seed)
+        self.agent_id = int(agent_id)  # global learner id: part of the Philox key of the index draws
         self.fmt: Optional[L.RowFmt] = None
         self.storage: Optional[torch.Tensor] = None
         self._size = 0
@@ -115,5 +116,6 @@ class ReplayBuffer:
         st = torch.cuda.current_stream(self.device).cuda_stream
         L.check(self._lib.b2rl_replay_sample_gather(
             self.storage.data_ptr(), 0, self._size, self.fmt, batch_size, 1, L.ptr(idx), idx_out.data_ptr(),
-            out.data_ptr(), C.c_uint64(self.seed), self.counters.data_ptr(), L.CTR_SAMPLE, 1, st), "replay_sample_gather")
+            out.data_ptr(), C.c_uint64(self.seed), self.counters.data_ptr(), L.CTR_SAMPLE, 1, self.agent_id, st),
+            "replay_sample_gather")
         return Batch(out, self.fmt, idx_out)

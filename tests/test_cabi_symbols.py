@@ -49,7 +49,7 @@ def test_bad_arguments_are_rejected_before_any_launch():
     assert lib.b2rl_workspace_floats(6) == -1
     assert lib.b2rl_workspace_floats(256) > 0
     fmt = L.RowFmt(11, 3, 27, 0)  # row_stride not a multiple of 4
-    rc = lib.b2rl_replay_sample_gather(16, 0, 10, fmt, 4, 1, None, None, 16, 0, None, 3, 1, None)
+    rc = lib.b2rl_replay_sample_gather(16, 0, 10, fmt, 4, 1, None, None, 16, 0, None, 3, 1, 0, None)
     assert rc == -1 and b"row_stride" in lib.b2rl_last_error()
     a = L.UpdateArgs()
     assert lib.b2rl_critic_update_sac(C.byref(a), None) == -1
