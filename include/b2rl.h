@@ -211,9 +211,16 @@ int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream);
 
 /* Replaces the autotune tail of update_actor (agents/agent.py:295-303): second no-grad
  * get_action with the UPDATED actor and fresh noise (a->eps2), alpha_loss, its gradient, and the
- * scalar Adam step on log_alpha (lr = log_alpha_lr). Writes out[ALPHA_LOSS], out[ALPHA];
- * bumps counters[ALPHA]. One launch. */
+ * scalar Adam step on log_alpha (lr = log_alpha_lr; 0 = gradient only, see b2rl_alpha_adam). Writes
+ * out[ALPHA_LOSS], out[ALPHA]; bumps counters[ALPHA]. One launch. */
 int b2rl_alpha_update(const b2rl_update_args_t* a, float log_alpha_lr, void* stream);
+
+/* Data-parallel variant of the temperature step: b2rl_alpha_update with log_alpha_lr == 0 only
+ * computes the LOCAL alpha_loss and its gradient (log_alpha state slot 1) and leaves log_alpha alone;
+ * after the gradient has been summed over ranks, this applies the scalar Adam step with
+ * g = grad_scale * state[1] (grad_scale = 1/world) and bumps counters[ALPHA]. */
+int b2rl_alpha_adam(float* log_alpha, uint64_t* counters, int32_t n_agents, float log_alpha_lr,
+                    float grad_scale, float* out, void* stream);
 
 /* Sum of squares of the gradient span [begin,end) of region 4, per agent, into sumsq[agent]
  * (first half of clip_grad_norm_, agents/agent.py:284-285). Deterministic two-stage reduction. */

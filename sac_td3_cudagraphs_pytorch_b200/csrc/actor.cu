@@ -247,15 +247,40 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
       float* st = A.log_alpha + (size_t)agent * 5;
       const float alpha = expf(st[0]);
       const float loss = alpha * (s / (float)B);
-      const uint64_t tstep = ctr[B2RL_CTR_ALPHA] + 1;
-      adam_scalar(st, loss, lr, (float)tstep, 0.9f, 0.999f, 1e-8f);
-      ctr[B2RL_CTR_ALPHA] = tstep;
+      if (lr > 0.f) {
+        const uint64_t tstep = ctr[B2RL_CTR_ALPHA] + 1;
+        adam_scalar(st, loss, lr, (float)tstep, 0.9f, 0.999f, 1e-8f);
+        ctr[B2RL_CTR_ALPHA] = tstep;
+      } else {
+        st[1] = loss;  // data parallel: local gradient only; b2rl_alpha_adam finishes after the all-reduce
+      }
       ctr[B2RL_CTR_TICKET] = 0;  // re-arm the ticket for the next launch / graph replay
       float* out = A.out + (size_t)agent * 8;
       out[B2RL_OUT_ALPHA_LOSS] = loss;
       out[B2RL_OUT_ALPHA] = expf(st[0]);
     }
   }
+}
+
+__global__ void alpha_adam_kernel(float* log_alpha, uint64_t* counters, int n_agents, float lr, float grad_scale,
+                                  float* out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_agents) return;
+  float* st = log_alpha + (size_t)a * 5;
+  uint64_t* ctr = counters + (size_t)a * 8;
+  const uint64_t tstep = ctr[B2RL_CTR_ALPHA] + 1;
+  adam_scalar(st, st[1] * grad_scale, lr, (float)tstep, 0.9f, 0.999f, 1e-8f);
+  ctr[B2RL_CTR_ALPHA] = tstep;
+  if (out) {
+    out[(size_t)a * 8 + B2RL_OUT_ALPHA_LOSS] = st[1];
+    out[(size_t)a * 8 + B2RL_OUT_ALPHA] = expf(st[0]);
+  }
+}
+
+cudaError_t launch_alpha_adam(float* log_alpha, uint64_t* counters, int n_agents, float lr, float grad_scale,
+                              float* out, cudaStream_t st) {
+  alpha_adam_kernel<<<(n_agents + 127) / 128, 128, 0, st>>>(log_alpha, counters, n_agents, lr, grad_scale, out);
+  return cudaGetLastError();
 }
 
 // ---- inference policy ----------------------------------------------------------------------------
@@ -311,6 +336,10 @@ cudaError_t init_actor() {
     e = cudaFuncSetAttribute(alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AlphaSmem));
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredictSmem));
+  if (e == cudaSuccess) {
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, alpha_adam_kernel);
+  }
   return e;
 }
 

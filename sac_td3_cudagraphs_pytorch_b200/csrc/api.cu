@@ -10,6 +10,7 @@ namespace b2rl {
 cudaError_t launch_critic_fused(const b2rl_update_args_t&, cudaStream_t);
 cudaError_t launch_actor_fused(const b2rl_update_args_t&, cudaStream_t);
 cudaError_t launch_alpha(const b2rl_update_args_t&, float, cudaStream_t);
+cudaError_t launch_alpha_adam(float*, uint64_t*, int, float, float, float*, cudaStream_t);
 cudaError_t launch_predict(const b2rl_update_args_t&, const float*, int, int, float, uint64_t, float*, cudaStream_t);
 cudaError_t launch_wgrad(const b2rl_update_args_t&, int, int, cudaStream_t);
 cudaError_t launch_adam(const b2rl_adam_args_t&, cudaStream_t);
@@ -175,8 +176,17 @@ int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream) { return ac
 int b2rl_alpha_update(const b2rl_update_args_t* a, float log_alpha_lr, void* stream) {
   if (int rc = check_update(a, false)) return rc;
   if (a->hp.td3) return fail(B2RL_E_INVALID, "alpha_update is SAC-only");
-  if (!(log_alpha_lr > 0.f)) return fail(B2RL_E_INVALID, "log_alpha_lr must be > 0");
+  if (!(log_alpha_lr >= 0.f)) return fail(B2RL_E_INVALID, "log_alpha_lr must be >= 0");
   return check_launch(b2rl::launch_alpha(*a, log_alpha_lr, (cudaStream_t)stream), "alpha_update");
+}
+
+int b2rl_alpha_adam(float* log_alpha, uint64_t* counters, int32_t n_agents, float log_alpha_lr, float grad_scale,
+                    float* out, void* stream) {
+  if (!log_alpha || !counters || n_agents < 1 || !(log_alpha_lr > 0.f))
+    return fail(B2RL_E_INVALID, "alpha_adam: bad arguments");
+  return check_launch(b2rl::launch_alpha_adam(log_alpha, counters, n_agents, log_alpha_lr, grad_scale, out,
+                                              (cudaStream_t)stream),
+                      "alpha_adam");
 }
 
 int b2rl_grad_sumsq(const float* arena, int64_t region_stride, int64_t arena_agent_stride, int64_t begin, int64_t end,

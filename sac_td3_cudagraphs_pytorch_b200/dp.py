@@ -1,0 +1,106 @@
+"""Large-batch data-parallel learner (BASELINE.json config 5): W replicas of one agent, each with its own
+replay buffer and its own batch; gradients of the mean loss are summed over ranks with one
+`all_reduce` per optimizer step on the flat gradient span of the arena (NCCL over NVLink on GPUs) and the
+`1/W` is folded into the Adam kernel (`grad_scale`). The reference has no counterpart (no
+torch.distributed anywhere); the parity oracle is a single rank run on the concatenation of
+the W local batches (mean of equal-sized means = global mean).
+
+Replicas stay bit-identical: every rank applies the same reduced gradient with the same arithmetic. The
+natural-layout shadow gradients (`w2n`) are not reduced — a ring all-reduce may sum two positions of the
+buffer in different orders — but re-derived from the reduced primary gradient by a transposed copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .arena import Arena, ArenaLayout
+
+
+class GradComm:
+    """Sum-all-reduce over a torch.distributed group (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_reduce_sum(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+
+def reduce_grad_span(arena: Arena, layout: ArenaLayout, comm: GradComm, which: str, agent: int = 0) -> None:
+    """All-reduce the gradients (region 4) of the critics or of the actor, then rebuild the w2n shadows."""
+    nets = layout.critic if which == "critic" else [layout.actor]
+    g = arena.flat[agent, L.REGION_G]
+    comm.all_reduce_sum(g[nets[0].begin:nets[-1].core_end])  # one contiguous bucket (shadows in between ride along)
+    with torch.no_grad():
+        for net in nets:
+            arena.tensor(net, "w2n", L.REGION_G, agent).copy_(arena.tensor(net, "w2t", L.REGION_G, agent))
+
+
+class DataParallelLearner:
+    """One rank of the data-parallel learner. `agent` must be constructed identically on every rank (same
+    torch seed => same initial parameters) except `agent_id=rank`, which keys its index/noise draws."""
+
+    def __init__(self, agent, rb, batch_size: int, comm: Optional[GradComm] = None):
+        self.agent, self.rb, self.B = agent, rb, int(batch_size)
+        self.comm = comm or GradComm()
+        dev = agent.device
+        self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
+        self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.launches = 0
+
+    def _seg(self, begin, end, lr, polyak, counter, clip=False):
+        return L.Seg(begin, end, lr, 1, int(polyak), counter, 1.0 / self.comm.world, int(clip))
+
+    def iteration(self, i: int, rows: Optional[torch.Tensor] = None, eps_q=None, eps_pi=None, eps_alpha=None) -> None:
+        """One iteration of orchestrator.py:337-352 with gradient averaging over ranks. `rows` / `eps_*`
+        inject this rank's batch and noise (parity tests); default: device-side sampling."""
+        ag, lib, lay, h, W = self.agent, self.agent._lib, self.agent.layout, self.agent.hps, self.comm.world
+        st = ag._stream()
+        if rows is None:
+            ag.counters[L.CTR_SIZE] = len(self.rb)
+            L.check(lib.b2rl_replay_sample_gather(
+                self.rb.storage.data_ptr(), 0, 0, self.rb.fmt, self.B, 1, None, self.idx.data_ptr(),
+                self.rows.data_ptr(), C.c_uint64(ag.seed), ag.counters.data_ptr(), L.CTR_Q, 0, ag.agent_id, st),
+                "replay_sample_gather")
+            rows = self.rows
+        do_actor = (i % (h.actor_update_delay + 1) == 0)
+        do_polyak = ag.td3 or ((ag.qnet_updates_so_far + 1) % h.crit_targ_update_freq == 0)
+        delay = int(h.actor_update_delay) if do_actor else 0
+
+        args = ag.update_args(rows, eps=ag._noise(eps_q, rows))
+        fn = lib.b2rl_critic_update_td3 if ag.td3 else lib.b2rl_critic_update_sac
+        L.check(fn(C.byref(args), st), "critic_update")
+        reduce_grad_span(ag.arena, lay, self.comm, "critic")
+        segs = [self._seg(lay.critic[0].begin, lay.critic[1].end, float(h.qnets_lr), do_polyak, L.CTR_Q)]
+        if ag.td3 and do_polyak and delay == 0:
+            segs.append(L.Seg(lay.actor.begin, lay.actor.end, 0.0, 0, 1, 0, 1.0, 0))
+        ag._launch_adam(segs)
+        ag.qnet_updates_so_far += 1
+        for j in range(delay):
+            e1 = None if eps_pi is None else eps_pi[j]
+            e2 = None if eps_alpha is None else eps_alpha[j]
+            args = ag.update_args(rows, eps=ag._noise(e1, rows), eps2=ag._noise(e2, rows))
+            fn = lib.b2rl_actor_update_td3 if ag.td3 else lib.b2rl_actor_update_sac
+            L.check(fn(C.byref(args), st), "actor_update")
+            reduce_grad_span(ag.arena, lay, self.comm, "actor")
+            clip = h.clip_norm > 0
+            if clip:  # clip_grad_norm_ acts on the averaged gradient: sum of squares AFTER the all-reduce
+                L.check(lib.b2rl_grad_sumsq(ag.arena.flat.data_ptr(), lay.region, ag.arena.agent_stride,
+                                            lay.actor.begin, lay.actor.core_end, 1, ag._sumsq.data_ptr(),
+                                            ag._sumsq_scratch.data_ptr(), st), "grad_sumsq")
+            ag._launch_adam([self._seg(lay.actor.begin, lay.actor.end, float(h.actor_lr),
+                                       ag.td3 and do_polyak and j == delay - 1, L.CTR_PI, clip)])
+            if ag.autotune:
+                L.check(lib.b2rl_alpha_update(C.byref(args), 0.0, st), "alpha_update (gradient only)")
+                self.comm.all_reduce_sum(ag._alpha_state[1:2])
+                L.check(lib.b2rl_alpha_adam(ag._alpha_state.data_ptr(), ag.counters.data_ptr(), 1,
+                                            float(h.log_alpha_lr), 1.0 / W, ag.out.data_ptr(), st), "alpha_adam")
+            ag.actor_updates_so_far += 1

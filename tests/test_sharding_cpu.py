@@ -64,3 +64,42 @@ def test_two_rank_population_matches_single_process(tmp_path):
     got = torch.load(out)
     want = torch.stack([_digest(i) for i in range(n_agents)])
     assert torch.equal(got, want)
+
+
+# ---------------------------------------------------------------- data-parallel gradient bucket (gloo)
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    from sac_td3_cudagraphs_pytorch_b200.arena import Arena, make_layout
+    from sac_td3_cudagraphs_pytorch_b200.dp import GradComm, reduce_grad_span
+    lay = make_layout(11, 3, False, True)
+    ar = Arena(lay, "cpu")
+    g = torch.Generator().manual_seed(100 + rank)
+    ar.flat[0, L.REGION_G].copy_(torch.randn(lay.region, generator=g))
+    comm = GradComm()
+    assert (comm.world, comm.rank) == (world, rank)
+    reduce_grad_span(ar, lay, comm, "critic")
+    reduce_grad_span(ar, lay, comm, "actor")
+    if rank == 0:
+        torch.save(ar.flat[0, L.REGION_G].clone(), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_all_reduce_and_shadow_rebuild(tmp_path):
+    from sac_td3_cudagraphs_pytorch_b200.arena import make_layout
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    lay = make_layout(11, 3, False, True)
+    locals_ = [torch.randn(lay.region, generator=torch.Generator().manual_seed(100 + r)) for r in range(2)]
+    want = locals_[0] + locals_[1]
+    for net in (*lay.critic, lay.actor):
+        assert torch.equal(got[net.begin:net.core_end], want[net.begin:net.core_end])      # summed over ranks
+        w2t = got[net.off["w2t"]:net.off["w2t"] + 65536].view(256, 256)
+        w2n = got[net.off["w2n"]:net.off["w2n"] + 65536].view(256, 256)
+        assert torch.equal(w2n, w2t.t())                                                     # shadow == primary^T
