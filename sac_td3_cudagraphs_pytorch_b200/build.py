@@ -40,6 +40,7 @@ def _digest() -> str:
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE / "b2rl.h", Path(__file__)]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
+    h.update(os.environ.get("B2RL_EXTRA_NVCC_FLAGS", "").encode())
     return h.hexdigest()
 
 
@@ -47,7 +48,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     digest = _digest()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(INCLUDE), "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
+    extra = os.environ.get("B2RL_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", str(INCLUDE), "-o", str(LIB)] + [str(CSRC / s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     (CSRC / ".build_log.txt").write_text(" ".join(cmd) + "\n" + log)

@@ -46,6 +46,17 @@ __host__ __device__ inline Workspace ws_carve(float* base, int B, int slot) {
   return w;
 }
 
+// ---- optional in-kernel phase timing (build with B2RL_EXTRA_NVCC_FLAGS=-DB2RL_TIMING; tools/phase_timing.py)
+#ifdef B2RL_TIMING
+static __device__ long long g_b2rl_timing[64];  // one copy per translation unit
+#define B2RL_TICK(slot)                                                                    \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_b2rl_timing[slot] = clock64(); \
+  } while (0)
+#else
+#define B2RL_TICK(slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // streaming 128-bit load/store that do not allocate in L1 (replay rows are touched once)

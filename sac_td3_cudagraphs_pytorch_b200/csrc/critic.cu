@@ -46,12 +46,14 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
 
   // ---- next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor
   //      plus clipped noise (agent.py:194-202)
+  B2RL_TICK(0);
   load_x(rows, rs, b0, O + AD + 2, O, M.x, 0);
   __syncthreads();
   {
     const Net act = resolve(td3 ? T : P, A.actor);
-    trunk_fwd(act, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0);
+    trunk_fwd(act, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0, 1);
     rowdot(act.w3, act.b3, act.out_dim, M.a.h2, M.s.u);
+    B2RL_TICK(10);
     __syncthreads();
     if (w < ROWS) {  // warp r <-> batch row b0+r, lane <-> action dim
       const int r = w;
@@ -88,12 +90,15 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
 
   // ---- target Q_k on (next_obs, a')  (agent.py:208-210), then swap the 4 values with the peer CTA
   {
+    B2RL_TICK(11);
     const Net q = resolve(T, A.critic[k]);
-    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0);
+    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0, 12);
     rowdot(q.w3, q.b3, 1, M.a.h2, &M.qn[k]);
+    B2RL_TICK(21);
     __syncthreads();
     if (t == 0) *cluster.map_shared_rank(&M.qn[k], k ^ 1) = M.qn[k];
     cluster.sync();
+    B2RL_TICK(22);
   }
 
   // ---- TD target (agent.py:212-228)
@@ -120,8 +125,10 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
     const Net q = resolve(P, A.critic[k]);
     const Workspace ws = ws_carve(wsb, B, k);
     float* part = ws.part + (size_t)rb * PART_LEN;
-    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, ws.h1, ws.h2, b0);
+    B2RL_TICK(23);
+    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, ws.h1, ws.h2, b0, 24);
     rowdot(q.w3, q.b3, 1, M.a.h2, &M.s.u[0]);
+    B2RL_TICK(33);
     __syncthreads();
     const float4 qv = M.s.u[0], yv = M.y;
     const float4 dlt = make_float4(qv.x - yv.x, qv.y - yv.y, qv.z - yv.z, qv.w - yv.w);
@@ -137,11 +144,19 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
     }
     const float w3 = t < ET ? __ldg(q.w3 + t) : 0.f;
     const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
+    B2RL_TICK(34);
     trunk_bwd(q, dh2, M.a, M.s, tog, rstd1, rstd2, ws.dz1, ws.dz2, part, b0);
+    B2RL_TICK(35);
   }
 }
 
 size_t critic_smem_bytes() { return sizeof(CriticSmem); }
+
+#ifdef B2RL_TIMING
+extern "C" int b2rl_debug_timing(long long* host64) {  // critic_fused_kernel's phase timestamps (debug builds)
+  return cudaMemcpyFromSymbol(host64, g_b2rl_timing, sizeof(long long) * 64) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 // loads the kernel (CUDA loads lazily; a first launch inside stream capture would fail) and opts in
 // to > 48 KB of dynamic shared memory

@@ -236,7 +236,8 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, int b0, floa
 // ---- the two hidden layers, forward. Leaves h1/h2/xh1/xh2 in `A`; rstd1/rstd2 in registers. -----------
 // Ends with a __syncthreads: A.h2 is readable by every thread on return.
 static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __restrict__ x, Acts& A, Scratch& S, int& tog,
-                                              float4& rstd1, float4& rstd2, float* ws_h1, float* ws_h2, int b0) {
+                                              float4& rstd1, float4& rstd2, float* ws_h1, float* ws_h2, int b0,
+                                              int tk = 54) {
   const int j = threadIdx.x;
   // per-column parameters are fetched before the GEMMs so that their L2 round trip is off the epilogues
   float b1 = 0.f, g1 = 1.f, be1 = 0.f, b2 = 0.f, g2 = 1.f, be2 = 0.f;
@@ -244,8 +245,11 @@ static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __rest
     b1 = __ldg(n.b1 + j); b2 = __ldg(n.b2 + j);
     if (n.ln) { g1 = __ldg(n.g1 + j); be1 = __ldg(n.be1 + j); g2 = __ldg(n.g2 + j); be2 = __ldg(n.be2 + j); }
   }
+  B2RL_TICK(tk + 0);
   gemm_rows(n.w1t, n.in_dim, x, S.red);
+  B2RL_TICK(tk + 1);
   __syncthreads();
+  B2RL_TICK(tk + 2);
   if (j < ET) {
     float4 xh;
     const float4 h = fwd_epilogue(reduce_partials(S.red), b1, g1, be1, n.ln, S.sred, tog, xh, rstd1);
@@ -253,9 +257,13 @@ static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __rest
     A.xh1[j] = xh;
     if (ws_h1) store_rows(ws_h1, b0, h);
   }
+  B2RL_TICK(tk + 3);
   __syncthreads();
+  B2RL_TICK(tk + 4);
   gemm_rows(n.w2t, HID, A.h1, S.red);
+  B2RL_TICK(tk + 5);
   __syncthreads();
+  B2RL_TICK(tk + 6);
   if (j < ET) {
     float4 xh;
     const float4 h = fwd_epilogue(reduce_partials(S.red), b2, g2, be2, n.ln, S.sred, tog, xh, rstd2);
@@ -263,7 +271,9 @@ static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __rest
     A.xh2[j] = xh;
     if (ws_h2) store_rows(ws_h2, b0, h);
   }
+  B2RL_TICK(tk + 7);
   __syncthreads();
+  B2RL_TICK(tk + 8);
 }
 
 // ---- the two hidden layers, backward (dX path). dh2 = gradient w.r.t. h2 for column j (threads < ET). ------
