@@ -14,8 +14,11 @@ struct ActorSmem {
   Acts pi;         // actor activations (kept for its backward pass)
   Acts q;          // this CTA's critic activations
   Scratch s;
+  NetStage nsA, nsQ;
+  float rowbuf[ROWS * RS_CAP];
   float4 da_peer[MAX_OUT];  // dLoss/da through the peer CTA's critic: [action dim] -> 4 rows
   float4 qv[2], logpi, dq[2];
+  float lo[MAX_OUT / 2], hi[MAX_OUT / 2];
   float eps[ROWS][MAX_OUT / 2], sg[ROWS][MAX_OUT / 2], yy[ROWS][MAX_OUT / 2], th[ROWS][MAX_OUT / 2];
 };
 
@@ -45,21 +48,36 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   float* part = ws.part + (size_t)rb * PART_LEN;
   const float alpha = td3 ? 0.f : expf(A.log_alpha[(size_t)agent * 5]);
   const float invB = 1.0f / (float)B;
-  int tog = 0;
-  float4 pr1, pr2, qr1, qr2;  // LayerNorm rstd of the actor / of the critic (threads < ET)
+
+  // ---- asynchronous burst: rows and small tensors
+  stage_rows(rows, rs, b0, M.rowbuf);
+  const Net act = stage_net(P, A.actor, M.nsA);
+  const Net q = stage_net(P, A.critic[k], M.nsQ);
+  if (t < AD) {
+    M.lo[t] = __ldg(A.min_ac + t);
+    M.hi[t] = __ldg(A.max_ac + t);
+  }
+  if (!td3 && t < ROWS * AD) {
+    const int r = t / AD, a = t - r * AD;
+    const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
+    const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_ACTOR_EPS);
+    M.eps[r][a] = z;
+    if (A.eps_out && k == 0) A.eps_out[e] = z;
+  }
+  cp_async_wait_all();
+  __syncthreads();
 
   // ---- actor forward on obs (agent.py:251 / :254-255)
-  load_x(rows, rs, b0, 0, O, M.x, 0);
+  tile_from_rows(M.rowbuf, rs, 0, O, M.x, 0);
   __syncthreads();
-  const Net act = resolve(P, A.actor);
-  trunk_fwd(act, M.x, M.pi, M.s, tog, pr1, pr2, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0);
+  trunk_fwd(act, M.x, M.pi, M.s, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0);
   rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
   __syncthreads();
   if (w < ROWS) {
     const int r = w;
     float lp = 0.f;
     if (l < AD) {
-      const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+      const float lo = M.lo[l], hi = M.hi[l];
       const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
       float act_v;
       if (td3) {
@@ -67,13 +85,10 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
         act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
         M.th[r][l] = th;
       } else {
-        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
-        const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, gid, STREAM_ACTOR_EPS);
-        if (A.eps_out && k == 0) A.eps_out[e] = z;
-        const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
+        const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), M.eps[r][l], scale, bias);
         act_v = g.action;
         lp = g.logp;
-        M.eps[r][l] = z; M.sg[r][l] = g.sigma; M.yy[r][l] = g.y; M.th[r][l] = g.th;
+        M.sg[r][l] = g.sigma; M.yy[r][l] = g.y; M.th[r][l] = g.th;
       }
       reinterpret_cast<float*>(&M.x[O + l])[r] = act_v;
     }
@@ -83,8 +98,7 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   __syncthreads();
 
   // ---- Q_k(obs, a_pi) with the critic's parameters held constant (agent.py:272-278)
-  const Net q = resolve(P, A.critic[k]);
-  trunk_fwd(q, M.x, M.q, M.s, tog, qr1, qr2, nullptr, nullptr, b0);
+  trunk_fwd(q, M.x, M.q, M.s, nullptr, nullptr, b0);
   rowdot(q.w3, q.b3, 1, M.q.h2, &M.qv[k]);
   __syncthreads();
   if (!td3) {
@@ -119,10 +133,10 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
 
   // ---- backward through critic k down to its action inputs
   {
-    const float w3 = t < ET ? __ldg(q.w3 + t) : 0.f;
+    const float w3 = t < ET ? q.w3[t] : 0.f;
     const float4 dq = M.dq[k];
     const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
-    trunk_bwd(q, dh2, M.q, M.s, tog, qr1, qr2, nullptr, nullptr, nullptr, b0);
+    trunk_bwd(q, dh2, M.q, M.s, nullptr, nullptr, nullptr, b0);
     rowdot(q.w1t + (size_t)O * HID, nullptr, AD, M.s.d, M.s.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
     __syncthreads();
   }
@@ -137,8 +151,7 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
     const int r = w;
     float g_a = 0.f, g_b = 0.f;
     if (l < AD) {
-      const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
-      const float scale = (hi - lo) * 0.5f;
+      const float scale = (M.hi[l] - M.lo[l]) * 0.5f;
       float ga = f4get(M.s.u[l], r);                    // through critic 0
       if (!td3) ga += f4get(M.da_peer[l], r);           // + through critic 1
       if (td3) {
@@ -163,7 +176,7 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
     part[PART_DB3 + t] = d.x + d.y + d.z + d.w;
   }
   const float4 dh2 = head_bwd(act.w3, act.out_dim, M.s.du);
-  trunk_bwd(act, dh2, M.pi, M.s, tog, pr1, pr2, ws.dz1, ws.dz2, part, b0);
+  trunk_bwd(act, dh2, M.pi, M.s, ws.dz1, ws.dz2, part, b0);
 }
 
 // ---- SAC temperature step -------------------------------------------------------------------
@@ -175,6 +188,7 @@ struct AlphaSmem {
   float4 x[XMAX];
   Acts pi;
   Scratch s;
+  NetStage ns;
   float4 logpi;
   int last;
 };
@@ -204,13 +218,12 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   const uint64_t step = ctr[B2RL_CTR_PI];
   float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
   float* part = ws_carve(wsb, B, 0).part;
-  int tog = 0;
-  float4 r1, r2;
 
+  const Net act = stage_net(P, A.actor, M.ns);
   load_x(rows, rs, b0, 0, O, M.x, 0);
+  cp_async_wait_all();
   __syncthreads();
-  const Net act = resolve(P, A.actor);
-  trunk_fwd(act, M.x, M.pi, M.s, tog, r1, r2, nullptr, nullptr, b0);
+  trunk_fwd(act, M.x, M.pi, M.s, nullptr, nullptr, b0);
   rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
   __syncthreads();
   if (w < ROWS) {
@@ -288,6 +301,7 @@ struct PredictSmem {
   float4 x[XMAX];
   Acts pi;
   Scratch s;
+  NetStage ns;
 };
 
 __global__ void __launch_bounds__(NT, 1)
@@ -301,12 +315,11 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   const bool td3 = A.hp.td3 != 0;
   const float* P = A.arena;
   const uint64_t step = draw;
-  int tog = 0;
-  float4 r1, r2;
+  const Net act = stage_net(P, A.actor, M.ns);
   load_x(obs, O, b0, 0, O, M.x, 0, min(ROWS, n - b0));
+  cp_async_wait_all();
   __syncthreads();
-  const Net act = resolve(P, A.actor);
-  trunk_fwd(act, M.x, M.pi, M.s, tog, r1, r2, nullptr, nullptr, b0);
+  trunk_fwd(act, M.x, M.pi, M.s, nullptr, nullptr, b0);
   rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
   __syncthreads();
   if (w < ROWS && l < AD && b0 + w < n) {

@@ -20,7 +20,10 @@ struct CriticSmem {
   float4 x[XMAX];  // [next_obs | a'] for the target pass, then [obs | act]
   Acts a;
   Scratch s;
-  float4 logpi, qn[2], y;  // per-row scalars
+  NetStage nsA, nsT, nsQ;      // staged small tensors of the actor, target critic k, online critic k
+  float rowbuf[ROWS * RS_CAP]; // this CTA's 4 transition rows
+  float lo[MAX_OUT / 2], hi[MAX_OUT / 2], eps[ROWS][MAX_OUT / 2];
+  float4 logpi, qn[2], y;      // per-row scalars
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
@@ -41,17 +44,33 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
   const uint64_t step = A.counters[(size_t)agent * 8 + B2RL_CTR_Q];
   float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
-  int tog = 0;
-  float4 rstd1, rstd2;
 
-  // ---- next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor
-  //      plus clipped noise (agent.py:194-202)
+  // ---- one asynchronous burst at kernel start: the 4 rows and every small tensor the kernel will touch
   B2RL_TICK(0);
-  load_x(rows, rs, b0, O + AD + 2, O, M.x, 0);
+  stage_rows(rows, rs, b0, M.rowbuf);
+  const Net act = stage_net(td3 ? T : P, A.actor, M.nsA);  // SAC samples from the ONLINE actor (agent.py:205),
+  const Net qt = stage_net(T, A.critic[k], M.nsT);         // TD3 uses the TARGET actor (agent.py:194-202)
+  const Net qo = stage_net(P, A.critic[k], M.nsQ);
+  if (t < AD) {
+    M.lo[t] = __ldg(A.min_ac + t);
+    M.hi[t] = __ldg(A.max_ac + t);
+  }
+  if (t < ROWS * AD) {
+    const int r = t / AD, a = t - r * AD;
+    const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
+    const bool need = !td3 || A.hp.targ_smoothing;
+    const float z = need ? noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_CRITIC_EPS) : 0.f;
+    M.eps[r][a] = z;
+    if (need && A.eps_out && k == 0) A.eps_out[e] = z;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- next action
+  tile_from_rows(M.rowbuf, rs, O + AD + 2, O, M.x, 0);
   __syncthreads();
   {
-    const Net act = resolve(td3 ? T : P, A.actor);
-    trunk_fwd(act, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0, 1);
+    trunk_fwd(act, M.x, M.a, M.s, nullptr, nullptr, b0, 1);
     rowdot(act.w3, act.b3, act.out_dim, M.a.h2, M.s.u);
     B2RL_TICK(10);
     __syncthreads();
@@ -59,23 +78,19 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
       const int r = w;
       float lp = 0.f;
       if (l < AD) {
-        const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+        const float lo = M.lo[l], hi = M.hi[l];
         const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;  // agents/nets.py:200-204
-        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
+        const float z = M.eps[r][l];
         float act_v;
         if (td3) {
           float th;
           act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
           if (A.hp.targ_smoothing) {
-            const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, gid, STREAM_CRITIC_EPS);
-            if (A.eps_out && k == 0) A.eps_out[e] = z;
             float n = __fmul_rn(z, A.hp.td3_std);
             n = fminf(fmaxf(n, -A.hp.td3_c), A.hp.td3_c);
             act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
           }
         } else {
-          const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, l, step, gid, STREAM_CRITIC_EPS);
-          if (A.eps_out && k == 0) A.eps_out[e] = z;
           const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias);
           act_v = g.action;
           lp = g.logp;
@@ -91,9 +106,8 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   // ---- target Q_k on (next_obs, a')  (agent.py:208-210), then swap the 4 values with the peer CTA
   {
     B2RL_TICK(11);
-    const Net q = resolve(T, A.critic[k]);
-    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, nullptr, nullptr, b0, 12);
-    rowdot(q.w3, q.b3, 1, M.a.h2, &M.qn[k]);
+    trunk_fwd(qt, M.x, M.a, M.s, nullptr, nullptr, b0, 12);
+    rowdot(qt.w3, qt.b3, 1, M.a.h2, &M.qn[k]);
     B2RL_TICK(21);
     __syncthreads();
     if (t == 0) *cluster.map_shared_rank(&M.qn[k], k ^ 1) = M.qn[k];
@@ -111,23 +125,21 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
       const float alpha = expf(A.log_alpha[(size_t)agent * 5]);
       qp = __fsub_rn(qp, __fmul_rn(alpha, f4get(M.logpi, r)));
     }
-    const float* row = rows + (size_t)(b0 + r) * rs;
-    const float rew = row[O + AD], done = row[O + AD + 1];
+    const float rew = M.rowbuf[r * rs + O + AD], done = M.rowbuf[r * rs + O + AD + 1];
     const float y = __fadd_rn(rew, __fmul_rn(__fmul_rn(1.0f - done, A.hp.gamma), qp));
     reinterpret_cast<float*>(&M.y)[r] = y;
     if (A.dbg_targ_q && k == 0) A.dbg_targ_q[(size_t)agent * B + b0 + r] = y;
   }
-  load_x(rows, rs, b0, 0, O + AD, M.x, 0);  // [obs | act] is contiguous in the row
+  tile_from_rows(M.rowbuf, rs, 0, O + AD, M.x, 0);  // [obs | act] is contiguous in the row
   __syncthreads();
 
   // ---- online Q_k, loss, backward (agent.py:230-235)
   {
-    const Net q = resolve(P, A.critic[k]);
     const Workspace ws = ws_carve(wsb, B, k);
     float* part = ws.part + (size_t)rb * PART_LEN;
     B2RL_TICK(23);
-    trunk_fwd(q, M.x, M.a, M.s, tog, rstd1, rstd2, ws.h1, ws.h2, b0, 24);
-    rowdot(q.w3, q.b3, 1, M.a.h2, &M.s.u[0]);
+    trunk_fwd(qo, M.x, M.a, M.s, ws.h1, ws.h2, b0, 24);
+    rowdot(qo.w3, qo.b3, 1, M.a.h2, &M.s.u[0]);
     B2RL_TICK(33);
     __syncthreads();
     const float4 qv = M.s.u[0], yv = M.y;
@@ -142,10 +154,10 @@ critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
       part[PART_DB3] = dq.x + dq.y + dq.z + dq.w;
       part[PART_SCAL] = dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z + dlt.w * dlt.w;
     }
-    const float w3 = t < ET ? __ldg(q.w3 + t) : 0.f;
+    const float w3 = t < ET ? qo.w3[t] : 0.f;
     const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
     B2RL_TICK(34);
-    trunk_bwd(q, dh2, M.a, M.s, tog, rstd1, rstd2, ws.dz1, ws.dz2, part, b0);
+    trunk_bwd(qo, dh2, M.a, M.s, ws.dz1, ws.dz2, part, b0);
     B2RL_TICK(35);
   }
 }

@@ -16,7 +16,7 @@
 
 namespace b2rl {
 
-struct Net {  // resolved pointers of one network inside one arena region
+struct Net {  // resolved pointers of one network; the small tensors may point into shared memory (NetStage)
   const float *w1t, *b1, *g1, *be1, *w2t, *b2, *g2, *be2, *w3, *b3, *w2n;
   int in_dim, out_dim, ln;
 };
@@ -29,19 +29,62 @@ __device__ __forceinline__ Net resolve(const float* region, const b2rl_net_t& n)
   return r;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory"); }
+
+// Everything of a network that the epilogues and the head touch (biases, LayerNorm affine, head weights), copied
+// once into shared memory with cp.async at kernel start: in the first version each epilogue began with an exposed
+// L2 round trip for these (profiles/r1_phase_timing_*.txt: 20 % of the kernel was such waits).
+constexpr int W3_STAGE = 16;  // head rows staged (1 for a critic, A or 2A for an actor when it fits)
+struct NetStage {
+  float b1[HID], g1[HID], be1[HID], b2[HID], g2[HID], be2[HID];
+  float w3[W3_STAGE * HID];
+  float b3[MAX_OUT];
+};
+// Issue the copies (all threads), return a Net whose small tensors point into `st`. Call cp_async_wait_all() and
+// __syncthreads() before the first epilogue.
+__device__ __forceinline__ Net stage_net(const float* region, const b2rl_net_t& d, NetStage& st) {
+  Net n = resolve(region, d);
+  const int t = threadIdx.x;
+  const int nv = d.layer_norm ? 6 : 2;
+  for (int i = t; i < nv * (HID / 4); i += NT) {  // 64 float4 per vector
+    const int v = i / (HID / 4), c = (i % (HID / 4)) * 4;
+    const float* src = d.layer_norm ? (v == 0 ? n.b1 : v == 1 ? n.g1 : v == 2 ? n.be1 : v == 3 ? n.b2 : v == 4 ? n.g2 : n.be2)
+                                    : (v == 0 ? n.b1 : n.b2);
+    float* dst = d.layer_norm ? (v == 0 ? st.b1 : v == 1 ? st.g1 : v == 2 ? st.be1 : v == 3 ? st.b2 : v == 4 ? st.g2 : st.be2)
+                              : (v == 0 ? st.b1 : st.b2);
+    cp_async16(dst + c, src + c);
+  }
+  for (int i = t; i < (d.out_dim + 3) / 4; i += NT) cp_async16(st.b3 + 4 * i, n.b3 + 4 * i);
+  n.b1 = st.b1; n.b2 = st.b2; n.b3 = st.b3;
+  if (d.layer_norm) { n.g1 = st.g1; n.be1 = st.be1; n.g2 = st.g2; n.be2 = st.be2; }
+  if (d.out_dim <= W3_STAGE) {
+    for (int i = t; i < d.out_dim * (HID / 4); i += NT) cp_async16(st.w3 + 4 * i, n.w3 + 4 * i);
+    n.w3 = st.w3;
+  }
+  return n;
+}
+
 struct Acts {  // what one forward pass leaves behind for its backward pass
   float4 h1[HID], h2[HID];    // post-ReLU activations, [feature] -> 4 rows
   float4 xh1[HID], xh2[HID];  // LayerNorm x-hat (or the pre-activation when layer_norm is off)
+  float2 st1[ROWS], st2[ROWS];  // per row (mean, rstd) of the two LayerNorms
 };
 
 constexpr int XMAX = 1024;  // max input width (O + A)
 
 struct Scratch {
   float red[KSPLIT * ROWS * HID];  // split-K partial sums [k-slice][row][col]
-  float4 sred[2][EW];              // block_sum4 ping-pong
-  float4 u[MAX_OUT];           // head outputs / small row-dot results: [output] -> 4 rows
+  float z[ROWS][HID];              // pre-activation rows (LayerNorm statistics are taken row-wise by one warp each)
+  float z2[ROWS][HID];
+  float2 stat[ROWS];
+  float4 u[MAX_OUT];               // head outputs / small row-dot results: [output] -> 4 rows
   float4 du[MAX_OUT];
-  float4 d[HID];               // gradient tile fed to the backward GEMM
+  float4 d[HID];                   // gradient tile fed to the backward GEMM
 };
 
 // ---- the GEMM: red[w][r][j] = sum_{k in slice(w)} W[k][j] * x[k].r  -----------------------------
@@ -108,6 +151,110 @@ static __device__ __noinline__ void gemm_rows(const float* __restrict__ W, int K
 #undef B2RL_LOADG
 #undef B2RL_FMAG
 
+// ---- row statistics: warp r < 4 reduces row r of a [4][256] shared buffer ---------------------------------
+__device__ __forceinline__ void row_sums(const float (*za)[HID], const float (*zb)[HID], float2* out, bool layernorm_stats) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (w >= ROWS) return;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = za[w][l + 32 * i];
+  float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+  s = warp_sum(s);
+  if (layernorm_stats) {  // (mean, rstd) with the biased variance taken around the mean (two-pass)
+    const float mean = s * (1.0f / HID);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    if (l == 0) out[w] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / HID) + LN_EPS));
+  } else {  // two plain means (LayerNorm backward: mean(dx), mean(dx * xhat))
+    float u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = zb[w][l + 32 * i];
+    float s2 = ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
+    s2 = warp_sum(s2);
+    if (l == 0) out[w] = make_float2(s * (1.0f / HID), s2 * (1.0f / HID));
+  }
+}
+
+// ---- forward epilogue of one layer (all NT threads; three barriers) ----------------------------------------
+// E1: thread (j = t & 255, rp = t >> 8) sums the k-slice partials of rows 2rp, 2rp+1 of column j, adds the bias.
+// E2: warp r takes LayerNorm statistics of row r.   E3: normalise, affine, ReLU; write h / xhat tiles (+ global H).
+__device__ __forceinline__ void layer_fwd_epilogue(const float* __restrict__ b, const float* __restrict__ g,
+                                                   const float* __restrict__ be, bool ln, Scratch& S, float4* hT,
+                                                   float4* xhT, float2* stat_keep, float* ws_h, int b0) {
+  const int t = threadIdx.x, j = t & (HID - 1), rp = t >> 8, r0 = 2 * rp;
+  float z0 = S.red[r0 * HID + j], z1 = S.red[(r0 + 1) * HID + j];
+#pragma unroll
+  for (int w = 1; w < KSPLIT; ++w) {
+    z0 += S.red[(w * ROWS + r0) * HID + j];
+    z1 += S.red[(w * ROWS + r0 + 1) * HID + j];
+  }
+  const float bj = b[j];
+  z0 += bj; z1 += bj;
+  float h0, h1, x0 = z0, x1 = z1;
+  if (ln) {
+    S.z[r0][j] = z0; S.z[r0 + 1][j] = z1;
+    __syncthreads();
+    row_sums(S.z, S.z, S.stat, true);
+    __syncthreads();
+    const float2 s0 = S.stat[r0], s1 = S.stat[r0 + 1];
+    if (t < ROWS) stat_keep[t] = S.stat[t];
+    const float gj = g[j], bej = be[j];
+    x0 = (z0 - s0.x) * s0.y; x1 = (z1 - s1.x) * s1.y;
+    h0 = fmaxf(fmaf(x0, gj, bej), 0.f); h1 = fmaxf(fmaf(x1, gj, bej), 0.f);
+  } else {
+    h0 = fmaxf(z0, 0.f); h1 = fmaxf(z1, 0.f);
+  }
+  reinterpret_cast<float2*>(&hT[j])[rp] = make_float2(h0, h1);
+  reinterpret_cast<float2*>(&xhT[j])[rp] = make_float2(x0, x1);
+  if (ws_h) {
+    ws_h[(size_t)(b0 + r0) * HID + j] = h0;
+    ws_h[(size_t)(b0 + r0 + 1) * HID + j] = h1;
+  }
+  __syncthreads();
+}
+
+// ---- backward epilogue of one layer: ReLU mask, LayerNorm backward (threads t < ET hold all 4 rows of a column) ---
+// dh: gradient w.r.t. the post-ReLU activation of column j. Returns dz (w.r.t. the Linear output) and writes this
+// CTA's column sums {sum_r dz, sum_r dn*xhat, sum_r dn} (d bias, d ln.weight, d ln.bias) to part[0..2][j].
+__device__ __forceinline__ float4 layer_bwd_epilogue(float4 dh, const float4* hT, const float4* xhT, const float2* stat,
+                                                     const float* __restrict__ g, bool ln, Scratch& S, float* part3) {
+  const int t = threadIdx.x, j = t;
+  float4 dn = make_float4(0.f, 0.f, 0.f, 0.f), xh = dn, dx = dn, dz;
+  if (t < ET) {
+    const float4 h = hT[j];
+    xh = xhT[j];
+    dn = make_float4(h.x > 0.f ? dh.x : 0.f, h.y > 0.f ? dh.y : 0.f, h.z > 0.f ? dh.z : 0.f, h.w > 0.f ? dh.w : 0.f);
+  }
+  if (ln) {
+    if (t < ET) {
+      const float gj = g[j];
+      dx = make_float4(dn.x * gj, dn.y * gj, dn.z * gj, dn.w * gj);
+      S.z[0][j] = dx.x; S.z[1][j] = dx.y; S.z[2][j] = dx.z; S.z[3][j] = dx.w;
+      S.z2[0][j] = dx.x * xh.x; S.z2[1][j] = dx.y * xh.y; S.z2[2][j] = dx.z * xh.z; S.z2[3][j] = dx.w * xh.w;
+    }
+    __syncthreads();
+    row_sums(S.z, S.z2, S.stat, false);
+    __syncthreads();
+    const float2 c0 = S.stat[0], c1 = S.stat[1], c2 = S.stat[2], c3 = S.stat[3];
+    dz.x = stat[0].y * (dx.x - c0.x - xh.x * c0.y);
+    dz.y = stat[1].y * (dx.y - c1.x - xh.y * c1.y);
+    dz.z = stat[2].y * (dx.z - c2.x - xh.z * c2.y);
+    dz.w = stat[3].y * (dx.w - c3.x - xh.w * c3.y);
+  } else {
+    dz = dn;
+  }
+  if (part3 && t < ET) {
+    part3[0 * HID + j] = dz.x + dz.y + dz.z + dz.w;
+    if (ln) {
+      part3[1 * HID + j] = dn.x * xh.x + dn.y * xh.y + dn.z * xh.z + dn.w * xh.w;
+      part3[2 * HID + j] = dn.x + dn.y + dn.z + dn.w;
+    }
+  }
+  return dz;
+}
+
 // thread j < ET: sum the KSPLIT partials of column j (fixed order)
 __device__ __forceinline__ float4 reduce_partials(const float* __restrict__ red) {
   const int j = threadIdx.x;
@@ -122,79 +269,24 @@ __device__ __forceinline__ float4 reduce_partials(const float* __restrict__ red)
   return make_float4(z[0], z[1], z[2], z[3]);
 }
 
-// ---- forward epilogue: bias, LayerNorm (biased variance, eps 1e-5, affine), ReLU -----------------
-// Returns h for column j = threadIdx.x; xhat/rstd are what the backward pass needs.
-__device__ __forceinline__ float4 fwd_epilogue(float4 z, float bj, float gj, float bej, bool ln, float4 (*sred)[EW],
-                                               int& tog, float4& xhat, float4& rstd) {
-  z.x += bj; z.y += bj; z.z += bj; z.w += bj;
-  float4 n;
-  if (ln) {
-    const float inv = 1.0f / HID;
-    float4 s = block_sum4(z, sred[tog]); tog ^= 1;
-    const float4 mean = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
-    const float4 d = make_float4(z.x - mean.x, z.y - mean.y, z.z - mean.z, z.w - mean.w);
-    s = block_sum4(make_float4(d.x * d.x, d.y * d.y, d.z * d.z, d.w * d.w), sred[tog]); tog ^= 1;
-    rstd = make_float4(1.0f / sqrtf(s.x * inv + LN_EPS), 1.0f / sqrtf(s.y * inv + LN_EPS),
-                       1.0f / sqrtf(s.z * inv + LN_EPS), 1.0f / sqrtf(s.w * inv + LN_EPS));
-    xhat = make_float4(d.x * rstd.x, d.y * rstd.y, d.z * rstd.z, d.w * rstd.w);
-    n = make_float4(fmaf(xhat.x, gj, bej), fmaf(xhat.y, gj, bej), fmaf(xhat.z, gj, bej), fmaf(xhat.w, gj, bej));
-  } else {
-    rstd = make_float4(1.f, 1.f, 1.f, 1.f);
-    xhat = z;
-    n = z;
-  }
-  return make_float4(fmaxf(n.x, 0.f), fmaxf(n.y, 0.f), fmaxf(n.z, 0.f), fmaxf(n.w, 0.f));
-}
-
-// ---- backward epilogue: ReLU mask, LayerNorm backward ---------------------------------------------
-// dh: gradient w.r.t. the post-ReLU activation of column j. Returns dz (gradient w.r.t. the Linear
-// output). colsum = {sum_r dz, sum_r dn*xhat, sum_r dn}: this CTA's contribution to d(bias),
-// d(ln.weight), d(ln.bias) for column j.
-__device__ __forceinline__ float4 bwd_epilogue(float4 dh, float4 h, float4 xhat, float4 rstd, float gj, bool ln,
-                                               float4 (*sred)[EW], int& tog, float (&colsum)[3]) {
-  const float4 dn = make_float4(h.x > 0.f ? dh.x : 0.f, h.y > 0.f ? dh.y : 0.f, h.z > 0.f ? dh.z : 0.f,
-                                h.w > 0.f ? dh.w : 0.f);
-  float4 dz;
-  if (ln) {
-    const float inv = 1.0f / HID;
-    const float4 dx = make_float4(dn.x * gj, dn.y * gj, dn.z * gj, dn.w * gj);
-    float4 s1 = block_sum4(dx, sred[tog]); tog ^= 1;
-    float4 s2 = block_sum4(make_float4(dx.x * xhat.x, dx.y * xhat.y, dx.z * xhat.z, dx.w * xhat.w), sred[tog]);
-    tog ^= 1;
-    dz.x = rstd.x * (dx.x - s1.x * inv - xhat.x * (s2.x * inv));
-    dz.y = rstd.y * (dx.y - s1.y * inv - xhat.y * (s2.y * inv));
-    dz.z = rstd.z * (dx.z - s1.z * inv - xhat.z * (s2.z * inv));
-    dz.w = rstd.w * (dx.w - s1.w * inv - xhat.w * (s2.w * inv));
-    colsum[1] = dn.x * xhat.x + dn.y * xhat.y + dn.z * xhat.z + dn.w * xhat.w;
-    colsum[2] = dn.x + dn.y + dn.z + dn.w;
-  } else {
-    dz = dn;
-    colsum[1] = colsum[2] = 0.f;
-  }
-  colsum[0] = dz.x + dz.y + dz.z + dz.w;
-  return dz;
-}
-
-// ---- small products against [n][256] row-major matrices ----------------------------------------------
+// ---- small products against [n][256] row-major matrices (global or staged in shared memory) -----------------
 // out[o] (4 rows) = bias[o] + sum_k W[o][k] * x[k]: warp w takes outputs w, w+NW, ...; lanes stride k.
 // Used for the heads (n = 1, A or 2A) and for dQ/da = dz1 . w1t[O+a][:] in the actor step.
 static __device__ __noinline__ void rowdot(const float* __restrict__ W, const float* __restrict__ bias, int n,
-                                       const float4* __restrict__ x, float4* __restrict__ out) {
+                                           const float4* __restrict__ x, float4* __restrict__ out) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   for (int o = w; o < n; o += NW) {
+    const float bo = (bias && l == 0) ? bias[o] : 0.f;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < HID / 32; ++i) {
       const int k = l + 32 * i;
-      const float wv = __ldg(W + (size_t)o * HID + k);
+      const float wv = W[(size_t)o * HID + k];
       const float4 xv = x[k];
       a.x = fmaf(wv, xv.x, a.x); a.y = fmaf(wv, xv.y, a.y); a.z = fmaf(wv, xv.z, a.z); a.w = fmaf(wv, xv.w, a.w);
     }
     a.x = warp_sum(a.x); a.y = warp_sum(a.y); a.z = warp_sum(a.z); a.w = warp_sum(a.w);
-    if (l == 0) {
-      const float bo = bias ? __ldg(bias + o) : 0.f;
-      out[o] = make_float4(a.x + bo, a.y + bo, a.z + bo, a.w + bo);
-    }
+    if (l == 0) out[o] = make_float4(a.x + bo, a.y + bo, a.z + bo, a.w + bo);
   }
 }
 
@@ -204,14 +296,15 @@ __device__ __forceinline__ float4 head_bwd(const float* __restrict__ W, int n, c
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (k >= ET) return a;
   for (int o = 0; o < n; ++o) {
-    const float wv = __ldg(W + (size_t)o * HID + k);
+    const float wv = W[(size_t)o * HID + k];
     const float4 d = du[o];
     a.x = fmaf(wv, d.x, a.x); a.y = fmaf(wv, d.y, a.y); a.z = fmaf(wv, d.z, a.z); a.w = fmaf(wv, d.w, a.w);
   }
   return a;
 }
 
-// ---- input tile: x[dst + k] = rows[b0 + r][off + k] for r = 0..3 --------------------------------------
+// ---- input tiles -------------------------------------------------------------------------------------------
+// from global rows: x[dst + k] = rows[b0 + r][off + k] for r = 0..3
 __device__ __forceinline__ void load_x(const float* __restrict__ rows, int row_stride, int b0, int off, int len,
                                        float4* __restrict__ x, int dst, int n_valid = ROWS) {
   for (int k = threadIdx.x; k < len; k += NT) {
@@ -224,6 +317,20 @@ __device__ __forceinline__ void load_x(const float* __restrict__ rows, int row_s
     x[dst + k] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
+// the CTA's 4 transition rows, copied once into shared memory (cp.async); later tiles are cut out of it
+constexpr int RS_CAP = 2056;  // max row_stride (2*(O) + A + 2 with O + A <= 1024)
+__device__ __forceinline__ void stage_rows(const float* __restrict__ rows, int row_stride, int b0, float* rowbuf) {
+  const int chunks = row_stride >> 2;
+  for (int i = threadIdx.x; i < ROWS * chunks; i += NT) {
+    const int r = i / chunks, c = (i - r * chunks) * 4;
+    cp_async16(rowbuf + r * row_stride + c, rows + (size_t)(b0 + r) * row_stride + c);
+  }
+}
+__device__ __forceinline__ void tile_from_rows(const float* rowbuf, int row_stride, int off, int len, float4* x, int dst) {
+  for (int k = threadIdx.x; k < len; k += NT)
+    x[dst + k] = make_float4(rowbuf[off + k], rowbuf[row_stride + off + k], rowbuf[2 * row_stride + off + k],
+                             rowbuf[3 * row_stride + off + k]);
+}
 
 __device__ __forceinline__ void store_rows(float* __restrict__ dst, int b0, float4 v) {  // dst [B][256]
   const int j = threadIdx.x;
@@ -233,81 +340,45 @@ __device__ __forceinline__ void store_rows(float* __restrict__ dst, int b0, floa
   dst[(size_t)(b0 + 3) * HID + j] = v.w;
 }
 
-// ---- the two hidden layers, forward. Leaves h1/h2/xh1/xh2 in `A`; rstd1/rstd2 in registers. -----------
+// ---- the two hidden layers, forward. Leaves h1/h2/xh1/xh2 and the LayerNorm statistics in `A`. ---------------
 // Ends with a __syncthreads: A.h2 is readable by every thread on return.
-static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __restrict__ x, Acts& A, Scratch& S, int& tog,
-                                              float4& rstd1, float4& rstd2, float* ws_h1, float* ws_h2, int b0,
-                                              int tk = 54) {
-  const int j = threadIdx.x;
-  // per-column parameters are fetched before the GEMMs so that their L2 round trip is off the epilogues
-  float b1 = 0.f, g1 = 1.f, be1 = 0.f, b2 = 0.f, g2 = 1.f, be2 = 0.f;
-  if (j < ET) {
-    b1 = __ldg(n.b1 + j); b2 = __ldg(n.b2 + j);
-    if (n.ln) { g1 = __ldg(n.g1 + j); be1 = __ldg(n.be1 + j); g2 = __ldg(n.g2 + j); be2 = __ldg(n.be2 + j); }
-  }
+static __device__ __noinline__ void trunk_fwd(const Net& n, const float4* __restrict__ x, Acts& A, Scratch& S,
+                                              float* ws_h1, float* ws_h2, int b0, int tk = 54) {
   B2RL_TICK(tk + 0);
   gemm_rows(n.w1t, n.in_dim, x, S.red);
   B2RL_TICK(tk + 1);
   __syncthreads();
   B2RL_TICK(tk + 2);
-  if (j < ET) {
-    float4 xh;
-    const float4 h = fwd_epilogue(reduce_partials(S.red), b1, g1, be1, n.ln, S.sred, tog, xh, rstd1);
-    A.h1[j] = h;
-    A.xh1[j] = xh;
-    if (ws_h1) store_rows(ws_h1, b0, h);
-  }
-  B2RL_TICK(tk + 3);
-  __syncthreads();
+  layer_fwd_epilogue(n.b1, n.g1, n.be1, n.ln, S, A.h1, A.xh1, A.st1, ws_h1, b0);
   B2RL_TICK(tk + 4);
   gemm_rows(n.w2t, HID, A.h1, S.red);
   B2RL_TICK(tk + 5);
   __syncthreads();
   B2RL_TICK(tk + 6);
-  if (j < ET) {
-    float4 xh;
-    const float4 h = fwd_epilogue(reduce_partials(S.red), b2, g2, be2, n.ln, S.sred, tog, xh, rstd2);
-    A.h2[j] = h;
-    A.xh2[j] = xh;
-    if (ws_h2) store_rows(ws_h2, b0, h);
-  }
-  B2RL_TICK(tk + 7);
-  __syncthreads();
+  layer_fwd_epilogue(n.b2, n.g2, n.be2, n.ln, S, A.h2, A.xh2, A.st2, ws_h2, b0);
   B2RL_TICK(tk + 8);
 }
 
 // ---- the two hidden layers, backward (dX path). dh2 = gradient w.r.t. h2 for column j (threads < ET). ------
 // Writes dz2/dz1 to the workspace (for wgrad.cu) and this CTA's column partial sums when `part` != NULL.
 // On return S.d holds dz1 (synchronised).
-static __device__ __noinline__ void trunk_bwd(const Net& n, float4 dh2, const Acts& A, Scratch& S, int& tog, float4 rstd1,
-                                              float4 rstd2, float* ws_dz1, float* ws_dz2, float* part, int b0) {
+static __device__ __noinline__ void trunk_bwd(const Net& n, float4 dh2, const Acts& A, Scratch& S, float* ws_dz1,
+                                              float* ws_dz2, float* part, int b0) {
   const int j = threadIdx.x;
-  float g1 = 1.f, g2 = 1.f;
-  if (j < ET && n.ln) { g1 = __ldg(n.g1 + j); g2 = __ldg(n.g2 + j); }
+  float4 dz = layer_bwd_epilogue(dh2, A.h2, A.xh2, A.st2, n.g2, n.ln, S, part ? part + 3 * HID : nullptr);
   if (j < ET) {
-    float cs[3];
-    const float4 dz = bwd_epilogue(dh2, A.h2[j], A.xh2[j], rstd2, g2, n.ln, S.sred, tog, cs);
     S.d[j] = dz;
     if (ws_dz2) store_rows(ws_dz2, b0, dz);
-    if (part) {
-      part[3 * HID + j] = cs[0];
-      part[4 * HID + j] = cs[1];
-      part[5 * HID + j] = cs[2];
-    }
   }
   __syncthreads();
   gemm_rows(n.w2n, HID, S.d, S.red);
   __syncthreads();
+  float4 dh1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < ET) dh1 = reduce_partials(S.red);
+  dz = layer_bwd_epilogue(dh1, A.h1, A.xh1, A.st1, n.g1, n.ln, S, part);
   if (j < ET) {
-    float cs[3];
-    const float4 dz = bwd_epilogue(reduce_partials(S.red), A.h1[j], A.xh1[j], rstd1, g1, n.ln, S.sred, tog, cs);
     if (ws_dz1) store_rows(ws_dz1, b0, dz);
-    if (part) {
-      part[0 * HID + j] = cs[0];
-      part[1 * HID + j] = cs[1];
-      part[2 * HID + j] = cs[2];
-    }
-    S.d[j] = dz;  // safe: every thread passed the barrier above, i.e. finished reading S.d in gemm_rows
+    S.d[j] = dz;  // safe: every thread passed a barrier after gemm_rows finished reading S.d
   }
   __syncthreads();
 }
