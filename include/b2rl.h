@@ -26,7 +26,7 @@ extern "C" {
 
 #define B2RL_VERSION 100 /* 0.1.0 */
 #define B2RL_HID 256     /* hidden width; agents/agent.py:56,101 hard-codes (256, 256) */
-#define B2RL_ROWS 4      /* batch rows per CTA in the fused kernels; batch must be a multiple */
+#define B2RL_ROWS 8      /* batch rows per CTA group of the fused kernels; a batch need not be a multiple (the tail is masked) */
 #define B2RL_MAX_OUT 64  /* max head width (2*A for SAC) */
 #define B2RL_MAX_SEG 8   /* max segments per adam_polyak_multi launch */
 
@@ -101,7 +101,7 @@ typedef struct b2rl_update_args {
   b2rl_rowfmt_t fmt;
   b2rl_net_t actor;            /* online actor                                         */
   b2rl_net_t critic[2];        /* twin critics (reference stacks them on dim 0, agent.py:106) */
-  int32_t batch;               /* B, multiple of B2RL_ROWS */
+  int32_t batch;               /* B >= 1 (a tail that does not fill a group of B2RL_ROWS rows is masked) */
   int32_t n_agents;
   int32_t agent_base;          /* global id of local agent 0: Philox streams are keyed on the GLOBAL id, so a
                                   population gives the same results however it is sharded over GPUs */

@@ -6,7 +6,7 @@ import ctypes as C
 from pathlib import Path
 
 HID = 256
-ROWS = 4
+ROWS = 8  # batch rows per CTA group of the fused kernels (a batch need not be a multiple)
 MAX_OUT = 64
 MAX_SEG = 8
 CTR_Q, CTR_PI, CTR_ALPHA, CTR_SAMPLE, CTR_TICKET, CTR_SIZE = 0, 1, 2, 3, 4, 5

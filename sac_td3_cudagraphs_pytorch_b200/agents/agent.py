@@ -186,7 +186,7 @@ class Agent:
         if batch not in self._ws:
             n = self._lib.b2rl_workspace_floats(batch)
             if n < 0:
-                raise L.B2rlError(f"batch size {batch} must be a positive multiple of {L.ROWS}")
+                raise L.B2rlError(f"batch size {batch} must be >= 1")
             self._ws[batch] = torch.zeros(n, dtype=torch.float32, device=self.device)
         return self._ws[batch]
 

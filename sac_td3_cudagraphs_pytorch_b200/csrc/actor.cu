@@ -1,44 +1,50 @@
-// actor.cu — fused actor step (forward, policy loss, backward through the critics' inputs into the
-// actor; agents/agent.py:247-283), the SAC temperature step (agents/agent.py:295-303) and the
-// inference policy (agents/agent.py:172-181), 4 batch rows per CTA.
-#include <cooperative_groups.h>
-
-#include "mlp_rows.cuh"
+// actor.cu — fused actor step (forward, twin-Q with constant critic parameters, loss, backward into the
+// actor), the SAC temperature step, and the inference policy. Replaces agents/agent.py:247-283, :295-303,
+// :172-181. Built from the cluster column-split blocks of mlp_cluster.cuh: 8 batch rows per cluster.
+#include "mlp_cluster.cuh"
 #include "policy.cuh"
 #include "rng.cuh"
 
 namespace b2rl {
 
-struct ActorSmem {
-  float4 x[XMAX];  // [obs | a_pi]
-  Acts pi;         // actor activations (kept for its backward pass)
-  Acts q;          // this CTA's critic activations
-  Scratch s;
-  NetStage nsA, nsQ;
-  float rowbuf[ROWS * RS_CAP];
-  float4 da_peer[MAX_OUT];  // dLoss/da through the peer CTA's critic: [action dim] -> 4 rows
-  float4 qv[2], logpi, dq[2];
-  float lo[MAX_OUT / 2], hi[MAX_OUT / 2];
-  float eps[ROWS][MAX_OUT / 2], sg[ROWS][MAX_OUT / 2], yy[ROWS][MAX_OUT / 2], th[ROWS][MAX_OUT / 2];
-};
+constexpr int MAX_A = MAX_OUT / 2;
 
-// SAC: the two CTAs of a cluster share 4 batch rows; CTA k evaluates and differentiates critic k
-// (both recompute the identical actor forward), they swap Q_k (one float4) to agree on the arg-min,
-// CTA 1 hands its dQ/da to CTA 0 through distributed shared memory and retires; CTA 0 runs the actor's
-// backward pass. TD3's loss uses critic 0 only (agent.py:274-275): CTA 1 retires at once.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1)
-actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
+struct ActorSmem {
+  Work s;
+  Acts pi;         // the actor's pass (kept for its backward pass)
+  Acts q;          // this group's critic pass
+  ActorStage nsA;
+  CriticStage nsQ;
+  Net nA, nQ;
+  float lo[MAX_A], hi[MAX_A];
+  float eps[RT][MAX_A], sg[RT][MAX_A], yy[RT][MAX_A], th[RT][MAX_A];
+  float4 da_peer[RQ * MAX_OUT];  // dLoss/da through the peer group's critic, same layout as Work::u
+  float qv[2][RT], logpi[RT], dq[2][RT], lossr[RT], lpv[RT];
+  // followed by the input tile float4[RQ * (O + A)]: [obs | a_pi]
+};
+__host__ __device__ inline size_t actor_smem_bytes(int in_dim) {
+  return sizeof(ActorSmem) + (size_t)RQ * in_dim * sizeof(float4);
+}
+
+// SAC: cluster of 4, rank = 2k + c. Group k evaluates and differentiates critic k for the cluster's 8 rows (both
+// groups recompute the identical actor forward), the groups swap Q_k (8 floats) to agree on the arg-min, group 1
+// hands its dQ/da to group 0 through distributed shared memory and retires; group 0 runs the actor's backward
+// pass. TD3's loss uses critic 0 only (agent.py:274-275): clusters of 2, one group.
+__global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ActorSmem& M = *reinterpret_cast<ActorSmem*>(smem_raw);
-  namespace cg = cooperative_groups;
+  Work& S = M.s;
   cg::cluster_group cluster = cg::this_cluster();
-  const int k = (int)cluster.block_rank();
+  const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+  const int k = rank >> 1;
+  const Group G{rank & 1, rank & ~1};
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int agent = blockIdx.y, rb = blockIdx.x >> 1, b0 = rb * ROWS;
+  const int agent = blockIdx.y, rb = blockIdx.x / csize, b0 = rb * RT;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const int ldx = O + AD, nvalid = min(RT, B - b0);
+  float4* X = reinterpret_cast<float4*>(smem_raw + sizeof(ActorSmem));
   const uint32_t gid = (uint32_t)(A.agent_base + agent);  // global agent id: keys the Philox streams
   const bool td3 = A.hp.td3 != 0;
-  if (td3 && k == 1) return;  // the TD3 path never touches the cluster barrier
 
   const float* P = A.arena + (size_t)agent * A.arena_agent_stride;
   const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
@@ -49,149 +55,170 @@ actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   const float alpha = td3 ? 0.f : expf(A.log_alpha[(size_t)agent * 5]);
   const float invB = 1.0f / (float)B;
 
-  // ---- asynchronous burst: rows and small tensors
-  stage_rows(rows, rs, b0, M.rowbuf);
-  const Net act = stage_net(P, A.actor, M.nsA);
-  const Net q = stage_net(P, A.critic[k], M.nsQ);
+  // ---- asynchronous burst: the observation tile and the small tensors
+  stage_tile(rows, rs, b0, nvalid, 0, O, X, ldx, 0);
+  stage_net(P, A.actor, M.nsA, M.nA);
+  stage_net(P, A.critic[k], M.nsQ, M.nQ);
+  const Net &act = M.nA, &q = M.nQ;
   if (t < AD) {
     M.lo[t] = __ldg(A.min_ac + t);
     M.hi[t] = __ldg(A.max_ac + t);
   }
-  if (!td3 && t < ROWS * AD) {
-    const int r = t / AD, a = t - r * AD;
-    const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
-    const float z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_ACTOR_EPS);
-    M.eps[r][a] = z;
-    if (A.eps_out && k == 0) A.eps_out[e] = z;
+  if (!td3) {
+    for (int i = t; i < RT * AD; i += NT) {
+      const int r = i / AD, a = i - r * AD;
+      float z = 0.f;
+      if (r < nvalid) {
+        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
+        z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_ACTOR_EPS);
+        if (A.eps_out && rank == 0) A.eps_out[e] = z;
+      }
+      M.eps[r][a] = z;
+    }
   }
   cp_async_wait_all();
   __syncthreads();
+  int zi = 0;
 
   // ---- actor forward on obs (agent.py:251 / :254-255)
-  tile_from_rows(M.rowbuf, rs, 0, O, M.x, 0);
+  trunk_fwd(cluster, G, act, X, ldx, &M.pi, S, zi, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0, nvalid);
+  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();
-  trunk_fwd(act, M.x, M.pi, M.s, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0);
-  rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
-  __syncthreads();
-  if (w < ROWS) {
-    const int r = w;
+  for (int r = w; r < RT; r += NW) {  // warp <-> batch row, lane <-> action dim
     float lp = 0.f;
     if (l < AD) {
       const float lo = M.lo[l], hi = M.hi[l];
       const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+      const float u0 = uref(S.u, r, l);
       float act_v;
       if (td3) {
         float th;
-        act_v = td3_action(f4get(M.s.u[l], r), scale, bias, th);
+        act_v = td3_action(u0, scale, bias, th);
         M.th[r][l] = th;
       } else {
-        const GaussSample g = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), M.eps[r][l], scale, bias);
+        const GaussSample g = gauss_sample(u0, uref(S.u, r, AD + l), M.eps[r][l], scale, bias);
         act_v = g.action;
         lp = g.logp;
         M.sg[r][l] = g.sigma; M.yy[r][l] = g.y; M.th[r][l] = g.th;
       }
-      reinterpret_cast<float*>(&M.x[O + l])[r] = act_v;
+      reinterpret_cast<float*>(&X[(r >> 2) * ldx + O + l])[r & 3] = act_v;
     }
     lp = warp_sum(lp);
-    if (l == 0) reinterpret_cast<float*>(&M.logpi)[r] = lp;
+    if (l == 0) M.logpi[r] = lp;
   }
   __syncthreads();
 
   // ---- Q_k(obs, a_pi) with the critic's parameters held constant (agent.py:272-278)
-  trunk_fwd(q, M.x, M.q, M.s, nullptr, nullptr, b0);
-  rowdot(q.w3, q.b3, 1, M.q.h2, &M.qv[k]);
+  trunk_fwd(cluster, G, q, X, ldx, &M.q, S, zi, nullptr, nullptr, b0, nvalid);
+  rowdot(q.w3, q.b3, 1, S.h[1], S.u);
   __syncthreads();
-  if (!td3) {
-    if (t == 0) *cluster.map_shared_rank(&M.qv[k], k ^ 1) = M.qv[k];
-    cluster.sync();
+  if (t < RT) {
+    const float qk = uref(S.u, t, 0);
+    M.qv[k][t] = qk;
+    if (!td3) *cluster.map_shared_rank(&M.qv[k][t], rank ^ 2) = qk;
   }
+  if (!td3) cluster.sync(); else __syncthreads();
 
   // ---- loss and dLoss/dQ_k per row: SAC  mean(alpha*logpi - min_k Q_k), TD3  mean(-Q_0)
-  if (t < ROWS) {
+  if (t < RT) {
     const int r = t;
-    const float q0 = f4get(M.qv[0], r);
+    const bool valid = r < nvalid;
+    const float q0 = M.qv[0][r];
     float lossr, d0 = -invB, d1 = 0.f;
     if (td3) {
       lossr = -q0;
     } else {
-      const float q1 = f4get(M.qv[1], r);
+      const float q1 = M.qv[1][r];
       const bool first = q0 <= q1;  // torch.min(0) returns the first minimal index on ties
       d0 = first ? -invB : 0.f;
       d1 = first ? 0.f : -invB;
-      lossr = __fsub_rn(__fmul_rn(alpha, f4get(M.logpi, r)), first ? q0 : q1);
+      lossr = __fsub_rn(__fmul_rn(alpha, M.logpi[r]), first ? q0 : q1);
     }
-    reinterpret_cast<float*>(&M.dq[0])[r] = d0;
-    reinterpret_cast<float*>(&M.dq[1])[r] = d1;
-    reinterpret_cast<float*>(&M.s.u[0])[r] = lossr;
+    M.dq[0][r] = valid ? d0 : 0.f;
+    M.dq[1][r] = valid ? d1 : 0.f;
+    M.lossr[r] = valid ? lossr : 0.f;
+    M.lpv[r] = valid ? M.logpi[r] : 0.f;
   }
   __syncthreads();
-  if (t == 0 && k == 0) {
-    const float4 lr4 = M.s.u[0], lp4 = M.logpi;
-    part[PART_SCAL] = lr4.x + lr4.y + lr4.z + lr4.w;
-    part[PART_SCAL + 1] = lp4.x + lp4.y + lp4.z + lp4.w;
+  if (t == 0 && rank == 0) {
+    float sl = 0.f, sp = 0.f;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { sl += M.lossr[r]; sp += M.lpv[r]; }
+    part[PART_SCAL] = sl;
+    part[PART_SCAL + 1] = sp;
   }
 
   // ---- backward through critic k down to its action inputs
+  float dh[RT];
   {
-    const float w3 = t < ET ? q.w3[t] : 0.f;
-    const float4 dq = M.dq[k];
-    const float4 dh2 = make_float4(dq.x * w3, dq.y * w3, dq.z * w3, dq.w * w3);
-    trunk_bwd(q, dh2, M.q, M.s, nullptr, nullptr, nullptr, b0);
-    rowdot(q.w1t + (size_t)O * HID, nullptr, AD, M.s.d, M.s.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
+    const float w3 = q.w3[t];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) dh[r] = M.dq[k][r] * w3;
+    trunk_bwd(cluster, G, q, dh, M.q, S, zi, nullptr, nullptr, nullptr, b0, nvalid);
+    rowdot(q.w1t + (size_t)O * HID, nullptr, AD, S.h[1], S.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
     __syncthreads();
   }
   if (!td3) {
-    if (k == 1 && t < AD) *cluster.map_shared_rank(&M.da_peer[t], 0) = M.s.u[t];
+    if (k == 1)
+      for (int i = t; i < RQ * AD; i += NT) {
+        const int qq = i / AD, a = i - qq * AD;
+        *cluster.map_shared_rank(&M.da_peer[qq * MAX_OUT + a], rank ^ 2) = S.u[qq * MAX_OUT + a];
+      }
     cluster.sync();
-    if (k == 1) return;
+    if (k == 1) {  // retire, keeping the cluster's barrier count in step with group 0
+      for (int i = 0; i < TRUNK_BWD_BARRIERS; ++i) cluster.sync();
+      return;
+    }
   }
 
-  // ---- backward through the action head (CTA 0)
-  if (w < ROWS) {
-    const int r = w;
-    float g_a = 0.f, g_b = 0.f;
+  // ---- backward through the action head (group 0)
+  for (int r = w; r < RT; r += NW) {
     if (l < AD) {
       const float scale = (M.hi[l] - M.lo[l]) * 0.5f;
-      float ga = f4get(M.s.u[l], r);                    // through critic 0
-      if (!td3) ga += f4get(M.da_peer[l], r);           // + through critic 1
+      float ga = uref(S.u, r, l);                       // through critic 0
+      if (!td3) ga += uref(M.da_peer, r, l);            // + through critic 1
+      float g_a = 0.f, g_b = 0.f;
       if (td3) {
         const float th = M.th[r][l];
         g_a = ga * scale * (1.0f - th * th);
-      } else {
+      } else if (r < nvalid) {
         GaussSample g;
         g.y = M.yy[r][l]; g.sigma = M.sg[r][l]; g.th = M.th[r][l];
         gauss_backward(g, M.eps[r][l], scale, ga, alpha * invB, g_a, g_b);
       }
-      reinterpret_cast<float*>(&M.s.du[l])[r] = g_a;
-      ws.dz3[(size_t)(b0 + r) * MAX_OUT + l] = g_a;
-      if (!td3) {
-        reinterpret_cast<float*>(&M.s.du[AD + l])[r] = g_b;
-        ws.dz3[(size_t)(b0 + r) * MAX_OUT + AD + l] = g_b;
+      uref(S.du, r, l) = g_a;
+      if (!td3) uref(S.du, r, AD + l) = g_b;
+      if (G.c == 0 && r < nvalid) {
+        ws.dz3[(size_t)(b0 + r) * MAX_OUT + l] = g_a;
+        if (!td3) ws.dz3[(size_t)(b0 + r) * MAX_OUT + AD + l] = g_b;
       }
     }
   }
   __syncthreads();
-  if (t < act.out_dim) {
-    const float4 d = M.s.du[t];
-    part[PART_DB3 + t] = d.x + d.y + d.z + d.w;
+  if (t < act.out_dim && G.c == 0) {
+    const float4 d0 = S.du[t], d1 = S.du[MAX_OUT + t];
+    part[PART_DB3 + t] = ((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w));
   }
-  const float4 dh2 = head_bwd(act.w3, act.out_dim, M.s.du);
-  trunk_bwd(act, dh2, M.pi, M.s, ws.dz1, ws.dz2, part, b0);
+  head_bwd(act.w3, act.out_dim, S.du, dh);
+  trunk_bwd(cluster, G, act, dh, M.pi, S, zi, ws.dz1, ws.dz2, part, b0, nvalid);
 }
 
 // ---- SAC temperature step -------------------------------------------------------------------
-// Every CTA: log-prob of a fresh sample from the UPDATED actor for its 4 rows; the last CTA to
-// finish (ticket in counters[4]) sums the per-CTA partials in a fixed order, forms
+// Every cluster of 2: log-prob of a fresh sample from the UPDATED actor for its 8 rows; the last cluster to
+// finish (ticket in counters[4]) sums the per-cluster partials in a fixed order, forms
 //   alpha_loss = mean(alpha * (-logpi - targ_ent)),  d/dlog_alpha = same value,
 // and applies torch's capturable Adam step to the scalar.
 struct AlphaSmem {
-  float4 x[XMAX];
-  Acts pi;
-  Scratch s;
-  NetStage ns;
-  float4 logpi;
+  Work s;
+  ActorStage ns;
+  Net n;
+  float logpi[RT];
   int last;
+  // followed by the observation tile float4[RQ * O]
 };
+__host__ __device__ inline size_t alpha_smem_bytes(int ob_dim) {
+  return sizeof(AlphaSmem) + (size_t)RQ * ob_dim * sizeof(float4);
+}
 
 __device__ __forceinline__ void adam_scalar(float* st /*{p,g,m,v}*/, float g, float lr, float t, float b1, float b2,
                                             float eps) {
@@ -208,9 +235,15 @@ __device__ __forceinline__ void adam_scalar(float* st /*{p,g,m,v}*/, float g, fl
 __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2rl_update_args_t A, float lr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlphaSmem& M = *reinterpret_cast<AlphaSmem*>(smem_raw);
+  Work& S = M.s;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const Group G{rank, 0};
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int agent = blockIdx.y, rb = blockIdx.x, b0 = rb * ROWS;
+  const int agent = blockIdx.y, rb = blockIdx.x >> 1, b0 = rb * RT, nblk = gridDim.x >> 1;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim, rs = A.fmt.row_stride, B = A.batch;
+  const int nvalid = min(RT, B - b0);
+  float4* X = reinterpret_cast<float4*>(smem_raw + sizeof(AlphaSmem));
   const uint32_t gid = (uint32_t)(A.agent_base + agent);
   const float* P = A.arena + (size_t)agent * A.arena_agent_stride;
   const float* rows = A.rows + (size_t)agent * A.rows_agent_stride;
@@ -219,42 +252,45 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
   float* part = ws_carve(wsb, B, 0).part;
 
-  const Net act = stage_net(P, A.actor, M.ns);
-  load_x(rows, rs, b0, 0, O, M.x, 0);
+  stage_tile(rows, rs, b0, nvalid, 0, O, X, O, 0);
+  stage_net(P, A.actor, M.ns, M.n);
+  const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
-  trunk_fwd(act, M.x, M.pi, M.s, nullptr, nullptr, b0);
-  rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
+  int zi = 0;
+  trunk_fwd(cluster, G, act, X, O, nullptr, S, zi, nullptr, nullptr, b0, nvalid);
+  if (rank != 0) return;  // (no peer touches this CTA's shared memory after the last all-gather's barrier)
+  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();
-  if (w < ROWS) {
-    const int r = w;
+  for (int r = w; r < RT; r += NW) {
     float lp = 0.f;
-    if (l < AD) {
+    if (l < AD && r < nvalid) {
       const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
       const int64_t e = ((int64_t)agent * B + b0 + r) * AD + l;
       const float z = noise_at(A.eps2, e, A.hp.seed, b0 + r, l, step, gid, STREAM_ALPHA_EPS);
       if (A.eps2_out) A.eps2_out[e] = z;
-      lp = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, (hi - lo) * 0.5f, (hi + lo) * 0.5f).logp;
+      lp = gauss_sample(uref(S.u, r, l), uref(S.u, r, AD + l), z,
+                        (hi - lo) * 0.5f, (hi + lo) * 0.5f).logp;
     }
     lp = warp_sum(lp);
-    if (l == 0) reinterpret_cast<float*>(&M.logpi)[r] = lp;
+    if (l == 0) M.logpi[r] = lp;
   }
   __syncthreads();
   if (t == 0) {
-    const float4 lp4 = M.logpi;
     const float te = A.hp.targ_ent;
-    // sum_r (-logpi_r - targ_ent), agent.py:300
-    part[(size_t)rb * PART_LEN + PART_SCAL + 2] = (-lp4.x - te) + (-lp4.y - te) + (-lp4.z - te) + (-lp4.w - te);
+    float s = 0.f;
+    for (int r = 0; r < nvalid; ++r) s += (-M.logpi[r] - te);  // sum_r (-logpi_r - targ_ent), agent.py:300
+    part[(size_t)rb * PART_LEN + PART_SCAL + 2] = s;
     __threadfence();
     const unsigned long long ticket = atomicAdd((unsigned long long*)&ctr[B2RL_CTR_TICKET], 1ULL);
-    M.last = (ticket == (unsigned long long)gridDim.x - 1);
+    M.last = (ticket == (unsigned long long)nblk - 1);
   }
   __syncthreads();
   if (!M.last) return;
-  if (w == 0) {  // the last CTA: lane-strided sum of the per-CTA partials, fixed shuffle tree
+  if (w == 0) {  // the last cluster: lane-strided sum of the per-cluster partials, fixed shuffle tree
     __threadfence();
     float s = 0.f;
-    for (int i = l; i < (int)gridDim.x; i += 32) s += __ldcg(&part[(size_t)i * PART_LEN + PART_SCAL + 2]);
+    for (int i = l; i < nblk; i += 32) s += __ldcg(&part[(size_t)i * PART_LEN + PART_SCAL + 2]);
     s = warp_sum(s);
     if (l == 0) {
       float* st = A.log_alpha + (size_t)agent * 5;
@@ -298,57 +334,72 @@ cudaError_t launch_alpha_adam(float* log_alpha, uint64_t* counters, int n_agents
 
 // ---- inference policy ----------------------------------------------------------------------------
 struct PredictSmem {
-  float4 x[XMAX];
-  Acts pi;
-  Scratch s;
-  NetStage ns;
+  Work s;
+  ActorStage ns;
+  Net n;
+  // followed by the observation tile float4[RQ * O]
 };
+__host__ __device__ inline size_t predict_smem_bytes(int ob_dim) {
+  return sizeof(PredictSmem) + (size_t)RQ * ob_dim * sizeof(float4);
+}
 
 __global__ void __launch_bounds__(NT, 1)
 predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __restrict__ obs, int n, int mode,
                float explore_std, uint64_t draw, float* __restrict__ actions) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PredictSmem& M = *reinterpret_cast<PredictSmem*>(smem_raw);
+  Work& S = M.s;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const Group G{rank, 0};
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int b0 = blockIdx.x * ROWS;
+  const int b0 = (blockIdx.x >> 1) * RT;
   const int O = A.fmt.ob_dim, AD = A.fmt.ac_dim;
+  const int nvalid = min(RT, n - b0);
+  float4* X = reinterpret_cast<float4*>(smem_raw + sizeof(PredictSmem));
   const bool td3 = A.hp.td3 != 0;
   const float* P = A.arena;
   const uint64_t step = draw;
-  const Net act = stage_net(P, A.actor, M.ns);
-  load_x(obs, O, b0, 0, O, M.x, 0, min(ROWS, n - b0));
+  stage_tile(obs, O, b0, nvalid, 0, O, X, O, 0);
+  stage_net(P, A.actor, M.ns, M.n);
+  const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
-  trunk_fwd(act, M.x, M.pi, M.s, nullptr, nullptr, b0);
-  rowdot(act.w3, act.b3, act.out_dim, M.pi.h2, M.s.u);
+  int zi = 0;
+  trunk_fwd(cluster, G, act, X, O, nullptr, S, zi, nullptr, nullptr, b0, nvalid);
+  if (rank != 0) return;
+  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();
-  if (w < ROWS && l < AD && b0 + w < n) {
-    const int r = w;
-    const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
-    const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
-    const int64_t e = (int64_t)(b0 + r) * AD + l;
-    float a;
-    if (td3) {  // agents/nets.py:149-159
-      float th;
-      a = td3_action(f4get(M.s.u[l], r), scale, bias, th);
-      if (mode == 1) a += noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS) * (scale * explore_std);
-    } else if (mode == 1) {  // sample
-      const float z = noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS);  // key != learner's
-      a = gauss_sample(f4get(M.s.u[l], r), f4get(M.s.u[AD + l], r), z, scale, bias).action;
-    } else {  // mode = tanh(mean)*scale + bias, agents/nets.py:233
-      a = __fadd_rn(__fmul_rn(tanhf(f4get(M.s.u[l], r)), scale), bias);
+  for (int r = w; r < nvalid; r += NW) {
+    if (l < AD) {
+      const float lo = __ldg(A.min_ac + l), hi = __ldg(A.max_ac + l);
+      const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+      const int64_t e = (int64_t)(b0 + r) * AD + l;
+      const float u0 = uref(S.u, r, l);
+      float a;
+      if (td3) {  // agents/nets.py:149-159
+        float th;
+        a = td3_action(u0, scale, bias, th);
+        if (mode == 1) a += noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS) * (scale * explore_std);
+      } else if (mode == 1) {  // sample
+        const float z = noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS);  // key != learner's
+        a = gauss_sample(u0, uref(S.u, r, AD + l), z, scale, bias).action;
+      } else {  // mode = tanh(mean)*scale + bias, agents/nets.py:233
+        a = __fadd_rn(__fmul_rn(tanhf(u0), scale), bias);
+      }
+      actions[e] = a;
     }
-    actions[e] = a;
   }
 }
 
+int max_in_dim_actor() { return (int)((MAX_DYN_SMEM - actor_smem_bytes(0)) / (1 * RQ * sizeof(float4))); }
+
 cudaError_t init_actor() {
-  cudaError_t e = cudaFuncSetAttribute(actor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(ActorSmem));
+  cudaError_t e = cudaFuncSetAttribute(actor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AlphaSmem));
+    e = cudaFuncSetAttribute(alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredictSmem));
+    e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
   if (e == cudaSuccess) {
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, alpha_adam_kernel);
@@ -357,21 +408,23 @@ cudaError_t init_actor() {
 }
 
 cudaError_t launch_actor_fused(const b2rl_update_args_t& a, cudaStream_t st) {
-  dim3 grid(2 * (a.batch / ROWS), a.n_agents);  // clusters of 2 along x: (row block, critic)
-  actor_fused_kernel<<<grid, NT, sizeof(ActorSmem), st>>>(a);
-  return cudaGetLastError();
+  const size_t smem = actor_smem_bytes(a.fmt.ob_dim + a.fmt.ac_dim);
+  if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
+  const int csize = a.hp.td3 ? 2 : 4;  // (row block, [critic,] column slice)
+  return launch_cluster(actor_fused_kernel, dim3(csize * row_blocks(a.batch), a.n_agents), csize, smem, st, a);
 }
 
 cudaError_t launch_alpha(const b2rl_update_args_t& a, float lr, cudaStream_t st) {
-  dim3 grid(a.batch / ROWS, a.n_agents);
-  alpha_kernel<<<grid, NT, sizeof(AlphaSmem), st>>>(a, lr);
-  return cudaGetLastError();
+  const size_t smem = alpha_smem_bytes(a.fmt.ob_dim);
+  if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
+  return launch_cluster(alpha_kernel, dim3(2 * row_blocks(a.batch), a.n_agents), 2, smem, st, a, lr);
 }
 
 cudaError_t launch_predict(const b2rl_update_args_t& a, const float* obs, int n, int mode, float explore_std,
                            uint64_t draw, float* actions, cudaStream_t st) {
-  predict_kernel<<<(n + ROWS - 1) / ROWS, NT, sizeof(PredictSmem), st>>>(a, obs, n, mode, explore_std, draw, actions);
-  return cudaGetLastError();
+  const size_t smem = predict_smem_bytes(a.fmt.ob_dim);
+  if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
+  return launch_cluster(predict_kernel, dim3(2 * row_blocks(n)), 2, smem, st, a, obs, n, mode, explore_std, draw, actions);
 }
 
 }  // namespace b2rl

@@ -19,6 +19,8 @@ cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
 cudaError_t launch_gather(const float*, int64_t, int64_t, b2rl_rowfmt_t, int, int, const int64_t*, int64_t*, float*,
                           uint64_t, uint64_t*, int, int, int, cudaStream_t);
 cudaError_t launch_extend(float*, int64_t, int64_t, b2rl_rowfmt_t, const float*, int, cudaStream_t);
+int max_in_dim_critic();
+int max_in_dim_actor();
 cudaError_t init_critic();
 cudaError_t init_actor();
 cudaError_t init_wgrad();
@@ -44,7 +46,9 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 static int check_fmt(const b2rl_rowfmt_t& f) {
   if (f.ob_dim < 1 || f.ac_dim < 1) return fail(B2RL_E_INVALID, "row format: ob_dim/ac_dim must be >= 1");
   if (f.ac_dim > B2RL_MAX_OUT / 2) return fail(B2RL_E_INVALID, "ac_dim %d > %d", f.ac_dim, B2RL_MAX_OUT / 2);
-  if (f.ob_dim + f.ac_dim > 1024) return fail(B2RL_E_INVALID, "ob_dim + ac_dim %d > 1024", f.ob_dim + f.ac_dim);
+  const int max_in = b2rl::max_in_dim_critic() < b2rl::max_in_dim_actor() ? b2rl::max_in_dim_critic() : b2rl::max_in_dim_actor();
+  if (f.ob_dim + f.ac_dim > max_in)  // the fused kernels keep their input tiles in shared memory
+    return fail(B2RL_E_INVALID, "ob_dim + ac_dim %d > %d", f.ob_dim + f.ac_dim, max_in);
   if (f.row_stride % 4 != 0 || f.row_stride < 2 * f.ob_dim + f.ac_dim + 2)
     return fail(B2RL_E_INVALID, "row_stride %d must be a multiple of 4 and >= 2*ob+ac+2", f.row_stride);
   return B2RL_OK;
@@ -65,7 +69,7 @@ static int check_net(const b2rl_net_t& n, const char* name, bool need_w2n) {
 static int check_update(const b2rl_update_args_t* a, bool actor_step) {
   if (!a) return fail(B2RL_E_INVALID, "null args");
   if (int rc = check_fmt(a->fmt)) return rc;
-  if (a->batch < B2RL_ROWS || a->batch % B2RL_ROWS) return fail(B2RL_E_INVALID, "batch %d must be a positive multiple of %d", a->batch, B2RL_ROWS);
+  if (a->batch < 1 || a->batch > (1 << 24)) return fail(B2RL_E_INVALID, "batch %d out of range", a->batch);
   if (a->n_agents < 1 || a->n_agents > 65535) return fail(B2RL_E_INVALID, "n_agents %d out of range", a->n_agents);
   if (a->agent_base < 0 || (int64_t)a->agent_base + a->n_agents > (1 << 30)) return fail(B2RL_E_INVALID, "agent ids must stay below 2^30");
   if (!a->arena || !a->rows || !a->min_ac || !a->max_ac || !a->counters || !a->workspace || !a->out)
@@ -123,7 +127,7 @@ int b2rl_init(void) {
 }
 
 int64_t b2rl_workspace_floats(int32_t batch) {
-  if (batch < B2RL_ROWS || batch % B2RL_ROWS) return -1;
+  if (batch < 1) return -1;
   return b2rl::ws_floats(batch);
 }
 

@@ -8,19 +8,21 @@
 namespace b2rl {
 
 constexpr int HID = B2RL_HID;    // 256
-constexpr int ROWS = B2RL_ROWS;  // batch rows per CTA
-constexpr int NT = 512;          // threads per CTA in the fused kernels: 16 warps feed the FFMA pipes
+constexpr int RT = B2RL_ROWS;    // batch rows per CTA group of the fused kernels (8)
+constexpr int RQ = RT / 4;       // row quads: row tiles are stored as float4 (one float per batch row of a quad)
+constexpr int CS = 2;            // CTAs per group: each computes HID / CS output columns of every layer
+constexpr int CW = HID / CS;     // 128
+constexpr int NT = HID;          // threads per CTA in the fused kernels: thread t <-> hidden unit t in the row-wise steps
 constexpr int NW = NT / 32;
-constexpr int ET = HID;          // "epilogue threads": thread t < ET <-> hidden unit t (warps 0..7)
-constexpr int EW = ET / 32;
-constexpr int KSPLIT = 8;        // GEMM k-slices (x 2 column halves = 16 warps)
+constexpr int KS = NW;           // product k-slices: one per warp
 constexpr int MAX_OUT = B2RL_MAX_OUT;
 constexpr float LN_EPS = 1e-5f;  // torch.nn.LayerNorm default (agents/nets.py:70)
 
-static_assert(ROWS == 4, "row tiles are stored as float4 (one float per batch row)");
+static_assert(RT == 8 && NT == 256 && CS == 2, "thread mappings of mlp_cluster.cuh");
+__host__ __device__ inline int row_blocks(int B) { return (B + RT - 1) / RT; }
 
 // workspace layout per agent (floats); `slot` = 0/1 for the twin critics, 0 for the actor
-//   H1, H2, DZ1, DZ2 : [2][B][256]   DZ3 : [2][B][MAX_OUT]   PART : [2][B/ROWS][PART_LEN]
+//   H1, H2, DZ1, DZ2 : [2][B][256]   DZ3 : [2][B][MAX_OUT]   PART : [2][ceil(B/8)][PART_LEN]
 constexpr int PART_VEC = 6;                               // db1 dg1 dbe1 db2 dg2 dbe2
 constexpr int PART_LEN = PART_VEC * HID + MAX_OUT + 8;    // + db3[MAX_OUT] + {loss terms}
 constexpr int PART_DB3 = PART_VEC * HID;
@@ -30,7 +32,7 @@ struct Workspace {
   float *h1, *h2, *dz1, *dz2, *dz3, *part;
 };
 __host__ __device__ inline int64_t ws_floats(int B) {
-  return (int64_t)2 * B * HID * 4 + (int64_t)2 * B * MAX_OUT + (int64_t)2 * (B / ROWS) * PART_LEN;
+  return (int64_t)2 * B * HID * 4 + (int64_t)2 * B * MAX_OUT + (int64_t)2 * row_blocks(B) * PART_LEN;
 }
 __host__ __device__ inline Workspace ws_carve(float* base, int B, int slot) {
   Workspace w;
@@ -42,7 +44,7 @@ __host__ __device__ inline Workspace ws_carve(float* base, int B, int slot) {
   float* p = base + 8 * bh;
   w.dz3 = p + (int64_t)slot * B * MAX_OUT;
   p += (int64_t)2 * B * MAX_OUT;
-  w.part = p + (int64_t)slot * (B / ROWS) * PART_LEN;
+  w.part = p + (int64_t)slot * row_blocks(B) * PART_LEN;
   return w;
 }
 
@@ -56,6 +58,27 @@ static __device__ long long g_b2rl_timing[64];  // one copy per translation unit
 #else
 #define B2RL_TICK(slot) do {} while (0)
 #endif
+
+// ---- cluster launches ----------------------------------------------------------------------------------------
+constexpr int MAX_DYN_SMEM = 232448;  // 227 KB: the opt-in dynamic shared memory limit of sm_100
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, int cluster_x, size_t smem, cudaStream_t st,
+                                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -76,28 +99,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-// barrier over the ET epilogue threads only (named barrier 1; barrier 0 is __syncthreads)
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory"); }
-
-// Sum of v[0..3] over the ET epilogue threads, result broadcast to each of them; fixed order =>
-// deterministic. `buf` is EW float4 of shared memory; callers alternate between two buffers so that
-// one barrier per call is enough. Must be called by exactly the threads t < ET.
-__device__ __forceinline__ float4 block_sum4(float4 v, float4* buf) {
-  v.x = warp_sum(v.x);
-  v.y = warp_sum(v.y);
-  v.z = warp_sum(v.z);
-  v.w = warp_sum(v.w);
-  if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = v;
-  epi_sync();
-  float4 s = buf[0];
-#pragma unroll
-  for (int w = 1; w < EW; ++w) {
-    const float4 t = buf[w];
-    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-  }
-  return s;
 }
 
 __device__ __forceinline__ float f4get(const float4& v, int i) {

@@ -1,0 +1,469 @@
+// mlp_cluster.cuh — building blocks of the fused SAC/TD3 kernels: a 2x256 MLP evaluated (and
+// differentiated) for a tile of RT = 8 batch rows by a GROUP of CS = 2 CTAs of one thread-block cluster.
+//
+// Why this shape: at batch 256 the update is a chain of ~20 dependent [256x256]x[256xB]
+// products. Batch rows are independent through the forward pass and through the dX half of the backward
+// pass, so a group that owns 8 rows runs every layer of every network back to back with no grid-wide
+// synchronisation; only the weight gradients (a contraction over the batch) need a second kernel (wgrad.cu).
+// Inside a group the OUTPUT COLUMNS of every layer are split: CTA c computes columns [128c, 128c+128) for the 8
+// rows, so it streams half of the layer's weights (128 KB of a 256x256 layer) from L2 — the first version, one
+// CTA per 4 rows streaming whole layers, was bound by exactly that L2->SM traffic (profiles/r1_*). The 8x128
+// slices are then exchanged through distributed shared memory (each CTA stores its slice into the Z buffer of
+// both), one cluster barrier, and both CTAs run the cheap row-wise part (LayerNorm, ReLU) for the full 8x256
+// tile redundantly, which leaves each holding the full operand of the next layer. (Four-way splits with 16
+// rows need clusters of 8 for the twin critics, of which only 15 fit on a B200 at one CTA per SM — one short
+// of the 16 that batch 256 needs; tools/probes/cluster_occupancy.cu.)
+// The products themselves are fp32 FFMA2 (fma.rn.f32x2: two fused multiply-adds per lane per issue slot, which
+// leaves issue slots for the shared-memory operand loads), weights go global/L2 -> registers with 128-bit
+// loads that are all in flight before the first multiply.
+//
+// Arithmetic restated from agents/nets.py:66-92 (Linear -> LayerNorm -> ReLU twice, then head).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace b2rl {
+namespace cg = cooperative_groups;
+
+struct Net {  // resolved pointers of one network; the small tensors may point into shared memory (NetStage)
+  const float *w1t, *b1, *g1, *be1, *w2t, *b2, *g2, *be2, *w3, *b3, *w2n;
+  int in_dim, out_dim, ln;
+};
+__device__ __forceinline__ Net resolve(const float* region, const b2rl_net_t& n) {
+  Net r;
+  r.w1t = region + n.w1t; r.b1 = region + n.b1; r.g1 = region + n.g1; r.be1 = region + n.be1;
+  r.w2t = region + n.w2t; r.b2 = region + n.b2; r.g2 = region + n.g2; r.be2 = region + n.be2;
+  r.w3 = region + n.w3;   r.b3 = region + n.b3; r.w2n = region + n.w2n;
+  r.in_dim = n.in_dim; r.out_dim = n.out_dim; r.ln = n.layer_norm;
+  return r;
+}
+
+// ---- asynchronous copies (LDGSTS): fire-and-forget, so a whole burst costs one L2 round trip ------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
+// Everything of a network that the row-wise steps and the head touch (biases, LayerNorm affine, head weights),
+// copied once into shared memory at kernel start.
+template <int W3R>  // head rows staged: 1 for a critic; 8 for an actor (a wider head is read from global memory)
+struct NetStage {
+  float b1[HID], g1[HID], be1[HID], b2[HID], g2[HID], be2[HID];
+  float w3[W3R * HID];
+  float b3[MAX_OUT];
+};
+using CriticStage = NetStage<1>;
+using ActorStage = NetStage<8>;
+// Issue the copies (all threads) and leave in `out` (shared memory: the fused kernels keep their Net descriptors
+// there, not on the stack — local memory sits in L1, which every cluster barrier invalidates) a Net whose small
+// tensors point into `st`. Call cp_async_wait_all() and __syncthreads() before the first use.
+template <int W3R>
+__device__ __forceinline__ void stage_net(const float* region, const b2rl_net_t& d, NetStage<W3R>& st, Net& out) {
+  Net n = resolve(region, d);
+  const int t = threadIdx.x;
+  const int nv = d.layer_norm ? 6 : 2;
+  for (int i = t; i < nv * (HID / 4); i += NT) {  // 64 float4 per vector
+    const int v = i / (HID / 4), c = (i % (HID / 4)) * 4;
+    const float* src = d.layer_norm ? (v == 0 ? n.b1 : v == 1 ? n.g1 : v == 2 ? n.be1 : v == 3 ? n.b2 : v == 4 ? n.g2 : n.be2)
+                                    : (v == 0 ? n.b1 : n.b2);
+    float* dst = d.layer_norm ? (v == 0 ? st.b1 : v == 1 ? st.g1 : v == 2 ? st.be1 : v == 3 ? st.b2 : v == 4 ? st.g2 : st.be2)
+                              : (v == 0 ? st.b1 : st.b2);
+    cp_async16(dst + c, src + c);
+  }
+  for (int i = t; i < (d.out_dim + 3) / 4; i += NT) cp_async16(st.b3 + 4 * i, n.b3 + 4 * i);
+  n.b1 = st.b1; n.b2 = st.b2; n.b3 = st.b3;
+  if (d.layer_norm) { n.g1 = st.g1; n.be1 = st.be1; n.g2 = st.g2; n.be2 = st.be2; }
+  if (d.out_dim <= W3R) {
+    for (int i = t; i < d.out_dim * (HID / 4); i += NT) cp_async16(st.w3 + 4 * i, n.w3 + 4 * i);
+    n.w3 = st.w3;
+  }
+  if (t == 0) out = n;
+}
+
+// ---- layouts in shared memory -------------------------------------------------------------------------------
+// Operand tile ("T-layout"): float4 T[q * ld + k] holds feature k of rows 4q..4q+3 (q < RQ = 2). The product reads
+// it as a broadcast, the row-wise steps write it with consecutive threads on consecutive k.
+// Z-layout: float Z[r * HID + j], row-major: what the exchange fills and the row statistics read.
+struct Acts {          // what one forward pass leaves behind for its backward pass
+  float4 xh1[RQ * HID], xh2[RQ * HID];  // LayerNorm x-hat (or the pre-activation when layer_norm is off)
+  float2 st1[RT], st2[RT];              // per row (mean, rstd) of the two LayerNorms
+};
+struct Work {          // per-CTA scratch shared by all passes
+  float red[KS * RT * CW];    // split-K partial sums [k-slice][row][col]; also row-wise scratch of the backward pass
+  float z[2][RT * HID];       // exchange targets (double buffered: the peer may run one layer ahead)
+  float4 h[2][RQ * HID];      // operand tiles: h1 / h2 of the running pass, dz tiles of the backward pass
+  float4 u[RQ * MAX_OUT];     // head outputs / small row-dot results: u[q * MAX_OUT + o]
+  float4 du[RQ * MAX_OUT];
+  float2 stat[RT];
+};
+
+struct Group {  // the CS CTAs that share 8 rows of one network
+  int c;        // this CTA's column slice
+  int base;     // cluster rank of slice 0
+};
+
+// ---- the product: red[w][r][j] = sum_{k in slice(w)} W[k][j0 + j] * X[r][k],  r < 8, j < 128 ---------------------
+// W is [K][256] row-major (w1t / w2t for the forward pass, w2n for dX). Warp w owns a contiguous slice of K;
+// lane l owns columns j0+4l..+3 for all 8 rows: per k one LDG.128 of weights (512 contiguous bytes per warp),
+// two broadcast LDS.128 of the rows' activations, 16 FFMA2.
+__device__ __forceinline__ void ffma2(float2& d, float w, const float2 x) {
+  float2 ww = make_float2(w, w);  // (ptxas folds the duplicate into FFMA2's scalar-broadcast operand form)
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&ww)), "l"(*reinterpret_cast<const unsigned long long*>(&x)));
+}
+__device__ __forceinline__ void fma_k(float2 (&acc)[4][4], const float4 wv, const float4 x0, const float4 x1) {
+  const float2 p0 = make_float2(x0.x, x0.y), p1 = make_float2(x0.z, x0.w);
+  const float2 p2 = make_float2(x1.x, x1.y), p3 = make_float2(x1.z, x1.w);
+  ffma2(acc[0][0], wv.x, p0); ffma2(acc[0][1], wv.x, p1); ffma2(acc[0][2], wv.x, p2); ffma2(acc[0][3], wv.x, p3);
+  ffma2(acc[1][0], wv.y, p0); ffma2(acc[1][1], wv.y, p1); ffma2(acc[1][2], wv.y, p2); ffma2(acc[1][3], wv.y, p3);
+  ffma2(acc[2][0], wv.z, p0); ffma2(acc[2][1], wv.z, p1); ffma2(acc[2][2], wv.z, p2); ffma2(acc[2][3], wv.z, p3);
+  ffma2(acc[3][0], wv.w, p0); ffma2(acc[3][1], wv.w, p1); ffma2(acc[3][2], wv.w, p2); ffma2(acc[3][3], wv.w, p3);
+}
+
+constexpr int KW = HID / KS;  // k per warp in a 256-deep layer (32)
+constexpr int CH = 8;         // k per register chunk of the general path
+
+static __device__ __noinline__ void gemm_slice(const float* __restrict__ W, int K, const float4* __restrict__ X, int ldx,
+                                               int j0, float* __restrict__ red) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float2 acc[4][4];  // [col][row pair]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[i][p] = make_float2(0.f, 0.f);
+
+  if (K == HID) {  // hidden layers: the warp's 32 weight rows are all in flight before the first multiply
+    const float* wp = W + (size_t)(w * KW) * HID + j0 + 4 * l;
+    const float4* xa = X + w * KW;
+    const float4* xb = xa + ldx;
+    float4 Wr[KW];
+#pragma unroll
+    for (int u = 0; u < KW; ++u) Wr[u] = ldg4(wp + (size_t)u * HID);
+#pragma unroll
+    for (int u = 0; u < KW; ++u) fma_k(acc, Wr[u], xa[u], xb[u]);
+  } else {  // first layers (K = O or O + A, any size): chunks of 8 k, two chunks in flight, tails clamped (x = 0)
+    const int ks = (K + KS - 1) / KS;
+    const int k0 = min(K, w * ks), n = min(K, k0 + ks) - k0;
+    if (n > 0) {
+      const float* wp = W + (size_t)k0 * HID + j0 + 4 * l;
+      const float4* xa = X + k0;
+      const float4* xb = xa + ldx;
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 A[CH], Bf[CH];
+#define B2RL_LOADC(buf, kk) \
+  _Pragma("unroll") for (int u = 0; u < CH; ++u) buf[u] = ldg4(wp + (size_t)min((kk) + u, n - 1) * HID);
+#define B2RL_FMAC(buf, kk)                                                        \
+  _Pragma("unroll") for (int u = 0; u < CH; ++u) {                                \
+    const int kc = min((kk) + u, n - 1);                                          \
+    const bool on = (kk) + u < n;                                                 \
+    fma_k(acc, buf[u], on ? xa[kc] : zero, on ? xb[kc] : zero);                   \
+  }
+      B2RL_LOADC(A, 0)
+      for (int kk = 0; kk < n; kk += 2 * CH) {
+        if (kk + CH < n) { B2RL_LOADC(Bf, kk + CH) }
+        B2RL_FMAC(A, kk)
+        if (kk + 2 * CH < n) { B2RL_LOADC(A, kk + 2 * CH) }
+        if (kk + CH < n) { B2RL_FMAC(Bf, kk + CH) }
+      }
+#undef B2RL_LOADC
+#undef B2RL_FMAC
+    }
+  }
+  float* rp = red + (size_t)(w * RT) * CW + 4 * l;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    *reinterpret_cast<float4*>(rp + (2 * p) * CW) = make_float4(acc[0][p].x, acc[1][p].x, acc[2][p].x, acc[3][p].x);
+    *reinterpret_cast<float4*>(rp + (2 * p + 1) * CW) = make_float4(acc[0][p].y, acc[1][p].y, acc[2][p].y, acc[3][p].y);
+  }
+}
+
+// ---- split-K reduction (fixed order) + bias + exchange of this CTA's 8x128 slice with the peer ------------------
+// Thread (r = t >> 5, cq = t & 31) owns row r, columns j0+4cq..+3. Ends with the cluster barrier; returns the
+// buffer that now holds the full 8x256 tile in both CTAs of the group. `zi` (which of the two z buffers the
+// next exchange fills) is a per-thread value that every thread of the cluster advances in step; two buffers
+// are enough because the peer can run at most one layer ahead (it needs this CTA's slice for the one after).
+__device__ __forceinline__ const float* reduce_gather(cg::cluster_group& cluster, const Group G, Work& S, int& zi,
+                                                      const float* __restrict__ bias) {
+  const int t = threadIdx.x, r = t >> 5, cq = t & 31, j = G.c * CW + 4 * cq;
+  const float* rp = S.red + (size_t)r * CW + 4 * cq;
+  float4 s = *reinterpret_cast<const float4*>(rp);
+#pragma unroll
+  for (int w = 1; w < KS; ++w) {
+    const float4 v = *reinterpret_cast<const float4*>(rp + (size_t)w * RT * CW);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  if (bias) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + j);
+    s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+  }
+  float* zl = S.z[zi];
+  zi ^= 1;
+  *reinterpret_cast<float4*>(zl + (size_t)r * HID + j) = s;
+  *reinterpret_cast<float4*>(cluster.map_shared_rank(zl, G.base + (G.c ^ 1)) + (size_t)r * HID + j) = s;
+  cluster.sync();  // (release/acquire at cluster scope: both slices are visible in both CTAs)
+  return zl;
+}
+
+// ---- row statistics: warp w reduces row w of a [8][256] buffer ---------------------------------------------------
+__device__ __forceinline__ void row_stats(const float* za, const float* zb, float2* out, bool layernorm_stats) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = za[w * HID + l + 32 * i];
+  float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+  if (layernorm_stats) {  // (mean, rstd) with the biased variance taken around the mean (two-pass)
+    s = warp_sum(s);
+    const float mean = s * (1.0f / HID);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    q = warp_sum(q);
+    if (l == 0) out[w] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / HID) + LN_EPS));
+  } else {  // two plain means (LayerNorm backward: mean(dx), mean(dx * xhat))
+    float u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = zb[w * HID + l + 32 * i];
+    float s2 = ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {  // the two reductions interleaved (independent shuffle chains)
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (l == 0) out[w] = make_float2(s * (1.0f / HID), s2 * (1.0f / HID));
+  }
+}
+
+// ---- forward row-wise step of one layer: LayerNorm, ReLU on the gathered 8x256 tile (thread <-> column) ---------
+// Writes the next operand tile hT, keeps x-hat in xhT (if non-null) and the statistics in stat_keep, and stores
+// this CTA's column slice of h to the workspace (for wgrad.cu) when ws_h != NULL. Ends with __syncthreads.
+__device__ __forceinline__ void layer_fwd_rows(const float* __restrict__ z, const float* __restrict__ g,
+                                               const float* __restrict__ be, bool ln, Work& S, float4* hT, float4* xhT,
+                                               float2* stat_keep, float* ws_h, int b0, int nvalid, const Group G) {
+  const int t = threadIdx.x, j = t;
+  float zv[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) zv[r] = z[r * HID + j];
+  float gj = 1.f, bej = 0.f;
+  if (ln) {
+    gj = g[j];
+    bej = be[j];
+    row_stats(z, z, S.stat, true);
+    __syncthreads();
+    if (stat_keep && t < RT) stat_keep[t] = S.stat[t];
+  }
+  float xh[RT], h[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    if (ln) {
+      const float2 s = S.stat[r];
+      xh[r] = (zv[r] - s.x) * s.y;
+      h[r] = fmaxf(fmaf(xh[r], gj, bej), 0.f);
+    } else {
+      xh[r] = zv[r];
+      h[r] = fmaxf(zv[r], 0.f);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < RQ; ++q) {
+    hT[q * HID + j] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    if (xhT) xhT[q * HID + j] = make_float4(xh[4 * q], xh[4 * q + 1], xh[4 * q + 2], xh[4 * q + 3]);
+  }
+  if (ws_h && (j >> 7) == G.c) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+      if (r < nvalid) ws_h[(size_t)(b0 + r) * HID + j] = h[r];
+  }
+  __syncthreads();
+}
+
+// ---- backward row-wise step of one layer: ReLU mask, LayerNorm backward (thread <-> column, all 8 rows) ---------
+// dh[r]: gradient w.r.t. the post-ReLU activation of column j. Leaves dz (w.r.t. the Linear output) in dh and
+// writes this CTA's slice of the column sums {sum_r dz, sum_r dn*xhat, sum_r dn} (d bias, d ln.weight, d ln.bias)
+// to part3[0..2][j]. Uses S.red as scratch. Rows beyond the batch carry dh = 0 and stay 0.
+__device__ __forceinline__ void layer_bwd_rows(float (&dh)[RT], const float4* xhT, const float2* stat,
+                                               const float* __restrict__ g, const float* __restrict__ be, bool ln,
+                                               Work& S, float* part3, const Group G) {
+  const int t = threadIdx.x, j = t;
+  float xh[RT], dn[RT];
+  const float gj = ln ? g[j] : 1.f, bej = ln ? be[j] : 0.f;
+  float* s1 = S.red;
+  float* s2 = S.red + RT * HID;
+#pragma unroll
+  for (int q = 0; q < RQ; ++q) {
+    const float4 x4 = xhT[q * HID + j];
+    xh[4 * q] = x4.x; xh[4 * q + 1] = x4.y; xh[4 * q + 2] = x4.z; xh[4 * q + 3] = x4.w;
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    const bool on = ln ? (fmaf(xh[r], gj, bej) > 0.f) : (xh[r] > 0.f);  // the forward ReLU(h) > 0, recomputed bit-exactly
+    dn[r] = on ? dh[r] : 0.f;
+    if (ln) {
+      const float dx = dn[r] * gj;
+      s1[r * HID + j] = dx;
+      s2[r * HID + j] = dx * xh[r];
+    }
+  }
+  if (ln) {
+    __syncthreads();
+    row_stats(s1, s2, S.stat, false);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const float2 c = S.stat[r];
+      dh[r] = stat[r].y * (dn[r] * gj - c.x - xh[r] * c.y);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) dh[r] = dn[r];
+  }
+  if (part3 && (j >> 7) == G.c) {
+    float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      a += dh[r];
+      b += dn[r] * xh[r];
+      c += dn[r];
+    }
+    part3[0 * HID + j] = a;
+    if (ln) {
+      part3[1 * HID + j] = b;
+      part3[2 * HID + j] = c;
+    }
+  }
+}
+
+// ---- small products against [n][256] row-major matrices (global or staged in shared memory) -----------------
+// out[q * MAX_OUT + o] (8 rows) = bias[o] + sum_k W[o][k] * X[.][k]: warp w takes outputs w, w+NW, ...; lanes
+// stride k. Used for the heads (n = 1, A or 2A) and for dQ/da = dz1 . w1t[O+a][:] in the actor step. Both CTAs of
+// a group compute all outputs (each holds the full tile); no exchange.
+static __device__ __noinline__ void rowdot(const float* __restrict__ W, const float* __restrict__ bias, int n,
+                                           const float4* __restrict__ X, float4* __restrict__ out) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  for (int o = w; o < n; o += NW) {
+    float a[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) a[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < HID / 32; ++i) {
+      const int k = l + 32 * i;
+      const float wv = W[(size_t)o * HID + k];
+      const float4 x0 = X[k], x1 = X[HID + k];
+      a[0] = fmaf(wv, x0.x, a[0]); a[1] = fmaf(wv, x0.y, a[1]); a[2] = fmaf(wv, x0.z, a[2]); a[3] = fmaf(wv, x0.w, a[3]);
+      a[4] = fmaf(wv, x1.x, a[4]); a[5] = fmaf(wv, x1.y, a[5]); a[6] = fmaf(wv, x1.z, a[6]); a[7] = fmaf(wv, x1.w, a[7]);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)  // eight independent shuffle chains
+#pragma unroll
+      for (int r = 0; r < RT; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], s);
+    if (l == 0) {
+      const float bo = bias ? bias[o] : 0.f;
+      out[o] = make_float4(a[0] + bo, a[1] + bo, a[2] + bo, a[3] + bo);
+      out[MAX_OUT + o] = make_float4(a[4] + bo, a[5] + bo, a[6] + bo, a[7] + bo);
+    }
+  }
+}
+
+// dh[r] (column k = threadIdx.x, 8 rows) = sum_o du[o] * W[o][k]   (head backward)
+__device__ __forceinline__ void head_bwd(const float* __restrict__ W, int n, const float4* __restrict__ du,
+                                         float (&dh)[RT]) {
+  const int k = threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < RT; ++r) dh[r] = 0.f;
+  for (int o = 0; o < n; ++o) {
+    const float wv = W[(size_t)o * HID + k];
+    const float4 d0 = du[o], d1 = du[MAX_OUT + o];
+    dh[0] = fmaf(wv, d0.x, dh[0]); dh[1] = fmaf(wv, d0.y, dh[1]); dh[2] = fmaf(wv, d0.z, dh[2]); dh[3] = fmaf(wv, d0.w, dh[3]);
+    dh[4] = fmaf(wv, d1.x, dh[4]); dh[5] = fmaf(wv, d1.y, dh[5]); dh[6] = fmaf(wv, d1.z, dh[6]); dh[7] = fmaf(wv, d1.w, dh[7]);
+  }
+}
+
+// scalar element (row r, slot o) of a u / du style array
+__device__ __forceinline__ float& uref(float4* u, int r, int o) {
+  return reinterpret_cast<float*>(&u[(r >> 2) * MAX_OUT + o])[r & 3];
+}
+
+// ---- input tiles: X[q * ld + dst + k].(r & 3) = rows[b0 + r][off + k], copied asynchronously (cp.async) ----------
+// Rows beyond the batch (r >= nvalid) repeat the last valid row: finite values whose results are masked later.
+__device__ __forceinline__ void stage_tile(const float* __restrict__ rows, int row_stride, int b0, int nvalid, int off,
+                                           int len, float4* X, int ld, int dst) {
+  for (int i = threadIdx.x; i < RT * len; i += NT) {
+    const int r = i / len, k = i - r * len;
+    const int rr = r < nvalid ? r : nvalid - 1;
+    cp_async4(reinterpret_cast<float*>(&X[(r >> 2) * ld + dst + k]) + (r & 3),
+              rows + (size_t)(b0 + rr) * row_stride + off + k);
+  }
+}
+
+__device__ __forceinline__ void store_tile(float4* T, const float (&v)[RT]) {  // operand tile, column = threadIdx.x
+  const int j = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < RQ; ++q) T[q * HID + j] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void store_slice(float* __restrict__ dst, int b0, int nvalid, const float (&v)[RT],
+                                            const Group G) {  // dst [B][256]: this CTA's 128 columns
+  const int j = threadIdx.x;
+  if ((j >> 7) != G.c) return;
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+    if (r < nvalid) dst[(size_t)(b0 + r) * HID + j] = v[r];
+}
+
+// ---- the two hidden layers, forward. Leaves h2 in S.h[1] (synchronised), x-hat / statistics in `A` if given. -----
+// `n` lives in shared memory.
+__device__ __forceinline__ void trunk_fwd(cg::cluster_group& cluster, const Group G, const Net& n,
+                                          const float4* __restrict__ X, int ldx, Acts* A, Work& S, int& zi,
+                                          float* ws_h1, float* ws_h2, int b0, int nvalid, int tk = 54) {
+  B2RL_TICK(tk + 0);
+  gemm_slice(n.w1t, n.in_dim, X, ldx, G.c * CW, S.red);
+  __syncthreads();
+  B2RL_TICK(tk + 1);
+  const float* z = reduce_gather(cluster, G, S, zi, n.b1);
+  B2RL_TICK(tk + 2);
+  layer_fwd_rows(z, n.g1, n.be1, n.ln, S, S.h[0], A ? A->xh1 : nullptr, A ? A->st1 : nullptr, ws_h1, b0, nvalid, G);
+  B2RL_TICK(tk + 3);
+  gemm_slice(n.w2t, HID, S.h[0], HID, G.c * CW, S.red);
+  __syncthreads();
+  B2RL_TICK(tk + 4);
+  z = reduce_gather(cluster, G, S, zi, n.b2);
+  B2RL_TICK(tk + 5);
+  layer_fwd_rows(z, n.g2, n.be2, n.ln, S, S.h[1], A ? A->xh2 : nullptr, A ? A->st2 : nullptr, ws_h2, b0, nvalid, G);
+  B2RL_TICK(tk + 6);
+}
+
+// ---- the two hidden layers, backward (dX path). dh = gradient w.r.t. h2 for column j = threadIdx.x, 8 rows. ------
+// Writes this CTA's slices of dz2/dz1 to the workspace (for wgrad.cu) and of the column partial sums when the
+// pointers are non-null. On return S.h[1] holds the dz1 tile (synchronised) and dh holds dz1.
+__device__ __forceinline__ void trunk_bwd(cg::cluster_group& cluster, const Group G, const Net& n, float (&dh)[RT],
+                                          const Acts& A, Work& S, int& zi, float* ws_dz1, float* ws_dz2, float* part,
+                                          int b0, int nvalid) {
+  const int j = threadIdx.x;
+  layer_bwd_rows(dh, A.xh2, A.st2, n.g2, n.be2, n.ln, S, part ? part + 3 * HID : nullptr, G);
+  store_tile(S.h[0], dh);
+  if (ws_dz2) store_slice(ws_dz2, b0, nvalid, dh, G);
+  __syncthreads();
+  gemm_slice(n.w2n, HID, S.h[0], HID, G.c * CW, S.red);
+  __syncthreads();
+  const float* z = reduce_gather(cluster, G, S, zi, nullptr);
+#pragma unroll
+  for (int r = 0; r < RT; ++r) dh[r] = z[r * HID + j];
+  layer_bwd_rows(dh, A.xh1, A.st1, n.g1, n.be1, n.ln, S, part, G);
+  store_tile(S.h[1], dh);
+  if (ws_dz1) store_slice(ws_dz1, b0, nvalid, dh, G);
+  __syncthreads();
+}
+
+// number of cluster barriers inside trunk_bwd (a retired group keeps the cluster's barrier count in step)
+constexpr int TRUNK_BWD_BARRIERS = 1;
+
+}  // namespace b2rl

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(WT) wgrad_kernel(const __grid_constant__ Wgrad
   WgradSmem& S = *reinterpret_cast<WgradSmem*>(wsm_raw);
   const b2rl_update_args_t& A = W.u;
   const int agent = blockIdx.y, t = threadIdx.x;
-  const int B = A.batch, nblk = B / ROWS;
+  const int B = A.batch, nblk = row_blocks(B);
   const int n_nets = W.actor_step ? 1 : 2;
   float* arena = A.arena + (size_t)agent * A.arena_agent_stride;
   float* G = arena + 4 * A.region_stride;  // region 4: gradients

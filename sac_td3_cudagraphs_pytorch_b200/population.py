@@ -98,7 +98,7 @@ class Population:
         self.sumsq_scratch = torch.zeros(N * 64, dtype=torch.float32, device=dev)
         ws = self._lib.b2rl_workspace_floats(self.B)
         if ws < 0:
-            raise L.B2rlError(f"batch size {self.B} must be a positive multiple of {L.ROWS}")
+            raise L.B2rlError(f"batch size {self.B} must be >= 1")
         self.workspace = torch.zeros(N, ws, dtype=torch.float32, device=dev)
         self.rows = torch.zeros(N, self.B, self.fmt.row_stride, dtype=torch.float32, device=dev)
         self.idx = torch.zeros(N, self.B, dtype=torch.int64, device=dev)

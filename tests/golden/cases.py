@@ -38,6 +38,15 @@ CASES = {
 }
 
 
+# ragged batches (B % 16 != 0: the last CTA group masks its tail) and B < 16; oracle-checked only (no fixture)
+RAGGED_CASES = {
+    "sac_ragged40": dict(base=SAC, ob=11, ac=3, lo=[-1.0] * 3, hi=[1.0] * 3, B=40, N=128, iters=1, seed=8000,
+                         over=dict(batch_size=40)),
+    "td3_ragged7": dict(base=TD3, ob=17, ac=6, lo=[-1.0] * 6, hi=[1.0] * 6, B=7, N=64, iters=1, seed=8100,
+                        over=dict(batch_size=7)),
+}
+
+
 def hps_dict(case: dict) -> dict:
     h = dict(case["base"])
     h.update(case.get("over", {}))
@@ -47,7 +56,7 @@ def hps_dict(case: dict) -> dict:
 
 def case_inputs(name: str) -> dict:
     """All inputs of a case, regenerated bit-identically from seeds."""
-    c = CASES[name]
+    c = CASES[name] if isinstance(name, str) else name
     h = hps_dict(c)
     td3 = h["prefer_td3_over_sac"]
     s = c["seed"]

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from tests.golden import portable as P
-from tests.golden.cases import CASES, case_inputs
+from tests.golden.cases import CASES, RAGGED_CASES, case_inputs
 from tests.golden.make_golden import GROUPS, LOG_KEYS
 from tests.helpers import (alpha_loss_scale, batch_of, check_close, check_param_after_first_adam, make_agent,
                            make_oracle, rel_dev)
@@ -28,9 +28,12 @@ def _dev(x):
 
 
 # ------------------------------------------------------------------------------- single steps
-@pytest.mark.parametrize("name", list(CASES))
+ALL_CASES = {**CASES, **RAGGED_CASES}
+
+
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_critic_step_matches_oracle(name):
-    inp = case_inputs(name)
+    inp = case_inputs(ALL_CASES[name])
     ag = make_agent(inp)
     o32, o64 = make_oracle(inp, torch.float32), make_oracle(inp, torch.float64)
     B = inp["B"]
@@ -55,9 +58,9 @@ def test_critic_step_matches_oracle(name):
         assert torch.equal(ag.arena.tensor(ag.layout.critic[k], "w2n"), w.contiguous())
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(ALL_CASES))
 def test_actor_step_matches_oracle(name):
-    inp = case_inputs(name)
+    inp = case_inputs(ALL_CASES[name])
     ag = make_agent(inp)
     o32, o64 = make_oracle(inp, torch.float32), make_oracle(inp, torch.float64)
     e1, e2 = inp["eps_pi"][0][0], inp["eps_alpha"][0][0]

@@ -182,5 +182,5 @@ def test_errors_are_loud():
               torch.device("cpu"), sac_hps())
     inp = case_inputs("sac_hopper")
     ag = make_agent(inp)
-    with pytest.raises(L.B2rlError, match="multiple of 4"):
-        ag.update_qnets(torch.zeros(6, ag.fmt.row_stride, device="cuda"))
+    with pytest.raises(L.B2rlError, match=">= 1"):
+        ag.update_qnets(torch.zeros(0, ag.fmt.row_stride, device="cuda"))

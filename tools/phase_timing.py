@@ -23,14 +23,13 @@ buf = (C.c_longlong * 64)()
 lib.b2rl_debug_timing.argtypes = [C.c_void_p]
 assert lib.b2rl_debug_timing(buf) == 0
 t = np.array(buf[:64], dtype=np.int64)
-names = {0: "start", 1: "A.l1 gemm start", 2: "A.l1 gemm end", 3: "A.l1 sync end", 4: "A.l1 epi end", 5: "A.sync end",
-         6: "A.l2 gemm end", 7: "A.l2 sync end", 8: "A.l2 epi end", 9: "A.sync end", 10: "A.head rowdot end",
-         11: "T start (after sample)", 12: "T.l1 gemm start", 13: "T.l1 gemm end", 14: "T.l1 sync", 15: "T.l1 epi end",
-         16: "T.sync", 17: "T.l2 gemm end", 18: "T.l2 sync", 19: "T.l2 epi end", 20: "T.sync", 21: "T.head end",
-         22: "cluster exchange done", 23: "Q start (y, load_x)", 24: "Q.l1 gemm start", 25: "Q.l1 gemm end", 26: "Q.l1 sync",
-         27: "Q.l1 epi end", 28: "Q.sync", 29: "Q.l2 gemm end", 30: "Q.l2 sync", 31: "Q.l2 epi end", 32: "Q.sync",
-         33: "Q.head end", 34: "bwd start", 35: "bwd end"}
+names = {0: "start", 1: "staged (cp.async burst done)", 10: "A head done", 11: "A sampled", 21: "T head done",
+         22: "twin exchange done", 23: "Q start (TD target)", 33: "Q head done", 34: "bwd start", 35: "bwd end"}
+for base, nm in ((2, "A"), (12, "T"), (24, "Q")):
+    for o, what in enumerate(("l1 gemm start", "l1 gemm+sync end", "l1 reduce+gather+barrier end", "l1 rows end",
+                              "l2 gemm+sync end", "l2 reduce+gather+barrier end", "l2 rows end")):
+        names[base + o] = f"{nm}.{what}"
 prev = t[0]
-for k in range(36):
-    print(f"{k:2d} {names.get(k,''):28s} +{(t[k]-prev):7d} cyc   total {(t[k]-t[0]):7d}")
+for k in sorted(names):
+    print(f"{k:2d} {names[k]:36s} +{(t[k]-prev):7d} cyc   total {(t[k]-t[0]):7d}")
     prev = t[k]
