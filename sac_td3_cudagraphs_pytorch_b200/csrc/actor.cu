@@ -78,10 +78,11 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   }
   cp_async_wait_all();
   __syncthreads();
-  int zi = 0;
+  exchange_init(S);
+  int gi = 0;
 
   // ---- actor forward on obs (agent.py:251 / :254-255)
-  trunk_fwd(cluster, G, act, X, ldx, &M.pi, S, zi, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0, nvalid);
+  gi = trunk_fwd(G, &act, X, ldx, &M.pi, &S, gi, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0, nvalid);
   rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();
   for (int r = w; r < RT; r += NW) {  // warp <-> batch row, lane <-> action dim
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   __syncthreads();
 
   // ---- Q_k(obs, a_pi) with the critic's parameters held constant (agent.py:272-278)
-  trunk_fwd(cluster, G, q, X, ldx, &M.q, S, zi, nullptr, nullptr, b0, nvalid);
+  gi = trunk_fwd(G, &q, X, ldx, &M.q, &S, gi, nullptr, nullptr, b0, nvalid);
   rowdot(q.w3, q.b3, 1, S.h[1], S.u);
   __syncthreads();
   if (t < RT) {
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
     const float w3 = q.w3[t];
 #pragma unroll
     for (int r = 0; r < RT; ++r) dh[r] = M.dq[k][r] * w3;
-    trunk_bwd(cluster, G, q, dh, M.q, S, zi, nullptr, nullptr, nullptr, b0, nvalid);
+    trunk_bwd(G, q, dh, M.q, S, gi, nullptr, nullptr, nullptr, b0, nvalid);
     rowdot(q.w1t + (size_t)O * HID, nullptr, AD, S.h[1], S.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
     __syncthreads();
   }
@@ -165,10 +166,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
         *cluster.map_shared_rank(&M.da_peer[qq * MAX_OUT + a], rank ^ 2) = S.u[qq * MAX_OUT + a];
       }
     cluster.sync();
-    if (k == 1) {  // retire, keeping the cluster's barrier count in step with group 0
-      for (int i = 0; i < TRUNK_BWD_BARRIERS; ++i) cluster.sync();
-      return;
-    }
+    if (k == 1) return;  // (group 0's remaining exchanges are mbarrier-based and stay inside the group)
   }
 
   // ---- backward through the action head (group 0)
@@ -200,7 +198,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
     part[PART_DB3 + t] = ((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w));
   }
   head_bwd(act.w3, act.out_dim, S.du, dh);
-  trunk_bwd(cluster, G, act, dh, M.pi, S, zi, ws.dz1, ws.dz2, part, b0, nvalid);
+  trunk_bwd(G, act, dh, M.pi, S, gi, ws.dz1, ws.dz2, part, b0, nvalid);
 }
 
 // ---- SAC temperature step -------------------------------------------------------------------
@@ -257,8 +255,9 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
-  int zi = 0;
-  trunk_fwd(cluster, G, act, X, O, nullptr, S, zi, nullptr, nullptr, b0, nvalid);
+  exchange_init(S);
+  int gi = 0;
+  gi = trunk_fwd(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
   if (rank != 0) return;  // (no peer touches this CTA's shared memory after the last all-gather's barrier)
   rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();
@@ -365,8 +364,9 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
-  int zi = 0;
-  trunk_fwd(cluster, G, act, X, O, nullptr, S, zi, nullptr, nullptr, b0, nvalid);
+  exchange_init(S);
+  int gi = 0;
+  gi = trunk_fwd(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
   if (rank != 0) return;
   rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();

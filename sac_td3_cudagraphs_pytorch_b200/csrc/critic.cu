@@ -87,10 +87,11 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
   cp_async_wait_all();
   __syncthreads();
   B2RL_TICK(1);
-  int zi = 0;
+  exchange_init(S);
+  int gi = 0;
 
   // ---- next action
-  trunk_fwd(cluster, G, act, XA, ldx, nullptr, S, zi, nullptr, nullptr, b0, nvalid, 2);
+  gi = trunk_fwd(G, &act, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 2);
   rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
   __syncthreads();
   B2RL_TICK(10);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
 
   // ---- target Q_k on (next_obs, a')  (agent.py:208-210), then swap the 8 values with the peer group
   B2RL_TICK(11);
-  trunk_fwd(cluster, G, qt, XA, ldx, nullptr, S, zi, nullptr, nullptr, b0, nvalid, 12);
+  gi = trunk_fwd(G, &qt, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 12);
   rowdot(qt.w3, qt.b3, 1, S.h[1], S.u);
   __syncthreads();
   B2RL_TICK(21);
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     const Workspace ws = ws_carve(wsb, B, k);
     float* part = ws.part + (size_t)rb * PART_LEN;
     B2RL_TICK(23);
-    trunk_fwd(cluster, G, qo, XB, ldx, &M.a, S, zi, ws.h1, ws.h2, b0, nvalid, 24);
+    gi = trunk_fwd(G, &qo, XB, ldx, &M.a, &S, gi, ws.h1, ws.h2, b0, nvalid, 24);
     rowdot(qo.w3, qo.b3, 1, S.h[1], S.u);
     __syncthreads();
     B2RL_TICK(33);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
 #pragma unroll
     for (int r = 0; r < RT; ++r) dh[r] = M.dq[r] * w3;
     B2RL_TICK(34);
-    trunk_bwd(cluster, G, qo, dh, M.a, S, zi, ws.dz1, ws.dz2, part, b0, nvalid);
+    trunk_bwd(G, qo, dh, M.a, S, gi, ws.dz1, ws.dz2, part, b0, nvalid);
     B2RL_TICK(35);
   }
 }

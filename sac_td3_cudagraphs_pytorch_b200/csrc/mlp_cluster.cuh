@@ -105,6 +105,7 @@ struct Work {          // per-CTA scratch shared by all passes
   float4 u[RQ * MAX_OUT];     // head outputs / small row-dot results: u[q * MAX_OUT + o]
   float4 du[RQ * MAX_OUT];
   float2 stat[RT];
+  uint64_t mbar[2];           // one mbarrier per z buffer: the peer's slice has landed (st.async complete_tx)
 };
 
 struct Group {  // the CS CTAs that share 8 rows of one network
@@ -188,14 +189,54 @@ static __device__ __noinline__ void gemm_slice(const float* __restrict__ W, int 
   }
 }
 
+// ---- mbarrier / st.async plumbing (PTX ISA: mbarrier, st.async; SASS: SYNCS.*, STAS) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_peer(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float4 v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
+          smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+// Once per kernel, before the first exchange: both mbarriers armed for one arrival (thread 0's expect_tx) per
+// phase, made visible to the peer, and one cluster barrier so that no st.async can reach an uninitialised barrier.
+__device__ __forceinline__ void exchange_init(Work& S) {
+  if (threadIdx.x == 0) {
+    mbar_init(&S.mbar[0], 1);
+    mbar_init(&S.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cg::this_cluster().sync();
+}
+
 // ---- split-K reduction (fixed order) + bias + exchange of this CTA's 8x128 slice with the peer ------------------
-// Thread (r = t >> 5, cq = t & 31) owns row r, columns j0+4cq..+3. Ends with the cluster barrier; returns the
-// buffer that now holds the full 8x256 tile in both CTAs of the group. `zi` (which of the two z buffers the
-// next exchange fills) is a per-thread value that every thread of the cluster advances in step; two buffers
-// are enough because the peer can run at most one layer ahead (it needs this CTA's slice for the one after).
-__device__ __forceinline__ const float* reduce_gather(cg::cluster_group& cluster, const Group G, Work& S, int& zi,
-                                                      const float* __restrict__ bias) {
+// Thread (r = t >> 5, cq = t & 31) owns row r, columns j0+4cq..+3. Its float4 goes to the local z buffer with a
+// plain store and to the peer's with st.async, which also counts 16 bytes on the PEER's mbarrier; thread 0 has
+// armed this CTA's mbarrier for the 4096 bytes the peer will send. No cluster barrier and no memory fence: each
+// CTA waits for exactly the data it needs. Returns the buffer that then holds the full 8x256 tile. `gi` counts
+// the exchanges (every thread of the cluster advances it in step): buffer gi & 1, mbarrier phase parity
+// (gi >> 1) & 1. Two buffers are enough because the peer can run at most one layer ahead — it needs this CTA's
+// slice for the layer after, and this CTA sends that only after it has finished reading the current buffer.
+__device__ __forceinline__ const float* reduce_gather(const Group G, Work& S, int& gi, const float* __restrict__ bias) {
   const int t = threadIdx.x, r = t >> 5, cq = t & 31, j = G.c * CW + 4 * cq;
+  const int b = gi & 1;
+  if (t == 0) mbar_expect(&S.mbar[b], RT * CW * sizeof(float));
   const float* rp = S.red + (size_t)r * CW + 4 * cq;
   float4 s = *reinterpret_cast<const float4*>(rp);
 #pragma unroll
@@ -207,11 +248,14 @@ __device__ __forceinline__ const float* reduce_gather(cg::cluster_group& cluster
     const float4 b = *reinterpret_cast<const float4*>(bias + j);
     s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
   }
-  float* zl = S.z[zi];
-  zi ^= 1;
-  *reinterpret_cast<float4*>(zl + (size_t)r * HID + j) = s;
-  *reinterpret_cast<float4*>(cluster.map_shared_rank(zl, G.base + (G.c ^ 1)) + (size_t)r * HID + j) = s;
-  cluster.sync();  // (release/acquire at cluster scope: both slices are visible in both CTAs)
+  float* zl = S.z[b];
+  float* dst = zl + (size_t)r * HID + j;
+  *reinterpret_cast<float4*>(dst) = s;
+  const uint32_t peer = (uint32_t)(G.base + (G.c ^ 1));
+  st_async_v4(map_peer(smem_u32(dst), peer), s, map_peer(smem_u32(&S.mbar[b]), peer));
+  __syncthreads();                           // this CTA's slice is visible to all its threads
+  mbar_wait(&S.mbar[b], (gi >> 1) & 1);      // the peer's slice has landed
+  ++gi;
   return zl;
 }
 
@@ -420,33 +464,38 @@ __device__ __forceinline__ void store_slice(float* __restrict__ dst, int b0, int
 }
 
 // ---- the two hidden layers, forward. Leaves h2 in S.h[1] (synchronised), x-hat / statistics in `A` if given. -----
-// `n` lives in shared memory.
-__device__ __forceinline__ void trunk_fwd(cg::cluster_group& cluster, const Group G, const Net& n,
-                                          const float4* __restrict__ X, int ldx, Acts* A, Work& S, int& zi,
-                                          float* ws_h1, float* ws_h2, int b0, int nvalid, int tk = 54) {
+// (__noinline__, every argument a register value, the Net in shared memory: ONE copy of this code serves all
+// passes of a kernel. Inlined, each fused kernel was > 100 KB of SASS executed once, and instruction fetch was its
+// largest stall reason.) Returns the advanced exchange counter.
+static __device__ __noinline__ int trunk_fwd(const Group G, const Net* np, const float4* __restrict__ X, int ldx,
+                                             Acts* A, Work* Sp, int gi, float* ws_h1, float* ws_h2, int b0, int nvalid,
+                                             int tk = 54) {
+  const Net& n = *np;
+  Work& S = *Sp;
   B2RL_TICK(tk + 0);
   gemm_slice(n.w1t, n.in_dim, X, ldx, G.c * CW, S.red);
   __syncthreads();
   B2RL_TICK(tk + 1);
-  const float* z = reduce_gather(cluster, G, S, zi, n.b1);
+  const float* z = reduce_gather(G, S, gi, n.b1);
   B2RL_TICK(tk + 2);
   layer_fwd_rows(z, n.g1, n.be1, n.ln, S, S.h[0], A ? A->xh1 : nullptr, A ? A->st1 : nullptr, ws_h1, b0, nvalid, G);
   B2RL_TICK(tk + 3);
   gemm_slice(n.w2t, HID, S.h[0], HID, G.c * CW, S.red);
   __syncthreads();
   B2RL_TICK(tk + 4);
-  z = reduce_gather(cluster, G, S, zi, n.b2);
+  z = reduce_gather(G, S, gi, n.b2);
   B2RL_TICK(tk + 5);
   layer_fwd_rows(z, n.g2, n.be2, n.ln, S, S.h[1], A ? A->xh2 : nullptr, A ? A->st2 : nullptr, ws_h2, b0, nvalid, G);
   B2RL_TICK(tk + 6);
+  return gi;
 }
 
 // ---- the two hidden layers, backward (dX path). dh = gradient w.r.t. h2 for column j = threadIdx.x, 8 rows. ------
 // Writes this CTA's slices of dz2/dz1 to the workspace (for wgrad.cu) and of the column partial sums when the
 // pointers are non-null. On return S.h[1] holds the dz1 tile (synchronised) and dh holds dz1.
-__device__ __forceinline__ void trunk_bwd(cg::cluster_group& cluster, const Group G, const Net& n, float (&dh)[RT],
-                                          const Acts& A, Work& S, int& zi, float* ws_dz1, float* ws_dz2, float* part,
-                                          int b0, int nvalid) {
+// (forceinline: `dh` stays in registers; the product inside is the shared gemm_slice.)
+__device__ __forceinline__ void trunk_bwd(const Group G, const Net& n, float (&dh)[RT], const Acts& A, Work& S, int& gi,
+                                          float* ws_dz1, float* ws_dz2, float* part, int b0, int nvalid) {
   const int j = threadIdx.x;
   layer_bwd_rows(dh, A.xh2, A.st2, n.g2, n.be2, n.ln, S, part ? part + 3 * HID : nullptr, G);
   store_tile(S.h[0], dh);
@@ -454,7 +503,7 @@ __device__ __forceinline__ void trunk_bwd(cg::cluster_group& cluster, const Grou
   __syncthreads();
   gemm_slice(n.w2n, HID, S.h[0], HID, G.c * CW, S.red);
   __syncthreads();
-  const float* z = reduce_gather(cluster, G, S, zi, nullptr);
+  const float* z = reduce_gather(G, S, gi, nullptr);
 #pragma unroll
   for (int r = 0; r < RT; ++r) dh[r] = z[r * HID + j];
   layer_bwd_rows(dh, A.xh1, A.st1, n.g1, n.be1, n.ln, S, part, G);
@@ -462,8 +511,5 @@ __device__ __forceinline__ void trunk_bwd(cg::cluster_group& cluster, const Grou
   if (ws_dz1) store_slice(ws_dz1, b0, nvalid, dh, G);
   __syncthreads();
 }
-
-// number of cluster barriers inside trunk_bwd (a retired group keeps the cluster's barrier count in step)
-constexpr int TRUNK_BWD_BARRIERS = 1;
 
 }  // namespace b2rl
