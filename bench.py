@@ -180,24 +180,20 @@ def run_b2rl(args, rank, world, device):
     value = world * K / elapsed
     finite = bool(torch.isfinite(ag.out).all())
 
-    # ---- end to end through the public API: per step 4 new transitions H2D (pinned) -> rb.extend ->
-    #      iteration -> losses D2H (pinned) and a sync, as a training loop that logs every step would
+    # ---- end to end through the public API (LearnerEngine.step): per step 4 new transitions H2D from pinned
+    #      memory -> replay write -> sample -> update(s) -> log block D2H into pinned memory -> stream sync, as a
+    #      training loop that logs every step would; the copies are nodes of the same graph as the kernels
     n_env = 4
-    host_rows = torch.zeros(n_env, fmt.row_stride).pin_memory()
-    host_rows.normal_()
-    dev_rows = torch.zeros(n_env, fmt.row_stride, device=device)
-    host_out = torch.zeros(8).pin_memory()
+    src_rows = torch.randn(n_env, fmt.row_stride)           # "what the envs just produced" (pageable host memory)
+    stage = eng.host_rows(n_env)                             # the engine's pinned staging buffer
     Ke = max(30, min(K, 3000))
-    for i in range(3):
-        dev_rows.copy_(host_rows, non_blocking=True); rb.extend_rows(dev_rows); eng.iteration(W + K + i)
+    for i in range(6):                                       # captures the step-graph variants
+        stage.copy_(src_rows); eng.step(W + K + i, n_env)
     barrier()
     t0 = time.perf_counter()
     for i in range(Ke):
-        dev_rows.copy_(host_rows, non_blocking=True)
-        rb.extend_rows(dev_rows)
-        eng.iteration(W + K + 3 + i)
-        host_out.copy_(ag.out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        stage.copy_(src_rows)                                # host write of this step's inputs into pinned memory
+        out = eng.step(W + K + 6 + i, n_env)                 # H2D + write + sample + update(s) + D2H, then stream sync
     barrier()
     e2e_elapsed = time.perf_counter() - t0
     if world > 1:

@@ -74,14 +74,18 @@ typedef struct b2rl_rowfmt {
 /* ---- device-side counters ----------------------------------------------------------------
  * uint64[8] in device memory, owned by the caller, zero-initialised:
  *   [0] critic Adam steps done  [1] actor Adam steps done  [2] alpha Adam steps done
- *   [3] replay samples drawn    [4] ticket (self-resetting)   [5] replay size   [6..7] spare
+ *   [3] replay samples drawn    [4] ticket (self-resetting)   [5] replay size
+ *   [6] replay write cursor     [7] ticket of b2rl_replay_extend_dev (self-resetting)
  * They advance on the device so that a captured graph can be replayed without host patches. */
 #define B2RL_CTR_Q 0
 #define B2RL_CTR_PI 1
 #define B2RL_CTR_ALPHA 2
 #define B2RL_CTR_SAMPLE 3
 #define B2RL_CTR_TICKET 4 /* alpha_update's last-CTA ticket */
-#define B2RL_CTR_SIZE 5   /* replay rows filled, written by the host side of the replay buffer */
+#define B2RL_CTR_SIZE 5   /* replay rows filled: written by the host side of the replay buffer, or advanced on the
+                             device by b2rl_replay_extend_dev */
+#define B2RL_CTR_CURSOR 6 /* round-robin write position (b2rl_replay_extend_dev) */
+#define B2RL_CTR_XTICKET 7
 
 typedef struct b2rl_hyper {
   int32_t td3;                 /* hps.prefer_td3_over_sac */
@@ -191,6 +195,13 @@ int b2rl_replay_sample_gather(const float* storage, int64_t storage_agent_stride
  * freshly packed rows [n][row_stride] to storage rows (cursor + i) % capacity. */
 int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_rowfmt_t fmt,
                        const float* new_rows, int32_t n, void* stream);
+
+/* Graph-capturable variant of b2rl_replay_extend (orchestrator.py:100-113): the write cursor and the fill count
+ * live on the device (counters[B2RL_CTR_CURSOR], counters[B2RL_CTR_SIZE]) and advance there, so one captured
+ * graph can hold "copy the new transitions in -> write them -> sample -> update" and be replayed without host
+ * patches. The last CTA to finish advances the counters (self-resetting ticket in counters[B2RL_CTR_XTICKET]). */
+int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, const float* new_rows, int32_t n,
+                           uint64_t* counters, void* stream);
 
 /* Replaces Agent.update_qnets up to and including `qf_loss.backward()` (agents/agent.py:186-235);
  * advances counters[Q] (the optimizer's step_t += 1) so that the Adam launch that follows sees t:

@@ -9,7 +9,7 @@ HID = 256
 ROWS = 8  # batch rows per CTA group of the fused kernels (a batch need not be a multiple)
 MAX_OUT = 64
 MAX_SEG = 8
-CTR_Q, CTR_PI, CTR_ALPHA, CTR_SAMPLE, CTR_TICKET, CTR_SIZE = 0, 1, 2, 3, 4, 5
+CTR_Q, CTR_PI, CTR_ALPHA, CTR_SAMPLE, CTR_TICKET, CTR_SIZE, CTR_CURSOR, CTR_XTICKET = 0, 1, 2, 3, 4, 5, 6, 7
 OUT_QF_LOSS, OUT_ACTOR_LOSS, OUT_ALPHA_LOSS, OUT_ALPHA, OUT_LOGPI_MEAN = 0, 1, 2, 3, 4
 REGION_P, REGION_T, REGION_M, REGION_V, REGION_G = range(5)
 
@@ -66,6 +66,7 @@ SYMBOLS = {
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_replay_extend": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, RowFmt, C.c_void_p, C.c_int32, C.c_void_p]),
+    "b2rl_replay_extend_dev": (C.c_int, [C.c_void_p, C.c_int64, RowFmt, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "b2rl_critic_update_sac": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_critic_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_actor_update_sac": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),

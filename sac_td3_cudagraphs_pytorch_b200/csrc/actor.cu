@@ -13,8 +13,7 @@ struct ActorSmem {
   Work s;
   Acts pi;         // the actor's pass (kept for its backward pass)
   Acts q;          // this group's critic pass
-  ActorStage nsA;
-  CriticStage nsQ;
+  NetStage nsA, nsQ;
   Net nA, nQ;
   float lo[MAX_A], hi[MAX_A];
   float eps[RT][MAX_A], sg[RT][MAX_A], yy[RT][MAX_A], th[RT][MAX_A];
@@ -55,35 +54,40 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   const float alpha = td3 ? 0.f : expf(A.log_alpha[(size_t)agent * 5]);
   const float invB = 1.0f / (float)B;
 
-  // ---- asynchronous burst: the observation tile and the small tensors
-  stage_tile(rows, rs, b0, nvalid, 0, O, X, ldx, 0);
-  stage_net(P, A.actor, M.nsA, M.nA);
-  stage_net(P, A.critic[k], M.nsQ, M.nQ);
+  // ---- prologue: the observation tile and the small tensors, one job per warp
+  exchange_init_arrive(S);
   const Net &act = M.nA, &q = M.nQ;
-  if (t < AD) {
-    M.lo[t] = __ldg(A.min_ac + t);
-    M.hi[t] = __ldg(A.max_ac + t);
-  }
-  if (!td3) {
-    for (int i = t; i < RT * AD; i += NT) {
-      const int r = i / AD, a = i - r * AD;
-      float z = 0.f;
-      if (r < nvalid) {
-        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
-        z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_ACTOR_EPS);
-        if (A.eps_out && rank == 0) A.eps_out[e] = z;
-      }
-      M.eps[r][a] = z;
+  if (w == 0) {
+    if (l < AD) {
+      M.lo[l] = __ldg(A.min_ac + l);
+      M.hi[l] = __ldg(A.max_ac + l);
     }
+    if (!td3) {
+      for (int i = l; i < RT * AD; i += 32) {
+        const int r = i / AD, a = i - r * AD;
+        float z = 0.f;
+        if (r < nvalid) {
+          const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
+          z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_ACTOR_EPS);
+          if (A.eps_out && rank == 0) A.eps_out[e] = z;
+        }
+        M.eps[r][a] = z;
+      }
+    }
+  } else if (w == 1) {
+    stage_net(P, &A.actor, &M.nsA, &M.nA, G.c * CW);
+  } else if (w == 2) {
+    stage_net(P, &A.critic[k], &M.nsQ, &M.nQ, G.c * CW);
+  } else if (w >= 4) {
+    stage_tile(rows, rs, b0, nvalid, 0, O, X, ldx, t - 128, 128);
   }
   cp_async_wait_all();
   __syncthreads();
-  exchange_init(S);
   int gi = 0;
 
   // ---- actor forward on obs (agent.py:251 / :254-255)
   gi = trunk_fwd(G, &act, X, ldx, &M.pi, &S, gi, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0, nvalid);
-  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
+  rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
   for (int r = w; r < RT; r += NW) {  // warp <-> batch row, lane <-> action dim
     float lp = 0.f;
@@ -111,14 +115,16 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
 
   // ---- Q_k(obs, a_pi) with the critic's parameters held constant (agent.py:272-278)
   gi = trunk_fwd(G, &q, X, ldx, &M.q, &S, gi, nullptr, nullptr, b0, nvalid);
-  rowdot(q.w3, q.b3, 1, S.h[1], S.u);
+  rowdot(q.p[F_W3], q.p[F_B3], 1, S.h[1], S.u);
   __syncthreads();
+  if (!td3 && t == 0) mbar_expect(&S.xbar[0], RT * sizeof(float));
   if (t < RT) {
     const float qk = uref(S.u, t, 0);
     M.qv[k][t] = qk;
-    if (!td3) *cluster.map_shared_rank(&M.qv[k][t], rank ^ 2) = qk;
+    if (!td3) st_async_f32(map_peer(smem_u32(&M.qv[k][t]), rank ^ 2), qk, map_peer(smem_u32(&S.xbar[0]), rank ^ 2));
   }
-  if (!td3) cluster.sync(); else __syncthreads();
+  __syncthreads();
+  if (!td3) mbar_wait(&S.xbar[0], 0);
 
   // ---- loss and dLoss/dQ_k per row: SAC  mean(alpha*logpi - min_k Q_k), TD3  mean(-Q_0)
   if (t < RT) {
@@ -150,23 +156,25 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   }
 
   // ---- backward through critic k down to its action inputs
-  float dh[RT];
   {
-    const float w3 = q.w3[t];
+    const float w3 = q.p[F_W3][t];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) dh[r] = M.dq[k][r] * w3;
-    trunk_bwd(G, q, dh, M.q, S, gi, nullptr, nullptr, nullptr, b0, nvalid);
-    rowdot(q.w1t + (size_t)O * HID, nullptr, AD, S.h[1], S.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
+    for (int r = 0; r < RT; ++r) S.red[DH_OFF + r * HID + t] = M.dq[k][r] * w3;  // dLoss/dh2 of critic k, column t
+    gi = trunk_bwd(G, &q, &M.q, &S, gi, nullptr, nullptr, nullptr, b0, nvalid);
+    rowdot(q.p[F_W1T] + (size_t)O * HID, nullptr, AD, S.h[1], S.u);  // dQ/da_i = sum_j dz1_j * W1[j][O+i]
     __syncthreads();
   }
   if (!td3) {
-    if (k == 1)
+    if (k == 1) {  // hand dQ/da to group 0 and retire
       for (int i = t; i < RQ * AD; i += NT) {
         const int qq = i / AD, a = i - qq * AD;
-        *cluster.map_shared_rank(&M.da_peer[qq * MAX_OUT + a], rank ^ 2) = S.u[qq * MAX_OUT + a];
+        st_async_v4(map_peer(smem_u32(&M.da_peer[qq * MAX_OUT + a]), rank ^ 2), S.u[qq * MAX_OUT + a],
+                    map_peer(smem_u32(&S.xbar[1]), rank ^ 2));
       }
-    cluster.sync();
-    if (k == 1) return;  // (group 0's remaining exchanges are mbarrier-based and stay inside the group)
+      return;
+    }
+    if (t == 0) mbar_expect(&S.xbar[1], RQ * AD * sizeof(float4));
+    mbar_wait(&S.xbar[1], 0);
   }
 
   // ---- backward through the action head (group 0)
@@ -197,8 +205,22 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
     const float4 d0 = S.du[t], d1 = S.du[MAX_OUT + t];
     part[PART_DB3 + t] = ((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w));
   }
-  head_bwd(act.w3, act.out_dim, S.du, dh);
-  trunk_bwd(G, act, dh, M.pi, S, gi, ws.dz1, ws.dz2, part, b0, nvalid);
+  {  // head backward: dLoss/dh2[r][t] = sum_o du[o][r] * W3[o][t]
+    float dh[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) dh[r] = 0.f;
+    const float* W3 = act.p[F_W3];
+#pragma unroll 1
+    for (int o = 0; o < act.out_dim; ++o) {
+      const float wv = W3[(size_t)o * HID + t];
+      const float4 d0 = S.du[o], d1 = S.du[MAX_OUT + o];
+      dh[0] = fmaf(wv, d0.x, dh[0]); dh[1] = fmaf(wv, d0.y, dh[1]); dh[2] = fmaf(wv, d0.z, dh[2]); dh[3] = fmaf(wv, d0.w, dh[3]);
+      dh[4] = fmaf(wv, d1.x, dh[4]); dh[5] = fmaf(wv, d1.y, dh[5]); dh[6] = fmaf(wv, d1.z, dh[6]); dh[7] = fmaf(wv, d1.w, dh[7]);
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) S.red[DH_OFF + r * HID + t] = dh[r];
+  }
+  gi = trunk_bwd(G, &act, &M.pi, &S, gi, ws.dz1, ws.dz2, part, b0, nvalid);
 }
 
 // ---- SAC temperature step -------------------------------------------------------------------
@@ -208,7 +230,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
 // and applies torch's capturable Adam step to the scalar.
 struct AlphaSmem {
   Work s;
-  ActorStage ns;
+  NetStage ns;
   Net n;
   float logpi[RT];
   int last;
@@ -250,16 +272,16 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
   float* part = ws_carve(wsb, B, 0).part;
 
-  stage_tile(rows, rs, b0, nvalid, 0, O, X, O, 0);
-  stage_net(P, A.actor, M.ns, M.n);
+  exchange_init_arrive(S);
+  if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
+  else stage_tile(rows, rs, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
-  exchange_init(S);
   int gi = 0;
   gi = trunk_fwd(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
   if (rank != 0) return;  // (no peer touches this CTA's shared memory after the last all-gather's barrier)
-  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
+  rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
   for (int r = w; r < RT; r += NW) {
     float lp = 0.f;
@@ -334,7 +356,7 @@ cudaError_t launch_alpha_adam(float* log_alpha, uint64_t* counters, int n_agents
 // ---- inference policy ----------------------------------------------------------------------------
 struct PredictSmem {
   Work s;
-  ActorStage ns;
+  NetStage ns;
   Net n;
   // followed by the observation tile float4[RQ * O]
 };
@@ -359,16 +381,16 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   const bool td3 = A.hp.td3 != 0;
   const float* P = A.arena;
   const uint64_t step = draw;
-  stage_tile(obs, O, b0, nvalid, 0, O, X, O, 0);
-  stage_net(P, A.actor, M.ns, M.n);
+  exchange_init_arrive(S);
+  if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
+  else stage_tile(obs, O, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
-  exchange_init(S);
   int gi = 0;
   gi = trunk_fwd(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
   if (rank != 0) return;
-  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
+  rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
   for (int r = w; r < nvalid; r += NW) {
     if (l < AD) {

@@ -19,6 +19,7 @@ cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
 cudaError_t launch_gather(const float*, int64_t, int64_t, b2rl_rowfmt_t, int, int, const int64_t*, int64_t*, float*,
                           uint64_t, uint64_t*, int, int, int, cudaStream_t);
 cudaError_t launch_extend(float*, int64_t, int64_t, b2rl_rowfmt_t, const float*, int, cudaStream_t);
+cudaError_t launch_extend_dev(float*, int64_t, b2rl_rowfmt_t, const float*, int, uint64_t*, cudaStream_t);
 int max_in_dim_critic();
 int max_in_dim_actor();
 cudaError_t init_critic();
@@ -157,6 +158,16 @@ int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_ro
     return fail(B2RL_E_INVALID, "bad capacity / cursor / n");
   if (n == 0) return B2RL_OK;
   return check_launch(b2rl::launch_extend(storage, capacity, cursor, fmt, new_rows, n, (cudaStream_t)stream), "replay_extend");
+}
+
+int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, const float* new_rows, int32_t n,
+                           uint64_t* counters, void* stream) {
+  if (int rc = check_fmt(fmt)) return rc;
+  if (!storage || !new_rows || !counters || !aligned16(storage) || !aligned16(new_rows))
+    return fail(B2RL_E_INVALID, "storage / new_rows / counters must be non-null, rows 16-byte aligned");
+  if (capacity < 1 || n < 1 || n > capacity) return fail(B2RL_E_INVALID, "bad capacity / n");
+  return check_launch(b2rl::launch_extend_dev(storage, capacity, fmt, new_rows, n, counters, (cudaStream_t)stream),
+                      "replay_extend_dev");
 }
 
 static int critic_update(const b2rl_update_args_t* a, int td3, void* stream) {

@@ -19,9 +19,8 @@ constexpr int MAX_A = MAX_OUT / 2;
 struct CriticSmem {
   Work s;
   Acts a;                      // the online critic's pass (kept for its backward pass)
-  ActorStage nsA;              // staged small tensors of the actor,
-  CriticStage nsT, nsQ;        // of target critic k and of online critic k
-  Net nA, nT, nQ;              // their descriptors (shared memory, not the stack: see stage_net)
+  NetStage nsA, nsT, nsQ;      // staged small tensors of the actor, of target critic k and of online critic k
+  Net nA, nT, nQ;              // their descriptors
   float lo[MAX_A], hi[MAX_A], eps[RT][MAX_A];
   float rd[RT][2];             // (reward, done) of the 8 rows
   float logpi[RT], qn[2][RT], y[RT], dq[RT], sq[RT];  // per-row scalars
@@ -55,25 +54,20 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
   const uint64_t step = A.counters[(size_t)agent * 8 + B2RL_CTR_Q];
   float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
 
-  // ---- one asynchronous burst at kernel start: both input tiles and every small tensor the kernel will touch
+  // ---- prologue: one asynchronous burst of both input tiles and every small tensor the kernel will touch. Each
+  //      warp has its own job (the jobs are instruction-bound: side by side they cost the longest, not the sum).
   B2RL_TICK(0);
-  stage_tile(rows, rs, b0, nvalid, O + AD + 2, O, XA, ldx, 0);
-  stage_tile(rows, rs, b0, nvalid, 0, O + AD, XB, ldx, 0);  // [obs | act] is contiguous in the row
-  if (t < 2 * RT) {
-    const int r = t >> 1, rr = r < nvalid ? r : nvalid - 1;
-    cp_async4(&M.rd[r][t & 1], rows + (size_t)(b0 + rr) * rs + O + AD + (t & 1));
-  }
-  stage_net(td3 ? T : P, A.actor, M.nsA, M.nA);  // SAC samples from the ONLINE actor (agent.py:205),
-  stage_net(T, A.critic[k], M.nsT, M.nT);        // TD3 uses the TARGET actor (agent.py:194-202)
-  stage_net(P, A.critic[k], M.nsQ, M.nQ);
+  exchange_init_arrive(S);
+  B2RL_TICK(40);
   const Net &act = M.nA, &qt = M.nT, &qo = M.nQ;
-  if (t < AD) {
-    M.lo[t] = __ldg(A.min_ac + t);
-    M.hi[t] = __ldg(A.max_ac + t);
-  }
-  {
+  const float* PA = td3 ? T : P;  // SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor (:194-202)
+  if (w == 0) {
+    if (l < AD) {
+      M.lo[l] = __ldg(A.min_ac + l);
+      M.hi[l] = __ldg(A.max_ac + l);
+    }
     const bool need = !td3 || A.hp.targ_smoothing;
-    for (int i = t; i < RT * AD; i += NT) {
+    for (int i = l; i < RT * AD; i += 32) {
       const int r = i / AD, a = i - r * AD;
       float z = 0.f;
       if (need && r < nvalid) {
@@ -83,16 +77,31 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
       }
       M.eps[r][a] = z;
     }
+  } else if (w == 1) {
+    stage_net(PA, &A.actor, &M.nsA, &M.nA, G.c * CW);
+  } else if (w == 2) {
+    stage_net(T, &A.critic[k], &M.nsT, &M.nT, G.c * CW);
+  } else if (w == 3) {
+    stage_net(P, &A.critic[k], &M.nsQ, &M.nQ, G.c * CW);
+  } else if (w < 6) {
+    stage_tile(rows, rs, b0, nvalid, O + AD + 2, O, XA, ldx, t - 128, 64);
+  } else {
+    stage_tile(rows, rs, b0, nvalid, 0, O + AD, XB, ldx, t - 192, 64);  // [obs | act] is contiguous in the row
+    if (t - 192 < 2 * RT) {
+      const int i = t - 192, r = i >> 1, rr = r < nvalid ? r : nvalid - 1;
+      cp_async4(&M.rd[r][i & 1], rows + (size_t)(b0 + rr) * rs + O + AD + (i & 1));
+    }
   }
+  B2RL_TICK(41);
   cp_async_wait_all();
+  B2RL_TICK(42);
   __syncthreads();
   B2RL_TICK(1);
-  exchange_init(S);
   int gi = 0;
 
   // ---- next action
   gi = trunk_fwd(G, &act, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 2);
-  rowdot(act.w3, act.b3, act.out_dim, S.h[1], S.u);
+  rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
   B2RL_TICK(10);
   for (int r = w; r < RT; r += NW) {  // warp <-> batch row, lane <-> action dim
@@ -126,15 +135,17 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
   // ---- target Q_k on (next_obs, a')  (agent.py:208-210), then swap the 8 values with the peer group
   B2RL_TICK(11);
   gi = trunk_fwd(G, &qt, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 12);
-  rowdot(qt.w3, qt.b3, 1, S.h[1], S.u);
+  rowdot(qt.p[F_W3], qt.p[F_B3], 1, S.h[1], S.u);
   __syncthreads();
   B2RL_TICK(21);
+  if (t == 0) mbar_expect(&S.xbar[0], RT * sizeof(float));
   if (t < RT) {
     const float q = uref(S.u, t, 0);
     M.qn[k][t] = q;
-    *cluster.map_shared_rank(&M.qn[k][t], rank ^ 2) = q;
+    st_async_f32(map_peer(smem_u32(&M.qn[k][t]), rank ^ 2), q, map_peer(smem_u32(&S.xbar[0]), rank ^ 2));
   }
-  cluster.sync();
+  __syncthreads();
+  mbar_wait(&S.xbar[0], 0);
   B2RL_TICK(22);
 
   // ---- TD target (agent.py:212-228)
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     float* part = ws.part + (size_t)rb * PART_LEN;
     B2RL_TICK(23);
     gi = trunk_fwd(G, &qo, XB, ldx, &M.a, &S, gi, ws.h1, ws.h2, b0, nvalid, 24);
-    rowdot(qo.w3, qo.b3, 1, S.h[1], S.u);
+    rowdot(qo.p[F_W3], qo.p[F_B3], 1, S.h[1], S.u);
     __syncthreads();
     B2RL_TICK(33);
     if (t < RT) {
@@ -184,12 +195,11 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
       part[PART_DB3] = sd;
       part[PART_SCAL] = ss;
     }
-    const float w3 = qo.w3[t];
-    float dh[RT];
+    const float w3 = qo.p[F_W3][t];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) dh[r] = M.dq[r] * w3;
+    for (int r = 0; r < RT; ++r) S.red[DH_OFF + r * HID + t] = M.dq[r] * w3;  // dLoss/dh2, column t (read back by thread t)
     B2RL_TICK(34);
-    trunk_bwd(G, qo, dh, M.a, S, gi, ws.dz1, ws.dz2, part, b0, nvalid);
+    gi = trunk_bwd(G, &qo, &M.a, &S, gi, ws.dz1, ws.dz2, part, b0, nvalid);
     B2RL_TICK(35);
   }
 }

@@ -52,11 +52,47 @@ extend_kernel(float* __restrict__ storage, int64_t capacity, int64_t cursor, int
   }
 }
 
+// graph-capturable write: cursor and size live in the device counters; the last CTA to finish advances them
+__global__ void __launch_bounds__(256)
+extend_dev_kernel(float* __restrict__ storage, int64_t capacity, int row_stride, const float* __restrict__ new_rows, int n,
+                  uint64_t* __restrict__ counters) {
+  const int chunks = row_stride >> 2;
+  const int64_t total = (int64_t)n * chunks;
+  const int64_t cursor = (int64_t)counters[B2RL_CTR_CURSOR];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / chunks), c = (int)(i - (int64_t)b * chunks);
+    const int64_t r = (cursor + b) % capacity;
+    st_stream4(storage + ((size_t)r * row_stride + 4 * c), ld_stream4(new_rows + ((size_t)b * row_stride + 4 * c)));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd((unsigned long long*)&counters[B2RL_CTR_XTICKET], 1ULL);
+    if (ticket == (unsigned long long)gridDim.x - 1) {  // every CTA has read the cursor
+      counters[B2RL_CTR_CURSOR] = (uint64_t)((cursor + n) % capacity);
+      const uint64_t size = counters[B2RL_CTR_SIZE] + (uint64_t)n;
+      counters[B2RL_CTR_SIZE] = size < (uint64_t)capacity ? size : (uint64_t)capacity;
+      counters[B2RL_CTR_XTICKET] = 0;
+    }
+  }
+}
+
+cudaError_t launch_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, const float* new_rows, int n,
+                              uint64_t* counters, cudaStream_t st) {
+  const int64_t total = (int64_t)n * (fmt.row_stride >> 2);
+  int ctas = (int)((total + 255) / 256);
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  extend_dev_kernel<<<ctas, 256, 0, st>>>(storage, capacity, fmt.row_stride, new_rows, n, counters);
+  return cudaGetLastError();
+}
+
 cudaError_t init_replay() {
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, gather_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, bump_sample_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, extend_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, extend_dev_kernel);
   return e;
 }
 

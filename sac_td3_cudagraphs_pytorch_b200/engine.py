@@ -43,7 +43,12 @@ class LearnerEngine:
                         for j in range(delay)]
         self.graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
         self._size_on_device = -1
+        self._cursor_on_device = -1
         self.launches_per_variant: dict[tuple, int] = {}
+        # end-to-end step (step()): pinned staging for the transitions coming in and the log block going out
+        self._h_new: dict[int, torch.Tensor] = {}
+        self._d_new: dict[int, torch.Tensor] = {}
+        self.host_out = torch.zeros(8, dtype=torch.float32).pin_memory()
 
     # -- what one iteration enqueues --------------------------------------------------------------
     def _enqueue(self, do_actor: bool, do_polyak: bool) -> int:
@@ -72,6 +77,58 @@ class LearnerEngine:
         if self._size_on_device != len(self.rb):
             self._size_on_device = len(self.rb)
             self.agent.counters[L.CTR_SIZE] = self._size_on_device
+        if self._cursor_on_device != self.rb._cursor:
+            self._cursor_on_device = self.rb._cursor
+            self.agent.counters[L.CTR_CURSOR] = self._cursor_on_device
+
+    # -- the whole environment-facing step as ONE graph replay ---------------------------------------
+    def host_rows(self, n: int) -> torch.Tensor:
+        """Pinned staging buffer [n, row_stride] for the transitions of the next step(): fill it in place
+        (replay.pack_rows(td, fmt, out=...)) and call step(i, n)."""
+        if n not in self._h_new:
+            self._h_new[n] = torch.zeros(n, self.agent.fmt.row_stride, dtype=torch.float32).pin_memory()
+            self._d_new[n] = torch.zeros(n, self.agent.fmt.row_stride, dtype=torch.float32, device=self.agent.device)
+        return self._h_new[n]
+
+    def step(self, i: int, n_new: int = 0) -> torch.Tensor:
+        """orchestrator.py:100-113 + :337-352 as one CUDA graph replay: host->device copy of the n_new freshly
+        collected transitions (from host_rows(n_new)), round-robin write (cursor and fill count on the device),
+        sample, critic update, delayed actor updates, Polyak, device->host copy of the log block. Synchronises
+        the stream and returns the pinned log block (_lib.OUT_* indices) — the loop a trainer that logs every
+        step runs. Needs graphs."""
+        ag, rb = self.agent, self.rb
+        assert self.use_graphs, "step() is the graph path"
+        do_actor = (i % (ag.hps.actor_update_delay + 1) == 0)
+        key = (do_actor, self._polyak_due(), int(n_new))
+        self._sync_size()
+        g = self.graphs.get(key)
+        if g is None:
+            if n_new:
+                self.host_rows(n_new)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(ag.device)
+            with torch.cuda.graph(g):
+                n = 0
+                if n_new:
+                    self._d_new[n_new].copy_(self._h_new[n_new], non_blocking=True)
+                    L.check(ag._lib.b2rl_replay_extend_dev(rb.storage.data_ptr(), rb.capacity, rb.fmt,
+                                                           self._d_new[n_new].data_ptr(), n_new, ag.counters.data_ptr(),
+                                                           ag._stream()), "replay_extend_dev")
+                    n += 1
+                n += self._enqueue(do_actor, key[1])
+                self.host_out.copy_(ag.out, non_blocking=True)
+            self.launches_per_variant[key] = n
+            self.graphs[key] = g
+        g.replay()
+        if n_new:  # host mirror of the device-side cursor / fill count
+            rb._cursor = (rb._cursor + n_new) % rb.capacity
+            rb._size = min(rb.capacity, rb._size + n_new)
+            self._cursor_on_device, self._size_on_device = rb._cursor, rb._size
+        ag.qnet_updates_so_far += 1
+        if do_actor:
+            ag.actor_updates_so_far += int(ag.hps.actor_update_delay)
+        torch.cuda.current_stream(ag.device).synchronize()
+        return self.host_out
 
     def iteration(self, i: int) -> None:
         """One learner iteration (orchestrator.py:337-352) — enqueue only, nothing is read back."""

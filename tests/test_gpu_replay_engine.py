@@ -105,6 +105,40 @@ def test_engine_graph_equals_eager_equals_api(name):
     assert torch.isfinite(agents[0].out).all()
 
 
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper"])
+def test_engine_step_graph_equals_extend_plus_iteration(name):
+    """LearnerEngine.step (H2D copy, device-cursor replay write, iteration, D2H copy in ONE graph) against the
+    separate calls rb.extend_rows + iteration: bitwise-equal learner state and replay storage, wrap-around included."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    from sac_td3_cudagraphs_pytorch_b200.engine import LearnerEngine
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    inp = case_inputs(name)
+    td = inp["storage"]
+    n0, cap, n_new, n_it = 200, 230, 4, 12   # 200 rows + 12 x 4 new ones > 230: the cursor wraps
+    agents = [make_agent(inp, seed=7) for _ in range(2)]
+    rbs = []
+    for _ in range(2):
+        rb = ReplayBuffer(cap, "cuda", seed=7)
+        rb.extend({k: v[:n0].cuda() for k, v in td.items()})
+        rbs.append(rb)
+    a_step, a_ref = LearnerEngine(agents[0], rbs[0], use_graphs=True), LearnerEngine(agents[1], rbs[1], use_graphs=True)
+    g = torch.Generator().manual_seed(3)
+    stage = a_step.host_rows(n_new)
+    for i in range(n_it):
+        rows = torch.randn(n_new, rbs[0].fmt.row_stride, generator=g)
+        stage.copy_(rows)
+        out = a_step.step(i, n_new)
+        rbs[1].extend_rows(rows.cuda())
+        a_ref.iteration(i)
+        torch.cuda.synchronize()
+        assert torch.equal(out, agents[1].out.cpu()), f"log block differs at step {i}"
+    assert _arena_equal(agents[0], agents[1])
+    assert torch.equal(rbs[0].storage, rbs[1].storage)
+    assert len(rbs[0]) == len(rbs[1]) == cap and rbs[0]._cursor == rbs[1]._cursor == (n0 + n_it * n_new) % cap
+    assert int(agents[0].counters[L.CTR_SIZE]) == cap and int(agents[0].counters[L.CTR_CURSOR]) == rbs[0]._cursor
+    assert int(agents[0].counters[L.CTR_XTICKET]) == 0
+
+
 @pytest.mark.parametrize("algo,ob,ac,bound", [("sac", 11, 3, 1.0), ("td3", 11, 3, 1.0), ("sac", 376, 17, 0.4)])
 def test_full_size_properties(algo, ob, ac, bound):
     """BASELINE.json sizes: batch 256, replay 1e6 (Hopper) / 2e5 (Humanoid, 618 MB), graphs on."""
