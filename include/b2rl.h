@@ -220,6 +220,17 @@ int b2rl_critic_update_td3(const b2rl_update_args_t* a, void* stream);
 int b2rl_actor_update_sac(const b2rl_update_args_t* a, void* stream);
 int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream);
 
+/* b2rl_{critic,actor}_update_* FOLLOWED BY b2rl_adam_polyak_multi(opt), as two launches instead of three: the
+ * weight-gradient kernel applies Adam (and the Polyak average) to each parameter whose gradient it has just
+ * produced — `optimizer.step()` (agents/agent.py:236,286) and `update_targ_nets` (:320-331) without a launch of
+ * their own. Same arithmetic as b2rl_adam_polyak_multi: results are bitwise equal. The algorithm is taken from
+ * a->hp.td3. opt->seg[0] must be an Adam segment (clip = 0, grad_scale = 1) over exactly the trained nets
+ * ([critic[0].begin, critic[1].end) / [actor.begin, actor.end)) with the matching counter; further segments must
+ * be Polyak-only spans (e.g. TD3's actor target in an iteration without actor update). Gradient clipping and
+ * data-parallel training need the gradients complete before the step: use the three-launch form there. */
+int b2rl_critic_update_opt(const b2rl_update_args_t* a, const b2rl_adam_args_t* opt, void* stream);
+int b2rl_actor_update_opt(const b2rl_update_args_t* a, const b2rl_adam_args_t* opt, void* stream);
+
 /* Replaces the autotune tail of update_actor (agents/agent.py:295-303): second no-grad
  * get_action with the UPDATED actor and fresh noise (a->eps2), alpha_loss, its gradient, and the
  * scalar Adam step on log_alpha (lr = log_alpha_lr; 0 = gradient only, see b2rl_alpha_adam). Writes

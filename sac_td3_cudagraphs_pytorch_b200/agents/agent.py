@@ -232,6 +232,17 @@ class Agent:
     def _seg(self, begin, end, lr=0.0, *, adam, polyak, counter=0, clip=False, grad_scale=1.0) -> L.Seg:
         return L.Seg(begin, end, lr, int(adam), int(polyak), counter, grad_scale, int(clip))
 
+    def _adam_args(self, segs: list) -> L.AdamArgs:
+        a = L.AdamArgs()
+        for i, s in enumerate(segs):
+            a.seg[i] = s
+        a.n_seg, a.n_agents = len(segs), 1
+        a.polyak, a.clip_norm = float(self.hps.polyak), float(self.hps.clip_norm)
+        a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-8
+        a.region_stride, a.arena_agent_stride = self.layout.region, self.arena.agent_stride
+        a.arena, a.counters, a.grad_sumsq = self.arena.flat.data_ptr(), self.counters.data_ptr(), self._sumsq.data_ptr()
+        return a
+
     def _launch_adam(self, segs: list) -> None:
         a = L.AdamArgs()
         for i, s in enumerate(segs):
@@ -263,14 +274,27 @@ class Agent:
         return segs
 
     # ------------------------------------------------------------------ enqueue-only steps (graph-safe)
-    def enqueue_critic_step(self, args: L.UpdateArgs, extra_segs: list = (), polyak: bool = False) -> None:
+    def enqueue_critic_step(self, args: L.UpdateArgs, extra_segs: list = (), polyak: bool = False,
+                            fused_opt: bool = True) -> None:
+        """update_qnets incl. optimizer.step(): fused kernel + weight gradients with Adam (and Polyak) applied in the
+        same launch (fused_opt), or the three-launch form (fused kernel, weight gradients, Adam/Polyak)."""
+        if fused_opt:
+            opt = self._adam_args(self.critic_segs(polyak) + list(extra_segs))
+            L.check(self._lib.b2rl_critic_update_opt(C.byref(args), C.byref(opt), self._stream()), "critic_update_opt")
+            return
         fn = self._lib.b2rl_critic_update_td3 if self.td3 else self._lib.b2rl_critic_update_sac
         L.check(fn(C.byref(args), self._stream()), "critic_update")
         self._launch_adam(self.critic_segs(polyak) + list(extra_segs))
 
-    def enqueue_actor_step(self, args: L.UpdateArgs, polyak: bool = False) -> None:
-        fn = self._lib.b2rl_actor_update_td3 if self.td3 else self._lib.b2rl_actor_update_sac
+    def enqueue_actor_step(self, args: L.UpdateArgs, polyak: bool = False, fused_opt: bool = True) -> None:
         st = self._stream()
+        if fused_opt and not self.hps.clip_norm > 0:  # (clipping needs the whole gradient's norm before the step)
+            opt = self._adam_args(self.actor_segs(polyak))
+            L.check(self._lib.b2rl_actor_update_opt(C.byref(args), C.byref(opt), st), "actor_update_opt")
+            if self.autotune:
+                L.check(self._lib.b2rl_alpha_update(C.byref(args), float(self.hps.log_alpha_lr), st), "alpha_update")
+            return
+        fn = self._lib.b2rl_actor_update_td3 if self.td3 else self._lib.b2rl_actor_update_sac
         L.check(fn(C.byref(args), st), "actor_update")
         if self.hps.clip_norm > 0:  # clip_grad_norm_ over the actor's parameters (agent.py:284-285)
             lay = self.layout
@@ -290,7 +314,7 @@ class Agent:
         """agents/agent.py:183-242. ``eps`` injects the N(0,1) noise (SAC next-action sample / TD3
         smoothing); default: Philox on the device."""
         rows = self._rows_of(batch)
-        self.enqueue_critic_step(self.update_args(rows, eps=self._noise(eps, rows), **dbg))
+        self.enqueue_critic_step(self.update_args(rows, eps=self._noise(eps, rows), **dbg), fused_opt=False)
         return {"loss/qf_loss": self.out[L.OUT_QF_LOSS].clone()}
 
     def update_actor(self, batch, eps: Optional[torch.Tensor] = None, eps_alpha: Optional[torch.Tensor] = None,
@@ -298,7 +322,7 @@ class Agent:
         """agents/agent.py:244-318 (policy step, then the temperature step when autotune)."""
         rows = self._rows_of(batch)
         self.enqueue_actor_step(self.update_args(rows, eps=self._noise(eps, rows), eps2=self._noise(eps_alpha, rows),
-                                                 **dbg))
+                                                 **dbg), fused_opt=False)
         out = {"loss/actor_loss": self.out[L.OUT_ACTOR_LOSS].clone()}
         if self.td3:
             return out

@@ -9,13 +9,11 @@
 // Polyak (torch.lerp, weight < 0.5):  targ = targ + polyak * (p_new - targ).
 // HBM-bound: 28 B/param for Adam, +8 B/param when fused with Polyak (the new p is still in registers),
 // 12 B/param for Polyak alone.
-#include "common.cuh"
+#include "adam_math.cuh"
 
 namespace b2rl {
 
-struct SegScalars {
-  float ssn, bc2s, gscale;
-};
+using SegScalars = AdamScalars;
 
 __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ b2rl_adam_args_t A) {
   const int agent = blockIdx.y;
@@ -29,12 +27,11 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   __shared__ SegScalars sc[B2RL_MAX_SEG];
   if (threadIdx.x < A.n_seg) {
     const b2rl_seg_t& s = A.seg[threadIdx.x];
-    SegScalars v = {0.f, 1.f, 1.f};
+    SegScalars v = {0.f, 1.f, 1.f, 1.f, 0.f};
     if (s.do_adam) {
       const float t = (float)ctr[s.counter];  // step count AFTER this step's bump (>= 1)
-      const float bc1 = 1.0f - powf(A.beta1, t), bc2 = 1.0f - powf(A.beta2, t);
-      v.ssn = -(s.lr / bc1);
-      v.bc2s = sqrtf(bc2);
+      v = adam_scalars(s.lr, A.beta1, A.beta2, t);
+      adam_finish(v, A.eps);
       v.gscale = s.grad_scale;
       if (s.clip) {  // clip_grad_norm_: g *= min(1, max_norm / (norm + 1e-6))
         const float norm = sqrtf(A.grad_sumsq[agent]) * s.grad_scale;
@@ -59,12 +56,9 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
         float* pp = &p.x; float* gp = &g.x; float* mp = &m.x; float* vp = &v.x;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float gg = gp[c] * k.gscale;
+          const float gg = __fmul_rn(gp[c], k.gscale);
           gp[c] = gg;
-          mp[c] = mp[c] + omb1 * (gg - mp[c]);
-          vp[c] = __fmul_rn(vp[c], A.beta2) + omb2 * gg * gg;
-          const float denom = sqrtf(vp[c]) / (k.bc2s * k.ssn) + A.eps / k.ssn;
-          pp[c] = pp[c] + mp[c] / denom;
+          adam_elem(pp[c], gg, mp[c], vp[c], k, A.beta2, omb1, omb2, A.eps);
         }
         // clip_grad_norm_ scales .grad in place (agent.py:284-285): keep region 4 what torch would show
         if (s.clip) *reinterpret_cast<float4*>(G + i) = g;
@@ -74,10 +68,10 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
       }
       if (s.do_polyak) {
         float4 tg = *reinterpret_cast<const float4*>(T + i);
-        tg.x = tg.x + A.polyak * (p.x - tg.x);
-        tg.y = tg.y + A.polyak * (p.y - tg.y);
-        tg.z = tg.z + A.polyak * (p.z - tg.z);
-        tg.w = tg.w + A.polyak * (p.w - tg.w);
+        tg.x = polyak_elem(tg.x, p.x, A.polyak);
+        tg.y = polyak_elem(tg.y, p.y, A.polyak);
+        tg.z = polyak_elem(tg.z, p.z, A.polyak);
+        tg.w = polyak_elem(tg.w, p.w, A.polyak);
         *reinterpret_cast<float4*>(T + i) = tg;
       }
     }

@@ -12,7 +12,7 @@ cudaError_t launch_actor_fused(const b2rl_update_args_t&, cudaStream_t);
 cudaError_t launch_alpha(const b2rl_update_args_t&, float, cudaStream_t);
 cudaError_t launch_alpha_adam(float*, uint64_t*, int, float, float, float*, cudaStream_t);
 cudaError_t launch_predict(const b2rl_update_args_t&, const float*, int, int, float, uint64_t, float*, cudaStream_t);
-cudaError_t launch_wgrad(const b2rl_update_args_t&, int, int, cudaStream_t);
+cudaError_t launch_wgrad(const b2rl_update_args_t&, int, int, const b2rl_adam_args_t*, cudaStream_t);
 cudaError_t launch_adam(const b2rl_adam_args_t&, cudaStream_t);
 cudaError_t launch_sumsq(const float*, int64_t, int64_t, int64_t, int64_t, int, float*, float*, cudaStream_t);
 cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
@@ -170,23 +170,48 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
                       "replay_extend_dev");
 }
 
-static int critic_update(const b2rl_update_args_t* a, int td3, void* stream) {
+// the fused optimizer's description: seg[0] = plain Adam (+ Polyak) on exactly the trained span, the rest Polyak-only
+static int check_opt(const b2rl_update_args_t* a, const b2rl_adam_args_t* o, int64_t begin, int64_t end, int counter) {
+  if (!o) return B2RL_OK;
+  if (o->n_seg < 1 || o->n_seg > B2RL_MAX_SEG) return fail(B2RL_E_INVALID, "opt: n_seg %d out of range", o->n_seg);
+  const b2rl_seg_t& s0 = o->seg[0];
+  if (!s0.do_adam || s0.clip || s0.grad_scale != 1.0f || s0.begin != begin || s0.end != end || s0.counter != counter)
+    return fail(B2RL_E_INVALID, "opt: seg[0] must be an unclipped, unscaled Adam segment over the trained nets");
+  for (int i = 1; i < o->n_seg; ++i) {
+    const b2rl_seg_t& s = o->seg[i];
+    if (s.do_adam || !s.do_polyak || s.begin < 0 || s.end < s.begin || (s.begin & 3) || (s.end & 3) || s.end > a->region_stride)
+      return fail(B2RL_E_INVALID, "opt: extra segment %d must be a 4-float aligned Polyak-only span", i);
+  }
+  return B2RL_OK;
+}
+
+static int critic_update(const b2rl_update_args_t* a, int td3, const b2rl_adam_args_t* opt, void* stream) {
   if (int rc = check_update(a, false)) return rc;
+  if (int rc = check_opt(a, opt, a->critic[0].begin, a->critic[1].end, B2RL_CTR_Q)) return rc;
   if ((a->hp.td3 != 0) != (td3 != 0)) return fail(B2RL_E_INVALID, "hp.td3 does not match the entry point");
   if (int rc = check_launch(b2rl::launch_critic_fused(*a, (cudaStream_t)stream), "critic_fused")) return rc;
-  return check_launch(b2rl::launch_wgrad(*a, 0, B2RL_CTR_Q, (cudaStream_t)stream), "critic wgrad");
+  return check_launch(b2rl::launch_wgrad(*a, 0, B2RL_CTR_Q, opt, (cudaStream_t)stream), "critic wgrad");
 }
-int b2rl_critic_update_sac(const b2rl_update_args_t* a, void* stream) { return critic_update(a, 0, stream); }
-int b2rl_critic_update_td3(const b2rl_update_args_t* a, void* stream) { return critic_update(a, 1, stream); }
+int b2rl_critic_update_sac(const b2rl_update_args_t* a, void* stream) { return critic_update(a, 0, nullptr, stream); }
+int b2rl_critic_update_td3(const b2rl_update_args_t* a, void* stream) { return critic_update(a, 1, nullptr, stream); }
+int b2rl_critic_update_opt(const b2rl_update_args_t* a, const b2rl_adam_args_t* opt, void* stream) {
+  if (!a || !opt) return fail(B2RL_E_INVALID, "null args");
+  return critic_update(a, a->hp.td3 != 0, opt, stream);
+}
 
-static int actor_update(const b2rl_update_args_t* a, int td3, void* stream) {
+static int actor_update(const b2rl_update_args_t* a, int td3, const b2rl_adam_args_t* opt, void* stream) {
   if (int rc = check_update(a, true)) return rc;
+  if (int rc = check_opt(a, opt, a->actor.begin, a->actor.end, B2RL_CTR_PI)) return rc;
   if ((a->hp.td3 != 0) != (td3 != 0)) return fail(B2RL_E_INVALID, "hp.td3 does not match the entry point");
   if (int rc = check_launch(b2rl::launch_actor_fused(*a, (cudaStream_t)stream), "actor_fused")) return rc;
-  return check_launch(b2rl::launch_wgrad(*a, 1, B2RL_CTR_PI, (cudaStream_t)stream), "actor wgrad");
+  return check_launch(b2rl::launch_wgrad(*a, 1, B2RL_CTR_PI, opt, (cudaStream_t)stream), "actor wgrad");
 }
-int b2rl_actor_update_sac(const b2rl_update_args_t* a, void* stream) { return actor_update(a, 0, stream); }
-int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream) { return actor_update(a, 1, stream); }
+int b2rl_actor_update_sac(const b2rl_update_args_t* a, void* stream) { return actor_update(a, 0, nullptr, stream); }
+int b2rl_actor_update_td3(const b2rl_update_args_t* a, void* stream) { return actor_update(a, 1, nullptr, stream); }
+int b2rl_actor_update_opt(const b2rl_update_args_t* a, const b2rl_adam_args_t* opt, void* stream) {
+  if (!a || !opt) return fail(B2RL_E_INVALID, "null args");
+  return actor_update(a, a->hp.td3 != 0, opt, stream);
+}
 
 int b2rl_alpha_update(const b2rl_update_args_t* a, float log_alpha_lr, void* stream) {
   if (int rc = check_update(a, false)) return rc;
@@ -250,9 +275,9 @@ int b2rl_launch_single(const b2rl_update_args_t* a, int32_t which, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   switch (which) {
     case 0: return check_launch(b2rl::launch_critic_fused(*a, st), "critic_fused");
-    case 1: return check_launch(b2rl::launch_wgrad(*a, 0, -1, st), "critic wgrad");
+    case 1: return check_launch(b2rl::launch_wgrad(*a, 0, -1, nullptr, st), "critic wgrad");
     case 2: return check_launch(b2rl::launch_actor_fused(*a, st), "actor_fused");
-    case 3: return check_launch(b2rl::launch_wgrad(*a, 1, -1, st), "actor wgrad");
+    case 3: return check_launch(b2rl::launch_wgrad(*a, 1, -1, nullptr, st), "actor wgrad");
     case 4:
       if (a->hp.td3) return fail(B2RL_E_INVALID, "alpha kernel is SAC-only");
       return check_launch(b2rl::launch_alpha(*a, 1e-3f, st), "alpha");

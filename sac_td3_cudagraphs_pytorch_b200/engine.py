@@ -25,12 +25,16 @@ from .replay import Batch, ReplayBuffer
 
 class LearnerEngine:
     def __init__(self, agent: Agent, rb: Optional[ReplayBuffer] = None, batch_size: Optional[int] = None,
-                 use_graphs: Optional[bool] = None, record_noise: bool = False):
+                 use_graphs: Optional[bool] = None, record_noise: bool = False, fused_opt: bool = False):
         self.agent = agent
         self.rb = rb if rb is not None else agent.rb
         assert self.rb is not None and self.rb.storage is not None, "the replay buffer must hold data"
         self.B = int(batch_size or agent.hps.batch_size)
         self.use_graphs = bool(agent.hps.cudagraphs) if use_graphs is None else use_graphs
+        # Adam + Polyak inside the weight-gradient kernel (b2rl_*_update_opt) instead of a launch of their own:
+        # bitwise-equal results; measured on B200 at batch 256 it is ~1 us per iteration SLOWER (the optimizer's
+        # dependent L2 round trips land on the tail of every gradient tile), so it is off by default
+        self.fused_opt = bool(fused_opt)
         dev = agent.device
         self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
@@ -62,11 +66,12 @@ class LearnerEngine:
         delay = int(ag.hps.actor_update_delay) if do_actor else 0
         # TD3's target actor is averaged once per iteration, after the last actor update if there is one
         extra = ag.polyak_segs(critics=False, actor=True) if (ag.td3 and do_polyak and delay == 0) else []
-        ag.enqueue_critic_step(self.args_q, extra_segs=extra, polyak=do_polyak)
-        n += 3
+        ag.enqueue_critic_step(self.args_q, extra_segs=extra, polyak=do_polyak, fused_opt=self.fused_opt)
+        n += 2 if self.fused_opt else 3
         for j in range(delay):
-            ag.enqueue_actor_step(self.args_pi[j], polyak=ag.td3 and do_polyak and j == delay - 1)
-            n += 3 + (1 if ag.autotune else 0) + (2 if ag.hps.clip_norm > 0 else 0)
+            ag.enqueue_actor_step(self.args_pi[j], polyak=ag.td3 and do_polyak and j == delay - 1,
+                                  fused_opt=self.fused_opt)
+            n += (5 if ag.hps.clip_norm > 0 else (2 if self.fused_opt else 3)) + (1 if ag.autotune else 0)
         return n
 
     def _polyak_due(self) -> bool:

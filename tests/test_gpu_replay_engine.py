@@ -80,7 +80,9 @@ def test_engine_graph_equals_eager_equals_api(name):
     n_it = 7
     agents = [make_agent(inp, seed=99) for _ in range(3)]
     rbs = [_rb(td["observations"].shape[0], td, seed=99) for _ in range(3)]
-    eng_graph = LearnerEngine(agents[0], rbs[0], use_graphs=True)
+    # the graph engine also takes the fused-optimizer path (Adam + Polyak inside the weight-gradient kernel),
+    # the eager one the three-launch path: bitwise equality below covers b2rl_*_update_opt
+    eng_graph = LearnerEngine(agents[0], rbs[0], use_graphs=True, fused_opt=True)
     eng_eager = LearnerEngine(agents[1], rbs[1], use_graphs=False, record_noise=True)
     api = agents[2]
     for i in range(n_it):
