@@ -203,6 +203,14 @@ int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_ro
 int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, const float* new_rows, int32_t n,
                            uint64_t* counters, void* stream);
 
+/* End of a captured learner step: copy the log block `out` (float[8] per agent, device) into `host_out` — pinned
+ * host memory, written by the kernel itself over PCIe/NVLink-C2C, no copy-engine node — then advance the device
+ * sequence number *seq_dev and publish it in *host_seq (system-scope fence in between): the host polls *host_seq
+ * instead of synchronising the stream. Replaces the `.item()` / clone-and-sync reads of the losses in the
+ * reference's logging path (orchestrator.py:341-352, :383). */
+int b2rl_publish_logs(const float* out, int32_t n_agents, float* host_out, uint64_t* seq_dev, uint64_t* host_seq,
+                      void* stream);
+
 /* Replaces Agent.update_qnets up to and including `qf_loss.backward()` (agents/agent.py:186-235);
  * advances counters[Q] (the optimizer's step_t += 1) so that the Adam launch that follows sees t:
  * next action (SAC: online tanh-Gaussian sample + log-prob, nets.py:222-234; TD3: target actor +

@@ -19,6 +19,7 @@ cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
 cudaError_t launch_gather(const float*, int64_t, int64_t, b2rl_rowfmt_t, int, int, const int64_t*, int64_t*, float*,
                           uint64_t, uint64_t*, int, int, int, cudaStream_t);
 cudaError_t launch_extend(float*, int64_t, int64_t, b2rl_rowfmt_t, const float*, int, cudaStream_t);
+cudaError_t launch_publish(const float*, int, float*, uint64_t*, uint64_t*, cudaStream_t);
 cudaError_t launch_extend_dev(float*, int64_t, b2rl_rowfmt_t, const float*, int, uint64_t*, cudaStream_t);
 int max_in_dim_critic();
 int max_in_dim_actor();
@@ -168,6 +169,12 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
   if (capacity < 1 || n < 1 || n > capacity) return fail(B2RL_E_INVALID, "bad capacity / n");
   return check_launch(b2rl::launch_extend_dev(storage, capacity, fmt, new_rows, n, counters, (cudaStream_t)stream),
                       "replay_extend_dev");
+}
+
+int b2rl_publish_logs(const float* out, int32_t n_agents, float* host_out, uint64_t* seq_dev, uint64_t* host_seq,
+                      void* stream) {
+  if (!out || !host_out || !seq_dev || !host_seq || n_agents < 1) return fail(B2RL_E_INVALID, "publish_logs: bad arguments");
+  return check_launch(b2rl::launch_publish(out, n_agents, host_out, seq_dev, host_seq, (cudaStream_t)stream), "publish_logs");
 }
 
 // the fused optimizer's description: seg[0] = plain Adam (+ Polyak) on exactly the trained span, the rest Polyak-only

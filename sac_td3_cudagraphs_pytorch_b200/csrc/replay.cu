@@ -87,12 +87,31 @@ cudaError_t launch_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fm
   return cudaGetLastError();
 }
 
+// last node of a captured step: log block -> pinned host memory, then the sequence number the host polls
+__global__ void publish_kernel(const float* __restrict__ out, int n, float* host_out, uint64_t* seq_dev,
+                               volatile uint64_t* host_seq) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) host_out[i] = out[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint64_t s = *seq_dev + 1ULL;
+    *seq_dev = s;
+    *host_seq = s;
+  }
+}
+cudaError_t launch_publish(const float* out, int n_agents, float* host_out, uint64_t* seq_dev, uint64_t* host_seq,
+                           cudaStream_t st) {
+  publish_kernel<<<1, 64, 0, st>>>(out, n_agents * 8, host_out, seq_dev, host_seq);
+  return cudaGetLastError();
+}
+
 cudaError_t init_replay() {
   cudaFuncAttributes fa;
   cudaError_t e = cudaFuncGetAttributes(&fa, gather_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, bump_sample_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, extend_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, extend_dev_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, publish_kernel);
   return e;
 }
 

@@ -53,6 +53,10 @@ class LearnerEngine:
         self._h_new: dict[int, torch.Tensor] = {}
         self._d_new: dict[int, torch.Tensor] = {}
         self.host_out = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._host_seq = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._host_seq_np = self._host_seq.numpy()  # (a view: polled without going through torch)
+        self._seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._seq = 0
 
     # -- what one iteration enqueues --------------------------------------------------------------
     def _enqueue(self, do_actor: bool, do_polyak: bool) -> int:
@@ -96,11 +100,12 @@ class LearnerEngine:
         return self._h_new[n]
 
     def step(self, i: int, n_new: int = 0) -> torch.Tensor:
-        """orchestrator.py:100-113 + :337-352 as one CUDA graph replay: host->device copy of the n_new freshly
-        collected transitions (from host_rows(n_new)), round-robin write (cursor and fill count on the device),
-        sample, critic update, delayed actor updates, Polyak, device->host copy of the log block. Synchronises
-        the stream and returns the pinned log block (_lib.OUT_* indices) — the loop a trainer that logs every
-        step runs. Needs graphs."""
+        """orchestrator.py:100-113 + :337-352 as ONE CUDA graph replay and no stream synchronisation: the replay
+        write reads the n_new freshly collected transitions straight from pinned host memory (host_rows(n_new);
+        cursor and fill count live on the device), then sample, critic update, delayed actor updates, Polyak,
+        and a last kernel that writes the log block into pinned host memory and publishes a sequence number,
+        which the host polls. Returns the pinned log block (_lib.OUT_* indices), valid on return — the loop a
+        trainer that logs every step runs. Needs graphs."""
         ag, rb = self.agent, self.rb
         assert self.use_graphs, "step() is the graph path"
         do_actor = (i % (ag.hps.actor_update_delay + 1) == 0)
@@ -108,22 +113,7 @@ class LearnerEngine:
         self._sync_size()
         g = self.graphs.get(key)
         if g is None:
-            if n_new:
-                self.host_rows(n_new)
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize(ag.device)
-            with torch.cuda.graph(g):
-                n = 0
-                if n_new:
-                    self._d_new[n_new].copy_(self._h_new[n_new], non_blocking=True)
-                    L.check(ag._lib.b2rl_replay_extend_dev(rb.storage.data_ptr(), rb.capacity, rb.fmt,
-                                                           self._d_new[n_new].data_ptr(), n_new, ag.counters.data_ptr(),
-                                                           ag._stream()), "replay_extend_dev")
-                    n += 1
-                n += self._enqueue(do_actor, key[1])
-                self.host_out.copy_(ag.out, non_blocking=True)
-            self.launches_per_variant[key] = n
-            self.graphs[key] = g
+            g = self._capture_step(key)
         g.replay()
         if n_new:  # host mirror of the device-side cursor / fill count
             rb._cursor = (rb._cursor + n_new) % rb.capacity
@@ -132,8 +122,33 @@ class LearnerEngine:
         ag.qnet_updates_so_far += 1
         if do_actor:
             ag.actor_updates_so_far += int(ag.hps.actor_update_delay)
-        torch.cuda.current_stream(ag.device).synchronize()
+        self._seq += 1
+        seq, want = self._host_seq_np, self._seq
+        while seq[0] != want:  # the device writes it after the log block (system-scope fence in between)
+            pass
         return self.host_out
+
+    def _capture_step(self, key) -> torch.cuda.CUDAGraph:
+        ag, rb = self.agent, self.rb
+        do_actor, do_polyak, n_new = key
+        if n_new:
+            self.host_rows(n_new)
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(ag.device)
+        with torch.cuda.graph(g):
+            n = 0
+            if n_new:  # pinned host memory is device-addressable (UVA): the write kernel is the host->device copy
+                L.check(ag._lib.b2rl_replay_extend_dev(rb.storage.data_ptr(), rb.capacity, rb.fmt,
+                                                       self._h_new[n_new].data_ptr(), n_new, ag.counters.data_ptr(),
+                                                       ag._stream()), "replay_extend_dev")
+                n += 1
+            n += self._enqueue(do_actor, do_polyak)
+            L.check(ag._lib.b2rl_publish_logs(ag.out.data_ptr(), 1, self.host_out.data_ptr(), self._seq_dev.data_ptr(),
+                                              self._host_seq.data_ptr(), ag._stream()), "publish_logs")
+            n += 1
+        self.launches_per_variant[key] = n
+        self.graphs[key] = g
+        return g
 
     def iteration(self, i: int) -> None:
         """One learner iteration (orchestrator.py:337-352) — enqueue only, nothing is read back."""
