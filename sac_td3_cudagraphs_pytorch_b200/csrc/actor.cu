@@ -29,6 +29,7 @@ __host__ __device__ inline size_t actor_smem_bytes(int in_dim) {
 // groups recompute the identical actor forward), the groups swap Q_k (8 floats) to agree on the arg-min, group 1
 // hands its dQ/da to group 0 through distributed shared memory and retires; group 0 runs the actor's backward
 // pass. TD3's loss uses critic 0 only (agent.py:274-275): clusters of 2, one group.
+template <bool WIDE>
 __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ActorSmem& M = *reinterpret_cast<ActorSmem*>(smem_raw);
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   int gi = 0;
 
   // ---- actor forward on obs (agent.py:251 / :254-255)
-  gi = trunk_fwd(G, &act, X, ldx, &M.pi, &S, gi, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0, nvalid);
+  gi = trunk_fwd<WIDE>(G, &act, X, ldx, &M.pi, &S, gi, k == 0 ? ws.h1 : nullptr, k == 0 ? ws.h2 : nullptr, b0, nvalid);
   rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
   for (int r = w; r < RT; r += NW) {  // warp <-> batch row, lane <-> action dim
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   __syncthreads();
 
   // ---- Q_k(obs, a_pi) with the critic's parameters held constant (agent.py:272-278)
-  gi = trunk_fwd(G, &q, X, ldx, &M.q, &S, gi, nullptr, nullptr, b0, nvalid);
+  gi = trunk_fwd<WIDE>(G, &q, X, ldx, &M.q, &S, gi, nullptr, nullptr, b0, nvalid);
   rowdot(q.p[F_W3], q.p[F_B3], 1, S.h[1], S.u);
   __syncthreads();
   if (!td3 && t == 0) mbar_expect(&S.xbar[0], RT * sizeof(float));
@@ -252,6 +253,7 @@ __device__ __forceinline__ void adam_scalar(float* st /*{p,g,m,v}*/, float g, fl
   st[0] = p; st[1] = g; st[2] = m; st[3] = v;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2rl_update_args_t A, float lr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlphaSmem& M = *reinterpret_cast<AlphaSmem*>(smem_raw);
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   cp_async_wait_all();
   __syncthreads();
   int gi = 0;
-  gi = trunk_fwd(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
+  gi = trunk_fwd<WIDE>(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
   if (rank != 0) return;  // (no peer touches this CTA's shared memory after the last all-gather's barrier)
   rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
@@ -364,6 +366,7 @@ __host__ __device__ inline size_t predict_smem_bytes(int ob_dim) {
   return sizeof(PredictSmem) + (size_t)RQ * ob_dim * sizeof(float4);
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(NT, 1)
 predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __restrict__ obs, int n, int mode,
                float explore_std, uint64_t draw, float* __restrict__ actions) {
@@ -388,7 +391,7 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   cp_async_wait_all();
   __syncthreads();
   int gi = 0;
-  gi = trunk_fwd(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
+  gi = trunk_fwd<WIDE>(G, &act, X, O, nullptr, &S, gi, nullptr, nullptr, b0, nvalid);
   if (rank != 0) return;
   rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
@@ -416,12 +419,17 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
 
 int max_in_dim_actor() { return (int)((MAX_DYN_SMEM - actor_smem_bytes(0)) / (1 * RQ * sizeof(float4))); }
 
+template <typename K>
+static cudaError_t opt_in_smem(K kernel) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+}
 cudaError_t init_actor() {
-  cudaError_t e = cudaFuncSetAttribute(actor_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(alpha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  cudaError_t e = opt_in_smem(actor_fused_kernel<false>);
+  if (e == cudaSuccess) e = opt_in_smem(actor_fused_kernel<true>);
+  if (e == cudaSuccess) e = opt_in_smem(alpha_kernel<false>);
+  if (e == cudaSuccess) e = opt_in_smem(alpha_kernel<true>);
+  if (e == cudaSuccess) e = opt_in_smem(predict_kernel<false>);
+  if (e == cudaSuccess) e = opt_in_smem(predict_kernel<true>);
   if (e == cudaSuccess) {
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, alpha_adam_kernel);
@@ -433,20 +441,26 @@ cudaError_t launch_actor_fused(const b2rl_update_args_t& a, cudaStream_t st) {
   const size_t smem = actor_smem_bytes(a.fmt.ob_dim + a.fmt.ac_dim);
   if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
   const int csize = a.hp.td3 ? 2 : 4;  // (row block, [critic,] column slice)
-  return launch_cluster(actor_fused_kernel, dim3(csize * row_blocks(a.batch), a.n_agents), csize, smem, st, a);
+  const dim3 grid(csize * row_blocks(a.batch), a.n_agents);
+  if (a.fmt.ob_dim + a.fmt.ac_dim > W1S_ROWS) return launch_cluster(actor_fused_kernel<true>, grid, csize, smem, st, a);
+  return launch_cluster(actor_fused_kernel<false>, grid, csize, smem, st, a);
 }
 
 cudaError_t launch_alpha(const b2rl_update_args_t& a, float lr, cudaStream_t st) {
   const size_t smem = alpha_smem_bytes(a.fmt.ob_dim);
   if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
-  return launch_cluster(alpha_kernel, dim3(2 * row_blocks(a.batch), a.n_agents), 2, smem, st, a, lr);
+  const dim3 grid(2 * row_blocks(a.batch), a.n_agents);
+  if (a.fmt.ob_dim > W1S_ROWS) return launch_cluster(alpha_kernel<true>, grid, 2, smem, st, a, lr);
+  return launch_cluster(alpha_kernel<false>, grid, 2, smem, st, a, lr);
 }
 
 cudaError_t launch_predict(const b2rl_update_args_t& a, const float* obs, int n, int mode, float explore_std,
                            uint64_t draw, float* actions, cudaStream_t st) {
   const size_t smem = predict_smem_bytes(a.fmt.ob_dim);
   if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
-  return launch_cluster(predict_kernel, dim3(2 * row_blocks(n)), 2, smem, st, a, obs, n, mode, explore_std, draw, actions);
+  if (a.fmt.ob_dim > W1S_ROWS)
+    return launch_cluster(predict_kernel<true>, dim3(2 * row_blocks(n)), 2, smem, st, a, obs, n, mode, explore_std, draw, actions);
+  return launch_cluster(predict_kernel<false>, dim3(2 * row_blocks(n)), 2, smem, st, a, obs, n, mode, explore_std, draw, actions);
 }
 
 }  // namespace b2rl

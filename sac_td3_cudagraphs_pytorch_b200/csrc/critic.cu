@@ -31,6 +31,7 @@ __host__ __device__ inline size_t critic_smem_bytes(int in_dim) {
   return sizeof(CriticSmem) + (size_t)2 * RQ * in_dim * sizeof(float4);
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_constant__ b2rl_update_args_t A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CriticSmem& M = *reinterpret_cast<CriticSmem*>(smem_raw);
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
   int gi = 0;
 
   // ---- next action
-  gi = trunk_fwd(G, &act, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 2);
+  gi = trunk_fwd<WIDE>(G, &act, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 2);
   rowdot(act.p[F_W3], act.p[F_B3], act.out_dim, S.h[1], S.u);
   __syncthreads();
   B2RL_TICK(10);
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
 
   // ---- target Q_k on (next_obs, a')  (agent.py:208-210), then swap the 8 values with the peer group
   B2RL_TICK(11);
-  gi = trunk_fwd(G, &qt, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 12);
+  gi = trunk_fwd<WIDE>(G, &qt, XA, ldx, nullptr, &S, gi, nullptr, nullptr, b0, nvalid, 12);
   rowdot(qt.p[F_W3], qt.p[F_B3], 1, S.h[1], S.u);
   __syncthreads();
   B2RL_TICK(21);
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     const Workspace ws = ws_carve(wsb, B, k);
     float* part = ws.part + (size_t)rb * PART_LEN;
     B2RL_TICK(23);
-    gi = trunk_fwd(G, &qo, XB, ldx, &M.a, &S, gi, ws.h1, ws.h2, b0, nvalid, 24);
+    gi = trunk_fwd<WIDE>(G, &qo, XB, ldx, &M.a, &S, gi, ws.h1, ws.h2, b0, nvalid, 24);
     rowdot(qo.p[F_W3], qo.p[F_B3], 1, S.h[1], S.u);
     __syncthreads();
     B2RL_TICK(33);
@@ -215,14 +216,18 @@ extern "C" int b2rl_debug_timing(long long* host64) {  // critic_fused_kernel's 
 int max_in_dim_critic() { return (int)((MAX_DYN_SMEM - critic_smem_bytes(0)) / (2 * RQ * sizeof(float4))); }
 
 cudaError_t init_critic() {
-  return cudaFuncSetAttribute(critic_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(critic_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(critic_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  return e;
 }
 
 cudaError_t launch_critic_fused(const b2rl_update_args_t& a, cudaStream_t st) {
   const size_t smem = critic_smem_bytes(a.fmt.ob_dim + a.fmt.ac_dim);
   if (smem > (size_t)MAX_DYN_SMEM) return cudaErrorInvalidValue;
   // clusters of 4 along x: (row block, critic, column slice)
-  return launch_cluster(critic_fused_kernel, dim3(4 * row_blocks(a.batch), a.n_agents), 4, smem, st, a);
+  const dim3 grid(4 * row_blocks(a.batch), a.n_agents);
+  if (a.fmt.ob_dim + a.fmt.ac_dim > W1S_ROWS) return launch_cluster(critic_fused_kernel<true>, grid, 4, smem, st, a);
+  return launch_cluster(critic_fused_kernel<false>, grid, 4, smem, st, a);
 }
 
 }  // namespace b2rl

@@ -538,6 +538,9 @@ __device__ __forceinline__ void store_slice(float* __restrict__ dst, int b0, int
 // ---- the two hidden layers, forward. Leaves h2 in S.h[1] (synchronised), x-hat / statistics in `A` if given. -----
 // One copy per kernel (__noinline__, every argument a register value, Net and Work in shared memory); the two
 // layers share one copy of the exchange and of the row-wise step (rolled loop). Returns the exchange counter.
+// WIDE: first layers wider than W1S_ROWS inputs exist (read from global memory by first_global); the narrow
+// instantiation does not carry that code (instruction footprint: see the header comment).
+template <bool WIDE>
 static __device__ __noinline__ int trunk_fwd(const Group G, const Net* np, const float4* __restrict__ X, int ldx,
                                              Acts* A, Work* Sp, int gi, float* ws_h1, float* ws_h2, int b0, int nvalid,
                                              int tk = 54) {
@@ -545,7 +548,7 @@ static __device__ __noinline__ int trunk_fwd(const Group G, const Net* np, const
   Work& S = *Sp;
   const int j0 = G.c * CW;
   B2RL_TICK(tk + 0);
-  if (n.w1s) first_smem(n.w1s, n.in_dim, X, ldx, S.red);
+  if (!WIDE || n.w1s) first_smem(n.w1s, n.in_dim, X, ldx, S.red);
   else first_global(n.p[F_W1T], n.in_dim, X, ldx, j0, S.red);
   WPipe P;  // the second layer's first weight groups: requested now, multiplied after the first layer's exchange
   hidden_prefetch(n.p[F_W2T], j0, P);  // and row-wise step, which hide their L2 latency
