@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ActorSmem& M = *reinterpret_cast<ActorSmem*>(smem_raw);
   Work& S = M.s;
+  exchange_init_arrive(S);  // (shared memory and the cluster barrier only: legal before the grid dependency)
+  pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   const int k = rank >> 1;
@@ -56,7 +58,6 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   const float invB = 1.0f / (float)B;
 
   // ---- prologue: the observation tile and the small tensors, one job per warp
-  exchange_init_arrive(S);
   const Net &act = M.nA, &q = M.nQ;
   if (w == 0) {
     if (l < AD) {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
 #pragma unroll
     for (int r = 0; r < RT; ++r) dh[r] = 0.f;
     const float* W3 = act.p[F_W3];
-#pragma unroll 1
+#pragma unroll 8  // (a head wider than the staged 8 rows is read from global memory: keep 8 loads in flight)
     for (int o = 0; o < act.out_dim; ++o) {
       const float wv = W3[(size_t)o * HID + t];
       const float4 d0 = S.du[o], d1 = S.du[MAX_OUT + o];
@@ -258,6 +259,8 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AlphaSmem& M = *reinterpret_cast<AlphaSmem*>(smem_raw);
   Work& S = M.s;
+  exchange_init_arrive(S);  // (shared memory and the cluster barrier only: legal before the grid dependency)
+  pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const Group G{rank, 0};
@@ -274,7 +277,6 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   float* wsb = A.workspace + (size_t)agent * A.workspace_agent_stride;
   float* part = ws_carve(wsb, B, 0).part;
 
-  exchange_init_arrive(S);
   if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
   else stage_tile(rows, rs, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
 
 __global__ void alpha_adam_kernel(float* log_alpha, uint64_t* counters, int n_agents, float lr, float grad_scale,
                                   float* out) {
+  pdl_enter();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_agents) return;
   float* st = log_alpha + (size_t)a * 5;
@@ -351,8 +354,7 @@ __global__ void alpha_adam_kernel(float* log_alpha, uint64_t* counters, int n_ag
 
 cudaError_t launch_alpha_adam(float* log_alpha, uint64_t* counters, int n_agents, float lr, float grad_scale,
                               float* out, cudaStream_t st) {
-  alpha_adam_kernel<<<(n_agents + 127) / 128, 128, 0, st>>>(log_alpha, counters, n_agents, lr, grad_scale, out);
-  return cudaGetLastError();
+  return launch_k(alpha_adam_kernel, dim3((n_agents + 127) / 128), dim3(128), 1, 0, st, log_alpha, counters, n_agents, lr, grad_scale, out);
 }
 
 // ---- inference policy ----------------------------------------------------------------------------
@@ -373,6 +375,8 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PredictSmem& M = *reinterpret_cast<PredictSmem*>(smem_raw);
   Work& S = M.s;
+  exchange_init_arrive(S);  // (shared memory and the cluster barrier only: legal before the grid dependency)
+  pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const Group G{rank, 0};
@@ -384,7 +388,6 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   const bool td3 = A.hp.td3 != 0;
   const float* P = A.arena;
   const uint64_t step = draw;
-  exchange_init_arrive(S);
   if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
   else stage_tile(obs, O, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;

@@ -16,6 +16,7 @@ namespace b2rl {
 using SegScalars = AdamScalars;
 
 __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ b2rl_adam_args_t A) {
+  pdl_enter();
   const int agent = blockIdx.y;
   float* P = A.arena + (size_t)agent * A.arena_agent_stride;
   float* T = P + A.region_stride;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* arena, int64_t region_stride,
                                                             int64_t agent_stride, int64_t begin, int64_t end,
                                                             float* scratch) {
+  pdl_enter();
   const int agent = blockIdx.y;
   const float* G = arena + (size_t)agent * agent_stride + 4 * region_stride;
   float s = 0.f;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* arena, 
   }
 }
 __global__ void sumsq_final_kernel(const float* scratch, int n_part, float* sumsq) {
+  pdl_enter();
   const int agent = blockIdx.x;
   if (threadIdx.x == 0) {
     float s = 0.f;
@@ -109,6 +112,7 @@ __global__ void sumsq_final_kernel(const float* scratch, int n_part, float* sums
 }
 
 __global__ void bump_kernel(uint64_t* counters, int which, int n_agents) {
+  pdl_enter();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < n_agents) counters[(size_t)a * 8 + which] += 1ULL;
 }
@@ -130,23 +134,19 @@ cudaError_t launch_adam(const b2rl_adam_args_t& a, cudaStream_t st) {
   int ctas = (int)((total / 4 + 255) / 256);
   if (ctas < 1) ctas = 1;
   if (ctas > 148 * 4) ctas = 148 * 4;  // grid-stride beyond four CTAs per SM
-  adam_polyak_kernel<<<dim3(ctas, a.n_agents), 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_k(adam_polyak_kernel, dim3(ctas, a.n_agents), dim3(256), 1, 0, st, a);
 }
 
 cudaError_t launch_sumsq(const float* arena, int64_t region_stride, int64_t agent_stride, int64_t begin, int64_t end,
                          int n_agents, float* sumsq, float* scratch, cudaStream_t st) {
-  sumsq_partial_kernel<<<dim3(SUMSQ_PARTS, n_agents), 256, 0, st>>>(arena, region_stride, agent_stride, begin, end,
-                                                                   scratch);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(sumsq_partial_kernel, dim3(SUMSQ_PARTS, n_agents), dim3(256), 1, 0, st, arena, region_stride, agent_stride,
+                           begin, end, scratch);
   if (e != cudaSuccess) return e;
-  sumsq_final_kernel<<<n_agents, 32, 0, st>>>(scratch, SUMSQ_PARTS, sumsq);
-  return cudaGetLastError();
+  return launch_k(sumsq_final_kernel, dim3(n_agents), dim3(32), 1, 0, st, (const float*)scratch, (int)SUMSQ_PARTS, sumsq);
 }
 
 cudaError_t launch_bump(uint64_t* counters, int which, int n_agents, cudaStream_t st) {
-  bump_kernel<<<(n_agents + 127) / 128, 128, 0, st>>>(counters, which, n_agents);
-  return cudaGetLastError();
+  return launch_k(bump_kernel, dim3((n_agents + 127) / 128), dim3(128), 1, 0, st, counters, which, n_agents);
 }
 
 }  // namespace b2rl

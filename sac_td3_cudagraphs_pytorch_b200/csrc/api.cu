@@ -2,6 +2,7 @@
 // kernel launches. No allocation, no synchronisation, no host read of device memory.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,6 +29,16 @@ cudaError_t init_actor();
 cudaError_t init_wgrad();
 cudaError_t init_adam();
 cudaError_t init_replay();
+}  // namespace b2rl
+
+namespace b2rl {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B2RL_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace b2rl
 
 static thread_local char g_err[512] = "";

@@ -62,22 +62,53 @@ static __device__ long long g_b2rl_timing[64];  // one copy per translation unit
 // ---- cluster launches ----------------------------------------------------------------------------------------
 constexpr int MAX_DYN_SMEM = 232448;  // 227 KB: the opt-in dynamic shared memory limit of sm_100
 
+// Every kernel of the update is launched with programmatic stream serialisation (programmatic dependent launch):
+// it calls pdl_enter() first thing, which (1) lets the NEXT kernel in the stream begin launching — its CTAs are
+// then resident and parked when this grid drains, instead of paying the launch latency after it — and (2) waits
+// until the PREVIOUS grid has completed and its writes are visible. Nothing is read or written before the wait,
+// so the data dependences are exactly those of plain stream order; inside a captured graph the edges become
+// programmatic dependencies. Measured (B200, batch 256): 0.3-1 us less per kernel, except the weight-gradient kernel
+// (300 small CTAs), which loses 1.5 us when its successor's CTAs are parked beside it — so that one is launched
+// plainly. B2RL_PDL=0 in the environment turns the attribute off everywhere (A/B measurements).
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();  // api.cu
+
+// cluster_x < 0: |cluster_x| CTAs per cluster (1 = none) and NO programmatic launch for this kernel
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, int cluster_x, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  const bool pdl = cluster_x > 0 && pdl_enabled();
+  if (cluster_x < 0) cluster_x = -cluster_x;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, int cluster_x, size_t smem, cudaStream_t st,
                                   Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(NT);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cluster_x;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+  return launch_k(kernel, grid, dim3(NT), cluster_x, smem, st, static_cast<Args&&>(args)...);
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

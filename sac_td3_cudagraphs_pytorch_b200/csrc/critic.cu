@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CriticSmem& M = *reinterpret_cast<CriticSmem*>(smem_raw);
   Work& S = M.s;
+  exchange_init_arrive(S);  // (shared memory and the cluster barrier only: legal before the grid dependency)
+  pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int k = rank >> 1;  // the critic this CTA's group owns
@@ -58,7 +60,6 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
   // ---- prologue: one asynchronous burst of both input tiles and every small tensor the kernel will touch. Each
   //      warp has its own job (the jobs are instruction-bound: side by side they cost the longest, not the sum).
   B2RL_TICK(0);
-  exchange_init_arrive(S);
   B2RL_TICK(40);
   const Net &act = M.nA, &qt = M.nT, &qo = M.nQ;
   const float* PA = td3 ? T : P;  // SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor (:194-202)

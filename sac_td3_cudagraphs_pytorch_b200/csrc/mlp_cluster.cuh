@@ -478,13 +478,15 @@ static __device__ __noinline__ void rowdot(const float* __restrict__ W, const fl
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll 1
   for (int o = w; o < n; o += NW) {
-    float a[RT];
+    float a[RT], wr[HID / 32];
 #pragma unroll
     for (int r = 0; r < RT; ++r) a[r] = 0.f;
-#pragma unroll 2
+#pragma unroll
+    for (int i = 0; i < HID / 32; ++i) wr[i] = W[(size_t)o * HID + l + 32 * i];  // one round trip per output row
+#pragma unroll
     for (int i = 0; i < HID / 32; ++i) {
       const int k = l + 32 * i;
-      const float wv = W[(size_t)o * HID + k];
+      const float wv = wr[i];
       const float4 x0 = X[k], x1 = X[HID + k];
       a[0] = fmaf(wv, x0.x, a[0]); a[1] = fmaf(wv, x0.y, a[1]); a[2] = fmaf(wv, x0.z, a[2]); a[3] = fmaf(wv, x0.w, a[3]);
       a[4] = fmaf(wv, x1.x, a[4]); a[5] = fmaf(wv, x1.y, a[5]); a[6] = fmaf(wv, x1.z, a[6]); a[7] = fmaf(wv, x1.w, a[7]);

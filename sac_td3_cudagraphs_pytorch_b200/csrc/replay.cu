@@ -16,6 +16,7 @@ gather_kernel(const float* __restrict__ storage, int64_t storage_agent_stride, i
               int batch, const int64_t* __restrict__ idx_in, int64_t* __restrict__ idx_out,
               float* __restrict__ rows_out, uint64_t seed, const uint64_t* __restrict__ counters, int step_counter,
               int agent_base) {
+  pdl_enter();
   const int agent = blockIdx.y;
   const int chunks = row_stride >> 2;
   const int64_t total = (int64_t)batch * chunks;
@@ -36,6 +37,7 @@ gather_kernel(const float* __restrict__ storage, int64_t storage_agent_stride, i
 // used when the sampler is driven on its own (inside the fused iteration the draw is keyed on the
 // critic step counter, which wgrad.cu advances, so no extra launch is needed there)
 __global__ void bump_sample_kernel(uint64_t* counters, int n_agents, int which) {
+  pdl_enter();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a < n_agents) counters[(size_t)a * 8 + which] += 1ULL;
 }
@@ -43,6 +45,7 @@ __global__ void bump_sample_kernel(uint64_t* counters, int n_agents, int which) 
 __global__ void __launch_bounds__(256)
 extend_kernel(float* __restrict__ storage, int64_t capacity, int64_t cursor, int row_stride,
               const float* __restrict__ new_rows, int n) {
+  pdl_enter();
   const int chunks = row_stride >> 2;
   const int64_t total = (int64_t)n * chunks;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -56,6 +59,7 @@ extend_kernel(float* __restrict__ storage, int64_t capacity, int64_t cursor, int
 __global__ void __launch_bounds__(256)
 extend_dev_kernel(float* __restrict__ storage, int64_t capacity, int row_stride, const float* __restrict__ new_rows, int n,
                   uint64_t* __restrict__ counters) {
+  pdl_enter();
   const int chunks = row_stride >> 2;
   const int64_t total = (int64_t)n * chunks;
   const int64_t cursor = (int64_t)counters[B2RL_CTR_CURSOR];
@@ -83,13 +87,13 @@ cudaError_t launch_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fm
   int ctas = (int)((total + 255) / 256);
   if (ctas > 148 * 8) ctas = 148 * 8;
   if (ctas < 1) ctas = 1;
-  extend_dev_kernel<<<ctas, 256, 0, st>>>(storage, capacity, fmt.row_stride, new_rows, n, counters);
-  return cudaGetLastError();
+  return launch_k(extend_dev_kernel, dim3(ctas), dim3(256), 1, 0, st, storage, capacity, (int)fmt.row_stride, new_rows, n, counters);
 }
 
 // last node of a captured step: log block -> pinned host memory, then the sequence number the host polls
 __global__ void publish_kernel(const float* __restrict__ out, int n, float* host_out, uint64_t* seq_dev,
                                volatile uint64_t* host_seq) {
+  pdl_enter();
   for (int i = threadIdx.x; i < n; i += blockDim.x) host_out[i] = out[i];
   __threadfence_system();
   __syncthreads();
@@ -101,8 +105,7 @@ __global__ void publish_kernel(const float* __restrict__ out, int n, float* host
 }
 cudaError_t launch_publish(const float* out, int n_agents, float* host_out, uint64_t* seq_dev, uint64_t* host_seq,
                            cudaStream_t st) {
-  publish_kernel<<<1, 64, 0, st>>>(out, n_agents * 8, host_out, seq_dev, host_seq);
-  return cudaGetLastError();
+  return launch_k(publish_kernel, dim3(1), dim3(64), 1, 0, st, out, n_agents * 8, host_out, seq_dev, (volatile uint64_t*)host_seq);
 }
 
 cudaError_t init_replay() {
@@ -122,12 +125,11 @@ cudaError_t launch_gather(const float* storage, int64_t storage_agent_stride, in
   int ctas = (int)((total + 255) / 256);
   if (ctas > 148 * 8) ctas = 148 * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
   if (ctas < 1) ctas = 1;
-  gather_kernel<<<dim3(ctas, n_agents), 256, 0, st>>>(storage, storage_agent_stride, size, fmt.row_stride, batch,
-                                                    idx_in, idx_out, rows_out, seed, counters, step_counter, agent_base);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_k(gather_kernel, dim3(ctas, n_agents), dim3(256), 1, 0, st, storage, storage_agent_stride, size,
+                           (int)fmt.row_stride, batch, idx_in, idx_out, rows_out, seed, (const uint64_t*)counters, step_counter,
+                           agent_base);
   if (e != cudaSuccess || idx_in || !counters || !bump) return e;
-  bump_sample_kernel<<<(n_agents + 127) / 128, 128, 0, st>>>(counters, n_agents, step_counter);
-  return cudaGetLastError();
+  return launch_k(bump_sample_kernel, dim3((n_agents + 127) / 128), dim3(128), 1, 0, st, counters, n_agents, step_counter);
 }
 
 cudaError_t launch_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_rowfmt_t fmt, const float* new_rows,
@@ -136,8 +138,7 @@ cudaError_t launch_extend(float* storage, int64_t capacity, int64_t cursor, b2rl
   int ctas = (int)((total + 255) / 256);
   if (ctas > 148 * 8) ctas = 148 * 8;
   if (ctas < 1) ctas = 1;
-  extend_kernel<<<ctas, 256, 0, st>>>(storage, capacity, cursor, fmt.row_stride, new_rows, n);
-  return cudaGetLastError();
+  return launch_k(extend_kernel, dim3(ctas), dim3(256), 1, 0, st, storage, capacity, cursor, (int)fmt.row_stride, new_rows, n);
 }
 
 }  // namespace b2rl

@@ -222,6 +222,7 @@ __device__ __forceinline__ void ticket_finish(const WgradArgs& W, int agent, uin
 // OPT: with the fused optimizer (two instantiations: the plain one carries none of the optimizer's code)
 template <bool OPT>
 __global__ void __launch_bounds__(WT) wgrad_kernel(const __grid_constant__ WgradArgs W) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char wsm_raw[];
   WgradSmem& S = *reinterpret_cast<WgradSmem*>(wsm_raw);
   __shared__ OptCtx oc_s;
@@ -363,9 +364,8 @@ cudaError_t launch_wgrad(const b2rl_update_args_t& a, int actor_step, int bump_c
   if (opt && opt->n_seg > 1) ctas += XTRA_CTAS;
   if (!opt) ctas += 1;  // the counter-bump CTA of the plain kernel
   dim3 grid(ctas, a.n_agents);
-  if (opt) wgrad_kernel<true><<<grid, WT, sizeof(WgradSmem), st>>>(W);
-  else wgrad_kernel<false><<<grid, WT, sizeof(WgradSmem), st>>>(W);
-  return cudaGetLastError();
+  if (opt) return launch_k(wgrad_kernel<true>, grid, dim3(WT), -1, sizeof(WgradSmem), st, W);
+  return launch_k(wgrad_kernel<false>, grid, dim3(WT), -1, sizeof(WgradSmem), st, W);
 }
 
 }  // namespace b2rl

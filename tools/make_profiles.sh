@@ -1,0 +1,15 @@
+#!/bin/bash
+# Runs ON THE GPU BOX (gpurun -- 'bash tools/make_profiles.sh TAG'): the ncu evidence behind bench.py's numbers.
+#  1. bench.py without ncu (the numbers) ; 2. launch list of the same command (gpu__time_duration per launch) ;
+#  3. one --set full capture of every kernel of one td3_hopper / sac_hopper iteration (cold-cache, serialised).
+TAG=${1:-r1}
+set -x
+python bench.py --steps 300 --warmup 10 > gpurun_out/${TAG}_bench_plain.json 2> gpurun_out/${TAG}_bench_plain.err || exit 1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
+  python bench.py --steps 30 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1
+for wl in td3_hopper sac_hopper; do
+  python tools/profile_target.py $wl 12 > gpurun_out/${TAG}_plain_$wl.log 2>&1 || exit 1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'critic_fused|actor_fused|wgrad|adam_polyak|gather|alpha_kernel' -s 30 -c 12 \
+    -o gpurun_out/${TAG}_full_$wl -f python tools/profile_target.py $wl 12 > gpurun_out/${TAG}_ncu_$wl.log 2>&1
+done
+ls -la gpurun_out | tail -12
