@@ -381,6 +381,9 @@ __device__ __forceinline__ void layer_fwd_rows(const float* __restrict__ z, cons
                                                float2* stat_keep, float* ws_h, int b0, int nvalid, const Group G, int tk) {
   const int t = threadIdx.x, j = t;
   float gj = 1.f, bej = 0.f;
+  float zc[RT];  // this thread's column, requested before the statistics so that its latency hides behind them
+#pragma unroll
+  for (int r = 0; r < RT; ++r) zc[r] = z[r * HID + j];
   if (ln) {
     gj = g[j];
     bej = be[j];
@@ -390,13 +393,13 @@ __device__ __forceinline__ void layer_fwd_rows(const float* __restrict__ z, cons
     if (stat_keep && t < RT) stat_keep[t] = S.stat[t];
   }
   const bool mine = ws_h && (j >> 7) == G.c;
-#pragma unroll 1
+#pragma unroll
   for (int q = 0; q < RQ; ++q) {
     float xh[4], h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = 4 * q + i;
-      const float zv = z[r * HID + j];
+      const float zv = zc[r];
       if (ln) {
         const float2 s = S.stat[r];
         xh[i] = (zv - s.x) * s.y;
