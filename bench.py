@@ -221,8 +221,13 @@ def run_b2rl(args, rank, world, device):
     fl = C.c_double(0.0)
     t_probe = time_kernel(lambda: L.check(lib.b2rl_ffma_probe(sink.data_ptr(), 4096, C.byref(fl), st())), iters=20, warm=3)
     ffma_peak = fl.value / t_probe / 1e12
+    tr = REPO / "profiles" / "r1_traffic.json"  # DRAM bytes per launch from the committed ncu --set full capture
+    traffic = None
+    if tr.exists() and args.workload == "td3_hopper":
+        t_ = json.loads(tr.read_text())["critic_fused_kernel"]
+        traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
     roof = {"bound": "fp32-ffma", "kernel": "critic_fused_kernel", "achieved": cf_flops / t_cf / 1e12, "peak": ffma_peak,
-            "unit": "TFLOP/s", "frac": cf_flops / t_cf / 1e12 / ffma_peak, "traffic": None,
+            "unit": "TFLOP/s", "frac": cf_flops / t_cf / 1e12 / ffma_peak, "traffic": traffic,
             "peak_source": "measured in this run by b2rl_ffma_probe (MEASURED_PEAKS.json has only HBM and bf16 tensor peaks)",
             "flops_per_launch": cf_flops, "us_per_launch": t_cf * 1e6, "whole_step_tflops": it_flops * K / elapsed / 1e12}
     # replay gather alone at a bandwidth-relevant size (HBM roofline): 65536 rows per launch
