@@ -203,6 +203,15 @@ int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_ro
 int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, const float* new_rows, int32_t n,
                            uint64_t* counters, void* stream);
 
+/* Large-batch hidden layer on the tensor cores (tcgen05.mma kind::tf32, operands staged by TMA, accumulator in
+ * TMEM): H = [ReLU](LayerNorm(X . W^T + bias)) for X [M][256] (row pitch ldx floats, 16-byte aligned rows) and W
+ * [256][256] in torch's natural layout — agents/nets.py:66-82 (fc_block_2) for M in the tens of thousands
+ * (BASELINE.json config 5 / stacked populations). Products are TF32 (~1e-3 relative), accumulation, LayerNorm and
+ * outputs fp32. H [M][256]; XH (x-hat, or the pre-activation when ln = 0) and stat (mean, rstd per row) may be
+ * NULL. Builds two TMA descriptors on the host, then enqueues one kernel. */
+int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* bias, const float* g,
+                   const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, void* stream);
+
 /* End of a captured learner step: copy the log block `out` (float[8] per agent, device) into `host_out` — pinned
  * host memory, written by the kernel itself over PCIe/NVLink-C2C, no copy-engine node — then advance the device
  * sequence number *seq_dev and publish it in *host_seq (system-scope fence in between): the host polls *host_seq

@@ -71,6 +71,8 @@ SYMBOLS = {
     "b2rl_critic_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_actor_update_sac": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_actor_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
+    "b2rl_tc_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_publish_logs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_critic_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),
     "b2rl_actor_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),

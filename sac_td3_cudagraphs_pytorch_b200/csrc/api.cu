@@ -29,6 +29,9 @@ cudaError_t init_actor();
 cudaError_t init_wgrad();
 cudaError_t init_adam();
 cudaError_t init_replay();
+cudaError_t init_tc();
+cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, int, int, float*,
+                             float*, float*, cudaStream_t);
 }  // namespace b2rl
 
 namespace b2rl {
@@ -132,6 +135,7 @@ int b2rl_init(void) {
   if (e == cudaSuccess) e = b2rl::init_wgrad();
   if (e == cudaSuccess) e = b2rl::init_adam();
   if (e == cudaSuccess) e = b2rl::init_replay();
+  if (e == cudaSuccess) e = b2rl::init_tc();
   if (e == cudaSuccess) {
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, b2rl::ffma_probe_kernel);
@@ -180,6 +184,16 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
   if (capacity < 1 || n < 1 || n > capacity) return fail(B2RL_E_INVALID, "bad capacity / n");
   return check_launch(b2rl::launch_extend_dev(storage, capacity, fmt, new_rows, n, counters, (cudaStream_t)stream),
                       "replay_extend_dev");
+}
+
+int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* bias, const float* g,
+                   const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, void* stream) {
+  if (!X || !W || !bias || !H || M < 1) return fail(B2RL_E_INVALID, "tc_linear: bad arguments");
+  if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "tc_linear: LayerNorm needs weight and bias");
+  if (!aligned16(X) || !aligned16(W) || !aligned16(H) || (XH && !aligned16(XH)) || ldx < B2RL_HID || (ldx & 3))
+    return fail(B2RL_E_INVALID, "tc_linear: 16-byte aligned tensors, ldx >= 256 and a multiple of 4");
+  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, bias, g, be, layer_norm, relu, H, XH, stat, (cudaStream_t)stream),
+                      "tc_linear");
 }
 
 int b2rl_publish_logs(const float* out, int32_t n_agents, float* host_out, uint64_t* seq_dev, uint64_t* host_seq,
