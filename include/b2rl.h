@@ -209,8 +209,80 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
  * (BASELINE.json config 5 / stacked populations). Products are TF32 (~1e-3 relative), accumulation, LayerNorm and
  * outputs fp32. H [M][256]; XH (x-hat, or the pre-activation when ln = 0) and stat (mean, rstd per row) may be
  * NULL. Builds two TMA descriptors on the host, then enqueues one kernel. */
-int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* bias, const float* g,
+int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
                    const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, void* stream);
+/* W_lo (here and in b2rl_tc_linear_bwd): NULL => plain TF32 products (~1e-3); else the "lo part" of W from
+ * b2rl_tc_split_lo => 3xTF32: x = hi + lo, a.b ~ hi.hi + lo.hi + hi.lo as three MMAs into the same TMEM accumulator
+ * — fp32-level accuracy (~1e-6) on the tensor cores (the activations' lo parts are made in shared memory). */
+int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, void* stream);
+
+/* ---- the wide (layer-by-layer, tensor-core) path for large batches: csrc/wide.cu, csrc/tc_linear.cu ------------------
+ * Each entry point is one batch-parallel kernel of agents/agent.py:186-235 / agents/nets.py; the host mirror
+ * (sac_td3_cudagraphs_pytorch_b200/wide.py) strings them together. Intermediates are [M][256] fp32 arrays in HBM. */
+
+/* First layer (agents/nets.py:66-72): H = ReLU(LayerNorm(X[:, :K] . w1t + b)); w1t [K][256] forward layout. */
+int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
+                    const float* be, int32_t layer_norm, float* H, float* XH, float* stat, void* stream);
+
+/* Backward dX product of the hidden layer on the tensor cores with the LayerNorm / ReLU backward of layer 1 in the
+ * epilogue: DZ1 = LNbwd(ReLU'(DZ2 . W2)); w2t = forward-layout copy of fc_block_2.fc.weight; part [ceil(M/128)][3][256]
+ * receives per-CTA column sums {sum dz, sum dn*xhat, sum dn}. */
+int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
+                       const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, void* stream);
+
+typedef struct b2rl_wide_policy {  /* policy head + action sample (agents/nets.py:143-147, :214-234; agent.py:194-205) */
+  const float* h2;      /* [M][256] */
+  const float* w3;      /* [out][256] */
+  const float* b3;
+  const float* rows;    /* [M][row_stride]: the obs-part of xn is copied from column src_off */
+  const float* min_ac;
+  const float* max_ac;
+  const float* eps;     /* [M][A] or NULL => Philox */
+  float* eps_out;       /* or NULL */
+  float* xn;            /* out [M][ldn]: [obs-part | action] */
+  float* logp;          /* out [M] (SAC) or NULL */
+  const uint64_t* counters;
+  int32_t M, O, A, out_dim, row_stride, ldn, src_off;
+  int32_t td3, smoothing, counter_idx, stream_id;
+  float td3_std, td3_c;
+  uint64_t seed;
+  uint32_t agent;
+  uint32_t reserved;
+} b2rl_wide_policy_t;
+int b2rl_wide_policy_head(const b2rl_wide_policy_t* p, void* stream);
+
+typedef struct b2rl_wide_q {  /* critic head; mode 1 adds the TD target, dLoss/dQ and squared-error partials (agent.py:212-233) */
+  const float* h2;
+  const float* w3;
+  const float* b3;
+  float* q_out;         /* [M] */
+  const float* qn0;     /* mode 1: twin target Q on (next_obs, a') */
+  const float* qn1;
+  const float* logp;    /* SAC */
+  const float* rows;    /* reward at column rd_off, done at rd_off + 1 */
+  const float* log_alpha;
+  float* dz3;           /* [M][B2RL_MAX_OUT], column 0 */
+  float* sq_part;       /* [ceil(M/8)] */
+  float* targ_out;      /* [M] or NULL */
+  int32_t M, mode, row_stride, rd_off, td3, bcq_mix;
+  float gamma;
+  uint32_t reserved;
+} b2rl_wide_q_t;
+int b2rl_wide_q_head(const b2rl_wide_q_t* q, void* stream);
+
+/* Head backward + ReLU mask + LayerNorm backward of layer 2: dz = LNbwd(ReLU'(dz3[:, :n_out] . w3)); part
+ * [ceil(M/128)][3][256] per-CTA column sums. */
+int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,
+                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, void* stream);
+/* Column-sum partials -> gradients of bias / ln.weight / ln.bias at float offsets off_* of the gradient region G. */
+int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
+                     void* stream);
+/* qf_loss -> out[B2RL_OUT_QF_LOSS] and the head-bias gradients of the twin critics. */
+int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
+                             float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream);
+/* The weight-gradient kernel on its own (wgrad.cu): reads rows, H1, H2, DZ1, DZ2, DZ3 of the workspace. skip_vectors:
+ * the bias / LayerNorm / loss reductions were done elsewhere (wide path). bump_counter: B2RL_CTR_* or -1. */
+int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream);
 
 /* End of a captured learner step: copy the log block `out` (float[8] per agent, device) into `host_out` — pinned
  * host memory, written by the kernel itself over PCIe/NVLink-C2C, no copy-engine node — then advance the device

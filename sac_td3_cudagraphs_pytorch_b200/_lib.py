@@ -56,6 +56,24 @@ class AdamArgs(C.Structure):
                 ("arena", C.c_void_p), ("counters", C.c_void_p), ("grad_sumsq", C.c_void_p)]
 
 
+class WidePolicy(C.Structure):
+    _fields_ = [("h2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p), ("rows", C.c_void_p), ("min_ac", C.c_void_p),
+                ("max_ac", C.c_void_p), ("eps", C.c_void_p), ("eps_out", C.c_void_p), ("xn", C.c_void_p), ("logp", C.c_void_p),
+                ("counters", C.c_void_p),
+                ("M", C.c_int32), ("O", C.c_int32), ("A", C.c_int32), ("out_dim", C.c_int32), ("row_stride", C.c_int32),
+                ("ldn", C.c_int32), ("src_off", C.c_int32), ("td3", C.c_int32), ("smoothing", C.c_int32),
+                ("counter_idx", C.c_int32), ("stream_id", C.c_int32), ("td3_std", C.c_float), ("td3_c", C.c_float),
+                ("seed", C.c_uint64), ("agent", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class WideQ(C.Structure):
+    _fields_ = [("h2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p), ("q_out", C.c_void_p), ("qn0", C.c_void_p),
+                ("qn1", C.c_void_p), ("logp", C.c_void_p), ("rows", C.c_void_p), ("log_alpha", C.c_void_p), ("dz3", C.c_void_p),
+                ("sq_part", C.c_void_p), ("targ_out", C.c_void_p),
+                ("M", C.c_int32), ("mode", C.c_int32), ("row_stride", C.c_int32), ("rd_off", C.c_int32), ("td3", C.c_int32),
+                ("bcq_mix", C.c_int32), ("gamma", C.c_float), ("reserved", C.c_uint32)]
+
+
 # name -> (restype, argtypes); every symbol include/b2rl.h declares
 SYMBOLS = {
     "b2rl_version": (C.c_int, []),
@@ -71,8 +89,21 @@ SYMBOLS = {
     "b2rl_critic_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_actor_update_sac": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_actor_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
-    "b2rl_tc_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_tc_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_tc_split_lo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "b2rl_wide_first": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_tc_linear_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_wide_policy_head": (C.c_int, [C.POINTER(WidePolicy), C.c_void_p]),
+    "b2rl_wide_q_head": (C.c_int, [C.POINTER(WideQ), C.c_void_p]),
+    "b2rl_wide_ln_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_wide_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "b2rl_wide_critic_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b2rl_wgrad": (C.c_int, [C.POINTER(UpdateArgs), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_publish_logs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_critic_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),
     "b2rl_actor_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),

@@ -13,7 +13,7 @@ cudaError_t launch_actor_fused(const b2rl_update_args_t&, cudaStream_t);
 cudaError_t launch_alpha(const b2rl_update_args_t&, float, cudaStream_t);
 cudaError_t launch_alpha_adam(float*, uint64_t*, int, float, float, float*, cudaStream_t);
 cudaError_t launch_predict(const b2rl_update_args_t&, const float*, int, int, float, uint64_t, float*, cudaStream_t);
-cudaError_t launch_wgrad(const b2rl_update_args_t&, int, int, const b2rl_adam_args_t*, cudaStream_t);
+cudaError_t launch_wgrad(const b2rl_update_args_t&, int, int, const b2rl_adam_args_t*, cudaStream_t, int skip_vec = 0);
 cudaError_t launch_adam(const b2rl_adam_args_t&, cudaStream_t);
 cudaError_t launch_sumsq(const float*, int64_t, int64_t, int64_t, int64_t, int, float*, float*, cudaStream_t);
 cudaError_t launch_bump(uint64_t*, int, int, cudaStream_t);
@@ -30,8 +30,21 @@ cudaError_t init_wgrad();
 cudaError_t init_adam();
 cudaError_t init_replay();
 cudaError_t init_tc();
-cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, int, int, float*,
-                             float*, float*, cudaStream_t);
+cudaError_t init_wide();
+cudaError_t launch_wide_first(const float*, int64_t, int, int, const float*, const float*, const float*, const float*, int, float*,
+                              float*, float*, cudaStream_t);
+cudaError_t launch_tc_linear_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*,
+                                 const float*, int, float*, float*, cudaStream_t);
+cudaError_t launch_wide_policy_head(const b2rl_wide_policy_t&, cudaStream_t);
+cudaError_t launch_wide_q_head(const b2rl_wide_q_t&, cudaStream_t);
+cudaError_t launch_wide_ln_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int,
+                               float*, float*, cudaStream_t);
+cudaError_t launch_wide_colsum(const float*, int, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
+cudaError_t launch_wide_critic_scalars(const float*, const float*, int, const float*, const float*, int, float*, int64_t, int64_t,
+                                       float*, cudaStream_t);
+cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*, int,
+                             int, float*, float*, float*, cudaStream_t);
+cudaError_t launch_tc_split_lo(const float*, float*, int, cudaStream_t);
 }  // namespace b2rl
 
 namespace b2rl {
@@ -136,6 +149,7 @@ int b2rl_init(void) {
   if (e == cudaSuccess) e = b2rl::init_adam();
   if (e == cudaSuccess) e = b2rl::init_replay();
   if (e == cudaSuccess) e = b2rl::init_tc();
+  if (e == cudaSuccess) e = b2rl::init_wide();
   if (e == cudaSuccess) {
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, b2rl::ffma_probe_kernel);
@@ -186,14 +200,68 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
                       "replay_extend_dev");
 }
 
-int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* bias, const float* g,
+int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, void* stream) {
+  if (!W || !W_lo || n < 1) return fail(B2RL_E_INVALID, "tc_split_lo: bad arguments");
+  return check_launch(b2rl::launch_tc_split_lo(W, W_lo, n, (cudaStream_t)stream), "tc_split_lo");
+}
+int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
                    const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, void* stream) {
   if (!X || !W || !bias || !H || M < 1) return fail(B2RL_E_INVALID, "tc_linear: bad arguments");
   if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "tc_linear: LayerNorm needs weight and bias");
   if (!aligned16(X) || !aligned16(W) || !aligned16(H) || (XH && !aligned16(XH)) || ldx < B2RL_HID || (ldx & 3))
     return fail(B2RL_E_INVALID, "tc_linear: 16-byte aligned tensors, ldx >= 256 and a multiple of 4");
-  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, bias, g, be, layer_norm, relu, H, XH, stat, (cudaStream_t)stream),
+  if (W_lo && !aligned16(W_lo)) return fail(B2RL_E_INVALID, "tc_linear: W_lo must be 16-byte aligned");
+  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, relu, H, XH, stat, (cudaStream_t)stream),
                       "tc_linear");
+}
+
+int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
+                    const float* be, int32_t layer_norm, float* H, float* XH, float* stat, void* stream) {
+  if (!X || !w1t || !b || !H || M < 1 || K < 1 || ldx < K) return fail(B2RL_E_INVALID, "wide_first: bad arguments");
+  if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "wide_first: LayerNorm needs weight and bias");
+  return check_launch(b2rl::launch_wide_first(X, ldx, M, K, w1t, b, g, be, layer_norm, H, XH, stat, (cudaStream_t)stream), "wide_first");
+}
+int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
+                       const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, void* stream) {
+  if (!DZ2 || !w2t || !xh1 || !DZ1 || !part || M < 1) return fail(B2RL_E_INVALID, "tc_linear_bwd: bad arguments");
+  if (layer_norm && (!g1 || !be1 || !stat1)) return fail(B2RL_E_INVALID, "tc_linear_bwd: LayerNorm needs weight, bias and statistics");
+  if (!aligned16(DZ2) || !aligned16(w2t) || !aligned16(DZ1)) return fail(B2RL_E_INVALID, "tc_linear_bwd: 16-byte aligned tensors");
+  return check_launch(b2rl::launch_tc_linear_bwd(DZ2, M, w2t, w2t_lo, xh1, stat1, g1, be1, layer_norm, DZ1, part, (cudaStream_t)stream),
+                      "tc_linear_bwd");
+}
+int b2rl_wide_policy_head(const b2rl_wide_policy_t* p, void* stream) {
+  if (!p || !p->h2 || !p->w3 || !p->b3 || !p->rows || !p->min_ac || !p->max_ac || !p->xn || !p->counters || p->M < 1 ||
+      p->A < 1 || p->A > 32 || p->out_dim < p->A || p->out_dim > B2RL_MAX_OUT || p->ldn < p->O + p->A)
+    return fail(B2RL_E_INVALID, "wide_policy_head: bad arguments");
+  return check_launch(b2rl::launch_wide_policy_head(*p, (cudaStream_t)stream), "wide_policy_head");
+}
+int b2rl_wide_q_head(const b2rl_wide_q_t* q, void* stream) {
+  if (!q || !q->h2 || !q->w3 || !q->b3 || !q->q_out || q->M < 1) return fail(B2RL_E_INVALID, "wide_q_head: bad arguments");
+  if (q->mode == 1 && (!q->qn0 || !q->qn1 || !q->rows || !q->dz3 || !q->sq_part || (!q->td3 && (!q->logp || !q->log_alpha))))
+    return fail(B2RL_E_INVALID, "wide_q_head: online mode needs the target Qs, rows, dz3, sq_part (and logp / log_alpha for SAC)");
+  return check_launch(b2rl::launch_wide_q_head(*q, (cudaStream_t)stream), "wide_q_head");
+}
+int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,
+                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, void* stream) {
+  if (!dz3 || !w3 || !xh || !dz || !part || M < 1 || n_out < 1 || n_out > B2RL_MAX_OUT) return fail(B2RL_E_INVALID, "wide_ln_bwd: bad arguments");
+  if (layer_norm && (!g || !be || !stat)) return fail(B2RL_E_INVALID, "wide_ln_bwd: LayerNorm needs weight, bias and statistics");
+  return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, (cudaStream_t)stream), "wide_ln_bwd");
+}
+int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
+                     void* stream) {
+  if (!part || !G || P < 1) return fail(B2RL_E_INVALID, "wide_colsum: bad arguments");
+  return check_launch(b2rl::launch_wide_colsum(part, P, G, off_b, off_g, off_be, layer_norm, (cudaStream_t)stream), "wide_colsum");
+}
+int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
+                             float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream) {
+  if (!sq0 || !sq1 || !dz3_0 || !dz3_1 || !G || !out || P < 1 || M < 1) return fail(B2RL_E_INVALID, "wide_critic_scalars: bad arguments");
+  return check_launch(b2rl::launch_wide_critic_scalars(sq0, sq1, P, dz3_0, dz3_1, M, G, off_b3_0, off_b3_1, out, (cudaStream_t)stream),
+                      "wide_critic_scalars");
+}
+int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream) {
+  if (int rc = check_update(a, actor_step != 0)) return rc;
+  if (bump_counter < -1 || bump_counter > 3) return fail(B2RL_E_INVALID, "wgrad: bad bump_counter");
+  return check_launch(b2rl::launch_wgrad(*a, actor_step != 0, bump_counter, nullptr, (cudaStream_t)stream, skip_vectors != 0), "wgrad");
 }
 
 int b2rl_publish_logs(const float* out, int32_t n_agents, float* host_out, uint64_t* seq_dev, uint64_t* host_seq,

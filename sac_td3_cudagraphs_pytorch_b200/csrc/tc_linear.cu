@@ -23,14 +23,24 @@
 
 namespace b2rl {
 
-constexpr int TCM = 128, TCN = 256, TCK = 32, TC_STAGES = 4, TC_THREADS = 192;
-constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN) * TCK * sizeof(float);  // 48 KB
-
-struct __align__(1024) TcSmem {
-  float a[TC_STAGES][TCM * TCK];  // 16 KB per stage, 128-byte rows, swizzle-128B
-  float b[TC_STAGES][TCN * TCK];  // 32 KB per stage
-  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full;
+constexpr int TCM = 128, TCN = 256, TCK = 32, TC_THREADS = 192;
+// PREC 0: TF32 products (operands truncated to 10 mantissa bits by the tensor core), 4-stage ring.
+// PREC 1: "3xTF32": x = hi + lo with hi = the TF32 truncation the tensor core applies anyway and lo = x - hi (exact in
+//         fp32, re-truncated to TF32: 2^-21 of x); a.b ~ hi.hi + lo.hi + hi.lo, three MMAs into the same accumulator —
+//         fp32-level accuracy (~1e-6) from the tensor cores. The weights' lo parts are precomputed (tc_split_lo), the
+//         activations' are made in shared memory by the (otherwise idle) epilogue warps; 2-stage ring of 96 KB.
+template <int PREC>
+struct __align__(1024) TcSmemT {
+  static constexpr int STAGES = PREC ? 2 : 4;
+  float a[STAGES][TCM * TCK];  // 16 KB per stage, 128-byte rows, swizzle-128B
+  float b[STAGES][TCN * TCK];  // 32 KB per stage
+  float alo[PREC ? STAGES : 1][PREC ? TCM * TCK : 4];
+  float blo[PREC ? STAGES : 1][PREC ? TCN * TCK : 4];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full;
   uint32_t tmem_base;
+  // backward epilogue (MODE 2): per-warp 32x32 transposition tile and per-warp column-sum partials
+  float tile[4][32][33];
+  float wpart[4][3][HID];
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,17 +91,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MODE 0: forward  H = [ReLU](LayerNorm(A . B^T + bias)), optional x-hat / statistics outputs.
+// MODE 2: backward dX: D = A . B^T with A = dz2 [M][256], B = w2t; epilogue = the ReLU mask and LayerNorm backward of
+//         layer 1 (x-hat and rstd read per row), H <- dz1, and this CTA's column sums {sum dz, sum dn*xhat, sum dn}
+//         -> part[cta][3][256] (bias / LayerNorm-affine gradients; deterministic: transposed through shared memory).
+template <int MODE, int PREC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M,
+tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const __grid_constant__ CUtensorMap mapBlo, int M,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
-                 float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat) {
+                 float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part) {
   extern __shared__ unsigned char tc_raw[];  // (the swizzle atoms need 1024-byte alignment: align by hand)
-  TcSmem& S = *reinterpret_cast<TcSmem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
+  using Smem = TcSmemT<PREC>;
+  constexpr int TC_STAGES = Smem::STAGES;
+  constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN * (PREC ? 2 : 1)) * TCK * sizeof(float);
+  Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * TCM;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 1); mbar_init_(&S.lo_ready[s], 128); }
     mbar_init_(&S.acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -113,6 +132,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_expect_(&S.full[s], TC_STAGE_BYTES);
         tma_load_2d(S.a[s], &mapA, kb * TCK, m0, &S.full[s]);
         tma_load_2d(S.b[s], &mapB, kb * TCK, 0, &S.full[s]);
+        if constexpr (PREC == 1) tma_load_2d(S.blo[s], &mapBlo, kb * TCK, 0, &S.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -120,10 +140,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % TC_STAGES;
         mbar_wait_(&S.full[s], (kb / TC_STAGES) & 1);
+        if constexpr (PREC == 1) mbar_wait_(&S.lo_ready[s], (kb / TC_STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < TCK / 8; ++k)  // UMMA K = 8 tf32 = 32 bytes: advance inside the 128-byte swizzle row
+        for (int k = 0; k < TCK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: advance inside the 128-byte swizzle row
           umma_tf32(tmem, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
+          if constexpr (PREC == 1) {
+            umma_tf32(tmem, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
+            umma_tf32(tmem, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+          }
+        }
         umma_commit(&S.empty[s]);  // (implies tcgen05.fence::before_thread_sync)
       }
       umma_commit(&S.acc_full);
@@ -131,56 +157,140 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
     const int lg = warp & 3;
     const int row = m0 + 32 * lg + lane;
+    if constexpr (PREC == 1) {  // the activations' lo parts, stage by stage, while the ring runs
+      const int et = threadIdx.x - 64;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % TC_STAGES;
+        mbar_wait_(&S.full[s], (kb / TC_STAGES) & 1);
+        const float4* src = reinterpret_cast<const float4*>(S.a[s]);
+        float4* dst = reinterpret_cast<float4*>(S.alo[s]);
+#pragma unroll
+        for (int i = 0; i < TCM * TCK / 4 / 128; ++i) {  // element-wise, so the swizzled layout carries over
+          const float4 x = src[et + 128 * i];
+          float4 lo;
+          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          dst[et + 128 * i] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
+      }
+    }
     mbar_wait_(&S.acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tl = tmem + ((uint32_t)(32 * lg) << 16);
     float v[32];
-    float mean = 0.f, rstd = 1.f;
-    if (ln) {
-      float s1 = 0.f;
-      for (int c = 0; c < TCN / 32; ++c) {
-        tmem_ld32(tl + c * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s1 += v[i] + __ldg(bias + c * 32 + i);
+    if constexpr (MODE == 0) {
+      float mean = 0.f, rstd = 1.f;
+      if (ln) {
+        float s1 = 0.f;
+        for (int c = 0; c < TCN / 32; ++c) {
+          tmem_ld32(tl + c * 32, v);
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) s1 += v[i] + __ldg(bias + c * 32 + i);
+        }
+        mean = s1 * (1.0f / TCN);
+        float s2 = 0.f;
+        for (int c = 0; c < TCN / 32; ++c) {
+          tmem_ld32(tl + c * 32, v);
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = v[i] + __ldg(bias + c * 32 + i) - mean;
+            s2 = fmaf(d, d, s2);
+          }
+        }
+        rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
+        if (stat && row < M) stat[row] = make_float2(mean, rstd);
       }
-      mean = s1 * (1.0f / TCN);
-      float s2 = 0.f;
       for (int c = 0; c < TCN / 32; ++c) {
         tmem_ld32(tl + c * 32, v);
+        float h[32];
+  #pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int j = c * 32 + i;
+          float x = v[i] + __ldg(bias + j);
+          if (ln) {
+            x = (x - mean) * rstd;
+            v[i] = x;  // x-hat
+            x = fmaf(x, __ldg(g + j), __ldg(be + j));
+          } else {
+            v[i] = x;  // pre-activation
+          }
+          h[i] = relu ? fmaxf(x, 0.f) : x;
+        }
+        if (row < M) {
+          float4* hp = reinterpret_cast<float4*>(H + (size_t)row * TCN + c * 32);
+  #pragma unroll
+          for (int i = 0; i < 8; ++i) hp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+          if (XH) {
+            float4* xp = reinterpret_cast<float4*>(XH + (size_t)row * TCN + c * 32);
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) xp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+        }
+      }
+    } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
+      const bool live = row < M;
+      const float* xr = XH + (size_t)(live ? row : 0) * TCN;
+      float s1 = 0.f, s2 = 0.f;
+      if (ln) {
+        for (int c = 0; c < TCN / 32; ++c) {
+          tmem_ld32(tl + c * 32, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int j = c * 32 + i;
+            const float x = live ? __ldg(xr + j) : 0.f, gj = __ldg(g + j);
+            const float dx = (fmaf(x, gj, __ldg(be + j)) > 0.f ? v[i] : 0.f) * gj;
+            s1 += dx;
+            s2 = fmaf(dx, x, s2);
+          }
+        }
+      }
+      const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[row].y : 1.f;
+      const int ew = warp - 2;  // epilogue warp 0..3
+      for (int c = 0; c < TCN / 32; ++c) {
+        tmem_ld32(tl + c * 32, v);
+        float dz[32], dnx[32], dn[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float d = v[i] + __ldg(bias + c * 32 + i) - mean;
-          s2 = fmaf(d, d, s2);
+          const int j = c * 32 + i;
+          const float x = live ? __ldg(xr + j) : 0.f;
+          if (ln) {
+            const float gj = __ldg(g + j);
+            dn[i] = fmaf(x, gj, __ldg(be + j)) > 0.f ? v[i] : 0.f;
+            dz[i] = rstd * (dn[i] * gj - m1 - x * m2);
+          } else {
+            dn[i] = x > 0.f ? v[i] : 0.f;
+            dz[i] = dn[i];
+          }
+          if (!live) dz[i] = 0.f;
+          dnx[i] = dn[i] * x;
+        }
+        if (live) {
+          float4* hp = reinterpret_cast<float4*>(H + (size_t)row * TCN + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hp[i] = make_float4(dz[4 * i], dz[4 * i + 1], dz[4 * i + 2], dz[4 * i + 3]);
+        }
+        // column sums over this warp's 32 rows: transpose through the warp's tile, lane <-> column
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float* src = q == 0 ? dz : q == 1 ? dnx : dn;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) S.tile[ew][lane][i] = src[i];
+          __syncwarp();
+          float cs = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) cs += S.tile[ew][r][lane];
+          S.wpart[ew][q][c * 32 + lane] = cs;
+          __syncwarp();
         }
       }
-      rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
-      if (stat && row < M) stat[row] = make_float2(mean, rstd);
-    }
-    for (int c = 0; c < TCN / 32; ++c) {
-      tmem_ld32(tl + c * 32, v);
-      float h[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int j = c * 32 + i;
-        float x = v[i] + __ldg(bias + j);
-        if (ln) {
-          x = (x - mean) * rstd;
-          v[i] = x;  // x-hat
-          x = fmaf(x, __ldg(g + j), __ldg(be + j));
-        } else {
-          v[i] = x;  // pre-activation
-        }
-        h[i] = relu ? fmaxf(x, 0.f) : x;
-      }
-      if (row < M) {
-        float4* hp = reinterpret_cast<float4*>(H + (size_t)row * TCN + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-        if (XH) {
-          float4* xp = reinterpret_cast<float4*>(XH + (size_t)row * TCN + c * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+      for (int i = threadIdx.x - 64; i < 3 * HID; i += 128) {
+        const int q = i / HID, j = i - q * HID;
+        part[((size_t)blockIdx.x * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
       }
     }
   }
@@ -215,16 +325,62 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t co
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-cudaError_t init_tc() {
-  return cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem) + 1024);
+// lo part of a weight matrix for the 3xTF32 mode: lo = w - tf32_truncate(w)
+__global__ void tc_split_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lo[i] = w[i] - __uint_as_float(__float_as_uint(w[i]) & 0xFFFFE000u);
+}
+cudaError_t launch_tc_split_lo(const float* w, float* lo, int n, cudaStream_t st) {
+  tc_split_lo_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, lo, n);
+  return cudaGetLastError();
 }
 
-cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W, const float* bias, const float* g,
-                             const float* be, int ln, int relu, float* H, float* XH, float* stat, cudaStream_t st) {
-  CUtensorMap ma, mb;
+template <typename K>
+static cudaError_t tc_opt_in(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes + 1024);
+}
+cudaError_t init_tc() {
+  cudaError_t e = tc_opt_in(tc_linear_kernel<0, 0>, sizeof(TcSmemT<0>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 0>, sizeof(TcSmemT<0>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 1>, sizeof(TcSmemT<1>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 1>, sizeof(TcSmemT<1>));
+  cudaFuncAttributes fa;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, tc_split_lo_kernel);
+  return e;
+}
+
+// Wlo: the precomputed lo part of W (tc_split_lo) => 3xTF32; NULL => plain TF32
+cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W, const float* Wlo, const float* bias,
+                             const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat, cudaStream_t st) {
+  CUtensorMap ma, mb, ml;
   if (!make_map(&ma, X, M, HID, ldx, TCM) || !make_map(&mb, W, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-  tc_linear_kernel<<<(M + TCM - 1) / TCM, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(ma, mb, M, bias, g, be, ln, relu, H, XH,
-                                                                                  reinterpret_cast<float2*>(stat));
+  const int grid = (M + TCM - 1) / TCM;
+  if (Wlo) {
+    if (!make_map(&ml, Wlo, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
+    tc_linear_kernel<0, 1><<<grid, TC_THREADS, sizeof(TcSmemT<1>) + 1024, st>>>(ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
+                                                                              reinterpret_cast<float2*>(stat), nullptr);
+  } else {
+    tc_linear_kernel<0, 0><<<grid, TC_THREADS, sizeof(TcSmemT<0>) + 1024, st>>>(ma, mb, mb, M, bias, g, be, ln, relu, H, XH,
+                                                                              reinterpret_cast<float2*>(stat), nullptr);
+  }
+  return cudaGetLastError();
+}
+
+// dz1 = LayerNormBackward(ReLU'(dz2 . W2)) and the column-sum partials; w2t is the forward-layout copy ([k][j])
+cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
+                                 const float* stat1, const float* g1, const float* be1, int ln, float* DZ1, float* part,
+                                 cudaStream_t st) {
+  CUtensorMap ma, mb, ml;
+  if (!make_map(&ma, DZ2, M, HID, HID, TCM) || !make_map(&mb, w2t, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
+  const int grid = (M + TCM - 1) / TCM;
+  float* xh = const_cast<float*>(xh1);
+  float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
+  if (w2t_lo) {
+    if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
+    tc_linear_kernel<2, 1><<<grid, TC_THREADS, sizeof(TcSmemT<1>) + 1024, st>>>(ma, mb, ml, M, nullptr, g1, be1, ln, 0, DZ1, xh, st1, part);
+  } else {
+    tc_linear_kernel<2, 0><<<grid, TC_THREADS, sizeof(TcSmemT<0>) + 1024, st>>>(ma, mb, mb, M, nullptr, g1, be1, ln, 0, DZ1, xh, st1, part);
+  }
   return cudaGetLastError();
 }
 

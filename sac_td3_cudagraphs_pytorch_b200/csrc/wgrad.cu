@@ -175,6 +175,7 @@ struct WgradArgs {
   int bump_counter;
   int has_opt;     // opt.seg[0]: Adam (+ Polyak) on the trained nets; opt.seg[1..]: Polyak-only spans
   int work_ctas;   // CTAs before the trailing extra-segment CTAs
+  int skip_vec;    // the vector / scalar reductions are done by the caller (wide path)
   b2rl_adam_args_t opt;
 };
 
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(WT) wgrad_kernel(const __grid_constant__ Wgrad
     }
     id -= t1 + t2 + t3;
     if (id < VEC_CTAS) {
+      if (W.skip_vec) return;
       setup();
       __syncthreads();
       if (id < PART_VEC) {  // one 256-wide column vector: sum the per-row-block partials
@@ -350,8 +352,9 @@ cudaError_t init_wgrad() {
 }
 
 cudaError_t launch_wgrad(const b2rl_update_args_t& a, int actor_step, int bump_counter, const b2rl_adam_args_t* opt,
-                         cudaStream_t st) {
+                         cudaStream_t st, int skip_vec) {
   WgradArgs W;
+  W.skip_vec = skip_vec;
   W.u = a;
   W.actor_step = actor_step;
   W.bump_counter = bump_counter;

@@ -1,0 +1,355 @@
+// wide.cu — the layer-by-layer ("wide") path of the update for LARGE batches (BASELINE.json config 5: batch 65 536;
+// stacked populations later): every step of agents/agent.py:186-235 as its own batch-parallel kernel around the
+// tensor-core hidden layers of tc_linear.cu, with all intermediates in HBM. The row-group kernels of
+// mlp_cluster.cuh are latency-optimal at batch 256 but stream each layer's weights from L2 once per 8 rows
+// (~10 TFLOP/s at any batch size); here the weights are read once per 128 rows by TMA and the products run on
+// tcgen05. Same arithmetic as the row path outside the products (LayerNorm two-pass statistics, policy heads,
+// TD target, losses); the Philox noise is keyed identically, so both paths draw the same samples.
+//
+// Kernels (all: grid over rows, no atomics, fixed summation order => bitwise reproducible):
+//   wide_first       X[M][K] . w1t -> LayerNorm -> ReLU  (first layers: K = O or O + A, FFMA)
+//   wide_policy_head h2 -> head -> tanh-Gaussian sample / TD3 smoothed action; writes [next_obs | a'] and log-prob
+//   wide_q_head      h2 -> Q; online mode: TD target from the twin target Qs, dQ, squared-error partials
+//   wide_ln_bwd      dLoss/dhead -> dh2 -> ReLU mask -> LayerNorm backward -> dz2, per-CTA column sums
+//   (tc_linear mode 2: dz2 . W2 -> LayerNorm backward of layer 1 in the TMEM epilogue -> dz1, column sums)
+//   wide_colsum      per-CTA column-sum partials -> bias / LayerNorm-affine gradients; loss scalar
+#include "common.cuh"
+#include "policy.cuh"
+#include "rng.cuh"
+
+namespace b2rl {
+
+constexpr int WF_ROWS = 32;  // rows per CTA of wide_first
+constexpr int WF_KC = 64;    // k chunk staged in shared memory
+
+// ---- first layer -------------------------------------------------------------------------------------------------
+// thread j <-> output column j; 32 rows per CTA. z[r][j] = b[j] + sum_k X[r][k] * w1t[k][j].
+__global__ void __launch_bounds__(256)
+wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const float* __restrict__ w1t,
+                  const float* __restrict__ b, const float* __restrict__ g, const float* __restrict__ be, int ln,
+                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat) {
+  __shared__ float xs[WF_ROWS][WF_KC + 1];
+  __shared__ float zs[WF_ROWS][HID];
+  __shared__ float2 st[WF_ROWS];
+  const int t = threadIdx.x, j = t, w = t >> 5, l = t & 31;
+  const int m0 = blockIdx.x * WF_ROWS;
+  float acc[WF_ROWS];
+#pragma unroll
+  for (int r = 0; r < WF_ROWS; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += WF_KC) {
+    const int kc = min(WF_KC, K - k0);
+    for (int i = t; i < WF_ROWS * kc; i += 256) {
+      const int r = i / kc, k = i - r * kc;
+      const int row = min(m0 + r, M - 1);  // (rows beyond M repeat the last one; their outputs are not stored)
+      xs[r][k] = __ldg(X + (size_t)row * ldx + k0 + k);
+    }
+    __syncthreads();
+    for (int k = 0; k < kc; ++k) {
+      const float wv = __ldg(w1t + (size_t)(k0 + k) * HID + j);
+#pragma unroll
+      for (int r = 0; r < WF_ROWS; ++r) acc[r] = fmaf(xs[r][k], wv, acc[r]);
+    }
+    __syncthreads();
+  }
+  const float bj = b[j];
+#pragma unroll
+  for (int r = 0; r < WF_ROWS; ++r) {
+    acc[r] += bj;
+    zs[r][j] = acc[r];
+  }
+  float gj = 1.f, bej = 0.f;
+  if (ln) {
+    gj = g[j];
+    bej = be[j];
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < WF_ROWS / 8; ++rr) {  // warp w: rows w, w+8, ... (two-pass mean / variance)
+      const int r = w + 8 * rr;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = zs[r][l + 32 * i];
+      float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      s = warp_sum(s);
+      const float mean = s * (1.0f / HID);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+      q = warp_sum(q);
+      if (l == 0) st[r] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / HID) + LN_EPS));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < WF_ROWS; ++r) {
+    const int row = m0 + r;
+    if (row >= M) break;
+    float x = acc[r], h;
+    if (ln) {
+      const float2 s = st[r];
+      x = (x - s.x) * s.y;
+      h = fmaxf(fmaf(x, gj, bej), 0.f);
+      if (stat && j == 0) stat[row] = s;
+    } else {
+      h = fmaxf(x, 0.f);
+    }
+    H[(size_t)row * HID + j] = h;
+    if (XH) XH[(size_t)row * HID + j] = x;
+  }
+}
+
+// ---- policy head: warp per row ----------------------------------------------------------------------------------------
+using WidePolicyArgs = b2rl_wide_policy_t;
+
+__global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_constant__ WidePolicyArgs P) {
+  extern __shared__ float w3s[];  // [out][256]
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  for (int i = t; i < P.out_dim * HID; i += 256) w3s[i] = __ldg(P.w3 + i);
+  __syncthreads();
+  const int row = blockIdx.x * 8 + w;
+  if (row >= P.M) return;
+  const uint64_t step = P.counters[P.counter_idx];
+  float h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = __ldg(P.h2 + (size_t)row * HID + l + 32 * i);
+  // the obs-part of the next network's input
+  const float* src = P.rows + (size_t)row * P.row_stride + P.src_off;
+  float* xr = P.xn + (size_t)row * P.ldn;
+  for (int k = l; k < P.O; k += 32) xr[k] = __ldg(src + k);
+  float u_mu = 0.f, u_ls = 0.f;  // lane a < A keeps head outputs a and A + a
+  for (int o = 0; o < P.out_dim; ++o) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
+    s = warp_sum(s) + __ldg(P.b3 + o);
+    if (o == l) u_mu = s;
+    if (o == P.A + l) u_ls = s;
+  }
+  float lp = 0.f;
+  if (l < P.A) {
+    const float lo = __ldg(P.min_ac + l), hi = __ldg(P.max_ac + l);
+    const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+    const int64_t e = (int64_t)row * P.A + l;
+    float act_v;
+    if (P.td3) {
+      float th;
+      act_v = td3_action(u_mu, scale, bias, th);
+      if (P.smoothing) {
+        const float z = noise_at(P.eps, e, P.seed, row, l, step, P.agent, P.stream_id);
+        if (P.eps_out) P.eps_out[e] = z;
+        float n = __fmul_rn(z, P.td3_std);
+        n = fminf(fmaxf(n, -P.td3_c), P.td3_c);
+        act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
+      }
+    } else {
+      const float z = noise_at(P.eps, e, P.seed, row, l, step, P.agent, P.stream_id);
+      if (P.eps_out) P.eps_out[e] = z;
+      const GaussSample gs = gauss_sample(u_mu, u_ls, z, scale, bias);
+      act_v = gs.action;
+      lp = gs.logp;
+    }
+    xr[P.O + l] = act_v;
+  }
+  if (P.logp) {
+    lp = warp_sum(lp);
+    if (l == 0) P.logp[row] = lp;
+  }
+}
+
+// ---- critic head: warp per row ------------------------------------------------------------------------------------------
+using WideQArgs = b2rl_wide_q_t;
+
+__global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant__ WideQArgs Q) {
+  __shared__ float sq_w[8];
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int row = blockIdx.x * 8 + w;
+  float sq = 0.f;
+  if (row < Q.M) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(__ldg(Q.w3 + l + 32 * i), __ldg(Q.h2 + (size_t)row * HID + l + 32 * i), s);
+    const float q = warp_sum(s) + __ldg(Q.b3);
+    if (l == 0) {
+      Q.q_out[row] = q;
+      if (Q.mode == 1) {  // agents/agent.py:212-233
+        const float q0 = Q.qn0[row], q1 = Q.qn1[row];
+        const float qmin = fminf(q0, q1);
+        float qp = Q.bcq_mix ? __fadd_rn(__fmul_rn(0.75f, qmin), __fmul_rn(0.25f, fmaxf(q0, q1))) : qmin;
+        if (!Q.td3) qp = __fsub_rn(qp, __fmul_rn(expf(Q.log_alpha[0]), Q.logp[row]));
+        const float* rr = Q.rows + (size_t)row * Q.row_stride + Q.rd_off;
+        const float y = __fadd_rn(rr[0], __fmul_rn(__fmul_rn(1.0f - rr[1], Q.gamma), qp));
+        if (Q.targ_out) Q.targ_out[row] = y;
+        const float dlt = q - y;
+        Q.dz3[(size_t)row * MAX_OUT] = dlt * (2.0f / (float)Q.M);
+        sq = dlt * dlt;
+      }
+    }
+  }
+  if (Q.mode == 1) {
+    if (l == 0) sq_w[w] = sq;
+    __syncthreads();
+    if (t == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += sq_w[i];
+      Q.sq_part[blockIdx.x] = s;
+    }
+  }
+}
+
+// ---- backward of the head and of layer 2's row-wise step: warp per row, 16 rows per warp, 128 per CTA -----------------
+// dh2[j] = sum_o dz3[row][o] * w3[o][j]; ReLU mask (recomputed from x-hat), LayerNorm backward -> dz2; per-CTA column
+// sums {sum dz, sum dn*xhat, sum dn} -> part[cta][3][256].
+constexpr int WB_ROWS = 128;
+__global__ void __launch_bounds__(256)
+wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __restrict__ w3, const float* __restrict__ xh,
+                   const float2* __restrict__ stat, const float* __restrict__ g, const float* __restrict__ be, int ln, int M,
+                   float* __restrict__ dz, float* __restrict__ part) {
+  extern __shared__ float wsm[];          // w3 [n_out][256], then the cross-warp reduction buffer [8][3][256]
+  float* w3s = wsm;
+  float* red = wsm + n_out * HID;
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  for (int i = t; i < n_out * HID; i += 256) w3s[i] = __ldg(w3 + i);
+  __syncthreads();
+  float gj[8], bj[8], sdz[8], sdx[8], sdn[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gj[i] = ln ? __ldg(g + l + 32 * i) : 1.f;
+    bj[i] = ln ? __ldg(be + l + 32 * i) : 0.f;
+    sdz[i] = sdx[i] = sdn[i] = 0.f;
+  }
+  const int r0 = blockIdx.x * WB_ROWS + w * (WB_ROWS / 8);
+  for (int rr = 0; rr < WB_ROWS / 8; ++rr) {
+    const int row = r0 + rr;
+    if (row >= M) break;
+    float dh[8], x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dh[i] = 0.f;
+      x[i] = __ldg(xh + (size_t)row * HID + l + 32 * i);
+    }
+    for (int o = 0; o < n_out; ++o) {
+      const float d = __ldg(dz3 + (size_t)row * MAX_OUT + o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dh[i] = fmaf(d, w3s[o * HID + l + 32 * i], dh[i]);
+    }
+    float dn[8], dx[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool on = ln ? (fmaf(x[i], gj[i], bj[i]) > 0.f) : (x[i] > 0.f);
+      dn[i] = on ? dh[i] : 0.f;
+      dx[i] = dn[i] * gj[i];
+      s1 += dx[i];
+      s2 = fmaf(dx[i], x[i], s2);
+    }
+    float rstd = 1.f, m1 = 0.f, m2 = 0.f;
+    if (ln) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      m1 = s1 * (1.0f / HID);
+      m2 = s2 * (1.0f / HID);
+      rstd = stat[row].y;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = ln ? rstd * (dx[i] - m1 - x[i] * m2) : dn[i];
+      dz[(size_t)row * HID + l + 32 * i] = z;
+      sdz[i] += z;
+      sdx[i] = fmaf(dn[i], x[i], sdx[i]);
+      sdn[i] += dn[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[(w * 3 + 0) * HID + l + 32 * i] = sdz[i];
+    red[(w * 3 + 1) * HID + l + 32 * i] = sdx[i];
+    red[(w * 3 + 2) * HID + l + 32 * i] = sdn[i];
+  }
+  __syncthreads();
+  for (int v = 0; v < 3; ++v) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += red[(ww * 3 + v) * HID + t];
+    part[((size_t)blockIdx.x * 3 + v) * HID + t] = s;
+  }
+}
+
+// ---- final reductions ----------------------------------------------------------------------------------------------------
+// G[off[v] + j] = sum_p part[p][v][j] (fixed order), v < 3 (v >= 1 only when layer_norm); block v handles vector v.
+__global__ void __launch_bounds__(256)
+wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G, int64_t off_b, int64_t off_g, int64_t off_be, int ln) {
+  const int v = blockIdx.x, j = threadIdx.x;
+  if (v > 0 && !ln) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int p = 0; p < P; ++p) s += part[((size_t)p * 3 + v) * HID + j];
+  G[(v == 0 ? off_b : v == 1 ? off_g : off_be) + j] = s;
+}
+// qf_loss = sum_k mean_b (q_k - y)^2  (agents/agent.py:233); d b3_k = sum_b dQ_k
+__global__ void __launch_bounds__(256)
+wide_critic_scalars_kernel(const float* __restrict__ sq0, const float* __restrict__ sq1, int P, const float* __restrict__ dz3_0,
+                           const float* __restrict__ dz3_1, int M, float* __restrict__ G, int64_t off_b3_0, int64_t off_b3_1,
+                           float* __restrict__ out) {
+  __shared__ float red[3][256];
+  const int t = threadIdx.x;
+  float a = 0.f, d0 = 0.f, d1 = 0.f;
+  for (int p = t; p < P; p += 256) a += sq0[p] + sq1[p];
+  for (int r = t; r < M; r += 256) {
+    d0 += dz3_0[(size_t)r * MAX_OUT];
+    d1 += dz3_1[(size_t)r * MAX_OUT];
+  }
+  red[0][t] = a; red[1][t] = d0; red[2][t] = d1;
+  __syncthreads();
+  if (t < 3) {
+    float s = 0.f;
+    for (int i = 0; i < 256; ++i) s += red[t][i];
+    if (t == 0) out[B2RL_OUT_QF_LOSS] = s / (float)M;
+    else G[t == 1 ? off_b3_0 : off_b3_1] = s;
+  }
+}
+
+// ---- launches ----------------------------------------------------------------------------------------------------------------
+cudaError_t init_wide() {
+  cudaError_t e = cudaFuncSetAttribute(wide_policy_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_OUT * HID * 4);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(wide_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_OUT + 24) * HID * 4);
+  cudaFuncAttributes fa;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_first_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_q_head_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_colsum_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_critic_scalars_kernel);
+  return e;
+}
+cudaError_t launch_wide_first(const float* X, int64_t ldx, int M, int K, const float* w1t, const float* b, const float* g,
+                              const float* be, int ln, float* H, float* XH, float* stat, cudaStream_t st) {
+  wide_first_kernel<<<(M + WF_ROWS - 1) / WF_ROWS, 256, 0, st>>>(X, ldx, M, K, w1t, b, g, be, ln, H, XH, reinterpret_cast<float2*>(stat));
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_policy_head(const WidePolicyArgs& p, cudaStream_t st) {
+  wide_policy_head_kernel<<<(p.M + 7) / 8, 256, (size_t)p.out_dim * HID * 4, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_q_head(const WideQArgs& q, cudaStream_t st) {
+  wide_q_head_kernel<<<(q.M + 7) / 8, 256, 0, st>>>(q);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_ln_bwd(const float* dz3, int n_out, const float* w3, const float* xh, const float* stat, const float* g,
+                               const float* be, int ln, int M, float* dz, float* part, cudaStream_t st) {
+  wide_ln_bwd_kernel<<<(M + WB_ROWS - 1) / WB_ROWS, 256, (size_t)(n_out + 24) * HID * 4, st>>>(
+      dz3, n_out, w3, xh, reinterpret_cast<const float2*>(stat), g, be, ln, M, dz, part);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
+                               cudaStream_t st) {
+  wide_colsum_kernel<<<3, 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float* dz3_0, const float* dz3_1, int M,
+                                       float* G, int64_t off0, int64_t off1, float* out, cudaStream_t st) {
+  wide_critic_scalars_kernel<<<1, 256, 0, st>>>(sq0, sq1, P, dz3_0, dz3_1, M, G, off0, off1, out);
+  return cudaGetLastError();
+}
+
+}  // namespace b2rl

