@@ -262,7 +262,7 @@ typedef struct b2rl_wide_q {  /* critic head; mode 1 adds the TD target, dLoss/d
   const float* rows;    /* reward at column rd_off, done at rd_off + 1 */
   const float* log_alpha;
   float* dz3;           /* [M][B2RL_MAX_OUT], column 0 */
-  float* sq_part;       /* [ceil(M/8)] */
+  float* sq_part;       /* [ceil(M/8)][2]: per-CTA {sum of squared errors, sum of dQ} */
   float* targ_out;      /* [M] or NULL */
   int32_t M, mode, row_stride, rd_off, td3, bcq_mix;
   float gamma;
@@ -277,7 +277,8 @@ int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const flo
 /* Column-sum partials -> gradients of bias / ln.weight / ln.bias at float offsets off_* of the gradient region G. */
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
                      void* stream);
-/* qf_loss -> out[B2RL_OUT_QF_LOSS] and the head-bias gradients of the twin critics. */
+/* qf_loss -> out[B2RL_OUT_QF_LOSS] and the head-bias gradients of the twin critics, from wide_q_head's per-CTA partials
+ * (sq0 / sq1 [P][2]; dz3_0 / dz3_1 are unused and may be NULL). */
 int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
                              float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream);
 /* The weight-gradient kernel on its own (wgrad.cu): reads rows, H1, H2, DZ1, DZ2, DZ3 of the workspace. skip_vectors:

@@ -254,7 +254,7 @@ int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int6
 }
 int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
                              float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream) {
-  if (!sq0 || !sq1 || !dz3_0 || !dz3_1 || !G || !out || P < 1 || M < 1) return fail(B2RL_E_INVALID, "wide_critic_scalars: bad arguments");
+  if (!sq0 || !sq1 || !G || !out || P < 1 || M < 1) return fail(B2RL_E_INVALID, "wide_critic_scalars: bad arguments");
   return check_launch(b2rl::launch_wide_critic_scalars(sq0, sq1, P, dz3_0, dz3_1, M, G, off_b3_0, off_b3_1, out, (cudaStream_t)stream),
                       "wide_critic_scalars");
 }

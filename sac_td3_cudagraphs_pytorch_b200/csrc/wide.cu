@@ -159,10 +159,10 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
 using WideQArgs = b2rl_wide_q_t;
 
 __global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant__ WideQArgs Q) {
-  __shared__ float sq_w[8];
+  __shared__ float sq_w[8], dq_w[8];
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const int row = blockIdx.x * 8 + w;
-  float sq = 0.f;
+  float sq = 0.f, dqv = 0.f;
   if (row < Q.M) {
     float s = 0.f;
 #pragma unroll
@@ -179,19 +179,21 @@ __global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant_
         const float y = __fadd_rn(rr[0], __fmul_rn(__fmul_rn(1.0f - rr[1], Q.gamma), qp));
         if (Q.targ_out) Q.targ_out[row] = y;
         const float dlt = q - y;
-        Q.dz3[(size_t)row * MAX_OUT] = dlt * (2.0f / (float)Q.M);
+        dqv = dlt * (2.0f / (float)Q.M);
+        Q.dz3[(size_t)row * MAX_OUT] = dqv;
         sq = dlt * dlt;
       }
     }
   }
   if (Q.mode == 1) {
-    if (l == 0) sq_w[w] = sq;
+    if (l == 0) { sq_w[w] = sq; dq_w[w] = dqv; }
     __syncthreads();
-    if (t == 0) {
-      float s = 0.f;
+    if (t == 0) {  // per-CTA partials {sum of squared errors, sum of dQ}: sq_part[2 * cta], [2 * cta + 1]
+      float s = 0.f, d = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += sq_w[i];
-      Q.sq_part[blockIdx.x] = s;
+      for (int i = 0; i < 8; ++i) { s += sq_w[i]; d += dq_w[i]; }
+      Q.sq_part[2 * blockIdx.x] = s;
+      Q.sq_part[2 * blockIdx.x + 1] = d;
     }
   }
 }
@@ -277,28 +279,36 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
 }
 
 // ---- final reductions ----------------------------------------------------------------------------------------------------
-// G[off[v] + j] = sum_p part[p][v][j] (fixed order), v < 3 (v >= 1 only when layer_norm); block v handles vector v.
+// G[off[v] + j] = sum_p part[p][v][j], v < 3 (v >= 1 only when layer_norm). Grid (8 column chunks, 3 vectors); thread
+// (c = t & 31, s = t >> 5) sums partials s, s + 8, ... of column 32 * chunk + c; fixed-order combine over s.
 __global__ void __launch_bounds__(256)
 wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G, int64_t off_b, int64_t off_g, int64_t off_be, int ln) {
-  const int v = blockIdx.x, j = threadIdx.x;
+  __shared__ float red[8][32];
+  const int v = blockIdx.y, t = threadIdx.x, c = t & 31, sl = t >> 5, j = blockIdx.x * 32 + c;
   if (v > 0 && !ln) return;
   float s = 0.f;
-#pragma unroll 8
-  for (int p = 0; p < P; ++p) s += part[((size_t)p * 3 + v) * HID + j];
-  G[(v == 0 ? off_b : v == 1 ? off_g : off_be) + j] = s;
+  for (int p = sl; p < P; p += 8) s += part[((size_t)p * 3 + v) * HID + j];
+  red[sl][c] = s;
+  __syncthreads();
+  if (sl == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += red[i][c];
+    G[(v == 0 ? off_b : v == 1 ? off_g : off_be) + j] = a;
+  }
 }
-// qf_loss = sum_k mean_b (q_k - y)^2  (agents/agent.py:233); d b3_k = sum_b dQ_k
+// qf_loss = sum_k mean_b (q_k - y)^2  (agents/agent.py:233); d b3_k = sum_b dQ_k. sq0 / sq1: the per-CTA partials
+// {sum sq, sum dQ} written by wide_q_head (online mode), P of them per critic.
 __global__ void __launch_bounds__(256)
-wide_critic_scalars_kernel(const float* __restrict__ sq0, const float* __restrict__ sq1, int P, const float* __restrict__ dz3_0,
-                           const float* __restrict__ dz3_1, int M, float* __restrict__ G, int64_t off_b3_0, int64_t off_b3_1,
-                           float* __restrict__ out) {
+wide_critic_scalars_kernel(const float* __restrict__ sq0, const float* __restrict__ sq1, int P, int M, float* __restrict__ G,
+                           int64_t off_b3_0, int64_t off_b3_1, float* __restrict__ out) {
   __shared__ float red[3][256];
   const int t = threadIdx.x;
   float a = 0.f, d0 = 0.f, d1 = 0.f;
-  for (int p = t; p < P; p += 256) a += sq0[p] + sq1[p];
-  for (int r = t; r < M; r += 256) {
-    d0 += dz3_0[(size_t)r * MAX_OUT];
-    d1 += dz3_1[(size_t)r * MAX_OUT];
+  for (int p = t; p < P; p += 256) {
+    a += sq0[2 * p] + sq1[2 * p];
+    d0 += sq0[2 * p + 1];
+    d1 += sq1[2 * p + 1];
   }
   red[0][t] = a; red[1][t] = d0; red[2][t] = d1;
   __syncthreads();
@@ -343,12 +353,12 @@ cudaError_t launch_wide_ln_bwd(const float* dz3, int n_out, const float* w3, con
 }
 cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
                                cudaStream_t st) {
-  wide_colsum_kernel<<<3, 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln);
+  wide_colsum_kernel<<<dim3(HID / 32, 3), 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln);
   return cudaGetLastError();
 }
-cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float* dz3_0, const float* dz3_1, int M,
-                                       float* G, int64_t off0, int64_t off1, float* out, cudaStream_t st) {
-  wide_critic_scalars_kernel<<<1, 256, 0, st>>>(sq0, sq1, P, dz3_0, dz3_1, M, G, off0, off1, out);
+cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float*, const float*, int M, float* G,
+                                       int64_t off0, int64_t off1, float* out, cudaStream_t st) {
+  wide_critic_scalars_kernel<<<1, 256, 0, st>>>(sq0, sq1, P, M, G, off0, off1, out);
   return cudaGetLastError();
 }
 

@@ -48,8 +48,14 @@ class DataParallelLearner:
     """One rank of the data-parallel learner. `agent` must be constructed identically on every rank (same
     torch seed => same initial parameters) except `agent_id=rank`, which keys its index/noise draws."""
 
-    def __init__(self, agent, rb, batch_size: int, comm: Optional[GradComm] = None):
+    def __init__(self, agent, rb, batch_size: int, comm: Optional[GradComm] = None, wide: Optional[str] = None):
+        """wide: None = row-group kernels; "3xtf32" / "tf32" = the critic step on the layer-by-layer tensor-core path
+        (wide.WideCritic), which is what a batch of tens of thousands wants."""
         self.agent, self.rb, self.B = agent, rb, int(batch_size)
+        self.wide = None
+        if wide:
+            from .wide import WideCritic
+            self.wide = WideCritic(agent, self.B, wide)
         self.comm = comm or GradComm()
         dev = agent.device
         self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
@@ -75,9 +81,12 @@ class DataParallelLearner:
         do_polyak = ag.td3 or ((ag.qnet_updates_so_far + 1) % h.crit_targ_update_freq == 0)
         delay = int(h.actor_update_delay) if do_actor else 0
 
-        args = ag.update_args(rows, eps=ag._noise(eps_q, rows))
-        fn = lib.b2rl_critic_update_td3 if ag.td3 else lib.b2rl_critic_update_sac
-        L.check(fn(C.byref(args), st), "critic_update")
+        if self.wide is not None:
+            self.wide.update_qnets(rows, eps=ag._noise(eps_q, rows), adam=False)
+        else:
+            args = ag.update_args(rows, eps=ag._noise(eps_q, rows))
+            fn = lib.b2rl_critic_update_td3 if ag.td3 else lib.b2rl_critic_update_sac
+            L.check(fn(C.byref(args), st), "critic_update")
         reduce_grad_span(ag.arena, lay, self.comm, "critic")
         segs = [self._seg(lay.critic[0].begin, lay.critic[1].end, float(h.qnets_lr), do_polyak, L.CTR_Q)]
         if ag.td3 and do_polyak and delay == 0:

@@ -40,7 +40,7 @@ class WideCritic:
         self.st1, self.st2 = torch.zeros(2, M, 2, **f32), torch.zeros(2, M, 2, **f32)
         self.P128, self.P8 = (M + 127) // 128, (M + 7) // 8
         self.part1, self.part2 = torch.zeros(2, self.P128, 3, 256, **f32), torch.zeros(2, self.P128, 3, 256, **f32)
-        self.sq = torch.zeros(2, self.P8, **f32)
+        self.sq = torch.zeros(2, self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
         self.ws = ag.workspace(M)
         self.wlo = torch.zeros(7, 256 * 256, **f32)  # lo parts of the seven 256x256 matrices a critic step multiplies by
 
@@ -55,8 +55,9 @@ class WideCritic:
         return self.ws.data_ptr() + 4 * (8 * self.M * 256 + slot * self.M * L.MAX_OUT)
 
     def update_qnets(self, rows: torch.Tensor, eps: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None,
-                     targ_out: Optional[torch.Tensor] = None) -> dict:
-        """rows: the sampled batch [M][row_stride] (replay.Batch.rows). Enqueue-only (graph-capturable)."""
+                     targ_out: Optional[torch.Tensor] = None, adam: bool = True) -> dict:
+        """rows: the sampled batch [M][row_stride] (replay.Batch.rows). Enqueue-only (graph-capturable).
+        adam=False: stop after the gradients (data parallel: all-reduce them, then step)."""
         ag, lib, M = self.ag, self._lib, self.M
         assert rows.shape == (M, ag.fmt.row_stride) and rows.is_contiguous()
         lay, st = ag.layout, ag._stream()
@@ -145,5 +146,6 @@ class WideCritic:
         args = ag.update_args(rows)
         L.check(lib.b2rl_wgrad(C.byref(args), 0, L.CTR_Q, 1, st), "wgrad")
         self._args = args
-        ag._launch_adam(ag.critic_segs(False))
+        if adam:
+            ag._launch_adam(ag.critic_segs(False))
         return {"loss/qf_loss": ag.out[L.OUT_QF_LOSS]}

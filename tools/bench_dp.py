@@ -17,6 +17,7 @@ from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+    wide = sys.argv[3] if len(sys.argv) > 3 and sys.argv[3] != "row" else None
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -29,7 +30,7 @@ def main():
     torch.manual_seed(0)
     ag = Agent({"ob_shape": (11,), "ac_shape": (3,)}, np.full(3, -1.0, np.float32), np.full(3, 1.0, np.float32), dev,
                sac_hps(batch_size=B), rb=rb, seed=11, agent_id=rank)
-    dp = DataParallelLearner(ag, rb, B, GradComm())
+    dp = DataParallelLearner(ag, rb, B, GradComm(), wide=wide)
     for i in range(3):
         dp.iteration(i)
     torch.cuda.synchronize()
@@ -48,7 +49,7 @@ def main():
         ms = float(el) / K * 1e3
         gf = 128.9 * (B / 65536)
         print(f"DP world={world} B={B}/gpu: {ms:.3f} ms/update, {1e3 / ms:.1f} updates/s, {world * B / ms * 1e3 / 1e6:.2f} M transitions/s, "
-              f"{world * gf / ms:.1f} TFLOP/s aggregate (fp32 FFMA path), finite={bool(torch.isfinite(ag.out).all())}, out={ag.out[:4].tolist()}", flush=True)
+              f"{world * gf / ms:.1f} TFLOP/s aggregate (critic: {wide or 'row-group FFMA2'} path), finite={bool(torch.isfinite(ag.out).all())}, out={ag.out[:4].tolist()}", flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
