@@ -241,6 +241,7 @@ typedef struct b2rl_wide_policy {  /* policy head + action sample (agents/nets.p
   float* eps_out;       /* or NULL */
   float* xn;            /* out [M][ldn]: [obs-part | action] */
   float* logp;          /* out [M] (SAC) or NULL */
+  float* save;          /* out [M][4][A] or NULL: eps, sigma, tanh(x), tanh(raw log-std) for the head's backward pass */
   const uint64_t* counters;
   int32_t M, O, A, out_dim, row_stride, ldn, src_off;
   int32_t td3, smoothing, counter_idx, stream_id;
@@ -281,6 +282,22 @@ int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int6
  * (sq0 / sq1 [P][2]; dz3_0 / dz3_1 are unused and may be NULL). */
 int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
                              float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream);
+/* Actor step, wide path (agents/agent.py:247-303). actor_loss: per-row loss and dLoss/dQ_k (column 0 of dzq_k
+ * [M][B2RL_MAX_OUT]; q1 / dzq1 NULL for TD3), per-CTA partials part [ceil(M/256)][2]. dqda: dQ/da = dz1 . w1t[O + a][:]
+ * (w1a = w1t + O * 256). actor_head_bwd: du [M][B2RL_MAX_OUT] = dLoss/d(head outputs) from dQ/da (summed over the
+ * critics) and the saved sampling intermediates; part_du [ceil(M/256)][B2RL_MAX_OUT]. actor_scalars: loss / mean
+ * log-prob / alpha -> out, d head.bias -> G. alpha_grad: alpha_state[1] <- alpha * mean(-logpi'' - targ_ent); follow
+ * with b2rl_alpha_adam. */
+int b2rl_wide_actor_loss(const float* q0, const float* q1, const float* logp, const float* log_alpha, int32_t td3, int32_t M,
+                         float* dzq0, float* dzq1, float* part, void* stream);
+int b2rl_wide_dqda(const float* dz1, const float* w1a, int32_t A, int32_t M, float* dqda, void* stream);
+int b2rl_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
+                             const float* max_ac, const float* log_alpha, int32_t td3, int32_t A, int32_t M, float* du,
+                             float* part_du, void* stream);
+int b2rl_wide_actor_scalars(const float* part_s, const float* part_du, int32_t P, int32_t M, int32_t out_dim, int32_t td3,
+                            const float* log_alpha, float* G, int64_t off_b3, float* out, void* stream);
+int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, void* stream);
+
 /* The weight-gradient kernel on its own (wgrad.cu): reads rows, H1, H2, DZ1, DZ2, DZ3 of the workspace. skip_vectors:
  * the bias / LayerNorm / loss reductions were done elsewhere (wide path). bump_counter: B2RL_CTR_* or -1. */
 int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream);

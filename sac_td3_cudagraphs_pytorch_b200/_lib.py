@@ -59,7 +59,7 @@ class AdamArgs(C.Structure):
 class WidePolicy(C.Structure):
     _fields_ = [("h2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p), ("rows", C.c_void_p), ("min_ac", C.c_void_p),
                 ("max_ac", C.c_void_p), ("eps", C.c_void_p), ("eps_out", C.c_void_p), ("xn", C.c_void_p), ("logp", C.c_void_p),
-                ("counters", C.c_void_p),
+                ("save", C.c_void_p), ("counters", C.c_void_p),
                 ("M", C.c_int32), ("O", C.c_int32), ("A", C.c_int32), ("out_dim", C.c_int32), ("row_stride", C.c_int32),
                 ("ldn", C.c_int32), ("src_off", C.c_int32), ("td3", C.c_int32), ("smoothing", C.c_int32),
                 ("counter_idx", C.c_int32), ("stream_id", C.c_int32), ("td3_std", C.c_float), ("td3_c", C.c_float),
@@ -103,6 +103,14 @@ SYMBOLS = {
     "b2rl_wide_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "b2rl_wide_critic_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b2rl_wide_actor_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "b2rl_wide_dqda": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b2rl_wide_actor_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_wide_actor_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "b2rl_wide_alpha_grad": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "b2rl_wgrad": (C.c_int, [C.POINTER(UpdateArgs), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_publish_logs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_critic_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),

@@ -39,6 +39,13 @@ cudaError_t launch_wide_policy_head(const b2rl_wide_policy_t&, cudaStream_t);
 cudaError_t launch_wide_q_head(const b2rl_wide_q_t&, cudaStream_t);
 cudaError_t launch_wide_ln_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int,
                                float*, float*, cudaStream_t);
+cudaError_t launch_wide_actor_loss(const float*, const float*, const float*, const float*, int, int, float*, float*, float*, cudaStream_t);
+cudaError_t launch_wide_dqda(const float*, const float*, int, int, float*, cudaStream_t);
+cudaError_t launch_wide_actor_head_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int,
+                                       int, float*, float*, cudaStream_t);
+cudaError_t launch_wide_actor_scalars(const float*, const float*, int, int, int, int, const float*, float*, int64_t, float*,
+                                      cudaStream_t);
+cudaError_t launch_wide_alpha_grad(const float*, int, float, float*, cudaStream_t);
 cudaError_t launch_wide_colsum(const float*, int, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
 cudaError_t launch_wide_critic_scalars(const float*, const float*, int, const float*, const float*, int, float*, int64_t, int64_t,
                                        float*, cudaStream_t);
@@ -257,6 +264,35 @@ int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, cons
   if (!sq0 || !sq1 || !G || !out || P < 1 || M < 1) return fail(B2RL_E_INVALID, "wide_critic_scalars: bad arguments");
   return check_launch(b2rl::launch_wide_critic_scalars(sq0, sq1, P, dz3_0, dz3_1, M, G, off_b3_0, off_b3_1, out, (cudaStream_t)stream),
                       "wide_critic_scalars");
+}
+int b2rl_wide_actor_loss(const float* q0, const float* q1, const float* logp, const float* log_alpha, int32_t td3, int32_t M,
+                         float* dzq0, float* dzq1, float* part, void* stream) {
+  if (!q0 || !dzq0 || !part || M < 1 || (!td3 && (!q1 || !dzq1 || !logp || !log_alpha)))
+    return fail(B2RL_E_INVALID, "wide_actor_loss: bad arguments");
+  return check_launch(b2rl::launch_wide_actor_loss(q0, q1, logp, log_alpha, td3, M, dzq0, dzq1, part, (cudaStream_t)stream), "wide_actor_loss");
+}
+int b2rl_wide_dqda(const float* dz1, const float* w1a, int32_t A, int32_t M, float* dqda, void* stream) {
+  if (!dz1 || !w1a || !dqda || A < 1 || A > 32 || M < 1) return fail(B2RL_E_INVALID, "wide_dqda: bad arguments");
+  return check_launch(b2rl::launch_wide_dqda(dz1, w1a, A, M, dqda, (cudaStream_t)stream), "wide_dqda");
+}
+int b2rl_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
+                             const float* max_ac, const float* log_alpha, int32_t td3, int32_t A, int32_t M, float* du,
+                             float* part_du, void* stream) {
+  if (!dqda0 || !save || !min_ac || !max_ac || !du || !part_du || A < 1 || A > 32 || M < 1 || (!td3 && !log_alpha))
+    return fail(B2RL_E_INVALID, "wide_actor_head_bwd: bad arguments");
+  return check_launch(b2rl::launch_wide_actor_head_bwd(dqda0, dqda1, save, min_ac, max_ac, log_alpha, td3, A, M, du, part_du,
+                                                       (cudaStream_t)stream), "wide_actor_head_bwd");
+}
+int b2rl_wide_actor_scalars(const float* part_s, const float* part_du, int32_t P, int32_t M, int32_t out_dim, int32_t td3,
+                            const float* log_alpha, float* G, int64_t off_b3, float* out, void* stream) {
+  if (!part_s || !part_du || !G || !out || P < 1 || M < 1 || out_dim < 1 || out_dim > B2RL_MAX_OUT)
+    return fail(B2RL_E_INVALID, "wide_actor_scalars: bad arguments");
+  return check_launch(b2rl::launch_wide_actor_scalars(part_s, part_du, P, M, out_dim, td3, log_alpha, G, off_b3, out, (cudaStream_t)stream),
+                      "wide_actor_scalars");
+}
+int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, void* stream) {
+  if (!logp2 || !alpha_state || M < 1) return fail(B2RL_E_INVALID, "wide_alpha_grad: bad arguments");
+  return check_launch(b2rl::launch_wide_alpha_grad(logp2, M, targ_ent, alpha_state, (cudaStream_t)stream), "wide_alpha_grad");
 }
 int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream) {
   if (int rc = check_update(a, actor_step != 0)) return rc;

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
     if (P.td3) {
       float th;
       act_v = td3_action(u_mu, scale, bias, th);
+      if (P.save) P.save[(size_t)row * 4 * P.A + 3 * P.A + l] = th;
       if (P.smoothing) {
         const float z = noise_at(P.eps, e, P.seed, row, l, step, P.agent, P.stream_id);
         if (P.eps_out) P.eps_out[e] = z;
@@ -146,6 +147,10 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
       const GaussSample gs = gauss_sample(u_mu, u_ls, z, scale, bias);
       act_v = gs.action;
       lp = gs.logp;
+      if (P.save) {  // what the head's backward pass needs: [M][4][A] = eps, sigma, tanh(x), tanh(raw log-std)
+        float* sv = P.save + (size_t)row * 4 * P.A;
+        sv[l] = z; sv[P.A + l] = gs.sigma; sv[2 * P.A + l] = gs.y; sv[3 * P.A + l] = gs.th;
+      }
     }
     xr[P.O + l] = act_v;
   }
@@ -320,6 +325,145 @@ wide_critic_scalars_kernel(const float* __restrict__ sq0, const float* __restric
   }
 }
 
+// ---- actor step: loss and dLoss/dQ per row (agents/agent.py:272-283); thread per row ------------------------------------
+// SAC  mean(alpha * logpi - min_k Q_k): the gradient goes to the arg-min critic (first index on ties, torch.min);
+// TD3  mean(-Q_0). dzq_k[row * MAX_OUT] <- dLoss/dQ_k; per-CTA partials {sum loss, sum logpi} -> part[cta][2].
+__global__ void __launch_bounds__(256)
+wide_actor_loss_kernel(const float* __restrict__ q0, const float* __restrict__ q1, const float* __restrict__ logp,
+                       const float* __restrict__ log_alpha, int td3, int M, float* __restrict__ dzq0, float* __restrict__ dzq1,
+                       float* __restrict__ part) {
+  __shared__ float red[2][8];
+  const int t = threadIdx.x, row = blockIdx.x * 256 + t;
+  float lossr = 0.f, lp = 0.f;
+  if (row < M) {
+    const float invM = 1.0f / (float)M;
+    const float a0 = q0[row];
+    float d0 = -invM, d1 = 0.f;
+    if (td3) {
+      lossr = -a0;
+    } else {
+      const float a1 = q1[row];
+      const bool first = a0 <= a1;
+      d0 = first ? -invM : 0.f;
+      d1 = first ? 0.f : -invM;
+      lp = logp[row];
+      lossr = __fsub_rn(__fmul_rn(expf(log_alpha[0]), lp), first ? a0 : a1);
+    }
+    dzq0[(size_t)row * MAX_OUT] = d0;
+    if (dzq1) dzq1[(size_t)row * MAX_OUT] = d1;
+  }
+  lossr = warp_sum(lossr);
+  lp = warp_sum(lp);
+  if ((t & 31) == 0) { red[0][t >> 5] = lossr; red[1][t >> 5] = lp; }
+  __syncthreads();
+  if (t < 2) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += red[t][i];
+    part[2 * blockIdx.x + t] = a;
+  }
+}
+
+// dQ/da[row][a] = sum_j dz1[row][j] * w1t[O + a][j]  (first-layer dX, action columns only); warp per row
+__global__ void __launch_bounds__(256)
+wide_dqda_kernel(const float* __restrict__ dz1, const float* __restrict__ w1a /* w1t + O * 256: [A][256] */, int A, int M,
+                 float* __restrict__ dqda) {
+  extern __shared__ float was[];
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  for (int i = t; i < A * HID; i += 256) was[i] = __ldg(w1a + i);
+  __syncthreads();
+  const int row = blockIdx.x * 8 + w;
+  if (row >= M) return;
+  float d[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] = __ldg(dz1 + (size_t)row * HID + l + 32 * i);
+  for (int a = 0; a < A; ++a) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(d[i], was[a * HID + l + 32 * i], s);
+    s = warp_sum(s);
+    if (l == 0) dqda[(size_t)row * A + a] = s;
+  }
+}
+
+// backward through the action head (agents/nets.py:143-147, :214-234): du[row][o] = dLoss/d(head output o); thread per row.
+// Per-CTA column sums of du (d head.bias) -> part_du[cta][MAX_OUT].
+__global__ void __launch_bounds__(256)
+wide_actor_head_bwd_kernel(const float* __restrict__ dqda0, const float* __restrict__ dqda1, const float* __restrict__ save,
+                           const float* __restrict__ min_ac, const float* __restrict__ max_ac, const float* __restrict__ log_alpha,
+                           int td3, int A, int M, float* __restrict__ du /* [M][MAX_OUT] */, float* __restrict__ part_du) {
+  __shared__ float red[8][MAX_OUT];
+  const int t = threadIdx.x, row = blockIdx.x * 256 + t, out = td3 ? A : 2 * A;
+  const bool live = row < M;
+  const float c_pi = td3 ? 0.f : expf(log_alpha[0]) / (float)M;
+  for (int a = 0; a < A; ++a) {
+    float g_a = 0.f, g_b = 0.f;
+    if (live) {
+      const float scale = (__ldg(max_ac + a) - __ldg(min_ac + a)) * 0.5f;
+      float ga = dqda0[(size_t)row * A + a];
+      if (dqda1) ga += dqda1[(size_t)row * A + a];
+      const float* sv = save + (size_t)row * 4 * A;
+      if (td3) {
+        const float th = sv[3 * A + a];
+        g_a = ga * scale * (1.0f - th * th);
+      } else {
+        GaussSample gs;
+        gs.sigma = sv[A + a]; gs.y = sv[2 * A + a]; gs.th = sv[3 * A + a];
+        gauss_backward(gs, sv[a], scale, ga, c_pi, g_a, g_b);
+      }
+      du[(size_t)row * MAX_OUT + a] = g_a;
+      if (!td3) du[(size_t)row * MAX_OUT + A + a] = g_b;
+    }
+    const float sa = warp_sum(g_a), sb = warp_sum(g_b);
+    if ((t & 31) == 0) {
+      red[t >> 5][a] = sa;
+      if (!td3) red[t >> 5][A + a] = sb;
+    }
+  }
+  __syncthreads();
+  if (t < out) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][t];
+    part_du[(size_t)blockIdx.x * MAX_OUT + t] = s;
+  }
+}
+
+// actor_loss, mean logpi, alpha -> out; d head.bias -> G. part_s [P][2], part_du [P][MAX_OUT] from the two kernels above.
+__global__ void __launch_bounds__(256)
+wide_actor_scalars_kernel(const float* __restrict__ part_s, const float* __restrict__ part_du, int P, int M, int out_dim, int td3,
+                          const float* __restrict__ log_alpha, float* __restrict__ G, int64_t off_b3, float* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t < out_dim) {
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += part_du[(size_t)p * MAX_OUT + t];
+    G[off_b3 + t] = s;
+  } else if (t >= 64 && t < 66) {
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += part_s[2 * p + (t - 64)];
+    if (t == 64) out[B2RL_OUT_ACTOR_LOSS] = s / (float)M;
+    else out[B2RL_OUT_LOGPI_MEAN] = s / (float)M;
+  } else if (t == 66 && !td3) {
+    out[B2RL_OUT_ALPHA] = expf(log_alpha[0]);
+  }
+}
+
+// temperature gradient (agents/agent.py:295-303): log_alpha state slot 1 <- alpha * mean(-logpi'' - targ_ent); one CTA
+__global__ void __launch_bounds__(256)
+wide_alpha_grad_kernel(const float* __restrict__ logp2, int M, float targ_ent, float* __restrict__ alpha_state) {
+  __shared__ float red[256];
+  const int t = threadIdx.x;
+  float s = 0.f;
+  for (int r = t; r < M; r += 256) s += (-logp2[r] - targ_ent);
+  red[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    float a = 0.f;
+    for (int i = 0; i < 256; ++i) a += red[i];
+    alpha_state[1] = expf(alpha_state[0]) * (a / (float)M);
+  }
+}
+
 // ---- launches ----------------------------------------------------------------------------------------------------------------
 cudaError_t init_wide() {
   cudaError_t e = cudaFuncSetAttribute(wide_policy_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_OUT * HID * 4);
@@ -330,6 +474,11 @@ cudaError_t init_wide() {
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_q_head_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_colsum_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_critic_scalars_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_actor_loss_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_dqda_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_actor_head_bwd_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_actor_scalars_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, wide_alpha_grad_kernel);
   return e;
 }
 cudaError_t launch_wide_first(const float* X, int64_t ldx, int M, int K, const float* w1t, const float* b, const float* g,
@@ -359,6 +508,31 @@ cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b
 cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float*, const float*, int M, float* G,
                                        int64_t off0, int64_t off1, float* out, cudaStream_t st) {
   wide_critic_scalars_kernel<<<1, 256, 0, st>>>(sq0, sq1, P, M, G, off0, off1, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wide_actor_loss(const float* q0, const float* q1, const float* logp, const float* log_alpha, int td3, int M,
+                                   float* dzq0, float* dzq1, float* part, cudaStream_t st) {
+  wide_actor_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(q0, q1, logp, log_alpha, td3, M, dzq0, dzq1, part);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_dqda(const float* dz1, const float* w1a, int A, int M, float* dqda, cudaStream_t st) {
+  wide_dqda_kernel<<<(M + 7) / 8, 256, (size_t)A * HID * 4, st>>>(dz1, w1a, A, M, dqda);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
+                                       const float* max_ac, const float* log_alpha, int td3, int A, int M, float* du,
+                                       float* part_du, cudaStream_t st) {
+  wide_actor_head_bwd_kernel<<<(M + 255) / 256, 256, 0, st>>>(dqda0, dqda1, save, min_ac, max_ac, log_alpha, td3, A, M, du, part_du);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_actor_scalars(const float* part_s, const float* part_du, int P, int M, int out_dim, int td3,
+                                      const float* log_alpha, float* G, int64_t off_b3, float* out, cudaStream_t st) {
+  wide_actor_scalars_kernel<<<1, 256, 0, st>>>(part_s, part_du, P, M, out_dim, td3, log_alpha, G, off_b3, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_wide_alpha_grad(const float* logp2, int M, float targ_ent, float* alpha_state, cudaStream_t st) {
+  wide_alpha_grad_kernel<<<1, 256, 0, st>>>(logp2, M, targ_ent, alpha_state);
   return cudaGetLastError();
 }
 

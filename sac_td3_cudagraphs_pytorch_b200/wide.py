@@ -18,7 +18,7 @@ import torch
 
 from . import _lib as L
 
-STREAM_CRITIC_EPS = 1  # csrc/rng.cuh
+STREAM_CRITIC_EPS, STREAM_ACTOR_EPS, STREAM_ALPHA_EPS = 1, 2, 3  # csrc/rng.cuh
 
 
 class WideCritic:
@@ -149,3 +149,184 @@ class WideCritic:
         if adam:
             ag._launch_adam(ag.critic_segs(False))
         return {"loss/qf_loss": ag.out[L.OUT_QF_LOSS]}
+
+
+class WideActor:
+    """``Agent.update_actor`` (agents/agent.py:244-318) on the wide path: actor forward, sample, twin Q with the
+    critics' parameters held constant, loss, backward through the arg-min critic down to its action inputs
+    (dQ/da), through the action head and the actor's two layers, weight gradients, Adam; then SAC's temperature
+    step with the UPDATED actor and fresh noise. Same conventions as WideCritic. Gradient clipping
+    (hps.clip_norm > 0) is not offered on this path."""
+
+    def __init__(self, agent, batch: int, precision: str = "3xtf32"):
+        assert precision in ("3xtf32", "tf32")
+        assert not agent.hps.clip_norm > 0, "the wide actor step has no gradient clipping: use the row-group path"
+        self.x3 = precision == "3xtf32"
+        self.ag, self.M = agent, int(batch)
+        ag, M, dev = agent, self.M, agent.device
+        self._lib = ag._lib
+        f32 = dict(dtype=torch.float32, device=dev)
+        O, A = ag.fmt.ob_dim, ag.ac_dim
+        self.ldn = (O + A + 3) & ~3
+        self.nq = 1 if ag.td3 else 2  # TD3's loss uses critic 0 only (agent.py:274-275)
+        self.t1, self.t2 = torch.empty(M, 256, **f32), torch.empty(M, 256, **f32)
+        self.xq = torch.zeros(M, self.ldn, **f32)                       # [obs | a_pi]
+        self.save = torch.zeros(M, 4, A, **f32)
+        self.logp, self.logp2 = torch.zeros(M, **f32), torch.zeros(M, **f32)
+        self.q = torch.zeros(2, M, **f32)
+        self.xa1, self.xa2 = torch.empty(M, 256, **f32), torch.empty(M, 256, **f32)       # actor x-hat
+        self.sa1, self.sa2 = torch.zeros(M, 2, **f32), torch.zeros(M, 2, **f32)
+        self.xq1, self.xq2 = torch.empty(2, M, 256, **f32), torch.empty(2, M, 256, **f32)  # critics' x-hat
+        self.sq1, self.sq2 = torch.zeros(2, M, 2, **f32), torch.zeros(2, M, 2, **f32)
+        self.dzq = torch.zeros(2, M, L.MAX_OUT, **f32)
+        self.dqda = torch.zeros(2, M, A, **f32)
+        self.P128, self.P256 = (M + 127) // 128, (M + 255) // 256
+        self.part = torch.zeros(2, self.P128, 3, 256, **f32)
+        self.part_s, self.part_du = torch.zeros(self.P256, 2, **f32), torch.zeros(self.P256, L.MAX_OUT, **f32)
+        self.ws = ag.workspace(M)
+        self.wlo = torch.zeros(6, 256 * 256, **f32)
+
+    _p = WideCritic._p
+    _ws = WideCritic._ws
+    _dz3 = WideCritic._dz3
+
+    def update_actor(self, rows: torch.Tensor, eps: Optional[torch.Tensor] = None, eps_alpha: Optional[torch.Tensor] = None,
+                     adam: bool = True) -> dict:
+        ag, lib, M = self.ag, self._lib, self.M
+        assert rows.shape == (M, ag.fmt.row_stride) and rows.is_contiguous()
+        lay, st = ag.layout, ag._stream()
+        O, A, rs = ag.fmt.ob_dim, ag.ac_dim, ag.fmt.row_stride
+        ln = int(bool(ag.hps.layer_norm))
+        RP, RG = L.REGION_P, 4
+        none = None
+        act, ao = lay.actor, lay.actor.off
+        la = ag._alpha_state.data_ptr()
+
+        def first(x_ptr, ldx, K, net, H, XH, stat):
+            o = net.off
+            L.check(lib.b2rl_wide_first(x_ptr, ldx, M, K, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
+                                        self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
+                                        H, XH, stat, st), "wide_first")
+
+        def lo_of(slot, w_ptr):
+            if not self.x3:
+                return none
+            dst = self.wlo[slot].data_ptr()
+            L.check(lib.b2rl_tc_split_lo(w_ptr, dst, 256 * 256, st), "tc_split_lo")
+            return dst
+
+        def hidden(x_ptr, net, H, XH, stat, slot):
+            o = net.off
+            w = self._p(RP, o["w2n"])
+            L.check(lib.b2rl_tc_linear(x_ptr, 256, M, w, lo_of(slot, w), self._p(RP, o["b2"]),
+                                       self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, 1,
+                                       H, XH, stat, st), "tc_linear")
+
+        def policy(h2_ptr, eps_t, stream_id, xn, logp, save):
+            p = L.WidePolicy()
+            p.h2, p.w3, p.b3 = h2_ptr, self._p(RP, ao["w3"]), self._p(RP, ao["b3"])
+            p.rows, p.min_ac, p.max_ac = rows.data_ptr(), ag.min_ac.data_ptr(), ag.max_ac.data_ptr()
+            p.eps, p.eps_out, p.xn, p.logp, p.save = L.ptr(eps_t), None, xn, logp, save
+            p.counters = ag.counters.data_ptr()
+            p.M, p.O, p.A, p.out_dim, p.row_stride, p.ldn, p.src_off = M, O, A, act.out_dim, rs, self.ldn, 0
+            p.td3, p.smoothing, p.counter_idx, p.stream_id = int(ag.td3), 0, L.CTR_PI, stream_id
+            p.td3_std, p.td3_c, p.seed, p.agent = 0.0, 0.0, ag._hyper.seed, ag.agent_id
+            L.check(lib.b2rl_wide_policy_head(C.byref(p), st), "wide_policy_head")
+
+        def bwd_layers(dz3_ptr, n_out, net, xh2, st2, xh1, st1, dz2_out, dz1_out, part, slot):
+            o = net.off
+            L.check(lib.b2rl_wide_ln_bwd(dz3_ptr, n_out, self._p(RP, o["w3"]), xh2, st2,
+                                         self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
+                                         dz2_out, part[0].data_ptr(), st), "wide_ln_bwd")
+            w2t = self._p(RP, o["w2t"])
+            L.check(lib.b2rl_tc_linear_bwd(dz2_out, M, w2t, lo_of(slot, w2t), xh1, st1,
+                                           self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
+                                           dz1_out, part[1].data_ptr(), st), "tc_linear_bwd")
+
+        # ---- actor forward on obs, sample (agent.py:251 / :254-255): H1 / H2 go to workspace slot 0 for wgrad
+        first(rows.data_ptr(), rs, O, act, self._ws(0, 0), self.xa1.data_ptr(), self.sa1.data_ptr())
+        hidden(self._ws(0, 0), act, self._ws(1, 0), self.xa2.data_ptr(), self.sa2.data_ptr(), 0)
+        policy(self._ws(1, 0), eps, STREAM_ACTOR_EPS, self.xq.data_ptr(), None if ag.td3 else self.logp.data_ptr(),
+               self.save.data_ptr())
+        # ---- Q_k(obs, a_pi) with the critics' parameters held constant (agent.py:272-278)
+        for k in range(self.nq):
+            net = lay.critic[k]
+            first(self.xq.data_ptr(), self.ldn, O + A, net, self.t1.data_ptr(), self.xq1[k].data_ptr(), self.sq1[k].data_ptr())
+            hidden(self.t1.data_ptr(), net, self.t2.data_ptr(), self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), 1 + k)
+            q = L.WideQ()
+            q.h2, q.w3, q.b3 = self.t2.data_ptr(), self._p(RP, net.off["w3"]), self._p(RP, net.off["b3"])
+            q.q_out, q.M, q.mode = self.q[k].data_ptr(), M, 0
+            L.check(lib.b2rl_wide_q_head(C.byref(q), st), "wide_q_head")
+        L.check(lib.b2rl_wide_actor_loss(self.q[0].data_ptr(), None if ag.td3 else self.q[1].data_ptr(),
+                                         None if ag.td3 else self.logp.data_ptr(), None if ag.td3 else la, int(ag.td3), M,
+                                         self.dzq[0].data_ptr(), None if ag.td3 else self.dzq[1].data_ptr(),
+                                         self.part_s.data_ptr(), st), "wide_actor_loss")
+        # ---- backward through critic k down to its action inputs
+        for k in range(self.nq):
+            net = lay.critic[k]
+            bwd_layers(self.dzq[k].data_ptr(), 1, net, self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), self.xq1[k].data_ptr(),
+                       self.sq1[k].data_ptr(), self.t1.data_ptr(), self.t2.data_ptr(), self.part, 3 + k)
+            L.check(lib.b2rl_wide_dqda(self.t2.data_ptr(), self._p(RP, net.off["w1t"]) + 4 * O * 256, A, M,
+                                       self.dqda[k].data_ptr(), st), "wide_dqda")
+        # ---- backward through the action head and the actor
+        G = self._p(RG, 0)
+        L.check(lib.b2rl_wide_actor_head_bwd(self.dqda[0].data_ptr(), None if ag.td3 else self.dqda[1].data_ptr(),
+                                             self.save.data_ptr(), ag.min_ac.data_ptr(), ag.max_ac.data_ptr(),
+                                             None if ag.td3 else la, int(ag.td3), A, M, self._dz3(0), self.part_du.data_ptr(), st),
+                "wide_actor_head_bwd")
+        bwd_layers(self._dz3(0), act.out_dim, act, self.xa2.data_ptr(), self.sa2.data_ptr(), self.xa1.data_ptr(),
+                   self.sa1.data_ptr(), self._ws(3, 0), self._ws(2, 0), self.part, 5)
+        L.check(lib.b2rl_wide_colsum(self.part[0].data_ptr(), self.P128, G, ao["b2"], ao["g2"] if ln else 0,
+                                     ao["be2"] if ln else 0, ln, st), "wide_colsum")
+        L.check(lib.b2rl_wide_colsum(self.part[1].data_ptr(), self.P128, G, ao["b1"], ao["g1"] if ln else 0,
+                                     ao["be1"] if ln else 0, ln, st), "wide_colsum")
+        L.check(lib.b2rl_wide_actor_scalars(self.part_s.data_ptr(), self.part_du.data_ptr(), self.P256, M, act.out_dim,
+                                            int(ag.td3), None if ag.td3 else la, G, ao["b3"], ag.out.data_ptr(), st),
+                "wide_actor_scalars")
+        args = ag.update_args(rows)
+        L.check(lib.b2rl_wgrad(C.byref(args), 1, L.CTR_PI, 1, st), "wgrad")
+        self._args = args
+        if not adam:
+            return {}
+        ag._launch_adam(ag.actor_segs(False))
+        out = {"loss/actor_loss": ag.out[L.OUT_ACTOR_LOSS]}
+        if ag.td3:
+            return out
+        if ag.autotune:
+            self.alpha_grad(rows, eps_alpha)
+            L.check(lib.b2rl_alpha_adam(la, ag.counters.data_ptr(), 1, float(ag.hps.log_alpha_lr), 1.0, ag.out.data_ptr(), st),
+                    "alpha_adam")
+            out["loss/alpha_loss"] = ag.out[L.OUT_ALPHA_LOSS]
+        out["vitals/alpha"] = ag.out[L.OUT_ALPHA]
+        return out
+
+    def alpha_grad(self, rows: torch.Tensor, eps_alpha: Optional[torch.Tensor] = None) -> None:
+        """agents/agent.py:295-300: log-prob of a fresh sample from the UPDATED actor; leaves the temperature's
+        gradient in its state slot 1 (finish with b2rl_alpha_adam, after an all-reduce when data parallel)."""
+        ag, lib, M = self.ag, self._lib, self.M
+        st, lay = ag._stream(), ag.layout
+        O, rs = ag.fmt.ob_dim, ag.fmt.row_stride
+        ln = int(bool(ag.hps.layer_norm))
+        act, o, RP = lay.actor, lay.actor.off, L.REGION_P
+        none = None
+        L.check(lib.b2rl_wide_first(rows.data_ptr(), rs, M, O, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
+                                    self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
+                                    self.t1.data_ptr(), none, none, st), "wide_first")
+        w = self._p(RP, o["w2n"])
+        wl = none
+        if self.x3:
+            wl = self.wlo[0].data_ptr()
+            L.check(lib.b2rl_tc_split_lo(w, wl, 256 * 256, st), "tc_split_lo")
+        L.check(lib.b2rl_tc_linear(self.t1.data_ptr(), 256, M, w, wl, self._p(RP, o["b2"]), self._p(RP, o["g2"]) if ln else none,
+                                   self._p(RP, o["be2"]) if ln else none, ln, 1, self.t2.data_ptr(), none, none, st), "tc_linear")
+        p = L.WidePolicy()
+        p.h2, p.w3, p.b3 = self.t2.data_ptr(), self._p(RP, o["w3"]), self._p(RP, o["b3"])
+        p.rows, p.min_ac, p.max_ac = rows.data_ptr(), ag.min_ac.data_ptr(), ag.max_ac.data_ptr()
+        p.eps, p.eps_out, p.xn, p.logp, p.save = L.ptr(eps_alpha), None, self.xq.data_ptr(), self.logp2.data_ptr(), None
+        p.counters = ag.counters.data_ptr()
+        p.M, p.O, p.A, p.out_dim, p.row_stride, p.ldn, p.src_off = M, O, ag.ac_dim, act.out_dim, rs, self.ldn, 0
+        p.td3, p.smoothing, p.counter_idx, p.stream_id = 0, 0, L.CTR_PI, STREAM_ALPHA_EPS
+        p.td3_std, p.td3_c, p.seed, p.agent = 0.0, 0.0, ag._hyper.seed, ag.agent_id
+        L.check(lib.b2rl_wide_policy_head(C.byref(p), st), "wide_policy_head")
+        L.check(lib.b2rl_wide_alpha_grad(self.logp2.data_ptr(), M, float(ag._hyper.targ_ent), ag._alpha_state.data_ptr(), st),
+                "wide_alpha_grad")

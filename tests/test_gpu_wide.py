@@ -69,3 +69,75 @@ def test_wide_critic_step_matches_oracle(name, precision):
         w = q.fc_stack.fc_block_2.fc.weight.detach()
         assert torch.equal(ag.arena.tensor(ag.layout.critic[k], "w2n"), w.contiguous())
     assert int(ag.counters[0]) == 1
+
+
+def kink_safe_actor(inp, batch, eps, margin=2e-5):
+    """As kink_safe, for the actor step: the actor's own layers on obs and the critics' layers on (obs, a_pi)."""
+    import numpy as np
+    ob = batch["observations"].double()
+    ok = torch.ones(ob.shape[0], dtype=torch.bool)
+    ln = bool(inp["hps"]["layer_norm"])
+
+    def trunk(x, q):
+        nonlocal ok
+        h = x
+        for blk in ("fc_block_1", "fc_block_2"):
+            z = h @ q[f"fc_stack.{blk}.fc.weight"].double().T + q[f"fc_stack.{blk}.fc.bias"].double()
+            if ln:
+                z = (z - z.mean(1, keepdim=True)) / torch.sqrt(z.var(1, unbiased=False, keepdim=True) + 1e-5)
+                z = z * q[f"fc_stack.{blk}.ln.weight"].double() + q[f"fc_stack.{blk}.ln.bias"].double()
+            ok &= z.abs().min(1).values > margin
+            h = torch.relu(z)
+        return h
+
+    a = inp["actor"]
+    u = trunk(ob, a) @ a["head.weight"].double().T + a["head.bias"].double()
+    lo, hi = torch.as_tensor(inp["min_ac"]).double(), torch.as_tensor(inp["max_ac"]).double()
+    scale, bias = (hi - lo) / 2, (hi + lo) / 2
+    A = inp["ac"]
+    if inp["hps"]["prefer_td3_over_sac"]:
+        act = torch.tanh(u) * scale + bias
+    else:
+        ls = -5.0 + 3.5 * (torch.tanh(u[:, A:]) + 1.0)
+        act = torch.tanh(u[:, :A] + eps.double() * torch.exp(ls)) * scale + bias
+    x = torch.cat([ob, act], 1)
+    trunk(x, inp["q1"])
+    trunk(x, inp["q2"])
+    return ok
+
+
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq"])
+def test_wide_actor_step_matches_oracle(name, precision):
+    from sac_td3_cudagraphs_pytorch_b200.replay import pack_rows
+    from sac_td3_cudagraphs_pytorch_b200.wide import WideActor
+    from tests.helpers import alpha_loss_scale
+    inp = case_inputs(name)
+    ag = make_agent(inp)
+    o32 = make_oracle(inp, torch.float32)
+    batch = batch_of(inp, 0)
+    e1, e2 = inp["eps_pi"][0][0], inp["eps_alpha"][0][0]
+    keep = kink_safe_actor(inp, batch, e1)
+    batch = {k: v[keep] for k, v in batch.items()}
+    e1, e2 = e1[keep].contiguous(), e2[keep].contiguous()
+    B = int(keep.sum())
+    assert B >= 0.75 * inp["B"]
+    rows = pack_rows({k: v.cuda() for k, v in batch.items()}, ag.fmt)
+    wa = WideActor(ag, B, precision)
+    TOL, GTOL = TOLS[precision]
+    out = wa.update_actor(rows, eps=e1.cuda(), eps_alpha=e2.cuda())
+    r32 = o32.update_actor(batch, e1, e2)
+    torch.cuda.synchronize()
+    for k in r32:
+        sc = alpha_loss_scale(inp["hps"]["alpha_init"], inp["ac"]) if k == "loss/alpha_loss" else None
+        d = rel_dev(out[k], r32[k], sc)
+        assert d <= 10 * TOL, f"{k}: {d:.3e}"
+    worst = 0.0
+    for n, p in ag.actor_params.items():
+        d = rel_dev(p.grad, o32.actor[n].grad)
+        worst = max(worst, d)
+        assert d <= GTOL, f"grad {n}: {d:.3e}"
+    print(f"\n[{name}] wide actor ({precision}, B={B}) vs fp32 oracle: worst gradient deviation {worst:.2e}")
+    if not ag.td3 and ag.autotune:
+        assert rel_dev(ag.log_alpha, o32.log_alpha) <= 1e-5
+    assert int(ag.counters[1]) == 1
