@@ -52,10 +52,12 @@ class DataParallelLearner:
         """wide: None = row-group kernels; "3xtf32" / "tf32" = the critic step on the layer-by-layer tensor-core path
         (wide.WideCritic), which is what a batch of tens of thousands wants."""
         self.agent, self.rb, self.B = agent, rb, int(batch_size)
-        self.wide = None
+        self.wide = self.wide_actor = None
         if wide:
-            from .wide import WideCritic
+            from .wide import WideActor, WideCritic
             self.wide = WideCritic(agent, self.B, wide)
+            if not agent.hps.clip_norm > 0:  # (the wide actor step has no gradient clipping)
+                self.wide_actor = WideActor(agent, self.B, wide)
         self.comm = comm or GradComm()
         dev = agent.device
         self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
@@ -97,8 +99,11 @@ class DataParallelLearner:
             e1 = None if eps_pi is None else eps_pi[j]
             e2 = None if eps_alpha is None else eps_alpha[j]
             args = ag.update_args(rows, eps=ag._noise(e1, rows), eps2=ag._noise(e2, rows))
-            fn = lib.b2rl_actor_update_td3 if ag.td3 else lib.b2rl_actor_update_sac
-            L.check(fn(C.byref(args), st), "actor_update")
+            if self.wide_actor is not None:
+                self.wide_actor.update_actor(rows, eps=ag._noise(e1, rows), adam=False)
+            else:
+                fn = lib.b2rl_actor_update_td3 if ag.td3 else lib.b2rl_actor_update_sac
+                L.check(fn(C.byref(args), st), "actor_update")
             reduce_grad_span(ag.arena, lay, self.comm, "actor")
             clip = h.clip_norm > 0
             if clip:  # clip_grad_norm_ acts on the averaged gradient: sum of squares AFTER the all-reduce
@@ -108,7 +113,10 @@ class DataParallelLearner:
             ag._launch_adam([self._seg(lay.actor.begin, lay.actor.end, float(h.actor_lr),
                                        ag.td3 and do_polyak and j == delay - 1, L.CTR_PI, clip)])
             if ag.autotune:
-                L.check(lib.b2rl_alpha_update(C.byref(args), 0.0, st), "alpha_update (gradient only)")
+                if self.wide_actor is not None:
+                    self.wide_actor.alpha_grad(rows, ag._noise(e2, rows))
+                else:
+                    L.check(lib.b2rl_alpha_update(C.byref(args), 0.0, st), "alpha_update (gradient only)")
                 self.comm.all_reduce_sum(ag._alpha_state[1:2])
                 L.check(lib.b2rl_alpha_adam(ag._alpha_state.data_ptr(), ag.counters.data_ptr(), 1,
                                             float(h.log_alpha_lr), 1.0 / W, ag.out.data_ptr(), st), "alpha_adam")
