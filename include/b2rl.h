@@ -298,6 +298,16 @@ int b2rl_wide_actor_scalars(const float* part_s, const float* part_du, int32_t P
                             const float* log_alpha, float* G, int64_t off_b3, float* out, void* stream);
 int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, void* stream);
 
+/* Weight gradient of one layer on the tensor cores (tc_wgrad.cu): C[m][n] = sum_b A[b][m] * Bm[b][n] for m < MA, with A
+ * [Bn][lda] (a_cols >= MA columns exist; 16-byte aligned rows) and Bm [Bn][256]; Ct, if not NULL, receives the transpose
+ * [256][MA]. Split over the batch, slices added in a fixed order. scratch: b2rl_tc_wgrad_scratch_floats(MA, Bn) floats.
+ * x3: 3xTF32 (fp32-level accuracy) or plain TF32. bump, if not NULL: a device counter incremented once (the update
+ * counter b2rl_wgrad advances: agents/agent.py:240 / :288 count optimizer steps). Replaces, for large batches, what
+ * loss.backward() does for the weights (agents/agent.py:235,283). */
+int b2rl_tc_wgrad(const float* A, int64_t lda, int32_t a_cols, int32_t MA, const float* Bm, int32_t Bn, float* C, float* Ct,
+                  float* scratch, int32_t x3, uint64_t* bump, void* stream);
+int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn);
+
 /* The weight-gradient kernel on its own (wgrad.cu): reads rows, H1, H2, DZ1, DZ2, DZ3 of the workspace. skip_vectors:
  * the bias / LayerNorm / loss reductions were done elsewhere (wide path). bump_counter: B2RL_CTR_* or -1. */
 int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream);

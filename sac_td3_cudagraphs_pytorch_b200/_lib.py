@@ -111,6 +111,9 @@ SYMBOLS = {
     "b2rl_wide_actor_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "b2rl_wide_alpha_grad": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "b2rl_tc_wgrad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "b2rl_tc_wgrad_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "b2rl_wgrad": (C.c_int, [C.POINTER(UpdateArgs), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_publish_logs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_critic_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),

@@ -20,7 +20,7 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libb2rl.so"
 STAMP = PKG / "csrc" / ".build_stamp"
 
-SOURCES = ["api.cu", "replay.cu", "critic.cu", "actor.cu", "wgrad.cu", "adam.cu", "tc_linear.cu", "wide.cu"]
+SOURCES = ["api.cu", "replay.cu", "critic.cu", "actor.cu", "wgrad.cu", "adam.cu", "tc_linear.cu", "wide.cu", "tc_wgrad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false" if False else "-Xcompiler", "-fPIC",

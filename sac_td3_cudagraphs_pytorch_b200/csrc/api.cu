@@ -31,6 +31,9 @@ cudaError_t init_adam();
 cudaError_t init_replay();
 cudaError_t init_tc();
 cudaError_t init_wide();
+cudaError_t init_tc_wgrad();
+int tc_wgrad_splits(int);
+cudaError_t launch_tc_wgrad(const float*, int64_t, int, int, const float*, int, float*, float*, float*, int, unsigned long long*, cudaStream_t);
 cudaError_t launch_wide_first(const float*, int64_t, int, int, const float*, const float*, const float*, const float*, int, float*,
                               float*, float*, cudaStream_t);
 cudaError_t launch_tc_linear_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*,
@@ -157,6 +160,7 @@ int b2rl_init(void) {
   if (e == cudaSuccess) e = b2rl::init_replay();
   if (e == cudaSuccess) e = b2rl::init_tc();
   if (e == cudaSuccess) e = b2rl::init_wide();
+  if (e == cudaSuccess) e = b2rl::init_tc_wgrad();
   if (e == cudaSuccess) {
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, b2rl::ffma_probe_kernel);
@@ -293,6 +297,18 @@ int b2rl_wide_actor_scalars(const float* part_s, const float* part_du, int32_t P
 int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, void* stream) {
   if (!logp2 || !alpha_state || M < 1) return fail(B2RL_E_INVALID, "wide_alpha_grad: bad arguments");
   return check_launch(b2rl::launch_wide_alpha_grad(logp2, M, targ_ent, alpha_state, (cudaStream_t)stream), "wide_alpha_grad");
+}
+int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn) {
+  if (MA < 1 || Bn < 1) return -1;
+  return (int64_t)b2rl::tc_wgrad_splits(Bn) * ((MA + 127) / 128 * 128) * B2RL_HID;
+}
+int b2rl_tc_wgrad(const float* A, int64_t lda, int32_t a_cols, int32_t MA, const float* Bm, int32_t Bn, float* C, float* Ct,
+                  float* scratch, int32_t x3, uint64_t* bump, void* stream) {
+  if (!A || !Bm || !C || !scratch || MA < 1 || a_cols < MA || lda < a_cols || (lda & 3) || Bn < 1)
+    return fail(B2RL_E_INVALID, "tc_wgrad: bad arguments");
+  if (!aligned16(A) || !aligned16(Bm) || !aligned16(C) || !aligned16(scratch)) return fail(B2RL_E_INVALID, "tc_wgrad: 16-byte aligned tensors");
+  if (Ct && (MA & 3)) return fail(B2RL_E_INVALID, "tc_wgrad: the transposed copy needs MA % 4 == 0");
+  return check_launch(b2rl::launch_tc_wgrad(A, lda, a_cols, MA, Bm, Bn, C, Ct, scratch, x3, (unsigned long long*)bump, (cudaStream_t)stream), "tc_wgrad");
 }
 int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream) {
   if (int rc = check_update(a, actor_step != 0)) return rc;

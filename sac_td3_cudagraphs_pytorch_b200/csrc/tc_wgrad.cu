@@ -1,0 +1,260 @@
+// tc_wgrad.cu — weight gradients for LARGE batches on the tensor cores:  D[m][n] = sum_b A[b][m] * Bm[b][n]
+// (dW1t = X0^T dZ1, dW2t = H1^T dZ2, dW3 = dZ3^T H2: the contraction over the batch that `loss.backward()` does for the
+// parameters, agents/agent.py:235,283). wgrad.cu's FFMA tiles each walk the whole batch and take 1 ms at B = 65 536;
+// here the batch is split over CTAs (split-K), each CTA accumulates a 128 x 256 tile in TMEM over its slice, and a second
+// kernel adds the slices in a fixed order (deterministic) and writes the transposed copy the w2n shadow needs.
+//
+// Both operands are MN-major (the batch index is the contraction and the slow one in memory). For 32-bit MN-major
+// operands tcgen05 accepts ONE shared-memory layout, SWIZZLE_128B_BASE32B (measured: with the plain 128-byte swizzle the
+// MMA returns zeros): 128-byte rows of 32 consecutive m, 32-byte units XORed with (row & 3), atoms of 4 batch rows —
+// in 16-byte units ((8,n),(4,k)):((1,LBO),(8,SBO)) (cute/atom/mma_traits_sm100.hpp). TMA writes exactly that with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and boxes of 32 columns x 32 batch rows: atoms 512 B apart (SBO), 32-column chunks
+// 4 KB apart (LBO). One tcgen05.mma kind::tf32 (K = 8) consumes two atoms (1 KB) of every chunk. PREC 1 = 3xTF32 as in tc_linear.cu (both operands are activations here: both lo parts are made in
+// shared memory by the epilogue warps).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace b2rl {
+
+constexpr int GM = 128, GN = 256, GK = 32, G_THREADS = 192;
+constexpr int G_A_BYTES = GM * GK * 4, G_B_BYTES = GN * GK * 4;  // 16 KB, 32 KB per stage
+
+template <int PREC>
+struct __align__(1024) GSmemT {
+  static constexpr int STAGES = PREC ? 2 : 4;
+  float a[STAGES][GM * GK];
+  float b[STAGES][GN * GK];
+  float alo[PREC ? STAGES : 1][PREC ? GM * GK : 4];
+  float blo[PREC ? STAGES : 1][PREC ? GN * GK : 4];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t gs32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n W_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra D_%=;\n bra W_%=;\n D_%=:\n}" ::"r"(gs32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void g_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(gs32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(gs32(bar))
+               : "memory");
+}
+// MN-major, SWIZZLE_128B_BASE32B (layout type 1): LBO = 4 KB between 32-column chunks [16,30), SBO = 512 B between 4-row atoms [32,46)
+__device__ __forceinline__ uint64_t g_desc(const void* smem, int byte_off) {
+  const uint64_t addr = (uint64_t)((gs32(smem) + (uint32_t)byte_off) & 0x3FFFFu) >> 4;
+  return addr | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+// as TC_IDESC of tc_linear.cu, with a_major = b_major = MN (bits 15, 16)
+constexpr uint32_t G_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GN >> 3) << 17) |
+                             ((uint32_t)(GM >> 4) << 24);
+__device__ __forceinline__ void g_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(
+      G_IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void g_split_lo(const float* src, float* dst, int n_float4, int et) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = et; i < n_float4; i += 128) {
+    const float4 x = s4[i];
+    float4 lo;
+    lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+    lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+    lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+    lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+    d4[i] = lo;
+  }
+}
+
+// grid (m tiles, splits): CTA (mt, sp) accumulates rows [sp * rows_per_split, ...) of the batch for output rows
+// [128 mt, 128 mt + 128) and writes its slice to part[sp][MA_pad][256].
+template <int PREC>
+__global__ void __launch_bounds__(G_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Bn, int rows_per_split,
+                int MA_pad, float* __restrict__ part) {
+  extern __shared__ unsigned char g_raw[];
+  using Smem = GSmemT<PREC>;
+  constexpr int ST = Smem::STAGES;
+  Smem& S = *reinterpret_cast<Smem*>(g_raw + ((1024u - (gs32(g_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GM, sp = blockIdx.y;
+  const int kb0 = sp * rows_per_split, kb1 = min(Bn, kb0 + rows_per_split);
+  const int KB = (max(kb1 - kb0, 0) + GK - 1) / GK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < ST; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.empty[s])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.lo_ready[s])), "r"(128) : "memory");
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_full)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gs32(&S.tmem_base)), "n"(GN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: 4 + 8 boxes of 32 columns x 32 batch rows per stage
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % ST;
+        if (kb >= ST) g_mbar_wait(&S.empty[s], ((kb / ST) - 1) & 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(G_A_BYTES + G_B_BYTES) : "memory");
+        const int row = kb0 + kb * GK;  // (rows beyond the batch are zero-filled by TMA: they add nothing)
+#pragma unroll
+        for (int c = 0; c < GM / 32; ++c) g_tma_2d(S.a[s] + c * 1024, &mapA, m0 + 32 * c, row, &S.full[s]);
+#pragma unroll
+        for (int c = 0; c < GN / 32; ++c) g_tma_2d(S.b[s] + c * 1024, &mapB, 32 * c, row, &S.full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % ST;
+        g_mbar_wait(&S.full[s], (kb / ST) & 1);
+        if constexpr (PREC == 1) g_mbar_wait(&S.lo_ready[s], (kb / ST) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < GK / 8; ++k) {  // 8 batch rows (two atoms, 1 KB) of every chunk per instruction
+          g_umma(tmem, g_desc(S.a[s], k * 1024), g_desc(S.b[s], k * 1024), (kb | k) != 0);
+          if constexpr (PREC == 1) {
+            g_umma(tmem, g_desc(S.alo[s], k * 1024), g_desc(S.b[s], k * 1024), 1);
+            g_umma(tmem, g_desc(S.a[s], k * 1024), g_desc(S.blo[s], k * 1024), 1);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gs32(&S.empty[s])) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gs32(&S.acc_full)) : "memory");
+    }
+  } else {  // ===== epilogue warps: lo parts while the ring runs (PREC 1), then TMEM -> this split's slice
+    const int et = threadIdx.x - 64, lg = warp & 3;
+    if constexpr (PREC == 1) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % ST;
+        g_mbar_wait(&S.full[s], (kb / ST) & 1);
+        g_split_lo(S.a[s], S.alo[s], GM * GK / 4, et);
+        g_split_lo(S.b[s], S.blo[s], GN * GK / 4, et);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.lo_ready[s])) : "memory");
+      }
+    }
+    float* dst = part + ((size_t)sp * MA_pad + m0 + 32 * lg + lane) * GN;
+    if (KB > 0) {
+      g_mbar_wait(&S.acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tl = tmem + ((uint32_t)(32 * lg) << 16);
+      for (int c = 0; c < GN / 32; ++c) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(tl + c * 32));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d4[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+      }
+    } else {  // an empty slice (more splits than slabs): zeros
+      for (int c = 0; c < GN / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(GN) : "memory");
+}
+
+// bump, if given, is incremented once (the update counter that wgrad.cu's extra CTA advances).
+// C[m][n] = sum_sp part[sp][m][n] for m < MA (fixed order); Ct [256][MA] = its transpose when given (MA = 256: the w2n shadow)
+__global__ void __launch_bounds__(256)
+tc_wgrad_reduce_kernel(const float* __restrict__ part, int S, int MA, int MA_pad, float* __restrict__ C, float* __restrict__ Ct,
+                       unsigned long long* bump) {
+  __shared__ float tile[32][33];
+  if (bump && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *bump += 1ull;  // the step's update counter (wgrad.cu's bump CTA)
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i;
+    float s = 0.f;
+    if (m < MA)
+      for (int sp = 0; sp < S; ++sp) s += part[((size_t)sp * MA_pad + m) * GN + n0 + tx];
+    tile[i][tx] = s;
+    if (m < MA) C[(size_t)m * GN + n0 + tx] = s;
+  }
+  if (Ct) {
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+      if (m0 + tx < MA) Ct[(size_t)(n0 + i) * MA + m0 + tx] = tile[tx][i];
+  }
+}
+
+typedef CUresult (*GEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static GEncodeFn g_encode() {
+  static GEncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (GEncodeFn)p;
+  }();
+  return fn;
+}
+// [rows][cols] fp32, pitch ld floats; boxes of 32 columns x 32 rows
+static bool g_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  GEncodeFn fn = g_encode();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)GK};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t init_tc_wgrad() {
+  cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<0>) + 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<1>) + 1024);
+  cudaFuncAttributes fa;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, tc_wgrad_reduce_kernel);
+  return e;
+}
+
+int tc_wgrad_splits(int Bn) {  // enough CTAs to fill the GPU, at least 4 slabs per CTA
+  int s = (Bn + 4 * GK - 1) / (4 * GK);
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+// A [Bn][lda] (columns 0..MA-1 used, a_cols columns exist), Bm [Bn][256] -> C [MA][256] (+ Ct [256][MA]); scratch >=
+// splits * MA_pad * 256 floats, MA_pad = MA rounded up to 128
+cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, const float* Bm, int Bn, float* C, float* Ct,
+                            float* scratch, int x3, unsigned long long* bump, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  if (!g_map(&ma, A, Bn, a_cols, lda) || !g_map(&mb, Bm, Bn, GN, GN)) return cudaErrorInvalidValue;
+  const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn);
+  const int rps = (((Bn + S - 1) / S) + GK - 1) / GK * GK;
+  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, scratch);
+  else tc_wgrad_kernel<0><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 31) / 32), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump);
+  return cudaGetLastError();
+}
+
+}  // namespace b2rl

@@ -21,6 +21,22 @@ from . import _lib as L
 STREAM_CRITIC_EPS, STREAM_ACTOR_EPS, STREAM_ALPHA_EPS = 1, 2, 3  # csrc/rng.cuh
 
 
+def _tc_wgrads(lib, ag, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, dz3, bump, st):
+    """dW1t = X0^T dZ1, dW2t = H1^T dZ2 (+ the w2n transposed shadow), dW3 = dZ3^T H2 of one network, on the tensor cores
+    (tc_wgrad.cu) into the arena's gradient region at G."""
+    o = net.off
+    f = lambda off: G + 4 * off
+    sc = scratch.data_ptr()
+    L.check(lib.b2rl_tc_wgrad(x0_ptr, ldx, ldx, net.in_dim, dz1, M, f(o["w1t"]), None, sc, x3, None, st), "tc_wgrad w1")
+    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), f(o["w2n"]), sc, x3, None, st), "tc_wgrad w2")
+    L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, st), "tc_wgrad w3")
+
+
+def _wgrad_scratch(lib, ag, M, dev):
+    mx = max(256, max(n.in_dim for n in [ag.layout.actor, *ag.layout.critic]))
+    return torch.empty(lib.b2rl_tc_wgrad_scratch_floats(mx, M), dtype=torch.float32, device=dev)
+
+
 class WideCritic:
     def __init__(self, agent, batch: int, precision: str = "3xtf32"):
         """precision: "3xtf32" (default; hi/lo operand split, three MMAs per product: fp32-level accuracy) or "tf32"
@@ -43,6 +59,7 @@ class WideCritic:
         self.sq = torch.zeros(2, self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
         self.ws = ag.workspace(M)
         self.wlo = torch.zeros(7, 256 * 256, **f32)  # lo parts of the seven 256x256 matrices a critic step multiplies by
+        self.gscratch = _wgrad_scratch(self._lib, ag, M, dev)
 
     # pointers into the arena: region r, float offset o
     def _p(self, region: int, off: int) -> int:
@@ -143,9 +160,9 @@ class WideCritic:
                                              lay.critic[0].off["b3"], lay.critic[1].off["b3"], ag.out.data_ptr(), st),
                 "wide_critic_scalars")
         # ---- weight gradients (wgrad.cu reads rows / H1 / H2 / DZ1 / DZ2 / DZ3 of the workspace), then Adam
-        args = ag.update_args(rows)
-        L.check(lib.b2rl_wgrad(C.byref(args), 0, L.CTR_Q, 1, st), "wgrad")
-        self._args = args
+        for k in range(2):
+            _tc_wgrads(lib, ag, M, int(self.x3), self.gscratch, G, lay.critic[k], rows.data_ptr(), rs, self._ws(0, k), self._ws(1, k),
+                       self._ws(2, k), self._ws(3, k), self._dz3(k), ag.counters.data_ptr() + 8 * L.CTR_Q if k == 1 else None, st)
         if adam:
             ag._launch_adam(ag.critic_segs(False))
         return {"loss/qf_loss": ag.out[L.OUT_QF_LOSS]}
@@ -185,6 +202,7 @@ class WideActor:
         self.part_s, self.part_du = torch.zeros(self.P256, 2, **f32), torch.zeros(self.P256, L.MAX_OUT, **f32)
         self.ws = ag.workspace(M)
         self.wlo = torch.zeros(6, 256 * 256, **f32)
+        self.gscratch = _wgrad_scratch(self._lib, ag, M, dev)
 
     _p = WideCritic._p
     _ws = WideCritic._ws
@@ -283,9 +301,8 @@ class WideActor:
         L.check(lib.b2rl_wide_actor_scalars(self.part_s.data_ptr(), self.part_du.data_ptr(), self.P256, M, act.out_dim,
                                             int(ag.td3), None if ag.td3 else la, G, ao["b3"], ag.out.data_ptr(), st),
                 "wide_actor_scalars")
-        args = ag.update_args(rows)
-        L.check(lib.b2rl_wgrad(C.byref(args), 1, L.CTR_PI, 1, st), "wgrad")
-        self._args = args
+        _tc_wgrads(lib, ag, M, int(self.x3), self.gscratch, G, act, rows.data_ptr(), rs, self._ws(0, 0), self._ws(1, 0),
+                   self._ws(2, 0), self._ws(3, 0), self._dz3(0), ag.counters.data_ptr() + 8 * L.CTR_PI, st)
         if not adam:
             return {}
         ag._launch_adam(ag.actor_segs(False))

@@ -48,3 +48,30 @@ def test_tc_linear_matches_torch(M, ln, relu, x3):
     assert eh <= tol and ex <= tol
     if ln:
         assert float((stat[:, 0].double() - mu[:, 0]).abs().max()) <= tol * 4
+
+
+@pytest.mark.parametrize("x3", [False, True])
+@pytest.mark.parametrize("Bn,MA,lda,transpose", [(4096, 256, 256, True), (1000, 14, 28, False), (300, 6, 64, False),
+                                                 (65536, 256, 256, True), (250, 393, 772, False)])
+def test_tc_wgrad_matches_torch(Bn, MA, lda, transpose, x3):
+    """C = A[:, :MA]^T . Bm on the tensor cores (MN-major operands, split over the batch) vs float64."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(Bn + MA)
+    A = torch.randn(Bn, lda, device="cuda", generator=g)
+    Bm = torch.randn(Bn, 256, device="cuda", generator=g)
+    Cc = torch.full((MA, 256), float("nan"), device="cuda")
+    Ct = torch.full((256, MA), float("nan"), device="cuda") if transpose else None
+    scratch = torch.empty(lib.b2rl_tc_wgrad_scratch_floats(MA, Bn), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b2rl_tc_wgrad(A.data_ptr(), lda, lda, MA, Bm.data_ptr(), Bn, Cc.data_ptr(), L.ptr(Ct), scratch.data_ptr(), int(x3), None, st),
+            "tc_wgrad")
+    torch.cuda.synchronize()
+    want = A[:, :MA].double().T @ Bm.double()
+    err = float((Cc.double() - want).abs().max()) / float(want.abs().max())
+    print(f"\nBn={Bn} MA={MA} 3xTF32={x3}: max rel err {err:.2e}")
+    # (the 65 536-row contraction chains 384 fp32 accumulations per TMEM element: fp32-class, not 4e-6)
+    assert err <= ((4e-6 if Bn <= 4096 else 2e-5) if x3 else 3e-3)
+    if transpose:
+        assert torch.equal(Ct, Cc.T.contiguous())
