@@ -11,8 +11,10 @@
 //            tcgen05.mma.cta_group::1.kind::tf32  M=128 N=256 K=8, four per k-slab, accumulating in TMEM;
 //            tcgen05.commit releases each ring slot back to the producer and finally signals the epilogue;
 //   warps 2-5 epilogue: thread <-> TMEM lane <-> one output ROW, so bias, the LayerNorm statistics (two passes over
-//            the row, all in registers: no shuffles, no shared memory), affine and ReLU are thread-local; rows are
-//            written with 128-bit stores.
+//            the row, no shuffles), affine and ReLU are thread-local. Per-column vectors sit in shared memory (as
+//            global loads they were 1280 exposed L1 round trips per warp and tile: ncu, long scoreboard); rows go
+//            to / come from global memory through a swizzled 32x32 per-warp tile so every warp instruction moves
+//            four full 128-byte row segments (thread-per-row stores touched 32 lines each).
 // Operands are fp32 in memory and are read by the tensor core as TF32 (10-bit mantissa, truncated): products carry
 // ~1e-3 relative error — the "looser stated bound" of the north star for tensor-core modes; the accumulation, the
 // LayerNorm and everything downstream are fp32. Both operands are K-major: X rows and the natural-layout weight
@@ -38,8 +40,10 @@ struct __align__(1024) TcSmemT {
   float blo[PREC ? STAGES : 1][PREC ? TCN * TCK : 4];
   uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full;
   uint32_t tmem_base;
-  // backward epilogue (MODE 2): per-warp 32x32 transposition tile and per-warp column-sum partials
-  float tile[4][32][33];
+  // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
+  // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials
+  alignas(128) float tile[4][32 * 32];
+  alignas(16) float cvec[3][HID];
   float wpart[4][3][HID];
 };
 
@@ -89,6 +93,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+
+// ---- the epilogue's staging tile: 32 rows x 32 fp32, 16-byte unit q of row r at unit q ^ (r & 7). Conflict-free for
+// thread-per-row float4 access (TMEM side), for 8-lanes-per-row float4 access (global side: 4 full 128-byte row
+// segments per warp instruction instead of 32 scattered 16-byte pieces) and for lane-per-column scalar reads.
+__device__ __forceinline__ float4* tile_q(float* t, int r, int q) { return reinterpret_cast<float4*>(t + r * 32 + ((q ^ (r & 7)) << 2)); }
+__device__ __forceinline__ void tile_put(float* t, int lane, const float (&v)[32]) {  // thread-per-row registers -> tile
+#pragma unroll
+  for (int q = 0; q < 8; ++q) *tile_q(t, lane, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+__device__ __forceinline__ void tile_get(float* t, int lane, float (&v)[32]) {  // tile -> thread-per-row registers
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 x = *tile_q(t, lane, q);
+    v[4 * q] = x.x, v[4 * q + 1] = x.y, v[4 * q + 2] = x.z, v[4 * q + 3] = x.w;
+  }
+}
+// tile -> rows of a [.][256] matrix at G (= row 0 of the tile, first column of the chunk), rows < rows_valid only
+__device__ __forceinline__ void tile_store(float* t, int lane, float* G, int rows_valid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), q = lane & 7;
+    if (r < rows_valid) *reinterpret_cast<float4*>(G + (size_t)r * TCN + q * 4) = *tile_q(t, r, q);
+  }
+}
+__device__ __forceinline__ void rows_fetch(const float* G, int lane, int rows_valid, float4 (&p)[8]) {  // global -> registers
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), q = lane & 7;
+    p[it] = r < rows_valid ? __ldg(reinterpret_cast<const float4*>(G + (size_t)r * TCN + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void rows_put(float* t, int lane, const float4 (&p)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) *tile_q(t, it * 4 + (lane >> 3), lane & 7) = p[it];
+}
+__device__ __forceinline__ float tile_colsum(const float* t, int lane) {  // sum over the 32 rows of column `lane`
+  float cs = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) cs += t[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)];
+  return cs;
 }
 
 // MODE 0: forward  H = [ReLU](LayerNorm(A . B^T + bias)), optional x-hat / statistics outputs.
@@ -155,10 +201,18 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       umma_commit(&S.acc_full);
     }
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
-    const int lg = warp & 3;
-    const int row = m0 + 32 * lg + lane;
+    const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
+    const int row0 = m0 + 32 * lg, row = row0 + lane;
+    const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
+    float* T = S.tile[ew];
+    for (int i = et; i < 3 * HID; i += 128) {  // per-column vectors: once per CTA into shared memory (broadcast reads)
+      const int q = i / HID, j = i - q * HID;
+      const float* src = q == 0 ? bias : q == 1 ? g : be;
+      S.cvec[q][j] = src ? __ldg(src + j) : (q == 1 ? 1.f : 0.f);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+    const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2];
     if constexpr (PREC == 1) {  // the activations' lo parts, stage by stage, while the ring runs
-      const int et = threadIdx.x - 64;
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % TC_STAGES;
         mbar_wait_(&S.full[s], (kb / TC_STAGES) & 1);
@@ -178,26 +232,26 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
       }
     }
-    mbar_wait_(&S.acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tl = tmem + ((uint32_t)(32 * lg) << 16);
     float v[32];
     if constexpr (MODE == 0) {
+      mbar_wait_(&S.acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float mean = 0.f, rstd = 1.f;
       if (ln) {
         float s1 = 0.f;
         for (int c = 0; c < TCN / 32; ++c) {
           tmem_ld32(tl + c * 32, v);
-  #pragma unroll
-          for (int i = 0; i < 32; ++i) s1 += v[i] + __ldg(bias + c * 32 + i);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s1 += v[i] + cb[c * 32 + i];
         }
         mean = s1 * (1.0f / TCN);
         float s2 = 0.f;
         for (int c = 0; c < TCN / 32; ++c) {
           tmem_ld32(tl + c * 32, v);
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float d = v[i] + __ldg(bias + c * 32 + i) - mean;
+            const float d = v[i] + cb[c * 32 + i] - mean;
             s2 = fmaf(d, d, s2);
           }
         }
@@ -207,88 +261,98 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int c = 0; c < TCN / 32; ++c) {
         tmem_ld32(tl + c * 32, v);
         float h[32];
-  #pragma unroll
+#pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int j = c * 32 + i;
-          float x = v[i] + __ldg(bias + j);
+          float x = v[i] + cb[j];
           if (ln) {
             x = (x - mean) * rstd;
             v[i] = x;  // x-hat
-            x = fmaf(x, __ldg(g + j), __ldg(be + j));
+            x = fmaf(x, cg[j], cbe[j]);
           } else {
             v[i] = x;  // pre-activation
           }
           h[i] = relu ? fmaxf(x, 0.f) : x;
         }
-        if (row < M) {
-          float4* hp = reinterpret_cast<float4*>(H + (size_t)row * TCN + c * 32);
-  #pragma unroll
-          for (int i = 0; i < 8; ++i) hp[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-          if (XH) {
-            float4* xp = reinterpret_cast<float4*>(XH + (size_t)row * TCN + c * 32);
-  #pragma unroll
-            for (int i = 0; i < 8; ++i) xp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
+        tile_put(T, lane, h);
+        __syncwarp();
+        tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+        __syncwarp();
+        if (XH) {
+          tile_put(T, lane, v);
+          __syncwarp();
+          tile_store(T, lane, XH + (size_t)row0 * TCN + c * 32, rows_valid);
+          __syncwarp();
         }
       }
     } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
       const bool live = row < M;
-      const float* xr = XH + (size_t)(live ? row : 0) * TCN;
+      const float* X0 = XH + (size_t)row0 * TCN;  // this warp's 32 rows of x-hat: fetched coalesced, one chunk ahead
+      float4 pf[8];
+      float x[32];
+      rows_fetch(X0, lane, rows_valid, pf);
+      mbar_wait_(&S.acc_full, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s1 = 0.f, s2 = 0.f;
       if (ln) {
         for (int c = 0; c < TCN / 32; ++c) {
+          rows_put(T, lane, pf);
+          __syncwarp();
+          tile_get(T, lane, x);
+          __syncwarp();
+          rows_fetch(X0 + ((c + 1) & 7) * 32, lane, rows_valid, pf);  // (the last one fetches chunk 0 for the second pass)
           tmem_ld32(tl + c * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = c * 32 + i;
-            const float x = live ? __ldg(xr + j) : 0.f, gj = __ldg(g + j);
-            const float dx = (fmaf(x, gj, __ldg(be + j)) > 0.f ? v[i] : 0.f) * gj;
+            const float gj = cg[j];
+            const float dx = (fmaf(x[i], gj, cbe[j]) > 0.f ? v[i] : 0.f) * gj;
             s1 += dx;
-            s2 = fmaf(dx, x, s2);
+            s2 = fmaf(dx, x[i], s2);
           }
         }
       }
       const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[row].y : 1.f;
-      const int ew = warp - 2;  // epilogue warp 0..3
       for (int c = 0; c < TCN / 32; ++c) {
+        rows_put(T, lane, pf);
+        __syncwarp();
+        tile_get(T, lane, x);
+        __syncwarp();
+        if (c + 1 < TCN / 32) rows_fetch(X0 + (c + 1) * 32, lane, rows_valid, pf);
         tmem_ld32(tl + c * 32, v);
-        float dz[32], dnx[32], dn[32];
+        float dz[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int j = c * 32 + i;
-          const float x = live ? __ldg(xr + j) : 0.f;
           if (ln) {
-            const float gj = __ldg(g + j);
-            dn[i] = fmaf(x, gj, __ldg(be + j)) > 0.f ? v[i] : 0.f;
-            dz[i] = rstd * (dn[i] * gj - m1 - x * m2);
+            const float gj = cg[j];
+            v[i] = fmaf(x[i], gj, cbe[j]) > 0.f ? v[i] : 0.f;  // dn: gradient at the LayerNorm output
+            dz[i] = rstd * (v[i] * gj - m1 - x[i] * m2);
           } else {
-            dn[i] = x > 0.f ? v[i] : 0.f;
-            dz[i] = dn[i];
+            v[i] = x[i] > 0.f ? v[i] : 0.f;
+            dz[i] = v[i];
           }
           if (!live) dz[i] = 0.f;
-          dnx[i] = dn[i] * x;
+          x[i] *= v[i];  // dn * x-hat
         }
-        if (live) {
-          float4* hp = reinterpret_cast<float4*>(H + (size_t)row * TCN + c * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) hp[i] = make_float4(dz[4 * i], dz[4 * i + 1], dz[4 * i + 2], dz[4 * i + 3]);
-        }
-        // column sums over this warp's 32 rows: transpose through the warp's tile, lane <-> column
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const float* src = q == 0 ? dz : q == 1 ? dnx : dn;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) S.tile[ew][lane][i] = src[i];
-          __syncwarp();
-          float cs = 0.f;
-#pragma unroll
-          for (int r = 0; r < 32; ++r) cs += S.tile[ew][r][lane];
-          S.wpart[ew][q][c * 32 + lane] = cs;
-          __syncwarp();
-        }
+        // dz: to global (coalesced through the tile) and its column sums; then the two LayerNorm-affine sums.
+        // Column sums over this warp's 32 rows: lane <-> column of the tile (deterministic, fixed order).
+        tile_put(T, lane, dz);
+        __syncwarp();
+        tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+        S.wpart[ew][0][c * 32 + lane] = tile_colsum(T, lane);
+        __syncwarp();
+        tile_put(T, lane, x);
+        __syncwarp();
+        S.wpart[ew][1][c * 32 + lane] = tile_colsum(T, lane);
+        __syncwarp();
+        tile_put(T, lane, v);
+        __syncwarp();
+        S.wpart[ew][2][c * 32 + lane] = tile_colsum(T, lane);
+        __syncwarp();
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-      for (int i = threadIdx.x - 64; i < 3 * HID; i += 128) {
+      for (int i = et; i < 3 * HID; i += 128) {
         const int q = i / HID, j = i - q * HID;
         part[((size_t)blockIdx.x * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
       }

@@ -12,8 +12,11 @@ for M in [int(x) for x in sys.argv[1:]] or [4096, 65536, 262144]:
     b = torch.randn(256, device="cuda"); g = torch.ones(256, device="cuda"); be = torch.zeros(256, device="cuda")
     H = torch.empty(M, 256, device="cuda"); XH = torch.empty(M, 256, device="cuda"); stat = torch.empty(M, 2, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    Wlo = torch.empty_like(W)
+    L.check(lib.b2rl_tc_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), st), "split")
+    x3 = False
     def ours(xh=True):
-        L.check(lib.b2rl_tc_linear(X.data_ptr(), 256, M, W.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(), 1, 1,
+        L.check(lib.b2rl_tc_linear(X.data_ptr(), 256, M, W.data_ptr(), Wlo.data_ptr() if x3 else None, b.data_ptr(), g.data_ptr(), be.data_ptr(), 1, 1,
                                    H.data_ptr(), XH.data_ptr() if xh else None, stat.data_ptr(), st), "tc")
     def ref():
         return torch.relu(torch.nn.functional.layer_norm(torch.addmm(b, X, W.t()), (256,), g, be))
@@ -27,8 +30,9 @@ for M in [int(x) for x in sys.argv[1:]] or [4096, 65536, 262144]:
         return e0.elapsed_time(e1) / n * 1e-3
     fl = 2.0 * M * 256 * 256
     t1, t1b = timeit(ours), timeit(lambda: ours(False))
+    x3 = True; t1x = timeit(ours); x3 = False
     torch.backends.cuda.matmul.allow_tf32 = False; t2 = timeit(ref)
     torch.backends.cuda.matmul.allow_tf32 = True; t3 = timeit(ref)
     by = M * 256 * 4
     print(f"M={M:7d}: b2rl_tc_linear {t1*1e6:8.1f} us = {fl/t1/1e12:6.1f} TFLOP/s, {3*by/t1/1e9:6.0f} GB/s (X in, H + XH out) | "
-          f"H only {t1b*1e6:8.1f} us {2*by/t1b/1e9:6.0f} GB/s | torch fp32 addmm+LN+ReLU {t2*1e6:8.1f} us | torch TF32 {t3*1e6:8.1f} us", flush=True)
+          f"3xTF32 {t1x*1e6:8.1f} us | H only {t1b*1e6:8.1f} us {2*by/t1b/1e9:6.0f} GB/s | torch fp32 addmm+LN+ReLU {t2*1e6:8.1f} us | torch TF32 {t3*1e6:8.1f} us", flush=True)
