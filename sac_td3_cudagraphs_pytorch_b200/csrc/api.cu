@@ -32,7 +32,7 @@ cudaError_t init_replay();
 cudaError_t init_tc();
 cudaError_t init_wide();
 cudaError_t init_tc_wgrad();
-int tc_wgrad_splits(int);
+int tc_wgrad_splits(int, int);
 cudaError_t launch_tc_wgrad(const float*, int64_t, int, int, const float*, int, float*, float*, float*, int, unsigned long long*, cudaStream_t);
 cudaError_t launch_wide_first(const float*, int64_t, int, int, const float*, const float*, const float*, const float*, int, float*,
                               float*, float*, cudaStream_t);
@@ -300,7 +300,7 @@ int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* a
 }
 int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn) {
   if (MA < 1 || Bn < 1) return -1;
-  return (int64_t)b2rl::tc_wgrad_splits(Bn) * ((MA + 127) / 128 * 128) * B2RL_HID;
+  return (int64_t)b2rl::tc_wgrad_splits(Bn, MA) * ((MA + 127) / 128 * 128) * B2RL_HID;
 }
 int b2rl_tc_wgrad(const float* A, int64_t lda, int32_t a_cols, int32_t MA, const float* Bm, int32_t Bn, float* C, float* Ct,
                   float* scratch, int32_t x3, uint64_t* bump, void* stream) {

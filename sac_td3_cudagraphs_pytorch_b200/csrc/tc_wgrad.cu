@@ -180,25 +180,36 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 }
 
 // bump, if given, is incremented once (the update counter that wgrad.cu's extra CTA advances).
-// C[m][n] = sum_sp part[sp][m][n] for m < MA (fixed order); Ct [256][MA] = its transpose when given (MA = 256: the w2n shadow)
+// C[m][n] = sum_sp part[sp][m][n] for m < MA (fixed order: four interleaved chains, then ((0+1)+(2+3))); Ct [256][MA] =
+// its transpose when given (MA = 256: the w2n shadow). One thread per output element: 32 columns x 8 rows per CTA.
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(const float* __restrict__ part, int S, int MA, int MA_pad, float* __restrict__ C, float* __restrict__ Ct,
                        unsigned long long* bump) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[8][33];
   if (bump && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *bump += 1ull;  // the step's update counter (wgrad.cu's bump CTA)
-  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int m = m0 + i;
-    float s = 0.f;
-    if (m < MA)
-      for (int sp = 0; sp < S; ++sp) s += part[((size_t)sp * MA_pad + m) * GN + n0 + tx];
-    tile[i][tx] = s;
-    if (m < MA) C[(size_t)m * GN + n0 + tx] = s;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int m = blockIdx.y * 8 + ty, n = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (m < MA) {
+    const float* src = part + (size_t)m * GN + n;
+    const size_t stride = (size_t)MA_pad * GN;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= S; sp += 4) {
+      a0 += src[(size_t)sp * stride];
+      a1 += src[(size_t)(sp + 1) * stride];
+      a2 += src[(size_t)(sp + 2) * stride];
+      a3 += src[(size_t)(sp + 3) * stride];
+    }
+    for (; sp < S; ++sp) a0 += src[(size_t)sp * stride];
+    s = (a0 + a1) + (a2 + a3);
+    C[(size_t)m * GN + n] = s;
   }
   if (Ct) {
+    tile[ty][tx] = s;
     __syncthreads();
-    for (int i = ty; i < 32; i += 8)
-      if (m0 + tx < MA) Ct[(size_t)(n0 + i) * MA + m0 + tx] = tile[tx][i];
+    const int mm = threadIdx.x & 7, nn = threadIdx.x >> 3;  // 8 consecutive m per 32-byte segment
+    if (blockIdx.y * 8 + mm < MA) Ct[(size_t)(blockIdx.x * 32 + nn) * MA + blockIdx.y * 8 + mm] = tile[mm][nn];
   }
 }
 
@@ -236,9 +247,11 @@ cudaError_t init_tc_wgrad() {
   return e;
 }
 
-int tc_wgrad_splits(int Bn) {  // enough CTAs to fill the GPU, at least 4 slabs per CTA
+int tc_wgrad_splits(int Bn, int MA) {  // one wave of 148 CTAs over (m tiles x splits), at least 4 slabs per CTA
+  const int mt = (MA + GM - 1) / GM;
+  const int cap = (148 + mt - 1) / mt;
   int s = (Bn + 4 * GK - 1) / (4 * GK);
-  return s < 1 ? 1 : (s > 64 ? 64 : s);
+  return s < 1 ? 1 : (s > cap ? cap : s);
 }
 
 // A [Bn][lda] (columns 0..MA-1 used, a_cols columns exist), Bm [Bn][256] -> C [MA][256] (+ Ct [256][MA]); scratch >=
@@ -247,13 +260,13 @@ cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, con
                             float* scratch, int x3, unsigned long long* bump, cudaStream_t st) {
   CUtensorMap ma, mb;
   if (!g_map(&ma, A, Bn, a_cols, lda) || !g_map(&mb, Bm, Bn, GN, GN)) return cudaErrorInvalidValue;
-  const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn);
+  const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn, MA);
   const int rps = (((Bn + S - 1) / S) + GK - 1) / GK * GK;
   if (x3) tc_wgrad_kernel<1><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, scratch);
   else tc_wgrad_kernel<0><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 31) / 32), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump);
+  tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump);
   return cudaGetLastError();
 }
 

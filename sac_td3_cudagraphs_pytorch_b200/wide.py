@@ -33,8 +33,8 @@ def _tc_wgrads(lib, ag, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, d
 
 
 def _wgrad_scratch(lib, ag, M, dev):
-    mx = max(256, max(n.in_dim for n in [ag.layout.actor, *ag.layout.critic]))
-    return torch.empty(lib.b2rl_tc_wgrad_scratch_floats(mx, M), dtype=torch.float32, device=dev)
+    dims = {1, 256} | {n.in_dim for n in [ag.layout.actor, *ag.layout.critic]}
+    return torch.empty(max(lib.b2rl_tc_wgrad_scratch_floats(d, M) for d in dims), dtype=torch.float32, device=dev)
 
 
 class WideCritic:
