@@ -4,10 +4,11 @@
 // config 5, batch 65 536; stacked populations), where the row-group kernels of mlp_cluster.cuh stream every layer's
 // weights from L2 once per 8 rows and top out at ~10 TFLOP/s.
 //
-// One CTA per 128-row tile, warp-specialised (192 threads):
+// Persistent CTAs (one per SM) over 128-row tiles, warp-specialised (256 threads); two TMEM accumulator buffers, so the
+// epilogue of one tile overlaps the loads and MMAs of the next:
 //   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of the A tile (128 x 32 fp32) and of the whole weight
 //            k-slab (256 x 32 fp32) into a 4-stage shared-memory ring, 128-byte swizzle, completion on mbarriers;
-//   warp 1   TMEM allocation (256 columns) and the MMA issuer: one elected thread issues
+//   warp 1   TMEM allocation (2 x 256 columns) and the MMA issuer: one elected thread issues
 //            tcgen05.mma.cta_group::1.kind::tf32  M=128 N=256 K=8, four per k-slab, accumulating in TMEM;
 //            tcgen05.commit releases each ring slot back to the producer and finally signals the epilogue;
 //   warps 2-5 epilogue: thread <-> TMEM lane <-> one output ROW, so bias, the LayerNorm statistics (two passes over
@@ -15,6 +16,7 @@
 //            global loads they were 1280 exposed L1 round trips per warp and tile: ncu, long scoreboard); rows go
 //            to / come from global memory through a swizzled 32x32 per-warp tile so every warp instruction moves
 //            four full 128-byte row segments (thread-per-row stores touched 32 lines each).
+//   warps 6-7 (3xTF32 only) split each arriving activation slab into its lo part for the second MMA.
 // Operands are fp32 in memory and are read by the tensor core as TF32 (10-bit mantissa, truncated): products carry
 // ~1e-3 relative error — the "looser stated bound" of the north star for tensor-core modes; the accumulation, the
 // LayerNorm and everything downstream are fp32. Both operands are K-major: X rows and the natural-layout weight
@@ -25,7 +27,7 @@
 
 namespace b2rl {
 
-constexpr int TCM = 128, TCN = 256, TCK = 32, TC_THREADS = 192;
+constexpr int TCM = 128, TCN = 256, TCK = 32, TC_THREADS = 256;
 // PREC 0: TF32 products (operands truncated to 10 mantissa bits by the tensor core), 4-stage ring.
 // PREC 1: "3xTF32": x = hi + lo with hi = the TF32 truncation the tensor core applies anyway and lo = x - hi (exact in
 //         fp32, re-truncated to TF32: 2^-21 of x); a.b ~ hi.hi + lo.hi + hi.lo, three MMAs into the same accumulator —
@@ -38,7 +40,7 @@ struct __align__(1024) TcSmemT {
   float b[STAGES][TCN * TCK];  // 32 KB per stage
   float alo[PREC ? STAGES : 1][PREC ? TCM * TCK : 4];
   float blo[PREC ? STAGES : 1][PREC ? TCN * TCK : 4];
-  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full;
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
   // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials
@@ -153,15 +155,18 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN * (PREC ? 2 : 1)) * TCK * sizeof(float);
   Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TCM;
+  const int n_tiles = (M + TCM - 1) / TCM;
+  // persistent: this CTA's tiles are blockIdx.x, + gridDim.x, ...; local tile i accumulates in TMEM buffer i & 1, so the
+  // epilogue of tile i runs while the ring and the tensor core work on tile i + 1
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 1); mbar_init_(&S.lo_ready[s], 128); }
-    mbar_init_(&S.acc_full, 1);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 1); mbar_init_(&S.lo_ready[s], 64); }
+    for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 256 fp32 columns x 128 lanes for the accumulator tile
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&S.tmem_base)), "n"(TCN) : "memory");
+  if (warp == 1) {  // TMEM: two accumulator tiles of 256 fp32 columns x 128 lanes (all 512 columns: one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&S.tmem_base)), "n"(2 * TCN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -171,39 +176,72 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr int KB = HID / TCK;  // 8 k-slabs
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % TC_STAGES;
-        if (kb >= TC_STAGES) mbar_wait_(&S.empty[s], ((kb / TC_STAGES) - 1) & 1);
-        mbar_expect_(&S.full[s], TC_STAGE_BYTES);
-        tma_load_2d(S.a[s], &mapA, kb * TCK, m0, &S.full[s]);
-        tma_load_2d(S.b[s], &mapB, kb * TCK, 0, &S.full[s]);
-        if constexpr (PREC == 1) tma_load_2d(S.blo[s], &mapBlo, kb * TCK, 0, &S.full[s]);
+    if (lane == 0) {  // ===== TMA producer: the ring runs on across tiles
+      int it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TCM;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          if (it >= TC_STAGES) mbar_wait_(&S.empty[s], ((it / TC_STAGES) - 1) & 1);
+          mbar_expect_(&S.full[s], TC_STAGE_BYTES);
+          tma_load_2d(S.a[s], &mapA, kb * TCK, m0, &S.full[s]);
+          tma_load_2d(S.b[s], &mapB, kb * TCK, 0, &S.full[s]);
+          if constexpr (PREC == 1) tma_load_2d(S.blo[s], &mapBlo, kb * TCK, 0, &S.full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % TC_STAGES;
-        mbar_wait_(&S.full[s], (kb / TC_STAGES) & 1);
-        if constexpr (PREC == 1) mbar_wait_(&S.lo_ready[s], (kb / TC_STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < TCK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: advance inside the 128-byte swizzle row
-          umma_tf32(tmem, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
-          if constexpr (PREC == 1) {
-            umma_tf32(tmem, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
-            umma_tf32(tmem, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
-          }
+      int it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i & 1;
+        const uint32_t acc = tmem + buf * TCN;
+        if (i >= 2) {  // the epilogue must have drained this buffer (tile i - 2)
+          mbar_wait_(&S.acc_empty[buf], ((i >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        umma_commit(&S.empty[s]);  // (implies tcgen05.fence::before_thread_sync)
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait_(&S.full[s], (it / TC_STAGES) & 1);
+          if constexpr (PREC == 1) mbar_wait_(&S.lo_ready[s], (it / TC_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < TCK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: advance inside the 128-byte swizzle row
+            umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
+            if constexpr (PREC == 1) {
+              umma_tf32(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
+              umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+            }
+          }
+          umma_commit(&S.empty[s]);  // (implies tcgen05.fence::before_thread_sync)
+        }
+        umma_commit(&S.acc_full[buf]);
       }
-      umma_commit(&S.acc_full);
+    }
+  } else if (warp >= 6) {  // ===== (3xTF32) the activations' lo parts, slab by slab as the ring fills
+    if constexpr (PREC == 1) {
+      const int lt = threadIdx.x - 192;  // 0..63
+      for (int it = 0; it < my_tiles * KB; ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait_(&S.full[s], (it / TC_STAGES) & 1);
+        const float4* src = reinterpret_cast<const float4*>(S.a[s]);
+        float4* dst = reinterpret_cast<float4*>(S.alo[s]);
+#pragma unroll 4
+        for (int i = 0; i < TCM * TCK / 4 / 64; ++i) {  // element-wise, so the swizzled layout carries over
+          const float4 x = src[lt + 64 * i];
+          float4 lo;
+          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          dst[lt + 64 * i] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
+      }
     }
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
     const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
-    const int row0 = m0 + 32 * lg, row = row0 + lane;
-    const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
     float* T = S.tile[ew];
     for (int i = et; i < 3 * HID; i += 128) {  // per-column vectors: once per CTA into shared memory (broadcast reads)
       const int q = i / HID, j = i - q * HID;
@@ -212,155 +250,159 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
     const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2];
-    if constexpr (PREC == 1) {  // the activations' lo parts, stage by stage, while the ring runs
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % TC_STAGES;
-        mbar_wait_(&S.full[s], (kb / TC_STAGES) & 1);
-        const float4* src = reinterpret_cast<const float4*>(S.a[s]);
-        float4* dst = reinterpret_cast<float4*>(S.alo[s]);
-#pragma unroll
-        for (int i = 0; i < TCM * TCK / 4 / 128; ++i) {  // element-wise, so the swizzled layout carries over
-          const float4 x = src[et + 128 * i];
-          float4 lo;
-          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          dst[et + 128 * i] = lo;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
-      }
-    }
-    const uint32_t tl = tmem + ((uint32_t)(32 * lg) << 16);
     float v[32];
-    if constexpr (MODE == 0) {
-      mbar_wait_(&S.acc_full, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float mean = 0.f, rstd = 1.f;
-      if (ln) {
-        float s1 = 0.f;
-        for (int c = 0; c < TCN / 32; ++c) {
-          tmem_ld32(tl + c * 32, v);
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x, buf = ti & 1;
+      const int row0 = tile * TCM + 32 * lg, row = row0 + lane;
+      const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
+      const uint32_t tl = tmem + buf * TCN + ((uint32_t)(32 * lg) << 16);
+      if constexpr (MODE == 0) {
+        mbar_wait_(&S.acc_full[buf], (ti >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float mean = 0.f, rstd = 1.f;
+        if (ln) {
+          float s1 = 0.f;
+          for (int c = 0; c < TCN / 32; ++c) {
+            tmem_ld32(tl + c * 32, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s1 += v[i] + cb[c * 32 + i];
+            for (int i = 0; i < 32; ++i) s1 += v[i] + cb[c * 32 + i];
+          }
+          mean = s1 * (1.0f / TCN);
+          float s2 = 0.f;
+          for (int c = 0; c < TCN / 32; ++c) {
+            tmem_ld32(tl + c * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float d = v[i] + cb[c * 32 + i] - mean;
+              s2 = fmaf(d, d, s2);
+            }
+          }
+          rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
+          if (stat && row < M) stat[row] = make_float2(mean, rstd);
         }
-        mean = s1 * (1.0f / TCN);
-        float s2 = 0.f;
         for (int c = 0; c < TCN / 32; ++c) {
           tmem_ld32(tl + c * 32, v);
+          if (c == TCN / 32 - 1) {  // last TMEM read of this tile: hand the buffer back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
+          }
+          float h[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float d = v[i] + cb[c * 32 + i] - mean;
-            s2 = fmaf(d, d, s2);
+            const int j = c * 32 + i;
+            float x = v[i] + cb[j];
+            if (ln) {
+              x = (x - mean) * rstd;
+              v[i] = x;  // x-hat
+              x = fmaf(x, cg[j], cbe[j]);
+            } else {
+              v[i] = x;  // pre-activation
+            }
+            h[i] = relu ? fmaxf(x, 0.f) : x;
+          }
+          tile_put(T, lane, h);
+          __syncwarp();
+          tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+          __syncwarp();
+          if (XH) {
+            tile_put(T, lane, v);
+            __syncwarp();
+            tile_store(T, lane, XH + (size_t)row0 * TCN + c * 32, rows_valid);
+            __syncwarp();
           }
         }
-        rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
-        if (stat && row < M) stat[row] = make_float2(mean, rstd);
-      }
-      for (int c = 0; c < TCN / 32; ++c) {
-        tmem_ld32(tl + c * 32, v);
-        float h[32];
+      } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
+        const bool live = row < M;
+        const float* X0 = XH + (size_t)row0 * TCN;  // this warp's 32 rows of x-hat: fetched coalesced, one chunk ahead
+        float4 pf[8];
+        float x[32];
+        rows_fetch(X0, lane, rows_valid, pf);
+        mbar_wait_(&S.acc_full[buf], (ti >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float s1 = 0.f, s2 = 0.f;
+        if (ln) {
+          for (int c = 0; c < TCN / 32; ++c) {
+            rows_put(T, lane, pf);
+            __syncwarp();
+            tile_get(T, lane, x);
+            __syncwarp();
+            rows_fetch(X0 + ((c + 1) & 7) * 32, lane, rows_valid, pf);  // (the last one fetches chunk 0 for the second pass)
+            tmem_ld32(tl + c * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = c * 32 + i;
-          float x = v[i] + cb[j];
-          if (ln) {
-            x = (x - mean) * rstd;
-            v[i] = x;  // x-hat
-            x = fmaf(x, cg[j], cbe[j]);
-          } else {
-            v[i] = x;  // pre-activation
+            for (int i = 0; i < 32; ++i) {
+              const int j = c * 32 + i;
+              const float gj = cg[j];
+              const float dx = (fmaf(x[i], gj, cbe[j]) > 0.f ? v[i] : 0.f) * gj;
+              s1 += dx;
+              s2 = fmaf(dx, x[i], s2);
+            }
           }
-          h[i] = relu ? fmaxf(x, 0.f) : x;
         }
-        tile_put(T, lane, h);
-        __syncwarp();
-        tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
-        __syncwarp();
-        if (XH) {
-          tile_put(T, lane, v);
-          __syncwarp();
-          tile_store(T, lane, XH + (size_t)row0 * TCN + c * 32, rows_valid);
-          __syncwarp();
-        }
-      }
-    } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
-      const bool live = row < M;
-      const float* X0 = XH + (size_t)row0 * TCN;  // this warp's 32 rows of x-hat: fetched coalesced, one chunk ahead
-      float4 pf[8];
-      float x[32];
-      rows_fetch(X0, lane, rows_valid, pf);
-      mbar_wait_(&S.acc_full, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float s1 = 0.f, s2 = 0.f;
-      if (ln) {
+        const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[row].y : 1.f;
         for (int c = 0; c < TCN / 32; ++c) {
           rows_put(T, lane, pf);
           __syncwarp();
           tile_get(T, lane, x);
           __syncwarp();
-          rows_fetch(X0 + ((c + 1) & 7) * 32, lane, rows_valid, pf);  // (the last one fetches chunk 0 for the second pass)
+          if (c + 1 < TCN / 32) rows_fetch(X0 + (c + 1) * 32, lane, rows_valid, pf);
           tmem_ld32(tl + c * 32, v);
+          if (c == TCN / 32 - 1) {  // last TMEM read of this tile
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
+          }
+          float dz[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int j = c * 32 + i;
-            const float gj = cg[j];
-            const float dx = (fmaf(x[i], gj, cbe[j]) > 0.f ? v[i] : 0.f) * gj;
-            s1 += dx;
-            s2 = fmaf(dx, x[i], s2);
+            if (ln) {
+              const float gj = cg[j];
+              v[i] = fmaf(x[i], gj, cbe[j]) > 0.f ? v[i] : 0.f;  // dn: gradient at the LayerNorm output
+              dz[i] = rstd * (v[i] * gj - m1 - x[i] * m2);
+            } else {
+              v[i] = x[i] > 0.f ? v[i] : 0.f;
+              dz[i] = v[i];
+            }
+            if (!live) dz[i] = 0.f;
+            x[i] *= v[i];  // dn * x-hat
           }
+          // dz: to global (coalesced through the tile) and its column sums; then the two LayerNorm-affine sums.
+          // Column sums over this warp's 32 rows: lane <-> column of the tile (deterministic, fixed order).
+          tile_put(T, lane, dz);
+          __syncwarp();
+          tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+          S.wpart[ew][0][c * 32 + lane] = tile_colsum(T, lane);
+          __syncwarp();
+          tile_put(T, lane, x);
+          __syncwarp();
+          S.wpart[ew][1][c * 32 + lane] = tile_colsum(T, lane);
+          __syncwarp();
+          tile_put(T, lane, v);
+          __syncwarp();
+          S.wpart[ew][2][c * 32 + lane] = tile_colsum(T, lane);
+          __syncwarp();
         }
-      }
-      const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[row].y : 1.f;
-      for (int c = 0; c < TCN / 32; ++c) {
-        rows_put(T, lane, pf);
-        __syncwarp();
-        tile_get(T, lane, x);
-        __syncwarp();
-        if (c + 1 < TCN / 32) rows_fetch(X0 + (c + 1) * 32, lane, rows_valid, pf);
-        tmem_ld32(tl + c * 32, v);
-        float dz[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int j = c * 32 + i;
-          if (ln) {
-            const float gj = cg[j];
-            v[i] = fmaf(x[i], gj, cbe[j]) > 0.f ? v[i] : 0.f;  // dn: gradient at the LayerNorm output
-            dz[i] = rstd * (v[i] * gj - m1 - x[i] * m2);
-          } else {
-            v[i] = x[i] > 0.f ? v[i] : 0.f;
-            dz[i] = v[i];
-          }
-          if (!live) dz[i] = 0.f;
-          x[i] *= v[i];  // dn * x-hat
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        for (int i = et; i < 3 * HID; i += 128) {
+          const int q = i / HID, j = i - q * HID;
+          part[((size_t)tile * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
         }
-        // dz: to global (coalesced through the tile) and its column sums; then the two LayerNorm-affine sums.
-        // Column sums over this warp's 32 rows: lane <-> column of the tile (deterministic, fixed order).
-        tile_put(T, lane, dz);
-        __syncwarp();
-        tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
-        S.wpart[ew][0][c * 32 + lane] = tile_colsum(T, lane);
-        __syncwarp();
-        tile_put(T, lane, x);
-        __syncwarp();
-        S.wpart[ew][1][c * 32 + lane] = tile_colsum(T, lane);
-        __syncwarp();
-        tile_put(T, lane, v);
-        __syncwarp();
-        S.wpart[ew][2][c * 32 + lane] = tile_colsum(T, lane);
-        __syncwarp();
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-      for (int i = et; i < 3 * HID; i += 128) {
-        const int q = i / HID, j = i - q * HID;
-        part[((size_t)blockIdx.x * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // (wpart is rewritten by the next tile)
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TCN) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TCN) : "memory");
+}
+
+static int tc_grid(int M) {  // persistent: one CTA per SM (or per tile when there are fewer)
+  static int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int tiles = (M + TCM - 1) / TCM;
+  return tiles < sms ? tiles : sms;
 }
 
 // ---- host side: tensor maps (driver entry point fetched through the runtime: libb2rl links no libcuda) -------------
@@ -418,7 +460,7 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
                              const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat, cudaStream_t st) {
   CUtensorMap ma, mb, ml;
   if (!make_map(&ma, X, M, HID, ldx, TCM) || !make_map(&mb, W, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-  const int grid = (M + TCM - 1) / TCM;
+  const int grid = tc_grid(M);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
     tc_linear_kernel<0, 1><<<grid, TC_THREADS, sizeof(TcSmemT<1>) + 1024, st>>>(ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
@@ -436,7 +478,7 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
                                  cudaStream_t st) {
   CUtensorMap ma, mb, ml;
   if (!make_map(&ma, DZ2, M, HID, HID, TCM) || !make_map(&mb, w2t, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-  const int grid = (M + TCM - 1) / TCM;
+  const int grid = tc_grid(M);
   float* xh = const_cast<float*>(xh1);
   float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
   if (w2t_lo) {
