@@ -180,36 +180,40 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 }
 
 // bump, if given, is incremented once (the update counter that wgrad.cu's extra CTA advances).
-// C[m][n] = sum_sp part[sp][m][n] for m < MA (fixed order: four interleaved chains, then ((0+1)+(2+3))); Ct [256][MA] =
-// its transpose when given (MA = 256: the w2n shadow). One thread per output element: 32 columns x 8 rows per CTA.
+// C[m][n] = sum_sp part[sp][m][n] for m < MA; Ct [256][MA] = its transpose when given (MA = 256: the w2n shadow).
+// A CTA owns 8 rows x 32 columns; its 8 warps each add every 8th slice (8 rows = 8 loads in flight), then the 8 partial
+// sums are added in warp order: a fixed order, so the result is deterministic, and a 1-row gradient (dW3 of a critic)
+// still has 8 warps sharing its 148 slices.
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(const float* __restrict__ part, int S, int MA, int MA_pad, float* __restrict__ C, float* __restrict__ Ct,
                        unsigned long long* bump) {
-  __shared__ float tile[8][33];
+  __shared__ float red[8][8][33];  // [split lane][row][column]
   if (bump && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *bump += 1ull;  // the step's update counter (wgrad.cu's bump CTA)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int m = blockIdx.y * 8 + ty, n = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (m < MA) {
-    const float* src = part + (size_t)m * GN + n;
-    const size_t stride = (size_t)MA_pad * GN;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int sp = 0;
-    for (; sp + 4 <= S; sp += 4) {
-      a0 += src[(size_t)sp * stride];
-      a1 += src[(size_t)(sp + 1) * stride];
-      a2 += src[(size_t)(sp + 2) * stride];
-      a3 += src[(size_t)(sp + 3) * stride];
-    }
-    for (; sp < S; ++sp) a0 += src[(size_t)sp * stride];
-    s = (a0 + a1) + (a2 + a3);
-    C[(size_t)m * GN + n] = s;
+  const int m0 = blockIdx.y * 8, n = blockIdx.x * 32 + tx;
+  const size_t stride = (size_t)MA_pad * GN;
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  for (int sp = ty; sp < S; sp += 8) {
+    const float* src = part + (size_t)sp * stride + (size_t)m0 * GN + n;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (m0 + r < MA) acc[r] += src[(size_t)r * GN];
   }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) red[ty][r][tx] = acc[r];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) s += red[l][ty][tx];  // thread (tx, ty) finishes row m0 + ty
+  if (m0 + ty < MA) C[(size_t)(m0 + ty) * GN + n] = s;
   if (Ct) {
-    tile[ty][tx] = s;
+    __syncthreads();
+    red[0][ty][tx] = s;
     __syncthreads();
     const int mm = threadIdx.x & 7, nn = threadIdx.x >> 3;  // 8 consecutive m per 32-byte segment
-    if (blockIdx.y * 8 + mm < MA) Ct[(size_t)(blockIdx.x * 32 + nn) * MA + blockIdx.y * 8 + mm] = tile[mm][nn];
+    if (m0 + mm < MA) Ct[(size_t)(blockIdx.x * 32 + nn) * MA + m0 + mm] = red[0][mm][nn];
   }
 }
 

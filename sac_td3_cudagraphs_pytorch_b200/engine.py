@@ -51,8 +51,11 @@ class LearnerEngine:
         self.launches_per_variant: dict[tuple, int] = {}
         # end-to-end step (step()): pinned staging for the transitions coming in and the log block going out
         self._h_new: dict[int, torch.Tensor] = {}
-        self._d_new: dict[int, torch.Tensor] = {}
-        self.host_out = torch.zeros(8, dtype=torch.float32).pin_memory()
+        # two slots each (step parity): one step may be in flight while the host prepares the next (step_async / wait)
+        self._host_outs = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.host_out = self._host_outs[0]
+        self._host_outs_np = [t.numpy() for t in self._host_outs]
+        self._waited = 0
         self._host_seq = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._host_seq_np = self._host_seq.numpy()  # (a view: polled without going through torch)
         self._seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -91,25 +94,30 @@ class LearnerEngine:
             self.agent.counters[L.CTR_CURSOR] = self._cursor_on_device
 
     # -- the whole environment-facing step as ONE graph replay ---------------------------------------
-    def host_rows(self, n: int) -> torch.Tensor:
-        """Pinned staging buffer [n, row_stride] for the transitions of the next step(): fill it in place
-        (replay.pack_rows(td, fmt, out=...)) and call step(i, n)."""
-        if n not in self._h_new:
-            self._h_new[n] = torch.zeros(n, self.agent.fmt.row_stride, dtype=torch.float32).pin_memory()
-            self._d_new[n] = torch.zeros(n, self.agent.fmt.row_stride, dtype=torch.float32, device=self.agent.device)
-        return self._h_new[n]
+    def host_rows(self, n: int, slot: Optional[int] = None) -> torch.Tensor:
+        """Pinned staging buffer [n, row_stride] for the transitions of the next step: fill it in place
+        (replay.pack_rows(td, fmt, out=...)) and call step(i, n) / step_async(i, n). There are two slots (the parity
+        of the step's sequence number; default: the next step's), so the buffer of step t may be filled while step
+        t - 1 is still running — but only after wait() of step t - 2, which read from the same slot."""
+        slot = (self._seq & 1) if slot is None else int(slot) & 1
+        if (n, slot) not in self._h_new:
+            self._h_new[(n, slot)] = torch.zeros(n, self.agent.fmt.row_stride, dtype=torch.float32).pin_memory()
+        return self._h_new[(n, slot)]
 
-    def step(self, i: int, n_new: int = 0) -> torch.Tensor:
+    def step_async(self, i: int, n_new: int = 0) -> int:
         """orchestrator.py:100-113 + :337-352 as ONE CUDA graph replay and no stream synchronisation: the replay
         write reads the n_new freshly collected transitions straight from pinned host memory (host_rows(n_new);
         cursor and fill count live on the device), then sample, critic update, delayed actor updates, Polyak,
-        and a last kernel that writes the log block into pinned host memory and publishes a sequence number,
-        which the host polls. Returns the pinned log block (_lib.OUT_* indices), valid on return — the loop a
-        trainer that logs every step runs. Needs graphs."""
+        and a last kernel that writes the log block into pinned host memory and publishes a sequence number.
+        Returns a ticket for wait(). At most two steps are in flight: a third first waits for the oldest (its
+        staging slots are about to be reused). Needs graphs."""
         ag, rb = self.agent, self.rb
         assert self.use_graphs, "step() is the graph path"
+        if self._seq - self._waited >= 2:
+            self.wait(self._seq - 1)
+        slot = self._seq & 1
         do_actor = (i % (ag.hps.actor_update_delay + 1) == 0)
-        key = (do_actor, self._polyak_due(), int(n_new))
+        key = (do_actor, self._polyak_due(), int(n_new), slot)
         self._sync_size()
         g = self.graphs.get(key)
         if g is None:
@@ -123,27 +131,37 @@ class LearnerEngine:
         if do_actor:
             ag.actor_updates_so_far += int(ag.hps.actor_update_delay)
         self._seq += 1
-        seq, want = self._host_seq_np, self._seq
-        while seq[0] != want:  # the device writes it after the log block (system-scope fence in between)
+        return self._seq
+
+    def wait(self, ticket: int, as_numpy: bool = False):
+        """Poll the sequence number the step's last kernel publishes; returns that step's pinned log block
+        (_lib.OUT_* indices; a torch tensor, or its numpy view), valid until the step two tickets later is launched."""
+        seq = self._host_seq_np
+        while seq[0] < ticket:  # the device writes it after the log block (system-scope fence in between)
             pass
-        return self.host_out
+        self._waited = max(self._waited, int(ticket))
+        return (self._host_outs_np if as_numpy else self._host_outs)[(ticket - 1) & 1]
+
+    def step(self, i: int, n_new: int = 0) -> torch.Tensor:
+        """step_async + wait: the loop of a trainer that reads the losses of every step before the next one."""
+        return self.wait(self.step_async(i, n_new))
 
     def _capture_step(self, key) -> torch.cuda.CUDAGraph:
         ag, rb = self.agent, self.rb
-        do_actor, do_polyak, n_new = key
+        do_actor, do_polyak, n_new, slot = key
         if n_new:
-            self.host_rows(n_new)
+            self.host_rows(n_new, slot)
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(ag.device)
         with torch.cuda.graph(g):
             n = 0
             if n_new:  # pinned host memory is device-addressable (UVA): the write kernel is the host->device copy
                 L.check(ag._lib.b2rl_replay_extend_dev(rb.storage.data_ptr(), rb.capacity, rb.fmt,
-                                                       self._h_new[n_new].data_ptr(), n_new, ag.counters.data_ptr(),
+                                                       self._h_new[(n_new, slot)].data_ptr(), n_new, ag.counters.data_ptr(),
                                                        ag._stream()), "replay_extend_dev")
                 n += 1
             n += self._enqueue(do_actor, do_polyak)
-            L.check(ag._lib.b2rl_publish_logs(ag.out.data_ptr(), 1, self.host_out.data_ptr(), self._seq_dev.data_ptr(),
+            L.check(ag._lib.b2rl_publish_logs(ag.out.data_ptr(), 1, self._host_outs[slot].data_ptr(), self._seq_dev.data_ptr(),
                                               self._host_seq.data_ptr(), ag._stream()), "publish_logs")
             n += 1
         self.launches_per_variant[key] = n

@@ -125,10 +125,9 @@ def test_engine_step_graph_equals_extend_plus_iteration(name):
         rbs.append(rb)
     a_step, a_ref = LearnerEngine(agents[0], rbs[0], use_graphs=True), LearnerEngine(agents[1], rbs[1], use_graphs=True)
     g = torch.Generator().manual_seed(3)
-    stage = a_step.host_rows(n_new)
     for i in range(n_it):
         rows = torch.randn(n_new, rbs[0].fmt.row_stride, generator=g)
-        stage.copy_(rows)
+        a_step.host_rows(n_new).copy_(rows)  # (two staging slots, alternating with the step's sequence number)
         out = a_step.step(i, n_new)
         rbs[1].extend_rows(rows.cuda())
         a_ref.iteration(i)
@@ -139,6 +138,43 @@ def test_engine_step_graph_equals_extend_plus_iteration(name):
     assert len(rbs[0]) == len(rbs[1]) == cap and rbs[0]._cursor == rbs[1]._cursor == (n0 + n_it * n_new) % cap
     assert int(agents[0].counters[L.CTR_SIZE]) == cap and int(agents[0].counters[L.CTR_CURSOR]) == rbs[0]._cursor
     assert int(agents[0].counters[L.CTR_XTICKET]) == 0
+
+
+@pytest.mark.parametrize("name", ["td3_hopper", "sac_hopper"])
+def test_engine_pipelined_steps_equal_synchronous_steps(name):
+    """step_async / wait with one step in flight (the host fills the other staging slot and launches step t before it
+    reads step t - 1's log block) = the same steps run one at a time: every log block and the final state, bitwise."""
+    from sac_td3_cudagraphs_pytorch_b200.engine import LearnerEngine
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    inp = case_inputs(name)
+    td = inp["storage"]
+    n0, cap, n_new, n_it = 200, 230, 4, 13
+    agents = [make_agent(inp, seed=7) for _ in range(2)]
+    rbs = []
+    for _ in range(2):
+        rb = ReplayBuffer(cap, "cuda", seed=7)
+        rb.extend({k: v[:n0].cuda() for k, v in td.items()})
+        rbs.append(rb)
+    e_pipe, e_sync = LearnerEngine(agents[0], rbs[0], use_graphs=True), LearnerEngine(agents[1], rbs[1], use_graphs=True)
+    g = torch.Generator().manual_seed(3)
+    rows = [torch.randn(n_new, rbs[0].fmt.row_stride, generator=g) for _ in range(n_it)]
+    want = []
+    for i in range(n_it):
+        e_sync.host_rows(n_new).copy_(rows[i])
+        want.append(e_sync.step(i, n_new).clone())
+    got, prev = [], None
+    for i in range(n_it):
+        e_pipe.host_rows(n_new).copy_(rows[i])
+        t = e_pipe.step_async(i, n_new)
+        if prev is not None:
+            got.append(e_pipe.wait(prev).clone())
+        prev = t
+    got.append(e_pipe.wait(prev).clone())
+    for i in range(n_it):
+        assert torch.equal(got[i], want[i]), f"log block differs at step {i}"
+    torch.cuda.synchronize()
+    assert _arena_equal(agents[0], agents[1])
+    assert torch.equal(rbs[0].storage, rbs[1].storage)
 
 
 @pytest.mark.parametrize("algo,ob,ac,bound", [("sac", 11, 3, 1.0), ("td3", 11, 3, 1.0), ("sac", 376, 17, 0.4)])
