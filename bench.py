@@ -95,7 +95,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": getattr(self, "window", "timed region")}
 
 
 # ------------------------------------------------------------------------------------------ b2rl arm
@@ -172,6 +172,15 @@ def run_b2rl(args, rank, world, device):
             launches += eng.launches(i)
         e1.record()
         barrier()
+        # nvidia-smi samples every 100 ms and the K timed steps may last less than that: keep the SAME load running
+        # (untimed) until the sampler has seen it a few times, so that `clocks` describes this load and not idle
+        t_load, extra = time.perf_counter(), W + K
+        while len(clk.rows) < 6 and time.perf_counter() - t_load < 4.0:
+            for _ in range(500):
+                eng.iteration(extra)
+                extra += 1
+            torch.cuda.synchronize()
+        clk.window = "timed region, then the same load kept running %.1f s for the 100 ms sampler" % (time.perf_counter() - t_load)
     elapsed = e0.elapsed_time(e1) * 1e-3
     if world > 1:
         t = torch.tensor([elapsed], device=device, dtype=torch.float64)

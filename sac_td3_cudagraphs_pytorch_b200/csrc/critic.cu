@@ -95,10 +95,14 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     }
   }
   B2RL_TICK(41);
+#ifdef B2RL_TIMING
+  if (blockIdx.x == 0 && blockIdx.y == 0 && l == 0) g_b2rl_timing[44 + w] = clock64();
+#endif
   cp_async_wait_all();
-  B2RL_TICK(42);
+#ifdef B2RL_TIMING
+  if (blockIdx.x == 0 && blockIdx.y == 0 && l == 0) g_b2rl_timing[52 + w] = clock64();
+#endif
   __syncthreads();
-  B2RL_TICK(1);
   int gi = 0;
 
   // ---- next action

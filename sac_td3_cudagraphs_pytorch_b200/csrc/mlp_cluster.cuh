@@ -67,13 +67,26 @@ struct NetStage {
   float w3[W3_ROWS * HID];
   float w1s[W1S_ROWS * CW];   // [in_dim][128]
 };
-// One warp's prologue job (lane = threadIdx.x & 31): issue the copies and leave the descriptor in `out`.
-// __noinline__: one copy of this code serves every network of a kernel (different warps, different arguments).
+// One warp's prologue job (lane = threadIdx.x & 31): copy the network's small tensors into `st` (cp.async, waited for
+// by the caller), leave the descriptor in `out`. __noinline__: one copy of this code serves every network of a kernel
+// (different warps, different arguments).
+// This job is the critical path of the prologue: every other warp's job is done ~2 000 cycles after kernel start and the
+// whole CTA waits for this one at the staging barrier. Measured with the in-kernel clock (tools/phase_timing.py; cycles
+// after kernel start at which the data had landed): rolled loops that index the offsets from the parameter block in
+// every iteration (a dependent ~130-cycle parameter load each) 5 500; THIS version, every offset loaded once up front,
+// 3 650; and, no better, so not kept: cp.async.bulk with one copy per lane 3 630 or all from one lane 4 080 (~190
+// cycles per bulk copy: too many small pieces for the TMA engine), ~40 unrolled LDG.128 + STS.128 3 650, offsets
+// passed by shuffle + fully rolled loops 3 500-4 300. The three networks' 45 KB per CTA (5.8 MB per launch) from L2 and
+// ~90 LDGSTS per SM set the floor, not the mechanism.
 static __device__ __noinline__ void stage_net(const float* region, const b2rl_net_t* d, NetStage* st, Net* out, int j0) {
   const int lane = threadIdx.x & 31;
   const int64_t* offs = &d->w1t;
+  int64_t o[F_N];
+#pragma unroll
+  for (int f = 0; f < F_N; ++f) o[f] = offs[f];
+  const int in_dim = d->in_dim, out_dim = d->out_dim;
   const bool ln = d->layer_norm != 0;
-  const bool w3s = d->out_dim <= W3_ROWS, w1s = d->in_dim <= W1S_ROWS;
+  const bool w3s = out_dim <= W3_ROWS, w1s = in_dim <= W1S_ROWS;
   if (lane < F_N) {
     const float* ptr = region + offs[lane];
     const int v = lane - 1 - (lane > 4);  // b1 g1 be1 -> 0 1 2, b2 g2 be2 -> 3 4 5
@@ -83,23 +96,27 @@ static __device__ __noinline__ void stage_net(const float* region, const b2rl_ne
     out->p[lane] = ptr;
   }
   if (lane == F_N) {
-    out->in_dim = d->in_dim; out->out_dim = d->out_dim; out->ln = d->layer_norm;
+    out->in_dim = in_dim; out->out_dim = out_dim; out->ln = d->layer_norm;
     out->w1s = w1s ? st->w1s : nullptr;
   }
-#pragma unroll 1
-  for (int i = lane; i < 6 * (HID / 4); i += 32) {  // 64 float4 per vector
-    const int v = i >> 6, c = (i & 63) * 4;
-    if (ln || v == 0 || v == 3) cp_async16(&st->vec[v][c], region + offs[v + 1 + (v > 2)] + c);
+  if (w1s) {  // the first layer's column slice first (the first product needs it): 512 contiguous bytes per input feature
+    const float* w1 = region + o[F_W1T] + j0 + 4 * lane;
+#pragma unroll 4
+    for (int k = 0; k < in_dim; ++k) cp_async16(st->w1s + k * CW + 4 * lane, w1 + (size_t)k * HID);
   }
-  if (lane < (d->out_dim + 3) / 4) cp_async16(st->b3 + 4 * lane, region + offs[F_B3] + 4 * lane);
+#pragma unroll
+  for (int v = 0; v < 6; ++v) {  // 64 float4 per vector: two per lane
+    if (ln || v == 0 || v == 3) {
+      const float* src = region + o[v + 1 + (v > 2)] + 4 * lane;
+      cp_async16(&st->vec[v][4 * lane], src);
+      cp_async16(&st->vec[v][4 * lane + 128], src + 128);
+    }
+  }
+  if (lane < (out_dim + 3) / 4) cp_async16(st->b3 + 4 * lane, region + o[F_B3] + 4 * lane);
   if (w3s) {
-#pragma unroll 1
-    for (int i = lane; i < d->out_dim * (HID / 4); i += 32) cp_async16(st->w3 + 4 * i, region + offs[F_W3] + 4 * i);
-  }
-  if (w1s) {
-    const float* w1 = region + offs[F_W1T] + j0;
-#pragma unroll 1
-    for (int k = 0; k < d->in_dim; ++k) cp_async16(st->w1s + k * CW + 4 * lane, w1 + (size_t)k * HID + 4 * lane);
+    const float* w3 = region + o[F_W3] + 4 * lane;
+#pragma unroll 2
+    for (int i = 0; i < out_dim * (HID / 128); ++i) cp_async16(st->w3 + 4 * lane + 128 * i, w3 + 128 * i);
   }
 }
 
@@ -266,6 +283,19 @@ static __device__ __noinline__ void first_global(const float* __restrict__ W, in
 
 // ---- mbarrier / st.async plumbing (PTX ISA: mbarrier, st.async; SASS: SYNCS.*, STAS) ------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
+          smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t map_peer(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -279,19 +309,6 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, float4 v, uint32_t r
 __device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rmbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v), "r"(rmbar)
                : "memory");
-}
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(
-          smem_u32(b)),
-      "r"(parity)
-      : "memory");
 }
 // Once per kernel, before the first exchange: the mbarriers armed for one arrival (thread 0's expect_tx) per
 // phase, made visible to the peers, and one cluster barrier so that no st.async can reach an uninitialised
@@ -516,13 +533,14 @@ __device__ __forceinline__ float& uref(float4* u, int r, int o) {
 // Executed by the `nth` threads whose index among them is `tid` (a prologue job of some warps).
 static __device__ __noinline__ void stage_tile(const float* __restrict__ rows, int row_stride, int b0, int nvalid, int off,
                                                int len, float4* X, int ld, int tid, int nth) {
-#pragma unroll 1
-  for (int r = 0; r < RT; ++r) {
+  const int lane = tid & 31, nw = nth >> 5;  // rows over the job's warps, features over the lanes (a narrow tile used to
+#pragma unroll 1                              // keep only its first warp busy, with all 8 rows in sequence)
+  for (int r = tid >> 5; r < RT; r += nw) {
     const int rr = r < nvalid ? r : nvalid - 1;
     const float* src = rows + (size_t)(b0 + rr) * row_stride + off;
     float* d = reinterpret_cast<float*>(&X[(r >> 2) * ld]) + (r & 3);
 #pragma unroll 1
-    for (int k = tid; k < len; k += nth) cp_async4(d + 4 * k, src + k);
+    for (int k = lane; k < len; k += 32) cp_async4(d + 4 * k, src + k);
   }
 }
 

@@ -23,12 +23,12 @@ buf = (C.c_longlong * 64)()
 lib.b2rl_debug_timing.argtypes = [C.c_void_p]
 assert lib.b2rl_debug_timing(buf) == 0
 t = np.array(buf[:64], dtype=np.int64)
-names = {0: "start", 40: "P.mbar init + cluster arrive", 41: "P.warp job issued", 42: "P.cp.async landed", 43: "P.syncthreads", 1: "staged (cp.async burst done)", 10: "A head done", 11: "A sampled", 21: "T head done",
+names = { **{44 + i: f"P.warp {i} job issued" for i in range(8)}, **{52 + i: f"P.warp {i} cp.async landed" for i in range(8)}, 0: "start", 40: "P.mbar init + cluster arrive", 41: "P.warp job issued", 42: "P.cp.async landed", 43: "P.before the first trunk_fwd call", 10: "A head done", 11: "A sampled", 21: "T head done",
          22: "twin exchange done", 23: "Q start (TD target)", 33: "Q head done", 34: "bwd start", 35: "bwd end"}
 for base, nm in ((2, "A"), (12, "T"), (24, "Q")):
     for o, what in enumerate(("l1 gemm start", "l1 gemm+sync end", "l1 reduce+gather+barrier end", "l1 rows end",
                               "l2 gemm+sync end", "l2 reduce+gather+barrier end", "l2 rows end")):
         names[base + o] = f"{nm}.{what}"
     names[base + 7] = f"{nm}.l2 stats done (inside l2 rows)"
-for k in sorted(names, key=lambda k: t[k]):
+for k in sorted((k for k in names if t[k] >= t[0]), key=lambda k: t[k]):
     print(f"{k:2d} {names[k]:36s} total {(t[k]-t[0]):7d}")
