@@ -272,8 +272,35 @@ def run_b2rl(args, rank, world, device):
               "frac": g_bytes / t_g / 1e9 / hbm_peak, "traffic": None, "rows_per_launch": GB,
               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
 
+    # the tensor-core hidden layer of the large-batch path (BASELINE.json config 5: batch 65 536) on its own: HBM-bound
+    # (X in, H and x-hat out: 3 x 4 bytes per element moved, 512 flops per element)
+    MT = 65536
+    Xt = torch.randn(MT, 256, device=device)
+    Wt = torch.randn(256, 256, device=device) / 16
+    Wlo = torch.empty_like(Wt)
+    vb, vg, vbe = torch.randn(256, device=device), torch.ones(256, device=device), torch.zeros(256, device=device)
+    Ht, XHt, stt = torch.empty(MT, 256, device=device), torch.empty(MT, 256, device=device), torch.empty(MT, 2, device=device)
+    L.check(lib.b2rl_tc_split_lo(Wt.data_ptr(), Wlo.data_ptr(), Wt.numel(), st()))
+    roof_tc = {}
+    for tag, lo in (("3xtf32", Wlo.data_ptr()), ("tf32", None)):
+        t_tc = time_kernel(lambda: L.check(lib.b2rl_tc_linear(Xt.data_ptr(), 256, MT, Wt.data_ptr(), lo, vb.data_ptr(), vg.data_ptr(),
+                                                              vbe.data_ptr(), 1, 1, Ht.data_ptr(), XHt.data_ptr(), stt.data_ptr(), st())),
+                           iters=100, warm=20)
+        tc_bytes = 3 * MT * 256 * 4 + 2 * 256 * 256 * 4
+        roof_tc[tag] = {"us_per_launch": t_tc * 1e6, "achieved": tc_bytes / t_tc / 1e9, "frac": tc_bytes / t_tc / 1e9 / hbm_peak,
+                        "tflops": 2.0 * MT * 256 * 256 / t_tc / 1e12}
+    tt = None
+    if tr.exists() and "tc_linear_kernel" in json.loads(tr.read_text()):
+        t_ = json.loads(tr.read_text())["tc_linear_kernel"]
+        tt = t_["dram_bytes_read"] + t_["dram_bytes_write"]
+    roof_tc = {"bound": "hbm", "kernel": "tc_linear_kernel<fwd, 3xTF32> (tcgen05, large-batch path, M=65536: X in, H + x-hat out)",
+               "achieved": roof_tc["3xtf32"]["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": roof_tc["3xtf32"]["frac"],
+               "traffic": tt, "us_per_launch": roof_tc["3xtf32"]["us_per_launch"], "tf32": roof_tc["tf32"],
+               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
+    del Xt, Ht, XHt
+
     return dict(value=value, elapsed=elapsed, launches=launches, clocks=clk.summary(), e2e=e2e, roofline=roof,
-                roofline_gather=roof_g, per_kernel_us=per_kernel, finite=finite, rb_rows=cap,
+                roofline_gather=roof_g, roofline_tc_linear=roof_tc, per_kernel_us=per_kernel, finite=finite, rb_rows=cap,
                 row_bytes=fmt.row_stride * 4)
 
 
@@ -465,7 +492,7 @@ def main():
                    "cadence": "sample + critic update + 2 actor updates every 3rd iteration + polyak, one CUDA graph replay per step",
                    "parallelism": f"{world} independent learner(s), one per GPU, no collective"},
         "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"],
-        "roofline": res["roofline"], "roofline_gather": res["roofline_gather"], "per_kernel_us": res["per_kernel_us"],
+        "roofline": res["roofline"], "roofline_gather": res["roofline_gather"], "roofline_tc_linear": res["roofline_tc_linear"], "per_kernel_us": res["per_kernel_us"],
         "outputs_finite": res["finite"],
     }
     if extra:

@@ -4,7 +4,7 @@
 #  3. one --set full capture of every kernel of one td3_hopper / sac_hopper iteration (cold-cache, serialised).
 TAG=${1:-r1}
 set -x
-python bench.py --steps 300 --warmup 10 > gpurun_out/${TAG}_bench_plain.json 2> gpurun_out/${TAG}_bench_plain.err || exit 1
+python bench.py > gpurun_out/${TAG}_bench_plain.json 2> gpurun_out/${TAG}_bench_plain.err || exit 1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
   python bench.py --steps 30 --warmup 3 > gpurun_out/${TAG}_ncu_bench.log 2>&1
 for wl in td3_hopper sac_hopper; do
@@ -13,3 +13,11 @@ for wl in td3_hopper sac_hopper; do
     -o gpurun_out/${TAG}_full_$wl -f python tools/profile_target.py $wl 12 > gpurun_out/${TAG}_ncu_$wl.log 2>&1
 done
 ls -la gpurun_out | tail -12
+# 4. the wide (tensor-core) path at batch 65 536: launch list of two DP iterations and one --set full capture of the
+#    tcgen05 kernels (tc_linear forward / backward, tc_wgrad)
+PYTHONPATH=. python tools/bench_dp.py 65536 20 3xtf32 > gpurun_out/${TAG}_plain_wide.log 2>&1 || exit 1
+PYTHONPATH=. timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches_wide.csv \
+  python tools/bench_dp.py 65536 2 3xtf32 > gpurun_out/${TAG}_ncu_wide.log 2>&1
+PYTHONPATH=. timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_linear_kernel|tc_wgrad_kernel' --launch-skip 40 -c 10 \
+  -o gpurun_out/${TAG}_full_wide -f python tools/bench_dp.py 65536 2 3xtf32 > gpurun_out/${TAG}_ncu_wide_full.log 2>&1
+ls -la gpurun_out | tail -8
