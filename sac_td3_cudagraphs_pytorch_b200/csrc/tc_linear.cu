@@ -6,8 +6,11 @@
 //
 // Persistent CTAs (one per SM) over 128-row tiles, warp-specialised (256 threads); two TMEM accumulator buffers, so the
 // epilogue of one tile overlaps the loads and MMAs of the next:
-//   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of the A tile (128 x 32 fp32) and of the whole weight
-//            k-slab (256 x 32 fp32) into a 4-stage shared-memory ring, 128-byte swizzle, completion on mbarriers;
+//   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of the A tile (128 x 32 fp32) and of HALF the weight k-slab
+//            (128 x 32 fp32), the latter multicast to both CTAs of the 2-CTA cluster (every tile needs the same
+//            weights: the multicast halves their L2->SM traffic, 256 KB (512 KB in 3xTF32) of the 384 (640) KB a tile
+//            reads), into a 4-stage shared-memory ring, 128-byte swizzle, completion on mbarriers; a ring slot is
+//            reused when BOTH CTAs' MMAs have released it (multicast tcgen05.commit);
 //   warp 1   TMEM allocation (2 x 256 columns) and the MMA issuer: one elected thread issues
 //            tcgen05.mma.cta_group::1.kind::tf32  M=128 N=256 K=8, four per k-slab, accumulating in TMEM;
 //            tcgen05.commit releases each ring slot back to the producer and finally signals the epilogue;
@@ -79,6 +82,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
       : "memory");
+}
+// multicast forms (2-CTA cluster): the load lands at the same shared-memory offset of every CTA in `mask` and counts its
+// bytes on the mbarrier at the same offset there; the commit arrives on the mbarrier of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          s32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(s32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
@@ -156,12 +176,18 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (M + TCM - 1) / TCM;
-  // persistent: this CTA's tiles are blockIdx.x, + gridDim.x, ...; local tile i accumulates in TMEM buffer i & 1, so the
-  // epilogue of tile i runs while the ring and the tensor core work on tile i + 1
-  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Persistent, in clusters of 2: cluster ci works on tile pairs ci, ci + n_clusters, ...; CTA `crank` of the cluster takes
+  // tile 2 * pair + crank (a ghost tile beyond the batch loads zeros and stores nothing, so that both CTAs run the same
+  // number of k-slabs: each loads HALF of every weight slab and multicasts it to both). Local tile i accumulates in TMEM
+  // buffer i & 1, so the epilogue of tile i runs while the ring and the tensor core work on tile i + 1.
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int n_clusters = (int)gridDim.x >> 1, ci = (int)blockIdx.x >> 1, n_pairs = (n_tiles + 1) >> 1;
+  const int my_tiles = (n_pairs - ci + n_clusters - 1) / n_clusters;
+  auto tile_of = [&](int i) { return 2 * (ci + i * n_clusters) + (int)crank; };
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 1); mbar_init_(&S.lo_ready[s], 64); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 2); mbar_init_(&S.lo_ready[s], 64); }  // empty: both CTAs' MMA commits
     for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,6 +198,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();  // the peer's barriers are initialised before anything of ours can land on them
   const uint32_t tmem = S.tmem_base;
   constexpr int KB = HID / TCK;  // 8 k-slabs
 
@@ -179,14 +206,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {  // ===== TMA producer: the ring runs on across tiles
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int m0 = ((int)blockIdx.x + i * (int)gridDim.x) * TCM;
+        const int m0 = tile_of(i) * TCM;
+        const int half = (int)crank * (TCN / 2);  // this CTA's rows of the weight slab
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % TC_STAGES;
-          if (it >= TC_STAGES) mbar_wait_(&S.empty[s], ((it / TC_STAGES) - 1) & 1);
+          if (it >= TC_STAGES) mbar_wait_(&S.empty[s], ((it / TC_STAGES) - 1) & 1);  // free in BOTH CTAs
           mbar_expect_(&S.full[s], TC_STAGE_BYTES);
           tma_load_2d(S.a[s], &mapA, kb * TCK, m0, &S.full[s]);
-          tma_load_2d(S.b[s], &mapB, kb * TCK, 0, &S.full[s]);
-          if constexpr (PREC == 1) tma_load_2d(S.blo[s], &mapBlo, kb * TCK, 0, &S.full[s]);
+          tma_load_2d_mc(S.b[s] + half * TCK, &mapB, kb * TCK, half, &S.full[s], 3);
+          if constexpr (PREC == 1) tma_load_2d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, &S.full[s], 3);
         }
       }
     }
@@ -213,7 +241,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
             }
           }
-          umma_commit(&S.empty[s]);  // (implies tcgen05.fence::before_thread_sync)
+          umma_commit_mc(&S.empty[s], 3);  // (implies tcgen05.fence::before_thread_sync) frees the slot in both CTAs
         }
         umma_commit(&S.acc_full[buf]);
       }
@@ -252,7 +280,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2];
     float v[32];
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int tile = (int)blockIdx.x + ti * (int)gridDim.x, buf = ti & 1;
+      const int tile = tile_of(ti), buf = ti & 1;
       const int row0 = tile * TCM + 32 * lg, row = row0 + lane;
       const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
       const uint32_t tl = tmem + buf * TCN + ((uint32_t)(32 * lg) << 16);
@@ -382,7 +410,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           __syncwarp();
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-        for (int i = et; i < 3 * HID; i += 128) {
+        for (int i = et; i < 3 * HID && tile < n_tiles; i += 128) {
           const int q = i / HID, j = i - q * HID;
           part[((size_t)tile * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
         }
@@ -392,6 +420,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync_all();  // (the peer's last commits arrive on this CTA's barriers: do not exit under them)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TCN) : "memory");
 }
 
@@ -401,8 +430,9 @@ static int tc_grid(int M) {  // persistent: one CTA per SM (or per tile when the
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  const int tiles = (M + TCM - 1) / TCM;
-  return tiles < sms ? tiles : sms;
+  const int pairs = ((M + TCM - 1) / TCM + 1) / 2;  // clusters of 2 CTAs, one tile pair at a time
+  const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+  return 2 * clusters;
 }
 
 // ---- host side: tensor maps (driver entry point fetched through the runtime: libb2rl links no libcuda) -------------
@@ -458,36 +488,34 @@ cudaError_t init_tc() {
 // Wlo: the precomputed lo part of W (tc_split_lo) => 3xTF32; NULL => plain TF32
 cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W, const float* Wlo, const float* bias,
                              const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat, cudaStream_t st) {
-  CUtensorMap ma, mb, ml;
-  if (!make_map(&ma, X, M, HID, ldx, TCM) || !make_map(&mb, W, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-  const int grid = tc_grid(M);
+  CUtensorMap ma, mb, ml;  // (the weight maps have boxes of HALF a slab: each CTA of a cluster loads one and multicasts it)
+  if (!make_map(&ma, X, M, HID, ldx, TCM) || !make_map(&mb, W, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
+  const dim3 grid(tc_grid(M)), block(TC_THREADS);
+  float2* st2 = reinterpret_cast<float2*>(stat);
+  float* none = nullptr;
   if (Wlo) {
-    if (!make_map(&ml, Wlo, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-    tc_linear_kernel<0, 1><<<grid, TC_THREADS, sizeof(TcSmemT<1>) + 1024, st>>>(ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
-                                                                              reinterpret_cast<float2*>(stat), nullptr);
-  } else {
-    tc_linear_kernel<0, 0><<<grid, TC_THREADS, sizeof(TcSmemT<0>) + 1024, st>>>(ma, mb, mb, M, bias, g, be, ln, relu, H, XH,
-                                                                              reinterpret_cast<float2*>(stat), nullptr);
+    if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
+    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
+                    st2, none);
   }
-  return cudaGetLastError();
+  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, bias, g, be, ln, relu, H, XH, st2,
+                  none);
 }
-
-// dz1 = LayerNormBackward(ReLU'(dz2 . W2)) and the column-sum partials; w2t is the forward-layout copy ([k][j])
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
                                  const float* stat1, const float* g1, const float* be1, int ln, float* DZ1, float* part,
                                  cudaStream_t st) {
   CUtensorMap ma, mb, ml;
-  if (!make_map(&ma, DZ2, M, HID, HID, TCM) || !make_map(&mb, w2t, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-  const int grid = tc_grid(M);
+  if (!make_map(&ma, DZ2, M, HID, HID, TCM) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
+  const dim3 grid(tc_grid(M)), block(TC_THREADS);
   float* xh = const_cast<float*>(xh1);
   float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
+  const float* none = nullptr;
   if (w2t_lo) {
-    if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN)) return cudaErrorInvalidValue;
-    tc_linear_kernel<2, 1><<<grid, TC_THREADS, sizeof(TcSmemT<1>) + 1024, st>>>(ma, mb, ml, M, nullptr, g1, be1, ln, 0, DZ1, xh, st1, part);
-  } else {
-    tc_linear_kernel<2, 0><<<grid, TC_THREADS, sizeof(TcSmemT<0>) + 1024, st>>>(ma, mb, mb, M, nullptr, g1, be1, ln, 0, DZ1, xh, st1, part);
+    if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
+    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, none, g1, be1, ln, 0, DZ1, xh, st1,
+                    part);
   }
-  return cudaGetLastError();
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1, part);
 }
 
 }  // namespace b2rl
