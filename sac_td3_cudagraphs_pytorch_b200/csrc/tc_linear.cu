@@ -231,15 +231,17 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % TC_STAGES;
           mbar_wait_(&S.full[s], (it / TC_STAGES) & 1);
-          if constexpr (PREC == 1) mbar_wait_(&S.lo_ready[s], (it / TC_STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int k = 0; k < TCK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: advance inside the 128-byte swizzle row
             umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
-            if constexpr (PREC == 1) {
-              umma_tf32(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
-              umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
-            }
+            if constexpr (PREC == 1) umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+          }
+          if constexpr (PREC == 1) {  // the two products whose operands TMA delivered run while the lo split is made
+            mbar_wait_(&S.lo_ready[s], (it / TC_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < TCK / 8; ++k) umma_tf32(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
           }
           umma_commit_mc(&S.empty[s], 3);  // (implies tcgen05.fence::before_thread_sync) frees the slot in both CTAs
         }

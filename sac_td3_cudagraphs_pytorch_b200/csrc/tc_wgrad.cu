@@ -123,12 +123,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % ST;
         g_mbar_wait(&S.full[s], (kb / ST) & 1);
-        if constexpr (PREC == 1) g_mbar_wait(&S.lo_ready[s], (kb / ST) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < GK / 8; ++k) {  // 8 batch rows (two atoms, 1 KB) of every chunk per instruction
+        for (int k = 0; k < GK / 8; ++k)  // 8 batch rows (two atoms, 1 KB) of every chunk per instruction
           g_umma(tmem, g_desc(S.a[s], k * 1024), g_desc(S.b[s], k * 1024), (kb | k) != 0);
-          if constexpr (PREC == 1) {
+        if constexpr (PREC == 1) {  // (the hi.hi product runs while the lo parts are made)
+          g_mbar_wait(&S.lo_ready[s], (kb / ST) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < GK / 8; ++k) {
             g_umma(tmem, g_desc(S.alo[s], k * 1024), g_desc(S.b[s], k * 1024), 1);
             g_umma(tmem, g_desc(S.a[s], k * 1024), g_desc(S.blo[s], k * 1024), 1);
           }
