@@ -28,10 +28,12 @@ def main():
     dev = torch.device(f"cuda:{local}")
     dist.init_process_group("nccl", device_id=dev)
     B, n_it = 64, 4
-    for algo in ("sac", "td3"):
+    # row-group kernels (fp32, tight bound) and the tensor-core wide path (3xTF32: fp32-class gradients, but a ReLU mask
+    # may flip where a pre-activation is within 1e-6 of zero, and Adam's first steps amplify: looser stated bound)
+    for algo, wide, tol in (("sac", None, 5e-5), ("td3", None, 5e-5), ("sac", "3xtf32", 1e-3), ("td3", "3xtf32", 1e-3)):
         mk = sac_hps if algo == "sac" else td3_hps
         ag = make_agent(mk(batch_size=B), rank, dev)
-        dp = DataParallelLearner(ag, None, B, GradComm())
+        dp = DataParallelLearner(ag, None, B, GradComm(), wide=wide)
         ref = make_agent(mk(batch_size=B * world), 0, dev) if rank == 0 else None
         delay = 2
         for i in range(n_it):
@@ -65,8 +67,8 @@ def main():
                         worst = max(worst, rel_dev(t, ref.arena.named(net, r)[name]))
             if algo == "sac":
                 worst = max(worst, rel_dev(ag.log_alpha, ref.log_alpha))
-            print(f"DP_RESULT {algo} world={world} worst_rel_dev_vs_single_rank={worst:.3e}", flush=True)
-            assert worst <= 5e-5, worst
+            print(f"DP_RESULT {algo} wide={wide} world={world} worst_rel_dev_vs_single_rank={worst:.3e}", flush=True)
+            assert worst <= tol, worst
             assert ag.counters[:3].tolist() == ref.counters[:3].tolist()
     dist.barrier()
     dist.destroy_process_group()
