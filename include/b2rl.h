@@ -128,6 +128,15 @@ typedef struct b2rl_update_args {
   float* out;                  /* dev float[8] per agent: {qf_loss, actor_loss, alpha_loss, alpha, ...} */
   float* dbg_targ_q;           /* dev [n_agents][B] or NULL   (TD target y, agent.py:226-228) */
   float* dbg_q;                /* dev [n_agents][2][B] or NULL (online Q values) */
+  /* In-kernel sampling (b2rl_critic_update_* only; agent.rb.sample(B), orchestrator.py:338, folded into the critic
+   * step): storage != NULL => every row group draws its batch indices itself — Philox keyed exactly as
+   * b2rl_replay_sample_gather keys them (hp.seed, batch row, counters[B2RL_CTR_Q], global agent id), so the batch is
+   * the same — reads its transitions straight from the replay storage, and the step also WRITES them to `rows` (and
+   * the indices to idx_out), which the kernels that follow (weight gradients, actor / alpha steps) read. */
+  const float* storage;        /* dev [n_agents][capacity][row_stride] or NULL */
+  int64_t storage_agent_stride;
+  int64_t storage_size;        /* rows filled; 0 => read counters[B2RL_CTR_SIZE] (graph replays while the buffer fills) */
+  int64_t* idx_out;            /* dev [n_agents][B] or NULL */
 } b2rl_update_args_t;
 
 #define B2RL_OUT_QF_LOSS 0

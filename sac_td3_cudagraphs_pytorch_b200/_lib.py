@@ -40,7 +40,9 @@ class UpdateArgs(C.Structure):
                 ("min_ac", C.c_void_p), ("max_ac", C.c_void_p), ("log_alpha", C.c_void_p),
                 ("eps", C.c_void_p), ("eps2", C.c_void_p), ("eps_out", C.c_void_p), ("eps2_out", C.c_void_p),
                 ("counters", C.c_void_p), ("workspace", C.c_void_p), ("workspace_agent_stride", C.c_int64),
-                ("out", C.c_void_p), ("dbg_targ_q", C.c_void_p), ("dbg_q", C.c_void_p)]
+                ("out", C.c_void_p), ("dbg_targ_q", C.c_void_p), ("dbg_q", C.c_void_p),
+                ("storage", C.c_void_p), ("storage_agent_stride", C.c_int64), ("storage_size", C.c_int64),
+                ("idx_out", C.c_void_p)]
 
 
 class Seg(C.Structure):

@@ -210,7 +210,9 @@ class Agent:
         return eps
 
     def update_args(self, rows: torch.Tensor, eps=None, eps2=None, eps_out=None, eps2_out=None,
-                    dbg_targ_q=None, dbg_q=None) -> L.UpdateArgs:
+                    dbg_targ_q=None, dbg_q=None, storage=None, storage_size: int = 0, idx_out=None) -> L.UpdateArgs:
+        """storage (the replay buffer's row tensor [capacity, row_stride]): the critic step samples the batch itself and
+        fills `rows` / `idx_out` (include/b2rl.h, b2rl_update_args_t.storage); default: `rows` holds the batch."""
         lay, B = self.layout, rows.shape[0]
         a = L.UpdateArgs()
         a.hp, a.fmt = self._hyper, self.fmt
@@ -226,7 +228,9 @@ class Agent:
         ws = self.workspace(B)
         a.workspace, a.workspace_agent_stride = ws.data_ptr(), ws.numel()
         a.out, a.dbg_targ_q, a.dbg_q = self.out.data_ptr(), L.ptr(dbg_targ_q), L.ptr(dbg_q)
-        a._keep = (rows, eps, eps2, eps_out, eps2_out, dbg_targ_q, dbg_q, ws)  # keep tensors alive with the struct
+        a.storage, a.storage_agent_stride, a.storage_size = L.ptr(storage), 0 if storage is None else storage.numel(), storage_size
+        a.idx_out = L.ptr(idx_out)
+        a._keep = (rows, eps, eps2, eps_out, eps2_out, dbg_targ_q, dbg_q, ws, storage, idx_out)  # keep tensors alive with the struct
         return a
 
     def _seg(self, begin, end, lr=0.0, *, adam, polyak, counter=0, clip=False, grad_scale=1.0) -> L.Seg:

@@ -85,13 +85,36 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     stage_net(T, &A.critic[k], &M.nsT, &M.nT, G.c * CW);
   } else if (w == 3) {
     stage_net(P, &A.critic[k], &M.nsQ, &M.nQ, G.c * CW);
-  } else if (w < 6) {
-    stage_tile(rows, rs, b0, nvalid, O + AD + 2, O, XA, ldx, t - 128, 64);
   } else {
-    stage_tile(rows, rs, b0, nvalid, 0, O + AD, XB, ldx, t - 192, 64);  // [obs | act] is contiguous in the row
-    if (t - 192 < 2 * RT) {
-      const int i = t - 192, r = i >> 1, rr = r < nvalid ? r : nvalid - 1;
-      cp_async4(&M.rd[r][i & 1], rows + (size_t)(b0 + rr) * rs + O + AD + (i & 1));
+    // In-kernel sampling (A.storage): lane i draws the replay index of tile row i & 7 — the Philox key of
+    // replay.cu::gather_kernel, so the batch is the one b2rl_replay_sample_gather would have gathered — and the tiles
+    // are read straight from the replay storage; cluster rank 0 also writes the rows out for the kernels that follow.
+    const float* src = rows;
+    int64_t myidx = -1;
+    if (A.storage) {
+      src = A.storage + (size_t)agent * A.storage_agent_stride;
+      const uint64_t size = A.storage_size ? (uint64_t)A.storage_size : A.counters[(size_t)agent * 8 + B2RL_CTR_SIZE];
+      const int r = l & 7, rr = r < nvalid ? r : nvalid - 1;
+      myidx = philox_index(A.hp.seed, (uint32_t)(b0 + rr), step, gid, size);
+    }
+    if (w < 6) {
+      stage_tile(src, rs, b0, nvalid, O + AD + 2, O, XA, ldx, t - 128, 64, myidx);
+    } else {
+      stage_tile(src, rs, b0, nvalid, 0, O + AD, XB, ldx, t - 192, 64, myidx);  // [obs | act] is contiguous in the row
+      if (w == 6) {
+        const int i = l, r = (i >> 1) & 7, rr = r < nvalid ? r : nvalid - 1;
+        const int64_t si = __shfl_sync(0xffffffffu, myidx, rr);
+        if (i < 2 * RT) cp_async4(&M.rd[r][i & 1], src + (size_t)(si >= 0 ? si : (int64_t)(b0 + rr)) * rs + O + AD + (i & 1));
+      } else if (A.storage && rank == 0) {  // warp 7: the sampled rows (and their indices) for the following kernels
+        float* dst = const_cast<float*>(rows);
+#pragma unroll 1
+        for (int r = 0; r < nvalid; ++r) {
+          const int64_t si = __shfl_sync(0xffffffffu, myidx, r);
+          for (int c = l; c < (rs >> 2); c += 32)
+            st_stream4(dst + (size_t)(b0 + r) * rs + 4 * c, ld_stream4(src + (size_t)si * rs + 4 * c));
+          if (l == 0 && A.idx_out) A.idx_out[(size_t)agent * B + b0 + r] = si;
+        }
+      }
     }
   }
   B2RL_TICK(41);

@@ -532,12 +532,14 @@ __device__ __forceinline__ float& uref(float4* u, int r, int o) {
 // Rows beyond the batch (r >= nvalid) repeat the last valid row: finite values whose results are masked later.
 // Executed by the `nth` threads whose index among them is `tid` (a prologue job of some warps).
 static __device__ __noinline__ void stage_tile(const float* __restrict__ rows, int row_stride, int b0, int nvalid, int off,
-                                               int len, float4* X, int ld, int tid, int nth) {
+                                               int len, float4* X, int ld, int tid, int nth, int64_t myidx = -1) {
   const int lane = tid & 31, nw = nth >> 5;  // rows over the job's warps, features over the lanes (a narrow tile used to
 #pragma unroll 1                              // keep only its first warp busy, with all 8 rows in sequence)
   for (int r = tid >> 5; r < RT; r += nw) {
     const int rr = r < nvalid ? r : nvalid - 1;
-    const float* src = rows + (size_t)(b0 + rr) * row_stride + off;
+    // in-kernel sampling: lane i of the warp holds the storage index of tile row i (myidx >= 0); else the batch row
+    const int64_t si = __shfl_sync(0xffffffffu, myidx, rr);
+    const float* src = rows + (size_t)(si >= 0 ? si : (int64_t)(b0 + rr)) * row_stride + off;
     float* d = reinterpret_cast<float*>(&X[(r >> 2) * ld]) + (r & 3);
 #pragma unroll 1
     for (int k = lane; k < len; k += 32) cp_async4(d + 4 * k, src + k);

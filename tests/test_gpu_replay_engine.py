@@ -140,6 +140,35 @@ def test_engine_step_graph_equals_extend_plus_iteration(name):
     assert int(agents[0].counters[L.CTR_XTICKET]) == 0
 
 
+@pytest.mark.parametrize("name", ["td3_hopper", "sac_hopper", "sac_humanoid"])
+def test_engine_in_kernel_sampling_equals_gather_launch(name):
+    """The critic kernel sampling its own batch from the replay storage (engine default) = a gather launch in front of
+    it: same indices, same batch rows, same parameters — bitwise — over iterations with and without actor updates;
+    a batch size that leaves a ragged last row group included."""
+    from sac_td3_cudagraphs_pytorch_b200.engine import LearnerEngine
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    inp = case_inputs(name)
+    td = inp["storage"]
+    for batch in (None, 28):
+        agents = [make_agent(inp, seed=7) for _ in range(2)]
+        rbs = []
+        for _ in range(2):
+            rb = ReplayBuffer(300, "cuda", seed=7)
+            rb.extend({k: v[:250].cuda() for k, v in td.items()})
+            rbs.append(rb)
+        e_in = LearnerEngine(agents[0], rbs[0], batch_size=batch, use_graphs=True, fused_sample=True)
+        e_ga = LearnerEngine(agents[1], rbs[1], batch_size=batch, use_graphs=True, fused_sample=False)
+        for i in range(7):
+            e_in.iteration(i)
+            e_ga.iteration(i)
+            torch.cuda.synchronize()
+            assert torch.equal(e_in.idx, e_ga.idx), f"indices differ at iteration {i}"
+            assert torch.equal(e_in.rows, e_ga.rows), f"batch rows differ at iteration {i}"
+            assert torch.equal(agents[0].out, agents[1].out)
+        assert _arena_equal(agents[0], agents[1])
+        assert e_in.launches(0) == e_ga.launches(0) - 1
+
+
 @pytest.mark.parametrize("name", ["td3_hopper", "sac_hopper"])
 def test_engine_pipelined_steps_equal_synchronous_steps(name):
     """step_async / wait with one step in flight (the host fills the other staging slot and launches step t before it
