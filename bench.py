@@ -231,9 +231,35 @@ def run_b2rl(args, rank, world, device):
     e2e_loop(12, True)                                       # captures the step-graph variants (both slots)
     e2e_sync = timed(False)
     e2e_pipe = timed(True)
+
+    # the same loop with the behaviour policy inside the step graph (Agent.predict per environment step):
+    # per step also 4 observations in (pinned), 4 actions out (pinned), read by the host before it launches the next step
+    src_obs = torch.randn(n_env, O)
+
+    def policy_loop(n):
+        prev, acc = None, 0.0
+        for _ in range(n):
+            eng.host_rows(n_env).copy_(src_rows)
+            eng.host_obs(n_env).copy_(src_obs)
+            t = eng.step_async(step_no[0], n_env, n_obs=n_env, explore=True)
+            step_no[0] += 1
+            acc += float(eng.wait_actions()[0, 0])           # the environments need the actions now
+            if prev is not None:
+                acc += float(eng.wait(prev, as_numpy=True)[L.OUT_QF_LOSS])
+            prev = t
+        return acc + float(eng.wait(prev, as_numpy=True)[L.OUT_QF_LOSS])
+
+    policy_loop(12)
+    barrier()
+    t0 = time.perf_counter()
+    policy_loop(Ke)
+    barrier()
+    e2e_policy = world * Ke / (time.perf_counter() - t0)
     e2e = {"value": e2e_pipe, "unit": "updates/s", "h2d_bytes_per_step": n_env * fmt.row_stride * 4,
            "d2h_bytes_per_step": 32, "steps": Ke, "mode": "one step in flight while the host prepares the next; "
-           "every step's losses are read, one step late", "sync_value": e2e_sync}
+           "every step's losses are read, one step late", "sync_value": e2e_sync,
+           "with_policy_value": e2e_policy, "with_policy": "the same plus Agent.predict on 4 observations inside the step graph "
+           "(pinned obs in, pinned actions out, actions read before the next step is launched)"}
 
     if rank != 0:
         return None

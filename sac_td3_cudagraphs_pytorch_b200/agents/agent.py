@@ -345,7 +345,8 @@ class Agent:
         """agents/agent.py:172-181: SAC mode / sample, TD3 action (+ exploration noise)."""
         return self.predict_device(in_td["observations"], explore=explore, eps=eps).cpu().numpy()
 
-    def predict_device(self, obs: torch.Tensor, *, explore: bool, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def predict_device(self, obs: torch.Tensor, *, explore: bool, eps: Optional[torch.Tensor] = None,
+                       draw: Optional[int] = None) -> torch.Tensor:
         obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
         n = obs.shape[0]
         act = torch.empty(n, self.ac_dim, dtype=torch.float32, device=self.device)
@@ -356,10 +357,12 @@ class Agent:
         if eps is not None:
             eps = eps.to(device=self.device, dtype=torch.float32).contiguous()
         args.eps = L.ptr(eps)
-        self._predict_draw += 1
+        if draw is None:
+            self._predict_draw += 1
+            draw = self._predict_draw
         std = float(self.hps.actor_noise_std) if self.td3 else 0.0
         L.check(self._lib.b2rl_actor_predict(C.byref(args), obs.data_ptr(), n, int(explore), std,
-                                             C.c_uint64(self._predict_draw), act.data_ptr(), self._stream()),
+                                             C.c_uint64(draw), act.data_ptr(), self._stream()),
                 "actor_predict")
         return act
 

@@ -387,7 +387,9 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   float4* X = reinterpret_cast<float4*>(smem_raw + sizeof(PredictSmem));
   const bool td3 = A.hp.td3 != 0;
   const float* P = A.arena;
-  const uint64_t step = draw;
+  // draw = ~0: key the exploration noise on the critic step counter (a captured step graph cannot take a new
+  // host value per replay; the counter advances once per learner iteration)
+  const uint64_t step = (draw == ~0ull && A.counters) ? A.counters[B2RL_CTR_Q] : draw;
   if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
   else stage_tile(obs, O, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;

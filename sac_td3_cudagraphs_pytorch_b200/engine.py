@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -64,6 +65,15 @@ class LearnerEngine:
         self.host_out = self._host_outs[0]
         self._host_outs_np = [t.numpy() for t in self._host_outs]
         self._waited = 0
+        # the behaviour policy inside the step graph (step_async(..., n_obs=)): observations in, actions out, both pinned
+        self._h_obs: dict[tuple, torch.Tensor] = {}
+        self._h_act: dict[tuple, torch.Tensor] = {}
+        self._d_act: dict[int, torch.Tensor] = {}
+        self._host_act_seq = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._host_act_seq_np = self._host_act_seq.numpy()
+        self._act_seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._act_seq, self._act_last = 0, None
+        self._keep: list = []
         self._host_seq = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._host_seq_np = self._host_seq.numpy()  # (a view: polled without going through torch)
         self._seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -113,20 +123,47 @@ class LearnerEngine:
             self._h_new[(n, slot)] = torch.zeros(n, self.agent.fmt.row_stride, dtype=torch.float32).pin_memory()
         return self._h_new[(n, slot)]
 
-    def step_async(self, i: int, n_new: int = 0) -> int:
+    def host_obs(self, n: int, slot: Optional[int] = None) -> torch.Tensor:
+        """Pinned staging buffer [n, ob_dim] for the observations the policy acts on in the next step
+        (step_async(..., n_obs=n)); two slots, like host_rows."""
+        slot = (self._seq & 1) if slot is None else int(slot) & 1
+        if (n, slot) not in self._h_obs:
+            ag = self.agent
+            self._h_obs[(n, slot)] = torch.zeros(n, ag.ob_dim, dtype=torch.float32).pin_memory()
+            blocks = (n * ag.ac_dim + 7) // 8  # b2rl_publish_logs copies blocks of 8 floats
+            self._h_act[(n, slot)] = torch.zeros(blocks * 8, dtype=torch.float32).pin_memory()
+            if n not in self._d_act:
+                self._d_act[n] = torch.zeros(blocks * 8, dtype=torch.float32, device=ag.device)
+        return self._h_obs[(n, slot)]
+
+    def wait_actions(self) -> "np.ndarray":
+        """Actions of the last step launched with n_obs > 0 ([n_obs, A], a view of pinned host memory written by the
+        device; valid until the step two launches later): polls the sequence number the step's policy part publishes
+        — it runs FIRST in the graph, so the environments can step while the update of the same replay runs."""
+        n, slot, want = self._act_last
+        seq = self._host_act_seq_np
+        while seq[0] < want:
+            pass
+        ag = self.agent
+        return self._h_act[(n, slot)].numpy()[: n * ag.ac_dim].reshape(n, ag.ac_dim)
+
+    def step_async(self, i: int, n_new: int = 0, n_obs: int = 0, explore: bool = True) -> int:
         """orchestrator.py:100-113 + :337-352 as ONE CUDA graph replay and no stream synchronisation: the replay
         write reads the n_new freshly collected transitions straight from pinned host memory (host_rows(n_new);
         cursor and fill count live on the device), then sample, critic update, delayed actor updates, Polyak,
         and a last kernel that writes the log block into pinned host memory and publishes a sequence number.
         Returns a ticket for wait(). At most two steps are in flight: a third first waits for the oldest (its
-        staging slots are about to be reused). Needs graphs."""
+        staging slots are about to be reused). Needs graphs.
+        n_obs > 0: the graph starts with the behaviour policy (Agent.predict, agents/agent.py:172-181, orchestrator.py
+        :67-75) on the n_obs observations in host_obs(n_obs) — parameters as they are BEFORE this step's update, as in
+        the reference loop — and publishes the actions to pinned host memory: wait_actions()."""
         ag, rb = self.agent, self.rb
         assert self.use_graphs, "step() is the graph path"
         if self._seq - self._waited >= 2:
             self.wait(self._seq - 1)
         slot = self._seq & 1
         do_actor = (i % (ag.hps.actor_update_delay + 1) == 0)
-        key = (do_actor, self._polyak_due(), int(n_new), slot)
+        key = (do_actor, self._polyak_due(), int(n_new), slot, int(n_obs), bool(explore))
         self._sync_size()
         g = self.graphs.get(key)
         if g is None:
@@ -140,6 +177,9 @@ class LearnerEngine:
         if do_actor:
             ag.actor_updates_so_far += int(ag.hps.actor_update_delay)
         self._seq += 1
+        if n_obs:
+            self._act_seq += 1
+            self._act_last = (int(n_obs), slot, self._act_seq)
         return self._seq
 
     def wait(self, ticket: int, as_numpy: bool = False):
@@ -151,19 +191,35 @@ class LearnerEngine:
         self._waited = max(self._waited, int(ticket))
         return (self._host_outs_np if as_numpy else self._host_outs)[(ticket - 1) & 1]
 
-    def step(self, i: int, n_new: int = 0) -> torch.Tensor:
+    def step(self, i: int, n_new: int = 0, n_obs: int = 0, explore: bool = True) -> torch.Tensor:
         """step_async + wait: the loop of a trainer that reads the losses of every step before the next one."""
-        return self.wait(self.step_async(i, n_new))
+        return self.wait(self.step_async(i, n_new, n_obs, explore))
 
     def _capture_step(self, key) -> torch.cuda.CUDAGraph:
         ag, rb = self.agent, self.rb
-        do_actor, do_polyak, n_new, slot = key
+        do_actor, do_polyak, n_new, slot, n_obs, explore = key
         if n_new:
             self.host_rows(n_new, slot)
+        if n_obs:
+            self.host_obs(n_obs, slot)
+            pa = L.UpdateArgs()
+            pa.hp, pa.fmt, pa.actor = ag._hyper, ag.fmt, ag.layout.actor.c_struct()
+            pa.arena, pa.region_stride = ag.arena.flat.data_ptr(), ag.layout.region
+            pa.min_ac, pa.max_ac, pa.counters = ag.min_ac.data_ptr(), ag.max_ac.data_ptr(), ag.counters.data_ptr()
+            self._keep.append(pa)
         g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(ag.device)
         with torch.cuda.graph(g):
             n = 0
+            if n_obs:  # the policy first: the environments get their actions while the update runs
+                std = float(ag.hps.actor_noise_std) if ag.td3 else 0.0
+                L.check(ag._lib.b2rl_actor_predict(C.byref(pa), self._h_obs[(n_obs, slot)].data_ptr(), n_obs, int(explore), std,
+                                                   C.c_uint64(2 ** 64 - 1), self._d_act[n_obs].data_ptr(), ag._stream()),
+                        "actor_predict")
+                L.check(ag._lib.b2rl_publish_logs(self._d_act[n_obs].data_ptr(), self._d_act[n_obs].numel() // 8,
+                                                  self._h_act[(n_obs, slot)].data_ptr(), self._act_seq_dev.data_ptr(),
+                                                  self._host_act_seq.data_ptr(), ag._stream()), "publish actions")
+                n += 2
             if n_new:  # pinned host memory is device-addressable (UVA): the write kernel is the host->device copy
                 L.check(ag._lib.b2rl_replay_extend_dev(rb.storage.data_ptr(), rb.capacity, rb.fmt,
                                                        self._h_new[(n_new, slot)].data_ptr(), n_new, ag.counters.data_ptr(),

@@ -170,6 +170,44 @@ def test_engine_in_kernel_sampling_equals_gather_launch(name):
 
 
 @pytest.mark.parametrize("name", ["td3_hopper", "sac_hopper"])
+@pytest.mark.parametrize("explore", [False, True])
+def test_engine_step_with_policy_in_the_graph(name, explore):
+    """step_async(..., n_obs=) runs Agent.predict inside the step graph, on the parameters BEFORE the step's update
+    (reference loop: predict, env step, extend, update), reading pinned observations and publishing pinned actions:
+    equal, bitwise, to the eager predict of a twin agent at the same point, and the learner is unaffected."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    from sac_td3_cudagraphs_pytorch_b200.engine import LearnerEngine
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    inp = case_inputs(name)
+    td = inp["storage"]
+    n0, cap, n_new, n_obs, n_it = 200, 230, 4, 5, 8
+    agents = [make_agent(inp, seed=7) for _ in range(2)]
+    rbs = []
+    for _ in range(2):
+        rb = ReplayBuffer(cap, "cuda", seed=7)
+        rb.extend({k: v[:n0].cuda() for k, v in td.items()})
+        rbs.append(rb)
+    e_pol, e_ref = LearnerEngine(agents[0], rbs[0], use_graphs=True), LearnerEngine(agents[1], rbs[1], use_graphs=True)
+    g = torch.Generator().manual_seed(5)
+    for i in range(n_it):
+        rows = torch.randn(n_new, rbs[0].fmt.row_stride, generator=g)
+        obs = torch.randn(n_obs, inp["ob"], generator=g)
+        draw = int(agents[1].counters[L.CTR_Q])  # the graph keys the exploration noise on the critic step counter
+        want = agents[1].predict_device(obs, explore=explore, draw=draw).cpu().numpy()
+        e_pol.host_rows(n_new).copy_(rows)
+        e_pol.host_obs(n_obs).copy_(obs)
+        tk = e_pol.step_async(i, n_new, n_obs=n_obs, explore=explore)
+        got = e_pol.wait_actions().copy()
+        out = e_pol.wait(tk).clone()
+        e_ref.host_rows(n_new).copy_(rows)
+        ref_out = e_ref.step(i, n_new)
+        assert (got == want).all(), f"actions differ at step {i}"
+        assert torch.equal(out, ref_out)
+    torch.cuda.synchronize()
+    assert _arena_equal(agents[0], agents[1])
+
+
+@pytest.mark.parametrize("name", ["td3_hopper", "sac_hopper"])
 def test_engine_pipelined_steps_equal_synchronous_steps(name):
     """step_async / wait with one step in flight (the host fills the other staging slot and launches step t before it
     reads step t - 1's log block) = the same steps run one at a time: every log block and the final state, bitwise."""
