@@ -137,6 +137,16 @@ typedef struct b2rl_update_args {
   int64_t storage_agent_stride;
   int64_t storage_size;        /* rows filled; 0 => read counters[B2RL_CTR_SIZE] (graph replays while the buffer fills) */
   int64_t* idx_out;            /* dev [n_agents][B] or NULL */
+  /* Replay write folded into the same step (agent.rb.extend(td), orchestrator.py:100-113; single learner, with
+   * `storage`): new_rows != NULL => the n_new transitions at new_rows (device or pinned host memory) are appended at
+   * counters[B2RL_CTR_CURSOR] (round robin over `capacity` rows) BEFORE the batch is drawn: the draw uses the grown
+   * size, a drawn index that falls on a new row is read from new_rows itself, one CTA writes the rows into the storage,
+   * and the weight-gradient launch of the critic step (which runs after every CTA has read them) advances
+   * counters[CURSOR] / counters[SIZE]. Same result as b2rl_replay_extend_dev followed by the critic step. */
+  const float* new_rows;
+  int64_t capacity;
+  int32_t n_new;
+  int32_t reserved2;
 } b2rl_update_args_t;
 
 #define B2RL_OUT_QF_LOSS 0

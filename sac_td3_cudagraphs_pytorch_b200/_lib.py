@@ -42,7 +42,8 @@ class UpdateArgs(C.Structure):
                 ("counters", C.c_void_p), ("workspace", C.c_void_p), ("workspace_agent_stride", C.c_int64),
                 ("out", C.c_void_p), ("dbg_targ_q", C.c_void_p), ("dbg_q", C.c_void_p),
                 ("storage", C.c_void_p), ("storage_agent_stride", C.c_int64), ("storage_size", C.c_int64),
-                ("idx_out", C.c_void_p)]
+                ("idx_out", C.c_void_p), ("new_rows", C.c_void_p), ("capacity", C.c_int64), ("n_new", C.c_int32),
+                ("reserved2", C.c_int32)]
 
 
 class Seg(C.Structure):

@@ -210,7 +210,8 @@ class Agent:
         return eps
 
     def update_args(self, rows: torch.Tensor, eps=None, eps2=None, eps_out=None, eps2_out=None,
-                    dbg_targ_q=None, dbg_q=None, storage=None, storage_size: int = 0, idx_out=None) -> L.UpdateArgs:
+                    dbg_targ_q=None, dbg_q=None, storage=None, storage_size: int = 0, idx_out=None,
+                    new_rows=None, n_new: int = 0) -> L.UpdateArgs:
         """storage (the replay buffer's row tensor [capacity, row_stride]): the critic step samples the batch itself and
         fills `rows` / `idx_out` (include/b2rl.h, b2rl_update_args_t.storage); default: `rows` holds the batch."""
         lay, B = self.layout, rows.shape[0]
@@ -230,7 +231,9 @@ class Agent:
         a.out, a.dbg_targ_q, a.dbg_q = self.out.data_ptr(), L.ptr(dbg_targ_q), L.ptr(dbg_q)
         a.storage, a.storage_agent_stride, a.storage_size = L.ptr(storage), 0 if storage is None else storage.numel(), storage_size
         a.idx_out = L.ptr(idx_out)
-        a._keep = (rows, eps, eps2, eps_out, eps2_out, dbg_targ_q, dbg_q, ws, storage, idx_out)  # keep tensors alive with the struct
+        if new_rows is not None:  # replay write folded into the critic step (include/b2rl.h): pinned host or device rows
+            a.new_rows, a.n_new, a.capacity = new_rows.data_ptr(), int(n_new), storage.shape[0]
+        a._keep = (rows, eps, eps2, eps_out, eps2_out, dbg_targ_q, dbg_q, ws, storage, idx_out, new_rows)  # keep tensors alive with the struct
         return a
 
     def _seg(self, begin, end, lr=0.0, *, adam, polyak, counter=0, clip=False, grad_scale=1.0) -> L.Seg:

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
   } else if (w == 2) {
     stage_net(P, &A.critic[k], &M.nsQ, &M.nQ, G.c * CW);
   } else if (w >= 4) {
-    stage_tile(rows, rs, b0, nvalid, 0, O, X, ldx, t - 128, 128);
+    stage_tile(batch_row(rows, rs, b0, nvalid), nvalid, 0, O, X, ldx, t - 128, 128);
   }
   cp_async_wait_all();
   __syncthreads();
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) alpha_kernel(const __grid_constant__ b2
   float* part = ws_carve(wsb, B, 0).part;
 
   if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
-  else stage_tile(rows, rs, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
+  else stage_tile(batch_row(rows, rs, b0, nvalid), nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();
@@ -391,7 +391,7 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   // host value per replay; the counter advances once per learner iteration)
   const uint64_t step = (draw == ~0ull && A.counters) ? A.counters[B2RL_CTR_Q] : draw;
   if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
-  else stage_tile(obs, O, b0, nvalid, 0, O, X, O, t - 32, NT - 32);
+  else stage_tile(batch_row(obs, O, b0, nvalid), nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;
   cp_async_wait_all();
   __syncthreads();

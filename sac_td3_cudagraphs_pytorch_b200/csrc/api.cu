@@ -126,6 +126,13 @@ static int check_update(const b2rl_update_args_t* a, bool actor_step) {
   for (int k = 0; k < 2; ++k)
     if (a->critic[k].in_dim != a->fmt.ob_dim + a->fmt.ac_dim || a->critic[k].out_dim != 1)
       return fail(B2RL_E_INVALID, "critic[%d] dims (%d -> %d) do not match the row format", k, a->critic[k].in_dim, a->critic[k].out_dim);
+  if (a->storage && (!aligned16(a->storage) || (a->storage_agent_stride & 3) || a->storage_size < 0))
+    return fail(B2RL_E_INVALID, "storage must be 16-byte aligned, its agent stride a multiple of 4 floats");
+  if (a->new_rows) {
+    if (!a->storage || a->n_agents != 1) return fail(B2RL_E_INVALID, "new_rows needs in-kernel sampling (storage) and a single learner");
+    if (!aligned16(a->new_rows) || a->capacity < 1 || a->n_new < 1 || a->n_new > a->capacity)
+      return fail(B2RL_E_INVALID, "new_rows: 16-byte aligned, 1 <= n_new <= capacity");
+  }
   return B2RL_OK;
 }
 
@@ -339,6 +346,7 @@ static int check_opt(const b2rl_update_args_t* a, const b2rl_adam_args_t* o, int
 
 static int critic_update(const b2rl_update_args_t* a, int td3, const b2rl_adam_args_t* opt, void* stream) {
   if (int rc = check_update(a, false)) return rc;
+  if (opt && a->new_rows) return fail(B2RL_E_INVALID, "new_rows is not supported by the fused-optimizer entry point");
   if (int rc = check_opt(a, opt, a->critic[0].begin, a->critic[1].end, B2RL_CTR_Q)) return rc;
   if ((a->hp.td3 != 0) != (td3 != 0)) return fail(B2RL_E_INVALID, "hp.td3 does not match the entry point");
   if (int rc = check_launch(b2rl::launch_critic_fused(*a, (cudaStream_t)stream), "critic_fused")) return rc;

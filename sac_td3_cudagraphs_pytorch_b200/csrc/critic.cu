@@ -89,29 +89,42 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
     // In-kernel sampling (A.storage): lane i draws the replay index of tile row i & 7 — the Philox key of
     // replay.cu::gather_kernel, so the batch is the one b2rl_replay_sample_gather would have gathered — and the tiles
     // are read straight from the replay storage; cluster rank 0 also writes the rows out for the kernels that follow.
-    const float* src = rows;
-    int64_t myidx = -1;
+    // With A.new_rows the replay write is folded in as well (include/b2rl.h): draw over the grown size, read a drawn
+    // new row from new_rows itself; the spare CTA of the wgrad launch that follows writes the new rows into the storage
+    // and advances cursor / size (a read of pinned host memory is a 2 us round trip: not in this kernel's prologue).
+    const float* myrow = batch_row(rows, rs, b0, nvalid);
+    int64_t myidx = -1, cursor = 0;
     if (A.storage) {
-      src = A.storage + (size_t)agent * A.storage_agent_stride;
-      const uint64_t size = A.storage_size ? (uint64_t)A.storage_size : A.counters[(size_t)agent * 8 + B2RL_CTR_SIZE];
+      const float* sto = A.storage + (size_t)agent * A.storage_agent_stride;
+      uint64_t size = A.storage_size ? (uint64_t)A.storage_size : A.counters[(size_t)agent * 8 + B2RL_CTR_SIZE];
+      if (A.new_rows) {
+        cursor = (int64_t)A.counters[(size_t)agent * 8 + B2RL_CTR_CURSOR];
+        size = min(size + (uint64_t)A.n_new, (uint64_t)A.capacity);
+      }
       const int r = l & 7, rr = r < nvalid ? r : nvalid - 1;
       myidx = philox_index(A.hp.seed, (uint32_t)(b0 + rr), step, gid, size);
+      myrow = sto + (size_t)myidx * rs;
+      if (A.new_rows) {
+        int64_t j = myidx - cursor;
+        if (j < 0) j += A.capacity;
+        if (j < A.n_new) myrow = A.new_rows + (size_t)j * rs;
+      }
     }
     if (w < 6) {
-      stage_tile(src, rs, b0, nvalid, O + AD + 2, O, XA, ldx, t - 128, 64, myidx);
+      stage_tile(myrow, nvalid, O + AD + 2, O, XA, ldx, t - 128, 64);
     } else {
-      stage_tile(src, rs, b0, nvalid, 0, O + AD, XB, ldx, t - 192, 64, myidx);  // [obs | act] is contiguous in the row
+      stage_tile(myrow, nvalid, 0, O + AD, XB, ldx, t - 192, 64);  // [obs | act] is contiguous in the row
       if (w == 6) {
         const int i = l, r = (i >> 1) & 7, rr = r < nvalid ? r : nvalid - 1;
-        const int64_t si = __shfl_sync(0xffffffffu, myidx, rr);
-        if (i < 2 * RT) cp_async4(&M.rd[r][i & 1], src + (size_t)(si >= 0 ? si : (int64_t)(b0 + rr)) * rs + O + AD + (i & 1));
+        const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), rr));
+        if (i < 2 * RT) cp_async4(&M.rd[r][i & 1], src + O + AD + (i & 1));
       } else if (A.storage && rank == 0) {  // warp 7: the sampled rows (and their indices) for the following kernels
         float* dst = const_cast<float*>(rows);
 #pragma unroll 1
         for (int r = 0; r < nvalid; ++r) {
+          const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), r));
           const int64_t si = __shfl_sync(0xffffffffu, myidx, r);
-          for (int c = l; c < (rs >> 2); c += 32)
-            st_stream4(dst + (size_t)(b0 + r) * rs + 4 * c, ld_stream4(src + (size_t)si * rs + 4 * c));
+          for (int c = l; c < (rs >> 2); c += 32) st_stream4(dst + (size_t)(b0 + r) * rs + 4 * c, ld_stream4(src + 4 * c));
           if (l == 0 && A.idx_out) A.idx_out[(size_t)agent * B + b0 + r] = si;
         }
       }

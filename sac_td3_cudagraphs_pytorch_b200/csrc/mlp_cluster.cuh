@@ -528,22 +528,27 @@ __device__ __forceinline__ float& uref(float4* u, int r, int o) {
   return reinterpret_cast<float*>(&u[(r >> 2) * MAX_OUT + o])[r & 3];
 }
 
-// ---- input tiles: X[q * ld + k].(r & 3) = rows[b0 + r][off + k], copied asynchronously (cp.async) ----------------
-// Rows beyond the batch (r >= nvalid) repeat the last valid row: finite values whose results are masked later.
-// Executed by the `nth` threads whose index among them is `tid` (a prologue job of some warps).
-static __device__ __noinline__ void stage_tile(const float* __restrict__ rows, int row_stride, int b0, int nvalid, int off,
-                                               int len, float4* X, int ld, int tid, int nth, int64_t myidx = -1) {
-  const int lane = tid & 31, nw = nth >> 5;  // rows over the job's warps, features over the lanes (a narrow tile used to
-#pragma unroll 1                              // keep only its first warp busy, with all 8 rows in sequence)
+// ---- input tiles: X[q * ld + k].(r & 3) = row r, feature off + k, copied asynchronously (cp.async) -----------------
+// `myrow` is per LANE: lane i of every calling warp holds the global-memory base of tile row i & 7 (the batch row, or —
+// in-kernel sampling — the sampled replay row); rows beyond the batch (r >= nvalid) repeat the last valid row: finite
+// values whose results are masked later. Executed by the `nth` threads whose index among them is `tid` (a prologue
+// job of some warps): rows over the job's warps, features over the lanes.
+static __device__ __noinline__ void stage_tile(const float* myrow, int nvalid, int off, int len, float4* X, int ld, int tid,
+                                               int nth) {
+  const int lane = tid & 31, nw = nth >> 5;
+#pragma unroll 1
   for (int r = tid >> 5; r < RT; r += nw) {
     const int rr = r < nvalid ? r : nvalid - 1;
-    // in-kernel sampling: lane i of the warp holds the storage index of tile row i (myidx >= 0); else the batch row
-    const int64_t si = __shfl_sync(0xffffffffu, myidx, rr);
-    const float* src = rows + (size_t)(si >= 0 ? si : (int64_t)(b0 + rr)) * row_stride + off;
+    const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), rr)) + off;
     float* d = reinterpret_cast<float*>(&X[(r >> 2) * ld]) + (r & 3);
 #pragma unroll 1
     for (int k = lane; k < len; k += 32) cp_async4(d + 4 * k, src + k);
   }
+}
+// the per-lane row base for a batch held in rows[.][row_stride]
+__device__ __forceinline__ const float* batch_row(const float* rows, int row_stride, int b0, int nvalid) {
+  const int r = threadIdx.x & 7;
+  return rows + (size_t)(b0 + (r < nvalid ? r : nvalid - 1)) * row_stride;
 }
 
 __device__ __forceinline__ void store_tile(float4* T, const float (&v)[RT]) {  // operand tile, column = threadIdx.x

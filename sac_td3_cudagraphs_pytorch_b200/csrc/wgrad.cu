@@ -338,6 +338,23 @@ __global__ void __launch_bounds__(WT) wgrad_kernel(const __grid_constant__ Wgrad
   if (!OPT) {  // the CTA after the last working one: bump the optimizer's step counter (the kernels that consumed the
     // old value for their noise streams ran earlier in the stream; Adam, later, reads the new one)
     if (id == 0 && t == 0 && W.bump_counter >= 0) A.counters[(size_t)agent * 8 + W.bump_counter] += 1ULL;
+    if (id == 0 && !W.actor_step && A.new_rows) {  // the replay write folded into the critic step: every CTA of
+      uint64_t* ctr = A.counters + (size_t)agent * 8;  // critic_fused has read the cursor and the size by now, and no
+      const int64_t cursor = (int64_t)ctr[B2RL_CTR_CURSOR];  // kernel before the next critic step reads the storage
+      const int rs = A.fmt.row_stride, chunks = rs >> 2;
+      float* sto = const_cast<float*>(A.storage) + (size_t)agent * A.storage_agent_stride;
+      for (int i = t; i < A.n_new * chunks; i += blockDim.x) {
+        const int r = i / chunks, c4 = i - r * chunks;
+        const int64_t d = (cursor + r) % A.capacity;
+        st_stream4(sto + (size_t)d * rs + 4 * c4, ld_stream4(A.new_rows + (size_t)r * rs + 4 * c4));
+      }
+      __syncthreads();
+      if (t == 0) {
+        ctr[B2RL_CTR_CURSOR] = (uint64_t)((cursor + A.n_new) % A.capacity);
+        const uint64_t size = ctr[B2RL_CTR_SIZE] + (uint64_t)A.n_new;
+        ctr[B2RL_CTR_SIZE] = size < (uint64_t)A.capacity ? size : (uint64_t)A.capacity;
+      }
+    }
     return;
   }
   setup();

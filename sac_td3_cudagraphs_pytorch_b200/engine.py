@@ -80,8 +80,9 @@ class LearnerEngine:
         self._seq = 0
 
     # -- what one iteration enqueues --------------------------------------------------------------
-    def _enqueue(self, do_actor: bool, do_polyak: bool) -> int:
+    def _enqueue(self, do_actor: bool, do_polyak: bool, args_q=None) -> int:
         ag, rb = self.agent, self.rb
+        args_q = args_q or self.args_q
         st = ag._stream()
         n = 0
         if not self.fused_sample:
@@ -92,7 +93,7 @@ class LearnerEngine:
         delay = int(ag.hps.actor_update_delay) if do_actor else 0
         # TD3's target actor is averaged once per iteration, after the last actor update if there is one
         extra = ag.polyak_segs(critics=False, actor=True) if (ag.td3 and do_polyak and delay == 0) else []
-        ag.enqueue_critic_step(self.args_q, extra_segs=extra, polyak=do_polyak, fused_opt=self.fused_opt)
+        ag.enqueue_critic_step(args_q, extra_segs=extra, polyak=do_polyak, fused_opt=self.fused_opt)
         n += 2 if self.fused_opt else 3
         for j in range(delay):
             ag.enqueue_actor_step(self.args_pi[j], polyak=ag.td3 and do_polyak and j == delay - 1,
@@ -220,12 +221,19 @@ class LearnerEngine:
                                                   self._h_act[(n_obs, slot)].data_ptr(), self._act_seq_dev.data_ptr(),
                                                   self._host_act_seq.data_ptr(), ag._stream()), "publish actions")
                 n += 2
-            if n_new:  # pinned host memory is device-addressable (UVA): the write kernel is the host->device copy
+            args_q = None
+            if n_new and self.fused_sample and not self.fused_opt:
+                # the replay write rides in the critic step too (b2rl_update_args_t.new_rows): the kernel reads the pinned
+                # rows itself (UVA), no separate write launch
+                args_q = ag.update_args(self.rows, eps_out=self.noise_q, storage=rb.storage, idx_out=self.idx,
+                                        new_rows=self._h_new[(n_new, slot)], n_new=n_new)
+                self._keep.append(args_q)
+            elif n_new:  # pinned host memory is device-addressable (UVA): the write kernel is the host->device copy
                 L.check(ag._lib.b2rl_replay_extend_dev(rb.storage.data_ptr(), rb.capacity, rb.fmt,
                                                        self._h_new[(n_new, slot)].data_ptr(), n_new, ag.counters.data_ptr(),
                                                        ag._stream()), "replay_extend_dev")
                 n += 1
-            n += self._enqueue(do_actor, do_polyak)
+            n += self._enqueue(do_actor, do_polyak, args_q)
             L.check(ag._lib.b2rl_publish_logs(ag.out.data_ptr(), 1, self._host_outs[slot].data_ptr(), self._seq_dev.data_ptr(),
                                               self._host_seq.data_ptr(), ag._stream()), "publish_logs")
             n += 1
