@@ -282,7 +282,7 @@ class Agent:
 
     # ------------------------------------------------------------------ enqueue-only steps (graph-safe)
     def enqueue_critic_step(self, args: L.UpdateArgs, extra_segs: list = (), polyak: bool = False,
-                            fused_opt: bool = True) -> None:
+                            fused_opt: bool = True, before_adam=None) -> None:
         """update_qnets incl. optimizer.step(): fused kernel + weight gradients with Adam (and Polyak) applied in the
         same launch (fused_opt), or the three-launch form (fused kernel, weight gradients, Adam/Polyak)."""
         if fused_opt:
@@ -291,9 +291,11 @@ class Agent:
             return
         fn = self._lib.b2rl_critic_update_td3 if self.td3 else self._lib.b2rl_critic_update_sac
         L.check(fn(C.byref(args), self._stream()), "critic_update")
+        if before_adam is not None:  # (the log block is final here: engine.py forks its publish node off this point)
+            before_adam()
         self._launch_adam(self.critic_segs(polyak) + list(extra_segs))
 
-    def enqueue_actor_step(self, args: L.UpdateArgs, polyak: bool = False, fused_opt: bool = True) -> None:
+    def enqueue_actor_step(self, args: L.UpdateArgs, polyak: bool = False, fused_opt: bool = True, before_adam=None) -> None:
         st = self._stream()
         if fused_opt and not self.hps.clip_norm > 0:  # (clipping needs the whole gradient's norm before the step)
             opt = self._adam_args(self.actor_segs(polyak))
@@ -308,6 +310,8 @@ class Agent:
             L.check(self._lib.b2rl_grad_sumsq(self.arena.flat.data_ptr(), lay.region, self.arena.agent_stride,
                                               lay.actor.begin, lay.actor.core_end, 1, self._sumsq.data_ptr(),
                                               self._sumsq_scratch.data_ptr(), st), "grad_sumsq")
+        if before_adam is not None:
+            before_adam()
         self._launch_adam(self.actor_segs(polyak))
         if self.autotune:
             L.check(self._lib.b2rl_alpha_update(C.byref(args), float(self.hps.log_alpha_lr), st), "alpha_update")

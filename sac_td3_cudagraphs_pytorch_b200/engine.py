@@ -74,13 +74,16 @@ class LearnerEngine:
         self._act_seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._act_seq, self._act_last = 0, None
         self._keep: list = []
+        self._side_stream = torch.cuda.Stream(device=dev)
         self._host_seq = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._host_seq_np = self._host_seq.numpy()  # (a view: polled without going through torch)
         self._seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._seq = 0
 
     # -- what one iteration enqueues --------------------------------------------------------------
-    def _enqueue(self, do_actor: bool, do_polyak: bool, args_q=None) -> int:
+    def _enqueue(self, do_actor: bool, do_polyak: bool, args_q=None, before_last_adam=None) -> int:
+        """before_last_adam: called right before the iteration's LAST Adam launch when nothing after that point writes
+        the log block (i.e. not when SAC's temperature step follows): step graphs fork their publish node there."""
         ag, rb = self.agent, self.rb
         args_q = args_q or self.args_q
         st = ag._stream()
@@ -93,11 +96,14 @@ class LearnerEngine:
         delay = int(ag.hps.actor_update_delay) if do_actor else 0
         # TD3's target actor is averaged once per iteration, after the last actor update if there is one
         extra = ag.polyak_segs(critics=False, actor=True) if (ag.td3 and do_polyak and delay == 0) else []
-        ag.enqueue_critic_step(args_q, extra_segs=extra, polyak=do_polyak, fused_opt=self.fused_opt)
+        hook = None if self.fused_opt else before_last_adam
+        ag.enqueue_critic_step(args_q, extra_segs=extra, polyak=do_polyak, fused_opt=self.fused_opt,
+                               before_adam=hook if delay == 0 else None)
         n += 2 if self.fused_opt else 3
         for j in range(delay):
             ag.enqueue_actor_step(self.args_pi[j], polyak=ag.td3 and do_polyak and j == delay - 1,
-                                  fused_opt=self.fused_opt)
+                                  fused_opt=self.fused_opt,
+                                  before_adam=hook if (j == delay - 1 and not ag.autotune) else None)
             n += (5 if ag.hps.clip_norm > 0 else (2 if self.fused_opt else 3)) + (1 if ag.autotune else 0)
         return n
 
@@ -233,9 +239,29 @@ class LearnerEngine:
                                                        self._h_new[(n_new, slot)].data_ptr(), n_new, ag.counters.data_ptr(),
                                                        ag._stream()), "replay_extend_dev")
                 n += 1
-            n += self._enqueue(do_actor, do_polyak, args_q)
-            L.check(ag._lib.b2rl_publish_logs(ag.out.data_ptr(), 1, self._host_outs[slot].data_ptr(), self._seq_dev.data_ptr(),
-                                              self._host_seq.data_ptr(), ag._stream()), "publish_logs")
+            # The log block is final before the iteration's last Adam launch (unless SAC's temperature step follows):
+            # the publish node forks off there and runs beside Adam instead of after it.
+            joined = []
+
+            def publish():
+                L.check(ag._lib.b2rl_publish_logs(ag.out.data_ptr(), 1, self._host_outs[slot].data_ptr(),
+                                                  self._seq_dev.data_ptr(), self._host_seq.data_ptr(), ag._stream()), "publish_logs")
+
+            def fork_publish():
+                main, ev = torch.cuda.current_stream(ag.device), torch.cuda.Event()
+                ev.record(main)
+                self._side_stream.wait_event(ev)
+                with torch.cuda.stream(self._side_stream):
+                    publish()
+                    done = torch.cuda.Event()
+                    done.record(self._side_stream)
+                joined.append(done)
+
+            n += self._enqueue(do_actor, do_polyak, args_q, before_last_adam=fork_publish)
+            if joined:
+                torch.cuda.current_stream(ag.device).wait_event(joined[0])
+            else:
+                publish()
             n += 1
         self.launches_per_variant[key] = n
         self.graphs[key] = g
