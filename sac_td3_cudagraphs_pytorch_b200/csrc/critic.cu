@@ -118,15 +118,16 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
         const int i = l, r = (i >> 1) & 7, rr = r < nvalid ? r : nvalid - 1;
         const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), rr));
         if (i < 2 * RT) cp_async4(&M.rd[r][i & 1], src + O + AD + (i & 1));
-      } else if (A.storage && rank == 0) {  // warp 7: the sampled rows (and their indices) for the following kernels
-        float* dst = const_cast<float*>(rows);
+      }
+    }
+    if (A.storage && rank == 0) {  // the sampled rows (and their indices) for the kernels that follow: two rows per warp
+      float* dst = const_cast<float*>(rows);
 #pragma unroll 1
-        for (int r = 0; r < nvalid; ++r) {
-          const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), r));
-          const int64_t si = __shfl_sync(0xffffffffu, myidx, r);
-          for (int c = l; c < (rs >> 2); c += 32) st_stream4(dst + (size_t)(b0 + r) * rs + 4 * c, ld_stream4(src + 4 * c));
-          if (l == 0 && A.idx_out) A.idx_out[(size_t)agent * B + b0 + r] = si;
-        }
+      for (int r = w - 4; r < nvalid; r += 4) {
+        const float* src = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(myrow), r));
+        const int64_t si = __shfl_sync(0xffffffffu, myidx, r);
+        for (int c = l; c < (rs >> 2); c += 32) st_stream4(dst + (size_t)(b0 + r) * rs + 4 * c, ld_stream4(src + 4 * c));
+        if (l == 0 && A.idx_out) A.idx_out[(size_t)agent * B + b0 + r] = si;
       }
     }
   }

@@ -39,10 +39,9 @@ class LearnerEngine:
         self.fused_opt = bool(fused_opt)
         # the critic kernel draws the batch indices and reads the replay storage itself (and writes the batch rows out
         # for the kernels that follow) instead of a gather launch in front of it: same indices, bitwise-equal results,
-        # one launch and one round trip of the batch through global memory less per iteration (16.64 k -> 16.98 k
-        # updates/s on TD3 Hopper). Default: on for narrow transitions; wide rows (Humanoid: 3 KB each) keep the gather
-        # launch — writing them out from one warp of the critic's prologue costs more than it saves (9.60 k vs 9.49 k)
-        self.fused_sample = (agent.fmt.row_stride <= 64) if fused_sample is None else bool(fused_sample)
+        # one launch and one round trip of the batch through global memory less per iteration (TD3 Hopper 16.46 k ->
+        # 16.96 k updates/s, SAC Humanoid 9.50 k -> 9.64 k: tools/bench_engine.py)
+        self.fused_sample = True if fused_sample is None else bool(fused_sample)
         dev = agent.device
         self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
