@@ -36,6 +36,8 @@ class GradComm:
 
 def reduce_grad_span(arena: Arena, layout: ArenaLayout, comm: GradComm, which: str, agent: int = 0) -> None:
     """All-reduce the gradients (region 4) of the critics or of the actor, then rebuild the w2n shadows."""
+    if comm.world == 1:  # nothing to reduce, and the weight-gradient kernels wrote the shadows themselves
+        return
     nets = layout.critic if which == "critic" else [layout.actor]
     g = arena.flat[agent, L.REGION_G]
     comm.all_reduce_sum(g[nets[0].begin:nets[-1].core_end])  # one contiguous bucket (shadows in between ride along)
@@ -48,7 +50,8 @@ class DataParallelLearner:
     """One rank of the data-parallel learner. `agent` must be constructed identically on every rank (same
     torch seed => same initial parameters) except `agent_id=rank`, which keys its index/noise draws."""
 
-    def __init__(self, agent, rb, batch_size: int, comm: Optional[GradComm] = None, wide: Optional[str] = None):
+    def __init__(self, agent, rb, batch_size: int, comm: Optional[GradComm] = None, wide: Optional[str] = None,
+                 graphs: Optional[bool] = None):
         """wide: None = row-group kernels; "3xtf32" / "tf32" = the critic step on the layer-by-layer tensor-core path
         (wide.WideCritic), which is what a batch of tens of thousands wants."""
         self.agent, self.rb, self.B = agent, rb, int(batch_size)
@@ -63,6 +66,13 @@ class DataParallelLearner:
         self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.launches = 0
+        # One CUDA graph per iteration variant (actor updates? Polyak?) when the batch is sampled on the device and there
+        # is no collective to capture (one rank): the wide path is ~110 launches per iteration, ~0.9 ms of host time to
+        # enqueue — all of a batch-16 384 iteration (tools/dp_cpu_time.py). With W > 1 the iteration stays eager.
+        self.graphs = (self.comm.world == 1 and rb is not None and bool(agent.hps.cudagraphs)) if graphs is None else bool(graphs)
+        self._graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._size_on_device = -1
+        self._warm: set = set()
 
     def _seg(self, begin, end, lr, polyak, counter, clip=False):
         return L.Seg(begin, end, lr, 1, int(polyak), counter, 1.0 / self.comm.world, int(clip))
@@ -71,16 +81,44 @@ class DataParallelLearner:
         """One iteration of orchestrator.py:337-352 with gradient averaging over ranks. `rows` / `eps_*`
         inject this rank's batch and noise (parity tests); default: device-side sampling."""
         ag, lib, lay, h, W = self.agent, self.agent._lib, self.agent.layout, self.agent.hps, self.comm.world
+        do_actor = (i % (h.actor_update_delay + 1) == 0)
+        do_polyak = ag.td3 or ((ag.qnet_updates_so_far + 1) % h.crit_targ_update_freq == 0)
+        if rows is None and self._size_on_device != len(self.rb):
+            self._size_on_device = len(self.rb)
+            ag.counters[L.CTR_SIZE] = self._size_on_device
+        if self.graphs and rows is None and eps_q is None and eps_pi is None and eps_alpha is None:
+            key = (do_actor, do_polyak)
+            g = self._graphs.get(key)
+            if g is None:  # first occurrence of the variant runs eagerly (lazy allocations), the second is captured
+                if key not in self._warm:
+                    self._warm.add(key)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize(ag.device)
+                    with torch.cuda.graph(g):
+                        self._enqueue(do_actor, do_polyak, None, None, None, None)
+                    self._graphs[key] = g  # (capture does not execute: the replay below is this iteration)
+            if g is not None:
+                g.replay()
+                return self._count(do_actor)
+        self._enqueue(do_actor, do_polyak, rows, eps_q, eps_pi, eps_alpha)
+        self._count(do_actor)
+
+    def _count(self, do_actor: bool) -> None:
+        ag = self.agent
+        ag.qnet_updates_so_far += 1
+        if do_actor:
+            ag.actor_updates_so_far += int(ag.hps.actor_update_delay)
+
+    def _enqueue(self, do_actor, do_polyak, rows, eps_q, eps_pi, eps_alpha) -> None:
+        ag, lib, lay, h, W = self.agent, self.agent._lib, self.agent.layout, self.agent.hps, self.comm.world
         st = ag._stream()
         if rows is None:
-            ag.counters[L.CTR_SIZE] = len(self.rb)
             L.check(lib.b2rl_replay_sample_gather(
                 self.rb.storage.data_ptr(), 0, 0, self.rb.fmt, self.B, 1, None, self.idx.data_ptr(),
                 self.rows.data_ptr(), C.c_uint64(ag.seed), ag.counters.data_ptr(), L.CTR_Q, 0, ag.agent_id, st),
                 "replay_sample_gather")
             rows = self.rows
-        do_actor = (i % (h.actor_update_delay + 1) == 0)
-        do_polyak = ag.td3 or ((ag.qnet_updates_so_far + 1) % h.crit_targ_update_freq == 0)
         delay = int(h.actor_update_delay) if do_actor else 0
 
         if self.wide is not None:
@@ -94,7 +132,6 @@ class DataParallelLearner:
         if ag.td3 and do_polyak and delay == 0:
             segs.append(L.Seg(lay.actor.begin, lay.actor.end, 0.0, 0, 1, 0, 1.0, 0))
         ag._launch_adam(segs)
-        ag.qnet_updates_so_far += 1
         for j in range(delay):
             e1 = None if eps_pi is None else eps_pi[j]
             e2 = None if eps_alpha is None else eps_alpha[j]
@@ -120,4 +157,3 @@ class DataParallelLearner:
                 self.comm.all_reduce_sum(ag._alpha_state[1:2])
                 L.check(lib.b2rl_alpha_adam(ag._alpha_state.data_ptr(), ag.counters.data_ptr(), 1,
                                             float(h.log_alpha_lr), 1.0 / W, ag.out.data_ptr(), st), "alpha_adam")
-            ag.actor_updates_so_far += 1

@@ -141,3 +141,31 @@ def test_wide_actor_step_matches_oracle(name, precision):
     if not ag.td3 and ag.autotune:
         assert rel_dev(ag.log_alpha, o32.log_alpha) <= 1e-5
     assert int(ag.counters[1]) == 1
+
+
+@pytest.mark.parametrize("name,wide", [("sac_hopper", "3xtf32"), ("td3_hopper", "3xtf32"), ("sac_hopper", None)])
+def test_dp_learner_graph_replay_equals_eager(name, wide):
+    """One-rank DataParallelLearner: the captured iteration graphs (one per variant: actor updates? Polyak?) replay the
+    same launches as the eager loop — parameters, optimizer state and counters bitwise equal after 9 iterations
+    (the first occurrence of every variant runs eagerly, the second is captured and replayed, later ones replay)."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    from sac_td3_cudagraphs_pytorch_b200.dp import DataParallelLearner, GradComm
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    inp = case_inputs(name)
+    agents, dps = [], []
+    for graphs in (True, False):
+        ag = make_agent(inp, seed=5)
+        rb = ReplayBuffer(300, "cuda", seed=5)
+        rb.extend({k: v[:250].cuda() for k, v in inp["storage"].items()})
+        agents.append(ag)
+        dps.append(DataParallelLearner(ag, rb, 200, GradComm(), wide=wide, graphs=graphs))
+    for i in range(9):
+        for dp in dps:
+            dp.iteration(i)
+    torch.cuda.synchronize()
+    assert len(dps[0]._graphs) >= 2 and not dps[1]._graphs
+    assert torch.equal(agents[0].arena.flat, agents[1].arena.flat)
+    assert torch.equal(agents[0].counters[:4], agents[1].counters[:4])
+    assert torch.equal(agents[0].out, agents[1].out)
+    assert agents[0].qnet_updates_so_far == agents[1].qnet_updates_so_far == 9
+    assert agents[0].actor_updates_so_far == agents[1].actor_updates_so_far
