@@ -64,18 +64,9 @@ __global__ void __launch_bounds__(NT, 1) actor_fused_kernel(const __grid_constan
       M.lo[l] = __ldg(A.min_ac + l);
       M.hi[l] = __ldg(A.max_ac + l);
     }
-    if (!td3) {
-      for (int i = l; i < RT * AD; i += 32) {
-        const int r = i / AD, a = i - r * AD;
-        float z = 0.f;
-        if (r < nvalid) {
-          const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
-          z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_ACTOR_EPS);
-          if (A.eps_out && rank == 0) A.eps_out[e] = z;
-        }
-        M.eps[r][a] = z;
-      }
-    }
+    if (!td3)
+      tile_noise<RT, MAX_A>(M.eps, A.eps, rank == 0 ? A.eps_out : nullptr, A.hp.seed, (int64_t)agent * B + b0, b0, nvalid, AD, step, gid,
+                            STREAM_ACTOR_EPS, true, l);
   } else if (w == 1) {
     stage_net(P, &A.actor, &M.nsA, &M.nA, G.c * CW);
   } else if (w == 2) {

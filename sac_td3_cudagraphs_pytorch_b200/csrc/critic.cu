@@ -68,17 +68,8 @@ __global__ void __launch_bounds__(NT, 1) critic_fused_kernel(const __grid_consta
       M.lo[l] = __ldg(A.min_ac + l);
       M.hi[l] = __ldg(A.max_ac + l);
     }
-    const bool need = !td3 || A.hp.targ_smoothing;
-    for (int i = l; i < RT * AD; i += 32) {
-      const int r = i / AD, a = i - r * AD;
-      float z = 0.f;
-      if (need && r < nvalid) {
-        const int64_t e = ((int64_t)agent * B + b0 + r) * AD + a;
-        z = noise_at(A.eps, e, A.hp.seed, b0 + r, a, step, gid, STREAM_CRITIC_EPS);
-        if (A.eps_out && rank == 0) A.eps_out[e] = z;
-      }
-      M.eps[r][a] = z;
-    }
+    tile_noise<RT, MAX_A>(M.eps, A.eps, rank == 0 ? A.eps_out : nullptr, A.hp.seed, (int64_t)agent * B + b0, b0, nvalid, AD, step, gid,
+                          STREAM_CRITIC_EPS, !td3 || A.hp.targ_smoothing, l);
   } else if (w == 1) {
     stage_net(PA, &A.actor, &M.nsA, &M.nA, G.c * CW);
   } else if (w == 2) {

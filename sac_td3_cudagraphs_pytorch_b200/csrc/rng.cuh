@@ -57,4 +57,37 @@ __device__ __forceinline__ float noise_at(const float* __restrict__ eps, int64_t
   return i == 0 ? z.x : (i == 1 ? z.y : (i == 2 ? z.z : z.w));
 }
 
+// The noise of one 8-row tile, dst[r][a] = noise_at(row b0 + r, action dim a): ONE Philox block (four normals) per lane
+// and step instead of one per element — the same values (noise_at takes component a & 3 of block a >> 2), a quarter of
+// the Philox / Box-Muller work (Humanoid, 17 action dims: 5 rounds of a lone warp in the prologue become 2).
+template <int ROWS, int LD>
+__device__ __forceinline__ void tile_noise(float (*dst)[LD], const float* __restrict__ eps, float* __restrict__ eps_out,
+                                           uint64_t seed, int64_t row0_elem, int b0, int nvalid, int AD, uint64_t step,
+                                           uint32_t agent, uint32_t stream, bool need, int lane) {
+  const int nb = (AD + 3) >> 2;
+  for (int i = lane; i < ROWS * nb; i += 32) {
+    const int r = i / nb, q = i - r * nb;
+    const bool on = need && r < nvalid;
+    const int64_t e = (row0_elem + r) * AD + 4 * q;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (on) {
+      if (eps) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (4 * q + u < AD) z[u] = eps[e + u];
+      } else {
+        const float4 v = box_muller4(philox_block(seed, (uint32_t)(b0 + r), (uint32_t)q, step, agent, stream));
+        z[0] = v.x, z[1] = v.y, z[2] = v.z, z[3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (4 * q + u < AD) {
+        dst[r][4 * q + u] = z[u];
+        if (on && eps_out) eps_out[e + u] = z[u];
+      }
+  }
+}
+
+
 }  // namespace b2rl

@@ -9,11 +9,12 @@ from sac_td3_cudagraphs_pytorch_b200 import _lib as L, td3_hps, sac_hps
 from sac_td3_cudagraphs_pytorch_b200.agents.agent import Agent
 lib = L.load()
 algo = sys.argv[1] if len(sys.argv) > 1 else "td3"
+O, A_ = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (11, 3)  # e.g. 376 17 for Humanoid
 B = 256
 torch.manual_seed(0)
-ag = Agent({"ob_shape": (11,), "ac_shape": (3,)}, np.full(3, -1.0, np.float32), np.full(3, 1.0, np.float32),
+ag = Agent({"ob_shape": (O,), "ac_shape": (A_,)}, np.full(A_, -1.0, np.float32), np.full(A_, 1.0, np.float32),
            torch.device("cuda"), (sac_hps if algo == "sac" else td3_hps)())
-rows = torch.randn(B, ag.fmt.row_stride, device="cuda"); rows[:, 15] = 0
+rows = torch.randn(B, ag.fmt.row_stride, device="cuda"); rows[:, O + A_ + 1] = 0
 a = ag.update_args(rows)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(5):
