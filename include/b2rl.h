@@ -289,6 +289,11 @@ typedef struct b2rl_wide_q {  /* critic head; mode 1 adds the TD target, dLoss/d
   uint32_t reserved;
 } b2rl_wide_q_t;
 int b2rl_wide_q_head(const b2rl_wide_q_t* q, void* stream);
+/* The critic's second layer (b2rl_tc_linear with ReLU) with that head fused into its epilogue — the thread that owns a row
+ * of h2 takes its dot product with w3 (q->h2 is ignored): no second pass over h2, and H may be NULL (target critics:
+ * h2 never goes to memory). agents/nets.py:88-92 + agents/agent.py:208-233. */
+int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
+                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_wide_q_t* q, void* stream);
 
 /* Head backward + ReLU mask + LayerNorm backward of layer 2: dz = LNbwd(ReLU'(dz3[:, :n_out] . w3)); part
  * [ceil(M/128)][3][256] per-CTA column sums. */

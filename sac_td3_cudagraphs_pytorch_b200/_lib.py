@@ -94,6 +94,8 @@ SYMBOLS = {
     "b2rl_actor_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_tc_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b2rl_tc_linear_q": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_tc_split_lo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "b2rl_wide_first": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

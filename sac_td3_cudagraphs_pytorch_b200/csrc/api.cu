@@ -53,7 +53,7 @@ cudaError_t launch_wide_colsum(const float*, int, float*, int64_t, int64_t, int6
 cudaError_t launch_wide_critic_scalars(const float*, const float*, int, const float*, const float*, int, float*, int64_t, int64_t,
                                        float*, cudaStream_t);
 cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*, int,
-                             int, float*, float*, float*, cudaStream_t);
+                             int, float*, float*, float*, const b2rl_wide_q_t*, cudaStream_t);
 cudaError_t launch_tc_split_lo(const float*, float*, int, cudaStream_t);
 }  // namespace b2rl
 
@@ -229,8 +229,21 @@ int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const
   if (!aligned16(X) || !aligned16(W) || !aligned16(H) || (XH && !aligned16(XH)) || ldx < B2RL_HID || (ldx & 3))
     return fail(B2RL_E_INVALID, "tc_linear: 16-byte aligned tensors, ldx >= 256 and a multiple of 4");
   if (W_lo && !aligned16(W_lo)) return fail(B2RL_E_INVALID, "tc_linear: W_lo must be 16-byte aligned");
-  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, relu, H, XH, stat, (cudaStream_t)stream),
+  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, relu, H, XH, stat, nullptr, (cudaStream_t)stream),
                       "tc_linear");
+}
+int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
+                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_wide_q_t* q, void* stream) {
+  if (!X || !W || !bias || !q || M < 1) return fail(B2RL_E_INVALID, "tc_linear_q: bad arguments");
+  if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "tc_linear_q: LayerNorm needs weight and bias");
+  if (!aligned16(X) || !aligned16(W) || (H && !aligned16(H)) || (XH && !aligned16(XH)) || ldx < B2RL_HID || (ldx & 3))
+    return fail(B2RL_E_INVALID, "tc_linear_q: 16-byte aligned tensors, ldx >= 256 and a multiple of 4");
+  if (W_lo && !aligned16(W_lo)) return fail(B2RL_E_INVALID, "tc_linear_q: W_lo must be 16-byte aligned");
+  if (!q->w3 || !q->b3 || !q->q_out || q->M != M || (q->mode != 0 && q->mode != 1)) return fail(B2RL_E_INVALID, "tc_linear_q: bad head");
+  if (q->mode == 1 && (!q->qn0 || !q->qn1 || !q->rows || !q->dz3 || !q->sq_part || (!q->td3 && (!q->logp || !q->log_alpha))))
+    return fail(B2RL_E_INVALID, "tc_linear_q: mode 1 needs the target Q values, the batch rows, dz3 and sq_part");
+  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, 1, H, XH, stat, q, (cudaStream_t)stream),
+                      "tc_linear_q");
 }
 
 int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,

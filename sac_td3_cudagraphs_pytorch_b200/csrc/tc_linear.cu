@@ -48,7 +48,7 @@ struct __align__(1024) TcSmemT {
   // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
   // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials
   alignas(128) float tile[4][32 * 32];
-  alignas(16) float cvec[3][HID];
+  alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
   float wpart[4][3][HID];
 };
 
@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapBlo, int M,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
-                 float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part) {
+                 float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part,
+                 const __grid_constant__ b2rl_wide_q_t Q) {
   extern __shared__ unsigned char tc_raw[];  // (the swizzle atoms need 1024-byte alignment: align by hand)
   using Smem = TcSmemT<PREC>;
   constexpr int TC_STAGES = Smem::STAGES;
@@ -273,13 +274,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
     const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
     float* T = S.tile[ew];
-    for (int i = et; i < 3 * HID; i += 128) {  // per-column vectors: once per CTA into shared memory (broadcast reads)
+    for (int i = et; i < 4 * HID; i += 128) {  // per-column vectors: once per CTA into shared memory (broadcast reads)
       const int q = i / HID, j = i - q * HID;
-      const float* src = q == 0 ? bias : q == 1 ? g : be;
+      const float* src = q == 0 ? bias : q == 1 ? g : q == 2 ? be : Q.w3;
       S.cvec[q][j] = src ? __ldg(src + j) : (q == 1 ? 1.f : 0.f);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-    const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2];
+    const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2], *cw3 = S.cvec[3];
+    const bool head = MODE == 0 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
     float v[32];
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int tile = tile_of(ti), buf = ti & 1;
@@ -310,6 +312,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
           if (stat && row < M) stat[row] = make_float2(mean, rstd);
         }
+        float qacc = 0.f;
         for (int c = 0; c < TCN / 32; ++c) {
           tmem_ld32(tl + c * 32, v);
           if (c == TCN / 32 - 1) {  // last TMEM read of this tile: hand the buffer back to the MMA issuer
@@ -329,16 +332,50 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               v[i] = x;  // pre-activation
             }
             h[i] = relu ? fmaxf(x, 0.f) : x;
+            if (head) qacc = fmaf(h[i], cw3[j], qacc);
           }
-          tile_put(T, lane, h);
-          __syncwarp();
-          tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
-          __syncwarp();
+          if (H) {  // (a target critic with the fused head never needs its h2 in memory)
+            tile_put(T, lane, h);
+            __syncwarp();
+            tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+            __syncwarp();
+          }
           if (XH) {
             tile_put(T, lane, v);
             __syncwarp();
             tile_store(T, lane, XH + (size_t)row0 * TCN + c * 32, rows_valid);
             __syncwarp();
+          }
+        }
+        if (head) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
+          float sq = 0.f, dqv = 0.f;
+          if (row < M) {
+            const float q = qacc + __ldg(Q.b3);
+            Q.q_out[row] = q;
+            if (Q.mode == 1) {
+              const float q0 = Q.qn0[row], q1 = Q.qn1[row];
+              const float qmin = fminf(q0, q1);
+              float qp = Q.bcq_mix ? __fadd_rn(__fmul_rn(0.75f, qmin), __fmul_rn(0.25f, fmaxf(q0, q1))) : qmin;
+              if (!Q.td3) qp = __fsub_rn(qp, __fmul_rn(expf(Q.log_alpha[0]), Q.logp[row]));
+              const float* rr = Q.rows + (size_t)row * Q.row_stride + Q.rd_off;
+              const float y = __fadd_rn(rr[0], __fmul_rn(__fmul_rn(1.0f - rr[1], Q.gamma), qp));
+              if (Q.targ_out) Q.targ_out[row] = y;
+              const float dlt = q - y;
+              dqv = dlt * (2.0f / (float)Q.M);
+              Q.dz3[(size_t)row * MAX_OUT] = dqv;
+              sq = dlt * dlt;
+            }
+          }
+          if (Q.mode == 1) {  // {sum of squared errors, sum of dQ} per 8 rows: the layout wide_critic_scalars reduces
+#pragma unroll
+            for (int sft = 1; sft < 8; sft <<= 1) {
+              sq += __shfl_xor_sync(0xffffffffu, sq, sft);
+              dqv += __shfl_xor_sync(0xffffffffu, dqv, sft);
+            }
+            if ((lane & 7) == 0 && row < M) {
+              Q.sq_part[2 * (row >> 3)] = sq;
+              Q.sq_part[2 * (row >> 3) + 1] = dqv;
+            }
           }
         }
       } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
@@ -489,7 +526,10 @@ cudaError_t init_tc() {
 
 // Wlo: the precomputed lo part of W (tc_split_lo) => 3xTF32; NULL => plain TF32
 cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W, const float* Wlo, const float* bias,
-                             const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat, cudaStream_t st) {
+                             const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat,
+                             const b2rl_wide_q_t* head, cudaStream_t st) {
+  b2rl_wide_q_t q = {};
+  if (head) q = *head;
   CUtensorMap ma, mb, ml;  // (the weight maps have boxes of HALF a slab: each CTA of a cluster loads one and multicasts it)
   if (!make_map(&ma, X, M, HID, ldx, TCM) || !make_map(&mb, W, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
   const dim3 grid(tc_grid(M)), block(TC_THREADS);
@@ -498,10 +538,10 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
     return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
-                    st2, none);
+                    st2, none, q);
   }
   return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, bias, g, be, ln, relu, H, XH, st2,
-                  none);
+                  none, q);
 }
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
                                  const float* stat1, const float* g1, const float* be1, int ln, float* DZ1, float* part,
@@ -512,12 +552,13 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   float* xh = const_cast<float*>(xh1);
   float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
   const float* none = nullptr;
+  const b2rl_wide_q_t q = {};
   if (w2t_lo) {
     if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
     return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, none, g1, be1, ln, 0, DZ1, xh, st1,
-                    part);
+                    part, q);
   }
-  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1, part);
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1, part, q);
 }
 
 }  // namespace b2rl

@@ -96,12 +96,15 @@ class WideCritic:
             L.check(lib.b2rl_tc_split_lo(w_ptr, dst, 256 * 256, st), "tc_split_lo")
             return dst
 
-        def hidden(x_ptr, net, region, H, XH, stat, slot):
+        def hidden(x_ptr, net, region, H, XH, stat, slot, head=None):
             o = net.off
             w = self._p(region, o["w2n"])
-            L.check(lib.b2rl_tc_linear(x_ptr, 256, M, w, lo_of(slot, w), self._p(region, o["b2"]),
-                                       self._p(region, o["g2"]) if ln else none, self._p(region, o["be2"]) if ln else none, ln, 1,
-                                       H, XH, stat, st), "tc_linear")
+            b2, g2, be2 = self._p(region, o["b2"]), self._p(region, o["g2"]) if ln else none, self._p(region, o["be2"]) if ln else none
+            if head is None:
+                L.check(lib.b2rl_tc_linear(x_ptr, 256, M, w, lo_of(slot, w), b2, g2, be2, ln, 1, H, XH, stat, st), "tc_linear")
+            else:  # the critic's scalar head in the same kernel's epilogue
+                L.check(lib.b2rl_tc_linear_q(x_ptr, 256, M, w, lo_of(slot, w), b2, g2, be2, ln, H, XH, stat, C.byref(head), st),
+                        "tc_linear_q")
 
         # ---- next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor (:194-202)
         ra = RT if ag.td3 else RP
@@ -122,7 +125,7 @@ class WideCritic:
 
         def q_head(net, region, k, mode):
             q = L.WideQ()
-            q.h2, q.w3, q.b3 = (self._ws(1, k) if mode else self.t2.data_ptr()), self._p(region, net.off["w3"]), self._p(region, net.off["b3"])
+            q.h2, q.w3, q.b3 = None, self._p(region, net.off["w3"]), self._p(region, net.off["b3"])
             q.q_out = (self.q if mode else self.qn)[k].data_ptr()
             q.qn0, q.qn1, q.logp = self.qn[0].data_ptr(), self.qn[1].data_ptr(), self.logp.data_ptr()
             q.rows, q.log_alpha = rows.data_ptr(), ag._alpha_state.data_ptr()
@@ -130,21 +133,20 @@ class WideCritic:
             q.targ_out = L.ptr(targ_out) if (mode and k == 0) else None
             q.M, q.mode, q.row_stride, q.rd_off, q.td3, q.bcq_mix = M, mode, rs, O + A, int(ag.td3), int(ag._hyper.bcq_mix)
             q.gamma = ag._hyper.gamma
-            L.check(lib.b2rl_wide_q_head(C.byref(q), st), "wide_q_head")
+            return q
 
         # ---- twin target Q on (next_obs, a')  (agent.py:208-210)
         for k in range(2):
             net = lay.critic[k]
             first(self.xn.data_ptr(), self.ldn, O + A, net, RT, self.t1.data_ptr(), none, none)
-            hidden(self.t1.data_ptr(), net, RT, self.t2.data_ptr(), none, none, 1 + k)
-            q_head(net, RT, k, 0)
+            hidden(self.t1.data_ptr(), net, RT, none, none, none, 1 + k, head=q_head(net, RT, k, 0))  # (h2 stays on chip)
         # ---- twin online Q, TD target, loss, backward (agent.py:212-235)
         G = self._p(RG, 0)
         for k in range(2):
             net, o = lay.critic[k], lay.critic[k].off
             first(rows.data_ptr(), rs, O + A, net, RP, self._ws(0, k), self.xh1[k].data_ptr(), self.st1[k].data_ptr())
-            hidden(self._ws(0, k), net, RP, self._ws(1, k), self.xh2[k].data_ptr(), self.st2[k].data_ptr(), 3 + k)
-            q_head(net, RP, k, 1)
+            hidden(self._ws(0, k), net, RP, self._ws(1, k), self.xh2[k].data_ptr(), self.st2[k].data_ptr(), 3 + k,
+                   head=q_head(net, RP, k, 1))
             L.check(lib.b2rl_wide_ln_bwd(self._dz3(k), 1, self._p(RP, o["w3"]), self.xh2[k].data_ptr(), self.st2[k].data_ptr(),
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
                                          self._ws(3, k), self.part2[k].data_ptr(), st), "wide_ln_bwd")
@@ -270,11 +272,14 @@ class WideActor:
         for k in range(self.nq):
             net = lay.critic[k]
             first(self.xq.data_ptr(), self.ldn, O + A, net, self.t1.data_ptr(), self.xq1[k].data_ptr(), self.sq1[k].data_ptr())
-            hidden(self.t1.data_ptr(), net, self.t2.data_ptr(), self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), 1 + k)
-            q = L.WideQ()
-            q.h2, q.w3, q.b3 = self.t2.data_ptr(), self._p(RP, net.off["w3"]), self._p(RP, net.off["b3"])
+            q = L.WideQ()  # the scalar head rides in the hidden layer's epilogue; h2 itself is not needed (x-hat is, for the backward)
+            q.h2, q.w3, q.b3 = None, self._p(RP, net.off["w3"]), self._p(RP, net.off["b3"])
             q.q_out, q.M, q.mode = self.q[k].data_ptr(), M, 0
-            L.check(lib.b2rl_wide_q_head(C.byref(q), st), "wide_q_head")
+            o = net.off
+            w2 = self._p(RP, o["w2n"])
+            L.check(lib.b2rl_tc_linear_q(self.t1.data_ptr(), 256, M, w2, lo_of(1 + k, w2), self._p(RP, o["b2"]),
+                                         self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, None,
+                                         self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), C.byref(q), st), "tc_linear_q")
         L.check(lib.b2rl_wide_actor_loss(self.q[0].data_ptr(), None if ag.td3 else self.q[1].data_ptr(),
                                          None if ag.td3 else self.logp.data_ptr(), None if ag.td3 else la, int(ag.td3), M,
                                          self.dzq[0].data_ptr(), None if ag.td3 else self.dzq[1].data_ptr(),
