@@ -58,7 +58,7 @@ class WideCritic:
         self.part1, self.part2 = torch.zeros(2, self.P128, 3, 256, **f32), torch.zeros(2, self.P128, 3, 256, **f32)
         self.sq = torch.zeros(2, self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
         self.ws = ag.workspace(M)
-        self.wlo = torch.zeros(7, 256 * 256, **f32)  # lo parts of the seven 256x256 matrices a critic step multiplies by
+        self.wlo = torch.zeros(2, ag.layout.region, **f32)  # lo parts (3xTF32) of the online and target regions, same offsets
         self.gscratch = _wgrad_scratch(self._lib, ag, M, dev)
 
     # pointers into the arena: region r, float offset o
@@ -89,12 +89,14 @@ class WideCritic:
                                         self._p(region, o["g1"]) if ln else none, self._p(region, o["be1"]) if ln else none, ln,
                                         H, XH, stat, st), "wide_first")
 
-        def lo_of(slot, w_ptr):  # the weights change every step: their lo parts are recomputed (256 KB each)
-            if not self.x3:
-                return none
-            dst = self.wlo[slot].data_ptr()
-            L.check(lib.b2rl_tc_split_lo(w_ptr, dst, 256 * 256, st), "tc_split_lo")
-            return dst
+        # the weights change every step: their lo parts are recomputed — ONE launch over the online + target regions
+        # (1.7 MB; they are neighbours in the arena), not one per matrix; every weight keeps its arena offset in the mirror
+        base = self._p(RP, 0)
+        if self.x3:
+            L.check(lib.b2rl_tc_split_lo(base, self.wlo.data_ptr(), 2 * lay.region, st), "tc_split_lo")
+
+        def lo_of(slot, w_ptr):
+            return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
 
         def hidden(x_ptr, net, region, H, XH, stat, slot, head=None):
             o = net.off
@@ -203,7 +205,7 @@ class WideActor:
         self.part = torch.zeros(2, self.P128, 3, 256, **f32)
         self.part_s, self.part_du = torch.zeros(self.P256, 2, **f32), torch.zeros(self.P256, L.MAX_OUT, **f32)
         self.ws = ag.workspace(M)
-        self.wlo = torch.zeros(6, 256 * 256, **f32)
+        self.wlo = torch.zeros(ag.layout.region, **f32)  # lo parts (3xTF32) of the online region, same offsets
         self.gscratch = _wgrad_scratch(self._lib, ag, M, dev)
 
     _p = WideCritic._p
@@ -228,12 +230,12 @@ class WideActor:
                                         self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
                                         H, XH, stat, st), "wide_first")
 
+        base = self._p(RP, 0)
+        if self.x3:  # one launch over the online region (the critic step's Adam has just changed the critics)
+            L.check(lib.b2rl_tc_split_lo(base, self.wlo.data_ptr(), lay.region, st), "tc_split_lo")
+
         def lo_of(slot, w_ptr):
-            if not self.x3:
-                return none
-            dst = self.wlo[slot].data_ptr()
-            L.check(lib.b2rl_tc_split_lo(w_ptr, dst, 256 * 256, st), "tc_split_lo")
-            return dst
+            return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
 
         def hidden(x_ptr, net, H, XH, stat, slot):
             o = net.off
@@ -336,8 +338,8 @@ class WideActor:
                                     self.t1.data_ptr(), none, none, st), "wide_first")
         w = self._p(RP, o["w2n"])
         wl = none
-        if self.x3:
-            wl = self.wlo[0].data_ptr()
+        if self.x3:  # (the actor's Adam step has just changed this matrix)
+            wl = self.wlo.data_ptr() + (w - self._p(RP, 0))
             L.check(lib.b2rl_tc_split_lo(w, wl, 256 * 256, st), "tc_split_lo")
         L.check(lib.b2rl_tc_linear(self.t1.data_ptr(), 256, M, w, wl, self._p(RP, o["b2"]), self._p(RP, o["g2"]) if ln else none,
                                    self._p(RP, o["be2"]) if ln else none, ln, 1, self.t2.data_ptr(), none, none, st), "tc_linear")
