@@ -323,3 +323,40 @@ def test_errors_are_loud():
     ag = make_agent(inp)
     with pytest.raises(L.B2rlError, match=">= 1"):
         ag.update_qnets(torch.zeros(0, ag.fmt.row_stride, device="cuda"))
+
+
+def test_bad_sampling_and_tensor_core_arguments_are_refused():
+    """Error behaviour of the entry points added for in-kernel sampling / the folded replay write and of the tcgen05
+    entry points: a negative return code with a message, nothing launched."""
+    import ctypes as C
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    inp = case_inputs("sac_hopper")
+    ag = make_agent(inp)
+    rows = torch.zeros(16, ag.fmt.row_stride, device="cuda")
+    storage = torch.zeros(64, ag.fmt.row_stride, device="cuda")
+    new = torch.zeros(4, ag.fmt.row_stride, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    # the replay write needs in-kernel sampling
+    a = ag.update_args(rows)
+    a.new_rows, a.n_new, a.capacity = new.data_ptr(), 4, 64
+    assert lib.b2rl_critic_update_sac(C.byref(a), st) < 0 and b"storage" in lib.b2rl_last_error()
+    # more new rows than the buffer holds
+    a = ag.update_args(rows, storage=storage, new_rows=new, n_new=4)
+    a.n_new = 100
+    assert lib.b2rl_critic_update_sac(C.byref(a), st) < 0 and b"n_new" in lib.b2rl_last_error()
+    # a misaligned replay storage
+    a = ag.update_args(rows, storage=storage)
+    a.storage = storage.data_ptr() + 4
+    assert lib.b2rl_critic_update_sac(C.byref(a), st) < 0
+    # tensor-core weight gradient: MA larger than the columns that exist / misaligned operand
+    x = torch.zeros(256, 64, device="cuda")
+    y = torch.zeros(256, 256, device="cuda")
+    c = torch.zeros(64, 256, device="cuda")
+    sc = torch.zeros(lib.b2rl_tc_wgrad_scratch_floats(64, 256), device="cuda")
+    assert lib.b2rl_tc_wgrad(x.data_ptr(), 64, 32, 64, y.data_ptr(), 256, c.data_ptr(), None, sc.data_ptr(), 0, None, st) < 0
+    assert lib.b2rl_tc_wgrad(x.data_ptr() + 4, 64, 64, 64, y.data_ptr(), 256, c.data_ptr(), None, sc.data_ptr(), 0, None, st) < 0
+    assert lib.b2rl_tc_wgrad_scratch_floats(0, 256) < 0
+    # fused critic head without a head
+    assert lib.b2rl_tc_linear_q(y.data_ptr(), 256, 256, y.data_ptr(), None, y.data_ptr(), None, None, 0, None, None, None, None, st) < 0
+    torch.cuda.synchronize()  # (nothing was launched: no sticky error)
