@@ -77,7 +77,7 @@ __device__ __forceinline__ void g_split_lo(const float* src, float* dst, int n_f
 template <int PREC>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Bn, int rows_per_split,
-                int MA_pad, float* __restrict__ part) {
+                int MA_pad, int MA, float* __restrict__ part) {
   extern __shared__ unsigned char g_raw[];
   using Smem = GSmemT<PREC>;
   constexpr int ST = Smem::STAGES;
@@ -153,7 +153,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
     float* dst = part + ((size_t)sp * MA_pad + m0 + 32 * lg + lane) * GN;
-    if (KB > 0) {
+    const bool live = m0 + 32 * lg + lane < MA;  // only rows that exist are written (dW1: 14 of 128, a critic's dW3: 1)
+    if (m0 + 32 * lg >= MA) {
+      // none of this warp's 32 rows exists: nothing to read back or write
+    } else if (KB > 0) {
       g_mbar_wait(&S.acc_full, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tl = tmem + ((uint32_t)(32 * lg) << 16);
@@ -170,10 +173,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             : "r"(tl + c * 32));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+        if (live) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d4[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) d4[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+        }
       }
-    } else {  // an empty slice (more splits than slabs): zeros
+    } else if (live) {  // an empty slice (more splits than slabs): zeros
       for (int c = 0; c < GN / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -269,8 +274,8 @@ cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, con
   if (!g_map(&ma, A, Bn, a_cols, lda) || !g_map(&mb, Bm, Bn, GN, GN)) return cudaErrorInvalidValue;
   const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn, MA);
   const int rps = (((Bn + S - 1) / S) + GK - 1) / GK * GK;
-  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, scratch);
-  else tc_wgrad_kernel<0><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, scratch);
+  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
+  else tc_wgrad_kernel<0><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump);
