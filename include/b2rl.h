@@ -404,8 +404,9 @@ int b2rl_bump_counter(uint64_t* counters, int32_t which, int32_t n_agents, void*
 /* Replaces the policies behind Agent.predict (agents/agent.py:172-181, nets.py:149-159,222-234):
  * actor forward on n observation rows [n][ob_dim] -> actions [n][A].
  *   mode 0: SAC mode / TD3 exploit;  1: SAC sample / TD3 explore (noise from a->eps [n][A], or
- *   Philox keyed on `draw`, which the caller advances per call; draw = UINT64_MAX with a->counters set: keyed on
- *   counters[B2RL_CTR_Q], for use inside a captured step graph). `obs` and `actions_out` may be pinned host memory
+ *   Philox keyed on (`draw`, a->agent_base = the learner's global id), `draw` < 2^31 advanced by the caller per call;
+ *   draw = UINT64_MAX with a->counters set: keyed on counters[B2RL_CTR_Q] | 2^31, for use inside a captured step graph,
+ *   a key space disjoint from the host-counted draws). `obs` and `actions_out` may be pinned host memory
  *   (device-addressable): the kernel then is the host<->device copy. */
 int b2rl_actor_predict(const b2rl_update_args_t* a, const float* obs, int32_t n, int32_t mode,
                        float explore_std, uint64_t draw, float* actions_out, void* stream);

@@ -56,9 +56,14 @@ class ArenaAdam:
         """No-op: the backward kernels overwrite every gradient element (nothing accumulates)."""
 
     def step(self) -> None:
-        """Apply Adam to the gradients currently in region 4 (advances the step count first)."""
+        """Apply Adam to the gradients currently in region 4 (advances the step count first). Like
+        torch.optim.Adam.step() it does NOT clip: gradient clipping (hps.clip_norm) is part of Agent.update_actor."""
         ag = self._agent
         st = ag._stream()
+        if not self.spans:  # the temperature: a scalar whose gradient sits in its state block (slot 1)
+            L.check(ag._lib.b2rl_alpha_adam(ag._alpha_state.data_ptr(), ag.counters.data_ptr(), 1, self.lr, 1.0,
+                                            ag.out.data_ptr(), st), "alpha_adam")  # (bumps counters[ALPHA] itself)
+            return
         L.check(ag._lib.b2rl_bump_counter(ag.counters.data_ptr(), self.counter, 1, st), "bump_counter")
         ag._launch_adam([ag._seg(b, e, self.lr, adam=True, polyak=False, counter=self.counter) for b, e in self.spans])
 
@@ -251,14 +256,7 @@ class Agent:
         return a
 
     def _launch_adam(self, segs: list) -> None:
-        a = L.AdamArgs()
-        for i, s in enumerate(segs):
-            a.seg[i] = s
-        a.n_seg, a.n_agents = len(segs), 1
-        a.polyak, a.clip_norm = float(self.hps.polyak), float(self.hps.clip_norm)
-        a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-8
-        a.region_stride, a.arena_agent_stride = self.layout.region, self.arena.agent_stride
-        a.arena, a.counters, a.grad_sumsq = self.arena.flat.data_ptr(), self.counters.data_ptr(), self._sumsq.data_ptr()
+        a = self._adam_args(segs)
         L.check(self._lib.b2rl_adam_polyak_multi(C.byref(a), self._stream()), "adam_polyak_multi")
 
     # segments used by the update functions and by engine.py
@@ -360,6 +358,7 @@ class Agent:
         args = L.UpdateArgs()
         args.hp, args.fmt, args.actor = self._hyper, self.fmt, self.layout.actor.c_struct()
         args.arena, args.region_stride = self.arena.flat.data_ptr(), self.layout.region
+        args.agent_base = self.agent_id  # part of the Philox key of the exploration noise
         args.min_ac, args.max_ac = self.min_ac.data_ptr(), self.max_ac.data_ptr()
         if eps is not None:
             eps = eps.to(device=self.device, dtype=torch.float32).contiguous()

@@ -23,7 +23,7 @@ STAMP = PKG / "csrc" / ".build_stamp"
 SOURCES = ["api.cu", "replay.cu", "critic.cu", "actor.cu", "wgrad.cu", "adam.cu", "tc_linear.cu", "wide.cu", "tc_wgrad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false" if False else "-Xcompiler", "-fPIC",
+    "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
     "-Xptxas", "-v", "-shared", "-cudart", "static",
 ]
 

@@ -379,8 +379,11 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
   const bool td3 = A.hp.td3 != 0;
   const float* P = A.arena;
   // draw = ~0: key the exploration noise on the critic step counter (a captured step graph cannot take a new
-  // host value per replay; the counter advances once per learner iteration)
-  const uint64_t step = (draw == ~0ull && A.counters) ? A.counters[B2RL_CTR_Q] : draw;
+  // host value per replay; the counter advances once per learner iteration). Bit 31 of the 32-bit step field separates
+  // these draws from the host-counted ones (draw = 1, 2, ... < 2^31), and the GLOBAL agent id is part of the key, so learners
+  // that share a seed (data-parallel ranks, population members) explore independently.
+  const uint64_t step = (draw == ~0ull && A.counters) ? (A.counters[B2RL_CTR_Q] | 0x80000000ull) : draw;
+  const uint32_t agent = (uint32_t)A.agent_base;
   if (w == 0) stage_net(P, &A.actor, &M.ns, &M.n, G.c * CW);
   else stage_tile(batch_row(obs, O, b0, nvalid), nvalid, 0, O, X, O, t - 32, NT - 32);
   const Net& act = M.n;
@@ -401,9 +404,9 @@ predict_kernel(const __grid_constant__ b2rl_update_args_t A, const float* __rest
       if (td3) {  // agents/nets.py:149-159
         float th;
         a = td3_action(u0, scale, bias, th);
-        if (mode == 1) a += noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS) * (scale * explore_std);
+        if (mode == 1) a += noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, agent, STREAM_ACTOR_EPS) * (scale * explore_std);
       } else if (mode == 1) {  // sample
-        const float z = noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, 0, STREAM_ACTOR_EPS);  // key != learner's
+        const float z = noise_at(A.eps, e, ~A.hp.seed, b0 + r, l, step, agent, STREAM_ACTOR_EPS);  // key != learner's
         a = gauss_sample(u0, uref(S.u, r, AD + l), z, scale, bias).action;
       } else {  // mode = tanh(mean)*scale + bias, agents/nets.py:233
         a = __fadd_rn(__fmul_rn(tanhf(u0), scale), bias);

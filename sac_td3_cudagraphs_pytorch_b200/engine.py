@@ -147,11 +147,26 @@ class LearnerEngine:
         device; valid until the step two launches later): polls the sequence number the step's policy part publishes
         — it runs FIRST in the graph, so the environments can step while the update of the same replay runs."""
         n, slot, want = self._act_last
-        seq = self._host_act_seq_np
-        while seq[0] < want:
-            pass
+        self._poll(self._host_act_seq_np, want, "the policy's actions")
         ag = self.agent
         return self._h_act[(n, slot)].numpy()[: n * ag.ac_dim].reshape(n, ag.ac_dim)
+
+    def _poll(self, seq, want: int, what: str, timeout_s: float = 30.0) -> None:
+        """Spin on a pinned sequence number the device publishes. Every 4096 empty polls the stream is queried: a step
+        that has FINISHED without publishing (a faulted replay: the publish kernel never ran) or a deadline miss raises
+        instead of hanging the host."""
+        spins, t0 = 0, None
+        while seq[0] < want:
+            spins += 1
+            if spins & 0xFFF:
+                continue
+            import time
+            t0 = t0 or time.monotonic()
+            done = torch.cuda.current_stream(self.agent.device).query()  # raises on a sticky CUDA error
+            if done and seq[0] < want:
+                raise L.B2rlError(f"the stream drained but {what} was never published (sequence {int(seq[0])} < {want})")
+            if time.monotonic() - t0 > timeout_s:
+                raise L.B2rlError(f"timed out after {timeout_s:.0f} s waiting for {what} (sequence {int(seq[0])} < {want})")
 
     def step_async(self, i: int, n_new: int = 0, n_obs: int = 0, explore: bool = True) -> int:
         """orchestrator.py:100-113 + :337-352 as ONE CUDA graph replay and no stream synchronisation: the replay
@@ -191,9 +206,7 @@ class LearnerEngine:
     def wait(self, ticket: int, as_numpy: bool = False):
         """Poll the sequence number the step's last kernel publishes; returns that step's pinned log block
         (_lib.OUT_* indices; a torch tensor, or its numpy view), valid until the step two tickets later is launched."""
-        seq = self._host_seq_np
-        while seq[0] < ticket:  # the device writes it after the log block (system-scope fence in between)
-            pass
+        self._poll(self._host_seq_np, ticket, "the step's log block")  # written after the log block (system-scope fence)
         self._waited = max(self._waited, int(ticket))
         return (self._host_outs_np if as_numpy else self._host_outs)[(ticket - 1) & 1]
 
@@ -210,7 +223,7 @@ class LearnerEngine:
             self.host_obs(n_obs, slot)
             pa = L.UpdateArgs()
             pa.hp, pa.fmt, pa.actor = ag._hyper, ag.fmt, ag.layout.actor.c_struct()
-            pa.arena, pa.region_stride = ag.arena.flat.data_ptr(), ag.layout.region
+            pa.arena, pa.region_stride, pa.agent_base = ag.arena.flat.data_ptr(), ag.layout.region, ag.agent_id
             pa.min_ac, pa.max_ac, pa.counters = ag.min_ac.data_ptr(), ag.max_ac.data_ptr(), ag.counters.data_ptr()
             self._keep.append(pa)
         g = torch.cuda.CUDAGraph()

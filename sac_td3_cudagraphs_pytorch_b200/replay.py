@@ -47,7 +47,9 @@ class Batch(dict):
 
 
 def pack_rows(td: Mapping[str, torch.Tensor], fmt: L.RowFmt, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[n] transitions given as the reference's six keys -> [n, row_stride] packed rows."""
+    """[n] transitions given as the reference's six keys -> [n, row_stride] packed rows.
+    Only ``dones`` is stored: the reference's writer sets ``dones = terminations`` (orchestrator.py:107-108) and the
+    update reads ``dones`` alone (agents/agent.py:226-228), so ``Batch["terminations"]`` returns the same column."""
     obs = td["observations"]
     n = obs.shape[0]
     if out is None:
@@ -106,11 +108,16 @@ class ReplayBuffer:
                idx_out: Optional[torch.Tensor] = None) -> Batch:
         if self._size == 0:
             raise RuntimeError("cannot sample from an empty replay buffer")
+        # (the returned Batch ALIASES these cached buffers: the next sample() of the same size overwrites it — pass
+        # `out` / `idx_out` to keep a batch)
         if out is None:
-            out = self._rows.setdefault(batch_size, torch.empty(batch_size, self.fmt.row_stride,
-                                                                dtype=torch.float32, device=self.device))
+            if batch_size not in self._rows:
+                self._rows[batch_size] = torch.empty(batch_size, self.fmt.row_stride, dtype=torch.float32, device=self.device)
+            out = self._rows[batch_size]
         if idx_out is None:
-            idx_out = self._idx.setdefault(batch_size, torch.empty(batch_size, dtype=torch.int64, device=self.device))
+            if batch_size not in self._idx:
+                self._idx[batch_size] = torch.empty(batch_size, dtype=torch.int64, device=self.device)
+            idx_out = self._idx[batch_size]
         if idx is not None:
             idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
         st = torch.cuda.current_stream(self.device).cuda_stream

@@ -20,6 +20,8 @@ CASES = {
     "sac_hopper": dict(base=SAC, ob=11, ac=3, lo=[-1.0] * 3, hi=[1.0] * 3, B=256, N=1024, iters=6, seed=1000),
     "td3_hopper": dict(base=TD3, ob=11, ac=3, lo=[-1.0] * 3, hi=[1.0] * 3, B=256, N=1024, iters=6, seed=2000),
     "sac_humanoid": dict(base=SAC, ob=376, ac=17, lo=[-0.4] * 17, hi=[0.4] * 17, B=64, N=256, iters=4, seed=3000),
+    # BASELINE.json configs[2] at its own batch size (the wide first layers' clamped tails are B-dependent code)
+    "sac_humanoid_b256": dict(base=SAC, ob=376, ac=17, lo=[-0.4] * 17, hi=[0.4] * 17, B=256, N=1024, iters=4, seed=3500),
     # option coverage: no LayerNorm, fixed alpha, BCQ mix under SAC, asymmetric per-dim bounds, odd dims
     "sac_noln_fixedalpha_bcq": dict(base=SAC, ob=5, ac=2, lo=[-1.0, -0.5], hi=[2.0, 0.5], B=32, N=128, iters=4,
                                     seed=4000, over=dict(layer_norm=False, autotune=False, bcq_style_targ_mix=True,

@@ -192,7 +192,8 @@ def test_engine_step_with_policy_in_the_graph(name, explore):
     for i in range(n_it):
         rows = torch.randn(n_new, rbs[0].fmt.row_stride, generator=g)
         obs = torch.randn(n_obs, inp["ob"], generator=g)
-        draw = int(agents[1].counters[L.CTR_Q])  # the graph keys the exploration noise on the critic step counter
+        # the graph keys the exploration noise on the critic step counter, bit 31 set (host-counted draws stay below 2^31)
+        draw = int(agents[1].counters[L.CTR_Q]) | 0x80000000
         want = agents[1].predict_device(obs, explore=explore, draw=draw).cpu().numpy()
         e_pol.host_rows(n_new).copy_(rows)
         e_pol.host_obs(n_obs).copy_(obs)

@@ -54,5 +54,79 @@ def main(names):
             row("log_alpha", ag.log_alpha, o32.log_alpha, o64.log_alpha)
 
 
+
+
+# ---- multi-step part: the golden protocol and N in {1, 10, 100} iterations (what tests/test_gpu_parity.py bounds) ------------
+def protocol_table(names):
+    import json
+
+    import numpy as np
+
+    from tests.golden import portable as P
+    from tests.golden.make_golden import GROUPS, run_oracle
+    from tests.test_gpu_parity import run_agent_protocol
+    gold = Path(__file__).resolve().parent.parent / "tests" / "golden"
+    print("\n== protocol trajectories (orchestrator.py:337-352 cadence): worst per-tensor max|a-b|/max|b| per group")
+    print(f"   {'case':28s} {'group':13s} {'cuda-vs-fixture':>16s} {'cuda-vs-o64':>12s} {'o32-vs-o64':>12s}")
+    for name in names:
+        inp = case_inputs(name)
+        z = np.load(gold / f"{name}.npz")
+        meta = json.loads(bytes(z["meta"]).decode())
+        rec = run_agent_protocol(inp, make_agent(inp))
+        r32, r64 = run_oracle(inp, torch.float32, capturable=True), run_oracle(inp, torch.float64, capturable=True)
+        for g in GROUPS:
+            if g not in rec:
+                continue
+            wf = wc = wr = 0.0
+            for n, t in rec[g].items():
+                wf = max(wf, P.summary_close(P.summarize(t), z[f"{g}/{n}"], 1.0)[1])
+                wc = max(wc, rel_dev(t, r64[g][n]))
+                wr = max(wr, rel_dev(r32[g][n], r64[g][n]))
+            print(f"   {name:28s} {g:13s} {wf:16.3e} {wc:12.3e} {wr:12.3e}")
+        print(f"   {name:28s} {'(fixture meta)':13s} reference fp32-vs-fp64 over all tensors and logs: "
+              f"{meta['reference_fp32_vs_fp64_oracle']:.3e}")
+
+
+def n_updates_table():
+    from tests.golden import portable as P
+    print("\n== parameters after N iterations vs the float64 oracle (tests/test_gpu_parity.py::test_params_after_n_updates)")
+    for name, n_iter in (("sac_hopper", 1), ("sac_hopper", 10), ("sac_hopper", 100), ("td3_hopper", 1), ("td3_hopper", 10),
+                         ("td3_hopper", 100), ("sac_humanoid_b256", 10)):
+        inp = case_inputs(name)
+        c = CASES[name]
+        s = c["seed"] + 50_000
+        ag = make_agent(inp)
+        o32, o64 = make_oracle(inp, torch.float32), make_oracle(inp, torch.float64)
+        delay = inp["hps"]["actor_update_delay"]
+        for i in range(n_iter):
+            idx = P.indices(s + i, c["N"], c["B"])
+            b32 = {k: v[idx] for k, v in inp["storage"].items()}
+            b64 = {k: (v.double() if v.is_floating_point() else v) for k, v in b32.items()}
+            eq = P.noise(s + 10_000 + i, c["B"], c["ac"])
+            ep = [P.noise(s + 20_000 + 10 * i + j, c["B"], c["ac"]) for j in range(delay)]
+            ea = [P.noise(s + 30_000 + 10 * i + j, c["B"], c["ac"]) for j in range(delay)]
+            o32.iteration(i, b32, eq, ep, ea)
+            o64.iteration(i, b64, eq.double(), [e.double() for e in ep], [e.double() for e in ea])
+            bd = {k: v.cuda() for k, v in b32.items()}
+            ag.update_qnets(bd, eps=eq.cuda())
+            ag.qnet_updates_so_far += 1
+            if i % (delay + 1) == 0:
+                for j in range(delay):
+                    ag.update_actor(bd, eps=ep[j].cuda(), eps_alpha=ea[j].cuda())
+            ag.update_targ_nets()
+        torch.cuda.synchronize()
+        groups = [("qnet", ag.qnet_params, o32.qnet, o64.qnet), ("qnet_target", ag.qnet_target, o32.qnet_target, o64.qnet_target),
+                  ("actor", ag.actor_params, o32.actor, o64.actor)]
+        for gname, got, r32, r64 in groups:
+            wc = max(rel_dev(got[n], r64[n]) for n in r32)
+            wr = max(rel_dev(r32[n], r64[n]) for n in r32)
+            w32 = max(rel_dev(got[n], r32[n]) for n in r32)
+            print(f"   {name:20s} N={n_iter:<4d} {gname:12s} cuda-vs-o64 {wc:10.3e}  o32-vs-o64 {wr:10.3e}  cuda-vs-o32 {w32:10.3e}")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1:] or list(CASES))
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CASES)
+    main(names)
+    protocol_table(names)
+    if len(names) == len(CASES):
+        n_updates_table()
