@@ -306,11 +306,11 @@ def run_b2rl(args, rank, world, device):
     Wlo = torch.empty_like(Wt)
     vb, vg, vbe = torch.randn(256, device=device), torch.ones(256, device=device), torch.zeros(256, device=device)
     Ht, XHt, stt = torch.empty(MT, 256, device=device), torch.empty(MT, 256, device=device), torch.empty(MT, 2, device=device)
-    L.check(lib.b2rl_tc_split_lo(Wt.data_ptr(), Wlo.data_ptr(), Wt.numel(), st()))
+    L.check(lib.b2rl_tc_split_lo(Wt.data_ptr(), Wlo.data_ptr(), Wt.numel(), None, st()))
     roof_tc = {}
     for tag, lo in (("3xtf32", Wlo.data_ptr()), ("tf32", None)):
         t_tc = time_kernel(lambda: L.check(lib.b2rl_tc_linear(Xt.data_ptr(), 256, MT, Wt.data_ptr(), lo, vb.data_ptr(), vg.data_ptr(),
-                                                              vbe.data_ptr(), 1, 1, Ht.data_ptr(), XHt.data_ptr(), stt.data_ptr(), st())),
+                                                              vbe.data_ptr(), 1, 1, Ht.data_ptr(), XHt.data_ptr(), stt.data_ptr(), None, st())),
                            iters=100, warm=20)
         tc_bytes = 3 * MT * 256 * 4 + 2 * 256 * 256 * 4
         roof_tc[tag] = {"us_per_launch": t_tc * 1e6, "achieved": tc_bytes / t_tc / 1e9, "frac": tc_bytes / t_tc / 1e9 / hbm_peak,

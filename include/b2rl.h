@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2RL_VERSION 100 /* 0.1.0 */
+#define B2RL_VERSION 110 /* 0.1.1 */
 #define B2RL_HID 256     /* hidden width; agents/agent.py:56,101 hard-codes (256, 256) */
 #define B2RL_ROWS 8      /* batch rows per CTA group of the fused kernels; a batch need not be a multiple (the tail is masked) */
 #define B2RL_MAX_OUT 64  /* max head width (2*A for SAC) */
@@ -222,6 +222,28 @@ int b2rl_replay_extend(float* storage, int64_t capacity, int64_t cursor, b2rl_ro
 int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, const float* new_rows, int32_t n,
                            uint64_t* counters, void* stream);
 
+/* ---- stacked agents on the wide path ------------------------------------------------------------------------------------
+ * Every entry point of the wide (layer-by-layer, tensor-core) path below takes a trailing `const b2rl_stack_t* stack`.
+ * NULL = one learner, M batch rows. Otherwise n_agents independent learners are processed by the same launches
+ * (BASELINE.json config 4: a population of agents, the reference's one-process-per-seed scale-out, spawner.py:148-178):
+ *   - M is the number of rows PER AGENT and every per-row array ([M][..]) is [n_agents][M][..], contiguous;
+ *   - every parameter / gradient pointer (weights, biases, LayerNorm affine, the gradient region G) addresses agent 0's
+ *     copy and agent g's is `param_stride` floats further (the arena's agent stride); lo parts: `lo_stride`;
+ *   - per-agent scalars: log_alpha / alpha state (`alpha_stride` floats), step counters (`counters_stride` uint64), the
+ *     log block `out` (`out_stride` floats); per-CTA partial-sum scratch arrays are [n_agents][P][..];
+ *   - Philox streams are keyed on the GLOBAL agent id `agent_base + g` and on the row index inside the agent's batch,
+ *     so the draws equal those of the single-learner path and do not depend on how a population is sharded.
+ * No data is shared between agents and nothing is reduced across them. */
+typedef struct b2rl_stack {
+  int32_t n_agents;        /* >= 1 */
+  int32_t agent_base;      /* global id of local agent 0 */
+  int64_t param_stride;    /* floats between consecutive agents' copies of a parameter / gradient tensor */
+  int64_t lo_stride;       /* floats between consecutive agents' lo-part tensors (b2rl_tc_split_lo) */
+  int64_t alpha_stride;    /* floats between agents' log_alpha state blocks */
+  int64_t counters_stride; /* uint64 between agents' counter blocks (8) */
+  int64_t out_stride;      /* floats between agents' log blocks (8) */
+} b2rl_stack_t;
+
 /* Large-batch hidden layer on the tensor cores (tcgen05.mma kind::tf32, operands staged by TMA, accumulator in
  * TMEM): H = [ReLU](LayerNorm(X . W^T + bias)) for X [M][256] (row pitch ldx floats, 16-byte aligned rows) and W
  * [256][256] in torch's natural layout — agents/nets.py:66-82 (fc_block_2) for M in the tens of thousands
@@ -229,11 +251,12 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
  * outputs fp32. H [M][256]; XH (x-hat, or the pre-activation when ln = 0) and stat (mean, rstd per row) may be
  * NULL. Builds two TMA descriptors on the host, then enqueues one kernel. */
 int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
-                   const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, void* stream);
+                   const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, const b2rl_stack_t* stack,
+                   void* stream);
 /* W_lo (here and in b2rl_tc_linear_bwd): NULL => plain TF32 products (~1e-3); else the "lo part" of W from
  * b2rl_tc_split_lo => 3xTF32: x = hi + lo, a.b ~ hi.hi + lo.hi + hi.lo as three MMAs into the same TMEM accumulator
  * — fp32-level accuracy (~1e-6) on the tensor cores (the activations' lo parts are made in shared memory). */
-int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, void* stream);
+int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, const b2rl_stack_t* stack, void* stream);
 
 /* ---- the wide (layer-by-layer, tensor-core) path for large batches: csrc/wide.cu, csrc/tc_linear.cu ------------------
  * Each entry point is one batch-parallel kernel of agents/agent.py:186-235 / agents/nets.py; the host mirror
@@ -241,13 +264,14 @@ int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, void* stream);
 
 /* First layer (agents/nets.py:66-72): H = ReLU(LayerNorm(X[:, :K] . w1t + b)); w1t [K][256] forward layout. */
 int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
-                    const float* be, int32_t layer_norm, float* H, float* XH, float* stat, void* stream);
+                    const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_stack_t* stack, void* stream);
 
 /* Backward dX product of the hidden layer on the tensor cores with the LayerNorm / ReLU backward of layer 1 in the
  * epilogue: DZ1 = LNbwd(ReLU'(DZ2 . W2)); w2t = forward-layout copy of fc_block_2.fc.weight; part [ceil(M/128)][3][256]
  * receives per-CTA column sums {sum dz, sum dn*xhat, sum dn}. */
 int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
-                       const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, void* stream);
+                       const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, const b2rl_stack_t* stack,
+                       void* stream);
 
 typedef struct b2rl_wide_policy {  /* policy head + action sample (agents/nets.py:143-147, :214-234; agent.py:194-205) */
   const float* h2;      /* [M][256] */
@@ -269,7 +293,7 @@ typedef struct b2rl_wide_policy {  /* policy head + action sample (agents/nets.p
   uint32_t agent;
   uint32_t reserved;
 } b2rl_wide_policy_t;
-int b2rl_wide_policy_head(const b2rl_wide_policy_t* p, void* stream);
+int b2rl_wide_policy_head(const b2rl_wide_policy_t* p, const b2rl_stack_t* stack, void* stream);
 
 typedef struct b2rl_wide_q {  /* critic head; mode 1 adds the TD target, dLoss/dQ and squared-error partials (agent.py:212-233) */
   const float* h2;
@@ -288,24 +312,25 @@ typedef struct b2rl_wide_q {  /* critic head; mode 1 adds the TD target, dLoss/d
   float gamma;
   uint32_t reserved;
 } b2rl_wide_q_t;
-int b2rl_wide_q_head(const b2rl_wide_q_t* q, void* stream);
+int b2rl_wide_q_head(const b2rl_wide_q_t* q, const b2rl_stack_t* stack, void* stream);
 /* The critic's second layer (b2rl_tc_linear with ReLU) with that head fused into its epilogue — the thread that owns a row
  * of h2 takes its dot product with w3 (q->h2 is ignored): no second pass over h2, and H may be NULL (target critics:
  * h2 never goes to memory). agents/nets.py:88-92 + agents/agent.py:208-233. */
 int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
-                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_wide_q_t* q, void* stream);
+                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_wide_q_t* q,
+                     const b2rl_stack_t* stack, void* stream);
 
 /* Head backward + ReLU mask + LayerNorm backward of layer 2: dz = LNbwd(ReLU'(dz3[:, :n_out] . w3)); part
  * [ceil(M/128)][3][256] per-CTA column sums. */
 int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,
-                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, void* stream);
+                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, const b2rl_stack_t* stack, void* stream);
 /* Column-sum partials -> gradients of bias / ln.weight / ln.bias at float offsets off_* of the gradient region G. */
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
-                     void* stream);
+                     const b2rl_stack_t* stack, void* stream);
 /* qf_loss -> out[B2RL_OUT_QF_LOSS] and the head-bias gradients of the twin critics, from wide_q_head's per-CTA partials
  * (sq0 / sq1 [P][2]; dz3_0 / dz3_1 are unused and may be NULL). */
 int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
-                             float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream);
+                             float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, const b2rl_stack_t* stack, void* stream);
 /* Actor step, wide path (agents/agent.py:247-303). actor_loss: per-row loss and dLoss/dQ_k (column 0 of dzq_k
  * [M][B2RL_MAX_OUT]; q1 / dzq1 NULL for TD3), per-CTA partials part [ceil(M/256)][2]. dqda: dQ/da = dz1 . w1t[O + a][:]
  * (w1a = w1t + O * 256). actor_head_bwd: du [M][B2RL_MAX_OUT] = dLoss/d(head outputs) from dQ/da (summed over the
@@ -313,24 +338,27 @@ int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, cons
  * log-prob / alpha -> out, d head.bias -> G. alpha_grad: alpha_state[1] <- alpha * mean(-logpi'' - targ_ent); follow
  * with b2rl_alpha_adam. */
 int b2rl_wide_actor_loss(const float* q0, const float* q1, const float* logp, const float* log_alpha, int32_t td3, int32_t M,
-                         float* dzq0, float* dzq1, float* part, void* stream);
-int b2rl_wide_dqda(const float* dz1, const float* w1a, int32_t A, int32_t M, float* dqda, void* stream);
+                         float* dzq0, float* dzq1, float* part, const b2rl_stack_t* stack, void* stream);
+int b2rl_wide_dqda(const float* dz1, const float* w1a, int32_t A, int32_t M, float* dqda, const b2rl_stack_t* stack, void* stream);
 int b2rl_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
                              const float* max_ac, const float* log_alpha, int32_t td3, int32_t A, int32_t M, float* du,
-                             float* part_du, void* stream);
+                             float* part_du, const b2rl_stack_t* stack, void* stream);
 int b2rl_wide_actor_scalars(const float* part_s, const float* part_du, int32_t P, int32_t M, int32_t out_dim, int32_t td3,
-                            const float* log_alpha, float* G, int64_t off_b3, float* out, void* stream);
-int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, void* stream);
+                            const float* log_alpha, float* G, int64_t off_b3, float* out, const b2rl_stack_t* stack, void* stream);
+int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, const b2rl_stack_t* stack, void* stream);
 
 /* Weight gradient of one layer on the tensor cores (tc_wgrad.cu): C[m][n] = sum_b A[b][m] * Bm[b][n] for m < MA, with A
  * [Bn][lda] (a_cols >= MA columns exist; 16-byte aligned rows) and Bm [Bn][256]; Ct, if not NULL, receives the transpose
  * [256][MA]. Split over the batch, slices added in a fixed order. scratch: b2rl_tc_wgrad_scratch_floats(MA, Bn) floats.
  * x3: 3xTF32 (fp32-level accuracy) or plain TF32. bump, if not NULL: a device counter incremented once (the update
- * counter b2rl_wgrad advances: agents/agent.py:240 / :288 count optimizer steps). Replaces, for large batches, what
+ * counter b2rl_wgrad advances: agents/agent.py:240 / :288 count optimizer steps; stacked: agent g's is bump +
+ * g * counters_stride). Stacked: A, Bm are [n_agents][Bn][..], C / Ct are gradient tensors (param_stride apart), and the
+ * number of batch splits depends on (MA, Bn) only — never on n_agents — so a population's gradients are bitwise the
+ * same however it is sharded. Replaces, for large batches, what
  * loss.backward() does for the weights (agents/agent.py:235,283). */
 int b2rl_tc_wgrad(const float* A, int64_t lda, int32_t a_cols, int32_t MA, const float* Bm, int32_t Bn, float* C, float* Ct,
-                  float* scratch, int32_t x3, uint64_t* bump, void* stream);
-int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn);
+                  float* scratch, int32_t x3, uint64_t* bump, const b2rl_stack_t* stack, void* stream);
+int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn, int32_t n_agents /* 0: the single-learner form (stack NULL) */);
 
 /* The weight-gradient kernel on its own (wgrad.cu): reads rows, H1, H2, DZ1, DZ2, DZ3 of the workspace. skip_vectors:
  * the bias / LayerNorm / loss reductions were done elsewhere (wide path). bump_counter: B2RL_CTR_* or -1. */

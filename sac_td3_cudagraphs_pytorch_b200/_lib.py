@@ -77,6 +77,14 @@ class WideQ(C.Structure):
                 ("bcq_mix", C.c_int32), ("gamma", C.c_float), ("reserved", C.c_uint32)]
 
 
+class Stack(C.Structure):
+    """b2rl_stack_t: agents stacked along the row dimension of the wide path (NULL = one learner)."""
+    _fields_ = [("n_agents", C.c_int32), ("agent_base", C.c_int32), ("param_stride", C.c_int64), ("lo_stride", C.c_int64),
+                ("alpha_stride", C.c_int64), ("counters_stride", C.c_int64), ("out_stride", C.c_int64)]
+
+
+_STK = C.POINTER(Stack)
+
 # name -> (restype, argtypes); every symbol include/b2rl.h declares
 SYMBOLS = {
     "b2rl_version": (C.c_int, []),
@@ -93,32 +101,32 @@ SYMBOLS = {
     "b2rl_actor_update_sac": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_actor_update_td3": (C.c_int, [C.POINTER(UpdateArgs), C.c_void_p]),
     "b2rl_tc_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_tc_linear_q": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b2rl_tc_split_lo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_tc_split_lo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _STK, C.c_void_p]),
     "b2rl_wide_first": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_tc_linear_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b2rl_wide_policy_head": (C.c_int, [C.POINTER(WidePolicy), C.c_void_p]),
-    "b2rl_wide_q_head": (C.c_int, [C.POINTER(WideQ), C.c_void_p]),
+                                    C.c_int32, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_wide_policy_head": (C.c_int, [C.POINTER(WidePolicy), _STK, C.c_void_p]),
+    "b2rl_wide_q_head": (C.c_int, [C.POINTER(WideQ), _STK, C.c_void_p]),
     "b2rl_wide_ln_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "b2rl_wide_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+                                  C.c_int32, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_wide_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _STK, C.c_void_p]),
     "b2rl_wide_critic_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+                                          C.c_int64, C.c_int64, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_wide_actor_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p]),
-    "b2rl_wide_dqda": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_wide_dqda": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_wide_actor_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                          C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_wide_actor_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
-    "b2rl_wide_alpha_grad": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_int64, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_wide_alpha_grad": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_tc_wgrad": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
-    "b2rl_tc_wgrad_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+                               C.c_void_p, C.c_int32, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_tc_wgrad_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "b2rl_wgrad": (C.c_int, [C.POINTER(UpdateArgs), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b2rl_publish_logs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2rl_critic_update_opt": (C.c_int, [C.POINTER(UpdateArgs), C.POINTER(AdamArgs), C.c_void_p]),
@@ -157,8 +165,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype, fn.argtypes = res, args
-    if lib.b2rl_version() != 100:
-        raise B2rlError(f"libb2rl version {lib.b2rl_version()} does not match the binding (100)")
+    if lib.b2rl_version() != 110:
+        raise B2rlError(f"libb2rl version {lib.b2rl_version()} does not match the binding (110)")
     _lib = lib
     return lib
 

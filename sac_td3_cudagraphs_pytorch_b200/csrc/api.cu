@@ -32,29 +32,31 @@ cudaError_t init_replay();
 cudaError_t init_tc();
 cudaError_t init_wide();
 cudaError_t init_tc_wgrad();
-int tc_wgrad_splits(int, int);
-cudaError_t launch_tc_wgrad(const float*, int64_t, int, int, const float*, int, float*, float*, float*, int, unsigned long long*, cudaStream_t);
+int tc_wgrad_splits(int, int, int);
+cudaError_t launch_tc_wgrad(const float*, int64_t, int, int, const float*, int, float*, float*, float*, int, unsigned long long*,
+                            const Stk&, int, cudaStream_t);
 cudaError_t launch_wide_first(const float*, int64_t, int, int, const float*, const float*, const float*, const float*, int, float*,
-                              float*, float*, cudaStream_t);
+                              float*, float*, const Stk&, cudaStream_t);
 cudaError_t launch_tc_linear_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*,
-                                 const float*, int, float*, float*, cudaStream_t);
-cudaError_t launch_wide_policy_head(const b2rl_wide_policy_t&, cudaStream_t);
-cudaError_t launch_wide_q_head(const b2rl_wide_q_t&, cudaStream_t);
+                                 const float*, int, float*, float*, const Stk&, cudaStream_t);
+cudaError_t launch_wide_policy_head(const b2rl_wide_policy_t&, const Stk&, cudaStream_t);
+cudaError_t launch_wide_q_head(const b2rl_wide_q_t&, const Stk&, cudaStream_t);
 cudaError_t launch_wide_ln_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int,
-                               float*, float*, cudaStream_t);
-cudaError_t launch_wide_actor_loss(const float*, const float*, const float*, const float*, int, int, float*, float*, float*, cudaStream_t);
-cudaError_t launch_wide_dqda(const float*, const float*, int, int, float*, cudaStream_t);
+                               float*, float*, const Stk&, cudaStream_t);
+cudaError_t launch_wide_actor_loss(const float*, const float*, const float*, const float*, int, int, float*, float*, float*,
+                                   const Stk&, cudaStream_t);
+cudaError_t launch_wide_dqda(const float*, const float*, int, int, float*, const Stk&, cudaStream_t);
 cudaError_t launch_wide_actor_head_bwd(const float*, const float*, const float*, const float*, const float*, const float*, int, int,
-                                       int, float*, float*, cudaStream_t);
+                                       int, float*, float*, const Stk&, cudaStream_t);
 cudaError_t launch_wide_actor_scalars(const float*, const float*, int, int, int, int, const float*, float*, int64_t, float*,
-                                      cudaStream_t);
-cudaError_t launch_wide_alpha_grad(const float*, int, float, float*, cudaStream_t);
-cudaError_t launch_wide_colsum(const float*, int, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
+                                      const Stk&, cudaStream_t);
+cudaError_t launch_wide_alpha_grad(const float*, int, float, float*, const Stk&, cudaStream_t);
+cudaError_t launch_wide_colsum(const float*, int, float*, int64_t, int64_t, int64_t, int, const Stk&, cudaStream_t);
 cudaError_t launch_wide_critic_scalars(const float*, const float*, int, const float*, const float*, int, float*, int64_t, int64_t,
-                                       float*, cudaStream_t);
+                                       float*, const Stk&, cudaStream_t);
 cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*, int,
-                             int, float*, float*, float*, const b2rl_wide_q_t*, cudaStream_t);
-cudaError_t launch_tc_split_lo(const float*, float*, int, cudaStream_t);
+                             int, float*, float*, float*, const b2rl_wide_q_t*, const Stk&, cudaStream_t);
+cudaError_t launch_tc_split_lo(const float*, float*, int, const Stk&, cudaStream_t);
 }  // namespace b2rl
 
 namespace b2rl {
@@ -81,6 +83,17 @@ static int check_launch(cudaError_t e, const char* what) {
   return fail(B2RL_E_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// the stacked-agents descriptor of the wide path (NULL = one learner)
+static int check_stack(const b2rl_stack_t* s, const char* what) {
+  if (!s) return B2RL_OK;
+  if (s->n_agents < 1 || s->n_agents > 65535) return fail(B2RL_E_INVALID, "%s: stack.n_agents %d out of range", what, s->n_agents);
+  if (s->agent_base < 0 || (int64_t)s->agent_base + s->n_agents > (1 << 30)) return fail(B2RL_E_INVALID, "%s: agent ids must stay below 2^30", what);
+  if (s->param_stride < 0 || s->lo_stride < 0 || s->alpha_stride < 0 || s->counters_stride < 0 || s->out_stride < 0 ||
+      (s->param_stride & 3) || (s->lo_stride & 3))
+    return fail(B2RL_E_INVALID, "%s: stack strides must be >= 0 (param / lo strides multiples of 4 floats)", what);
+  return B2RL_OK;
+}
+using b2rl::make_stk;
 
 static int check_fmt(const b2rl_rowfmt_t& f) {
   if (f.ob_dim < 1 || f.ac_dim < 1) return fail(B2RL_E_INVALID, "row format: ob_dim/ac_dim must be >= 1");
@@ -218,23 +231,28 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
                       "replay_extend_dev");
 }
 
-int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, void* stream) {
+int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, const b2rl_stack_t* stack, void* stream) {
   if (!W || !W_lo || n < 1) return fail(B2RL_E_INVALID, "tc_split_lo: bad arguments");
-  return check_launch(b2rl::launch_tc_split_lo(W, W_lo, n, (cudaStream_t)stream), "tc_split_lo");
+  if (int rc = check_stack(stack, "tc_split_lo")) return rc;
+  return check_launch(b2rl::launch_tc_split_lo(W, W_lo, n, make_stk(stack), (cudaStream_t)stream), "tc_split_lo");
 }
 int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
-                   const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, void* stream) {
+                   const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, const b2rl_stack_t* stack,
+                   void* stream) {
   if (!X || !W || !bias || !H || M < 1) return fail(B2RL_E_INVALID, "tc_linear: bad arguments");
+  if (int rc = check_stack(stack, "tc_linear")) return rc;
   if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "tc_linear: LayerNorm needs weight and bias");
   if (!aligned16(X) || !aligned16(W) || !aligned16(H) || (XH && !aligned16(XH)) || ldx < B2RL_HID || (ldx & 3))
     return fail(B2RL_E_INVALID, "tc_linear: 16-byte aligned tensors, ldx >= 256 and a multiple of 4");
   if (W_lo && !aligned16(W_lo)) return fail(B2RL_E_INVALID, "tc_linear: W_lo must be 16-byte aligned");
-  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, relu, H, XH, stat, nullptr, (cudaStream_t)stream),
-                      "tc_linear");
+  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, relu, H, XH, stat, nullptr, make_stk(stack),
+                                             (cudaStream_t)stream), "tc_linear");
 }
 int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
-                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_wide_q_t* q, void* stream) {
+                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_wide_q_t* q,
+                     const b2rl_stack_t* stack, void* stream) {
   if (!X || !W || !bias || !q || M < 1) return fail(B2RL_E_INVALID, "tc_linear_q: bad arguments");
+  if (int rc = check_stack(stack, "tc_linear_q")) return rc;
   if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "tc_linear_q: LayerNorm needs weight and bias");
   if (!aligned16(X) || !aligned16(W) || (H && !aligned16(H)) || (XH && !aligned16(XH)) || ldx < B2RL_HID || (ldx & 3))
     return fail(B2RL_E_INVALID, "tc_linear_q: 16-byte aligned tensors, ldx >= 256 and a multiple of 4");
@@ -242,93 +260,109 @@ int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, con
   if (!q->w3 || !q->b3 || !q->q_out || q->M != M || (q->mode != 0 && q->mode != 1)) return fail(B2RL_E_INVALID, "tc_linear_q: bad head");
   if (q->mode == 1 && (!q->qn0 || !q->qn1 || !q->rows || !q->dz3 || !q->sq_part || (!q->td3 && (!q->logp || !q->log_alpha))))
     return fail(B2RL_E_INVALID, "tc_linear_q: mode 1 needs the target Q values, the batch rows, dz3 and sq_part");
-  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, 1, H, XH, stat, q, (cudaStream_t)stream),
-                      "tc_linear_q");
+  return check_launch(b2rl::launch_tc_linear(X, ldx, M, W, W_lo, bias, g, be, layer_norm, 1, H, XH, stat, q, make_stk(stack),
+                                             (cudaStream_t)stream), "tc_linear_q");
 }
 
 int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
-                    const float* be, int32_t layer_norm, float* H, float* XH, float* stat, void* stream) {
+                    const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_stack_t* stack, void* stream) {
   if (!X || !w1t || !b || !H || M < 1 || K < 1 || ldx < K) return fail(B2RL_E_INVALID, "wide_first: bad arguments");
+  if (int rc = check_stack(stack, "wide_first")) return rc;
   if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "wide_first: LayerNorm needs weight and bias");
-  return check_launch(b2rl::launch_wide_first(X, ldx, M, K, w1t, b, g, be, layer_norm, H, XH, stat, (cudaStream_t)stream), "wide_first");
+  return check_launch(b2rl::launch_wide_first(X, ldx, M, K, w1t, b, g, be, layer_norm, H, XH, stat, make_stk(stack), (cudaStream_t)stream), "wide_first");
 }
 int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
-                       const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, void* stream) {
+                       const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, const b2rl_stack_t* stack,
+                       void* stream) {
   if (!DZ2 || !w2t || !xh1 || !DZ1 || !part || M < 1) return fail(B2RL_E_INVALID, "tc_linear_bwd: bad arguments");
+  if (int rc = check_stack(stack, "tc_linear_bwd")) return rc;
   if (layer_norm && (!g1 || !be1 || !stat1)) return fail(B2RL_E_INVALID, "tc_linear_bwd: LayerNorm needs weight, bias and statistics");
   if (!aligned16(DZ2) || !aligned16(w2t) || !aligned16(DZ1)) return fail(B2RL_E_INVALID, "tc_linear_bwd: 16-byte aligned tensors");
-  return check_launch(b2rl::launch_tc_linear_bwd(DZ2, M, w2t, w2t_lo, xh1, stat1, g1, be1, layer_norm, DZ1, part, (cudaStream_t)stream),
+  return check_launch(b2rl::launch_tc_linear_bwd(DZ2, M, w2t, w2t_lo, xh1, stat1, g1, be1, layer_norm, DZ1, part, make_stk(stack), (cudaStream_t)stream),
                       "tc_linear_bwd");
 }
-int b2rl_wide_policy_head(const b2rl_wide_policy_t* p, void* stream) {
+int b2rl_wide_policy_head(const b2rl_wide_policy_t* p, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_policy_head")) return rc;
   if (!p || !p->h2 || !p->w3 || !p->b3 || !p->rows || !p->min_ac || !p->max_ac || !p->xn || !p->counters || p->M < 1 ||
       p->A < 1 || p->A > 32 || p->out_dim < p->A || p->out_dim > B2RL_MAX_OUT || p->ldn < p->O + p->A)
     return fail(B2RL_E_INVALID, "wide_policy_head: bad arguments");
-  return check_launch(b2rl::launch_wide_policy_head(*p, (cudaStream_t)stream), "wide_policy_head");
+  return check_launch(b2rl::launch_wide_policy_head(*p, make_stk(stack), (cudaStream_t)stream), "wide_policy_head");
 }
-int b2rl_wide_q_head(const b2rl_wide_q_t* q, void* stream) {
+int b2rl_wide_q_head(const b2rl_wide_q_t* q, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_q_head")) return rc;
   if (!q || !q->h2 || !q->w3 || !q->b3 || !q->q_out || q->M < 1) return fail(B2RL_E_INVALID, "wide_q_head: bad arguments");
   if (q->mode == 1 && (!q->qn0 || !q->qn1 || !q->rows || !q->dz3 || !q->sq_part || (!q->td3 && (!q->logp || !q->log_alpha))))
     return fail(B2RL_E_INVALID, "wide_q_head: online mode needs the target Qs, rows, dz3, sq_part (and logp / log_alpha for SAC)");
-  return check_launch(b2rl::launch_wide_q_head(*q, (cudaStream_t)stream), "wide_q_head");
+  return check_launch(b2rl::launch_wide_q_head(*q, make_stk(stack), (cudaStream_t)stream), "wide_q_head");
 }
 int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,
-                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, void* stream) {
+                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_ln_bwd")) return rc;
   if (!dz3 || !w3 || !xh || !dz || !part || M < 1 || n_out < 1 || n_out > B2RL_MAX_OUT) return fail(B2RL_E_INVALID, "wide_ln_bwd: bad arguments");
   if (layer_norm && (!g || !be || !stat)) return fail(B2RL_E_INVALID, "wide_ln_bwd: LayerNorm needs weight, bias and statistics");
-  return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, (cudaStream_t)stream), "wide_ln_bwd");
+  return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, make_stk(stack), (cudaStream_t)stream), "wide_ln_bwd");
 }
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
-                     void* stream) {
+                     const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_colsum")) return rc;
   if (!part || !G || P < 1) return fail(B2RL_E_INVALID, "wide_colsum: bad arguments");
-  return check_launch(b2rl::launch_wide_colsum(part, P, G, off_b, off_g, off_be, layer_norm, (cudaStream_t)stream), "wide_colsum");
+  return check_launch(b2rl::launch_wide_colsum(part, P, G, off_b, off_g, off_be, layer_norm, make_stk(stack), (cudaStream_t)stream), "wide_colsum");
 }
 int b2rl_wide_critic_scalars(const float* sq0, const float* sq1, int32_t P, const float* dz3_0, const float* dz3_1, int32_t M,
-                             float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, void* stream) {
+                             float* G, int64_t off_b3_0, int64_t off_b3_1, float* out, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_critic_scalars")) return rc;
   if (!sq0 || !sq1 || !G || !out || P < 1 || M < 1) return fail(B2RL_E_INVALID, "wide_critic_scalars: bad arguments");
-  return check_launch(b2rl::launch_wide_critic_scalars(sq0, sq1, P, dz3_0, dz3_1, M, G, off_b3_0, off_b3_1, out, (cudaStream_t)stream),
+  return check_launch(b2rl::launch_wide_critic_scalars(sq0, sq1, P, dz3_0, dz3_1, M, G, off_b3_0, off_b3_1, out, make_stk(stack), (cudaStream_t)stream),
                       "wide_critic_scalars");
 }
 int b2rl_wide_actor_loss(const float* q0, const float* q1, const float* logp, const float* log_alpha, int32_t td3, int32_t M,
-                         float* dzq0, float* dzq1, float* part, void* stream) {
+                         float* dzq0, float* dzq1, float* part, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_actor_loss")) return rc;
   if (!q0 || !dzq0 || !part || M < 1 || (!td3 && (!q1 || !dzq1 || !logp || !log_alpha)))
     return fail(B2RL_E_INVALID, "wide_actor_loss: bad arguments");
-  return check_launch(b2rl::launch_wide_actor_loss(q0, q1, logp, log_alpha, td3, M, dzq0, dzq1, part, (cudaStream_t)stream), "wide_actor_loss");
+  return check_launch(b2rl::launch_wide_actor_loss(q0, q1, logp, log_alpha, td3, M, dzq0, dzq1, part, make_stk(stack), (cudaStream_t)stream), "wide_actor_loss");
 }
-int b2rl_wide_dqda(const float* dz1, const float* w1a, int32_t A, int32_t M, float* dqda, void* stream) {
+int b2rl_wide_dqda(const float* dz1, const float* w1a, int32_t A, int32_t M, float* dqda, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_dqda")) return rc;
   if (!dz1 || !w1a || !dqda || A < 1 || A > 32 || M < 1) return fail(B2RL_E_INVALID, "wide_dqda: bad arguments");
-  return check_launch(b2rl::launch_wide_dqda(dz1, w1a, A, M, dqda, (cudaStream_t)stream), "wide_dqda");
+  return check_launch(b2rl::launch_wide_dqda(dz1, w1a, A, M, dqda, make_stk(stack), (cudaStream_t)stream), "wide_dqda");
 }
 int b2rl_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
                              const float* max_ac, const float* log_alpha, int32_t td3, int32_t A, int32_t M, float* du,
-                             float* part_du, void* stream) {
+                             float* part_du, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_actor_head_bwd")) return rc;
   if (!dqda0 || !save || !min_ac || !max_ac || !du || !part_du || A < 1 || A > 32 || M < 1 || (!td3 && !log_alpha))
     return fail(B2RL_E_INVALID, "wide_actor_head_bwd: bad arguments");
   return check_launch(b2rl::launch_wide_actor_head_bwd(dqda0, dqda1, save, min_ac, max_ac, log_alpha, td3, A, M, du, part_du,
-                                                       (cudaStream_t)stream), "wide_actor_head_bwd");
+                                                       make_stk(stack), (cudaStream_t)stream), "wide_actor_head_bwd");
 }
 int b2rl_wide_actor_scalars(const float* part_s, const float* part_du, int32_t P, int32_t M, int32_t out_dim, int32_t td3,
-                            const float* log_alpha, float* G, int64_t off_b3, float* out, void* stream) {
+                            const float* log_alpha, float* G, int64_t off_b3, float* out, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_actor_scalars")) return rc;
   if (!part_s || !part_du || !G || !out || P < 1 || M < 1 || out_dim < 1 || out_dim > B2RL_MAX_OUT)
     return fail(B2RL_E_INVALID, "wide_actor_scalars: bad arguments");
-  return check_launch(b2rl::launch_wide_actor_scalars(part_s, part_du, P, M, out_dim, td3, log_alpha, G, off_b3, out, (cudaStream_t)stream),
+  return check_launch(b2rl::launch_wide_actor_scalars(part_s, part_du, P, M, out_dim, td3, log_alpha, G, off_b3, out, make_stk(stack), (cudaStream_t)stream),
                       "wide_actor_scalars");
 }
-int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, void* stream) {
+int b2rl_wide_alpha_grad(const float* logp2, int32_t M, float targ_ent, float* alpha_state, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "wide_alpha_grad")) return rc;
   if (!logp2 || !alpha_state || M < 1) return fail(B2RL_E_INVALID, "wide_alpha_grad: bad arguments");
-  return check_launch(b2rl::launch_wide_alpha_grad(logp2, M, targ_ent, alpha_state, (cudaStream_t)stream), "wide_alpha_grad");
+  return check_launch(b2rl::launch_wide_alpha_grad(logp2, M, targ_ent, alpha_state, make_stk(stack), (cudaStream_t)stream), "wide_alpha_grad");
 }
-int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn) {
-  if (MA < 1 || Bn < 1) return -1;
-  return (int64_t)b2rl::tc_wgrad_splits(Bn, MA) * ((MA + 127) / 128 * 128) * B2RL_HID;
+int64_t b2rl_tc_wgrad_scratch_floats(int32_t MA, int32_t Bn, int32_t n_agents) {
+  if (MA < 1 || Bn < 1 || n_agents < 0) return -1;
+  const int64_t per_agent = (int64_t)b2rl::tc_wgrad_splits(Bn, MA, n_agents > 0) * ((MA + 127) / 128 * 128) * B2RL_HID;
+  return per_agent * (n_agents > 0 ? n_agents : 1);
 }
 int b2rl_tc_wgrad(const float* A, int64_t lda, int32_t a_cols, int32_t MA, const float* Bm, int32_t Bn, float* C, float* Ct,
-                  float* scratch, int32_t x3, uint64_t* bump, void* stream) {
+                  float* scratch, int32_t x3, uint64_t* bump, const b2rl_stack_t* stack, void* stream) {
+  if (int rc = check_stack(stack, "tc_wgrad")) return rc;
   if (!A || !Bm || !C || !scratch || MA < 1 || a_cols < MA || lda < a_cols || (lda & 3) || Bn < 1)
     return fail(B2RL_E_INVALID, "tc_wgrad: bad arguments");
   if (!aligned16(A) || !aligned16(Bm) || !aligned16(C) || !aligned16(scratch)) return fail(B2RL_E_INVALID, "tc_wgrad: 16-byte aligned tensors");
   if (Ct && (MA & 3)) return fail(B2RL_E_INVALID, "tc_wgrad: the transposed copy needs MA % 4 == 0");
-  return check_launch(b2rl::launch_tc_wgrad(A, lda, a_cols, MA, Bm, Bn, C, Ct, scratch, x3, (unsigned long long*)bump, (cudaStream_t)stream), "tc_wgrad");
+  return check_launch(b2rl::launch_tc_wgrad(A, lda, a_cols, MA, Bm, Bn, C, Ct, scratch, x3, (unsigned long long*)bump, make_stk(stack),
+                                            stack != nullptr, (cudaStream_t)stream), "tc_wgrad");
 }
 int b2rl_wgrad(const b2rl_update_args_t* a, int32_t actor_step, int32_t bump_counter, int32_t skip_vectors, void* stream) {
   if (int rc = check_update(a, actor_step != 0)) return rc;

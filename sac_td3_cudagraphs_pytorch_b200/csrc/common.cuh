@@ -111,6 +111,18 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, int clust
   return launch_k(kernel, grid, dim3(NT), cluster_x, smem, st, static_cast<Args&&>(args)...);
 }
 
+// stacked agents on the wide path (include/b2rl.h b2rl_stack_t): the device-side copy, n = 1 and zero strides when NULL
+struct Stk {
+  int n;
+  unsigned base;
+  long long ps, ls, as, cs, os;  // param / lo / alpha / counters / out strides
+};
+inline Stk make_stk(const b2rl_stack_t* s) {
+  Stk k = {1, 0u, 0, 0, 0, 0, 0};
+  if (s) k = {s->n_agents, (unsigned)s->agent_base, s->param_stride, s->lo_stride, s->alpha_stride, s->counters_stride, s->out_stride};
+  return k;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // streaming 128-bit load/store that do not allocate in L1 (replay rows are touched once)

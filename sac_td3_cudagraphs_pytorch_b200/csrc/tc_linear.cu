@@ -63,9 +63,11 @@ __device__ __forceinline__ void mbar_wait_(uint64_t* b, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s32(dst)),
-               "l"(map), "r"(c0), "r"(c1), "r"(s32(bar))
+// (the maps are rank 3: {k, row, agent} — agent = 0 for a single learner — so that rows beyond an agent's batch are
+// zero-filled by TMA instead of running on into the next agent's rows)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar))
                : "memory");
 }
 // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor fields:
@@ -85,11 +87,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 }
 // multicast forms (2-CTA cluster): the load lands at the same shared-memory offset of every CTA in `mask` and counts its
 // bytes on the mbarrier at the same offset there; the commit arrives on the mbarrier of every CTA in `mask`
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
           s32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(s32(bar)), "h"(mask)
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar)), "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
@@ -169,23 +171,27 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                  const __grid_constant__ CUtensorMap mapBlo, int M,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part,
-                 const __grid_constant__ b2rl_wide_q_t Q) {
+                 const __grid_constant__ b2rl_wide_q_t Q, const Stk K) {
   extern __shared__ unsigned char tc_raw[];  // (the swizzle atoms need 1024-byte alignment: align by hand)
   using Smem = TcSmemT<PREC>;
   constexpr int TC_STAGES = Smem::STAGES;
   constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN * (PREC ? 2 : 1)) * TCK * sizeof(float);
   Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (M + TCM - 1) / TCM;
+  const int n_tiles = (M + TCM - 1) / TCM;  // per agent (M = rows per agent)
   // Persistent, in clusters of 2: cluster ci works on tile pairs ci, ci + n_clusters, ...; CTA `crank` of the cluster takes
   // tile 2 * pair + crank (a ghost tile beyond the batch loads zeros and stores nothing, so that both CTAs run the same
   // number of k-slabs: each loads HALF of every weight slab and multicasts it to both). Local tile i accumulates in TMEM
   // buffer i & 1, so the epilogue of tile i runs while the ring and the tensor core work on tile i + 1.
+  // Stacked agents: the pairs of all agents form one list, pair p belongs to agent p / pairs_per_agent — a pair never
+  // straddles two agents, so both CTAs of a cluster always want the same agent's weight slab (the multicast stands).
   uint32_t crank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-  const int n_clusters = (int)gridDim.x >> 1, ci = (int)blockIdx.x >> 1, n_pairs = (n_tiles + 1) >> 1;
+  const int ppa = (n_tiles + 1) >> 1;  // pairs per agent
+  const int n_clusters = (int)gridDim.x >> 1, ci = (int)blockIdx.x >> 1, n_pairs = ppa * K.n;
   const int my_tiles = (n_pairs - ci + n_clusters - 1) / n_clusters;
-  auto tile_of = [&](int i) { return 2 * (ci + i * n_clusters) + (int)crank; };
+  auto agent_of = [&](int i) { return (ci + i * n_clusters) / ppa; };
+  auto tile_of = [&](int i) { return 2 * ((ci + i * n_clusters) % ppa) + (int)crank; };  // tile inside the agent's batch
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 2); mbar_init_(&S.lo_ready[s], 64); }  // empty: both CTAs' MMA commits
@@ -207,15 +213,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {  // ===== TMA producer: the ring runs on across tiles
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int m0 = tile_of(i) * TCM;
+        const int m0 = tile_of(i) * TCM, ag = agent_of(i);
         const int half = (int)crank * (TCN / 2);  // this CTA's rows of the weight slab
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % TC_STAGES;
           if (it >= TC_STAGES) mbar_wait_(&S.empty[s], ((it / TC_STAGES) - 1) & 1);  // free in BOTH CTAs
           mbar_expect_(&S.full[s], TC_STAGE_BYTES);
-          tma_load_2d(S.a[s], &mapA, kb * TCK, m0, &S.full[s]);
-          tma_load_2d_mc(S.b[s] + half * TCK, &mapB, kb * TCK, half, &S.full[s], 3);
-          if constexpr (PREC == 1) tma_load_2d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, &S.full[s], 3);
+          tma_load_3d(S.a[s], &mapA, kb * TCK, m0, ag, &S.full[s]);
+          tma_load_3d_mc(S.b[s] + half * TCK, &mapB, kb * TCK, half, ag, &S.full[s], 3);
+          if constexpr (PREC == 1) tma_load_3d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, ag, &S.full[s], 3);
         }
       }
     }
@@ -274,18 +280,25 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
     const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
     float* T = S.tile[ew];
-    for (int i = et; i < 4 * HID; i += 128) {  // per-column vectors: once per CTA into shared memory (broadcast reads)
-      const int q = i / HID, j = i - q * HID;
-      const float* src = q == 0 ? bias : q == 1 ? g : q == 2 ? be : Q.w3;
-      S.cvec[q][j] = src ? __ldg(src + j) : (q == 1 ? 1.f : 0.f);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
     const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2], *cw3 = S.cvec[3];
     const bool head = MODE == 0 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
     float v[32];
+    int cur_agent = -1;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int tile = tile_of(ti), buf = ti & 1;
-      const int row0 = tile * TCM + 32 * lg, row = row0 + lane;
+      const int tile = tile_of(ti), buf = ti & 1, ag = agent_of(ti);
+      if (ag != cur_agent) {  // per-column vectors of this agent: into shared memory once (broadcast reads); all four
+        if (cur_agent >= 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps are done with the previous agent's
+        cur_agent = ag;
+        const size_t po = (size_t)ag * K.ps;
+        for (int i = et; i < 4 * HID; i += 128) {
+          const int q = i / HID, j = i - q * HID;
+          const float* src = q == 0 ? bias : q == 1 ? g : q == 2 ? be : Q.w3;
+          S.cvec[q][j] = src ? __ldg(src + po + j) : (q == 1 ? 1.f : 0.f);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const size_t arow = (size_t)ag * M;           // first row of this agent in the stacked arrays
+      const int row0 = tile * TCM + 32 * lg, row = row0 + lane;  // inside the agent's batch
       const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
       const uint32_t tl = tmem + buf * TCN + ((uint32_t)(32 * lg) << 16);
       if constexpr (MODE == 0) {
@@ -310,7 +323,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
           }
           rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
-          if (stat && row < M) stat[row] = make_float2(mean, rstd);
+          if (stat && row < M) stat[arow + row] = make_float2(mean, rstd);
         }
         float qacc = 0.f;
         for (int c = 0; c < TCN / 32; ++c) {
@@ -337,32 +350,33 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (H) {  // (a target critic with the fused head never needs its h2 in memory)
             tile_put(T, lane, h);
             __syncwarp();
-            tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+            tile_store(T, lane, H + (arow + row0) * TCN + c * 32, rows_valid);
             __syncwarp();
           }
           if (XH) {
             tile_put(T, lane, v);
             __syncwarp();
-            tile_store(T, lane, XH + (size_t)row0 * TCN + c * 32, rows_valid);
+            tile_store(T, lane, XH + (arow + row0) * TCN + c * 32, rows_valid);
             __syncwarp();
           }
         }
         if (head) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
           float sq = 0.f, dqv = 0.f;
+          const size_t grow = arow + row;
           if (row < M) {
-            const float q = qacc + __ldg(Q.b3);
-            Q.q_out[row] = q;
+            const float q = qacc + __ldg(Q.b3 + (size_t)ag * K.ps);
+            Q.q_out[grow] = q;
             if (Q.mode == 1) {
-              const float q0 = Q.qn0[row], q1 = Q.qn1[row];
+              const float q0 = Q.qn0[grow], q1 = Q.qn1[grow];
               const float qmin = fminf(q0, q1);
               float qp = Q.bcq_mix ? __fadd_rn(__fmul_rn(0.75f, qmin), __fmul_rn(0.25f, fmaxf(q0, q1))) : qmin;
-              if (!Q.td3) qp = __fsub_rn(qp, __fmul_rn(expf(Q.log_alpha[0]), Q.logp[row]));
-              const float* rr = Q.rows + (size_t)row * Q.row_stride + Q.rd_off;
+              if (!Q.td3) qp = __fsub_rn(qp, __fmul_rn(expf(Q.log_alpha[(size_t)ag * K.as]), Q.logp[grow]));
+              const float* rr = Q.rows + grow * Q.row_stride + Q.rd_off;
               const float y = __fadd_rn(rr[0], __fmul_rn(__fmul_rn(1.0f - rr[1], Q.gamma), qp));
-              if (Q.targ_out) Q.targ_out[row] = y;
+              if (Q.targ_out) Q.targ_out[grow] = y;
               const float dlt = q - y;
               dqv = dlt * (2.0f / (float)Q.M);
-              Q.dz3[(size_t)row * MAX_OUT] = dqv;
+              Q.dz3[grow * MAX_OUT] = dqv;
               sq = dlt * dlt;
             }
           }
@@ -373,14 +387,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               dqv += __shfl_xor_sync(0xffffffffu, dqv, sft);
             }
             if ((lane & 7) == 0 && row < M) {
-              Q.sq_part[2 * (row >> 3)] = sq;
-              Q.sq_part[2 * (row >> 3) + 1] = dqv;
+              const size_t pi = (size_t)ag * ((M + 7) >> 3) + (row >> 3);
+              Q.sq_part[2 * pi] = sq;
+              Q.sq_part[2 * pi + 1] = dqv;
             }
           }
         }
       } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
         const bool live = row < M;
-        const float* X0 = XH + (size_t)row0 * TCN;  // this warp's 32 rows of x-hat: fetched coalesced, one chunk ahead
+        const float* X0 = XH + (arow + row0) * TCN;  // this warp's 32 rows of x-hat: fetched coalesced, one chunk ahead
         float4 pf[8];
         float x[32];
         rows_fetch(X0, lane, rows_valid, pf);
@@ -405,7 +420,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             }
           }
         }
-        const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[row].y : 1.f;
+        const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[arow + row].y : 1.f;
         for (int c = 0; c < TCN / 32; ++c) {
           rows_put(T, lane, pf);
           __syncwarp();
@@ -436,7 +451,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           // Column sums over this warp's 32 rows: lane <-> column of the tile (deterministic, fixed order).
           tile_put(T, lane, dz);
           __syncwarp();
-          tile_store(T, lane, H + (size_t)row0 * TCN + c * 32, rows_valid);
+          tile_store(T, lane, H + (arow + row0) * TCN + c * 32, rows_valid);
           S.wpart[ew][0][c * 32 + lane] = tile_colsum(T, lane);
           __syncwarp();
           tile_put(T, lane, x);
@@ -451,7 +466,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
         for (int i = et; i < 3 * HID && tile < n_tiles; i += 128) {
           const int q = i / HID, j = i - q * HID;
-          part[((size_t)tile * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
+          part[(((size_t)ag * n_tiles + tile) * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // (wpart is rewritten by the next tile)
       }
@@ -463,13 +478,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TCN) : "memory");
 }
 
-static int tc_grid(int M) {  // persistent: one CTA per SM (or per tile when there are fewer)
+static int tc_grid(int M, int n_agents) {  // persistent: one CTA per SM (or per tile when there are fewer)
   static int sms = [] {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
   }();
-  const int pairs = ((M + TCM - 1) / TCM + 1) / 2;  // clusters of 2 CTAs, one tile pair at a time
+  const int pairs = (((M + TCM - 1) / TCM + 1) / 2) * n_agents;  // clusters of 2 CTAs, one tile pair at a time
   const int clusters = pairs < sms / 2 ? pairs : sms / 2;
   return 2 * clusters;
 }
@@ -488,25 +503,29 @@ static EncodeTiledFn encode_fn() {
   }();
   return fn;
 }
-// [rows][cols] fp32, row pitch `ld` floats; box = 32 columns (128 bytes = the swizzle span) x box_rows rows
-static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// [n_agents][rows][cols] fp32, row pitch `ld` floats, `agent_stride` floats between agents; box = 32 columns (128 bytes =
+// the swizzle span) x box_rows rows x 1 agent
+static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int n_agents,
+                     int64_t agent_stride) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)TCK, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (n_agents <= 1) agent_stride = rows * ld;  // (one agent: any legal stride)
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(n_agents < 1 ? 1 : n_agents)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)agent_stride * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)TCK, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // lo part of a weight matrix for the 3xTF32 mode: lo = w - tf32_truncate(w)
-__global__ void tc_split_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, int n) {
+__global__ void tc_split_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, int n, long long ps, long long ls) {
+  w += (size_t)blockIdx.y * ps, lo += (size_t)blockIdx.y * ls;  // stacked agents: blockIdx.y = agent
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) lo[i] = w[i] - __uint_as_float(__float_as_uint(w[i]) & 0xFFFFE000u);
 }
-cudaError_t launch_tc_split_lo(const float* w, float* lo, int n, cudaStream_t st) {
-  tc_split_lo_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, lo, n);
+cudaError_t launch_tc_split_lo(const float* w, float* lo, int n, const Stk& k, cudaStream_t st) {
+  tc_split_lo_kernel<<<dim3((n + 255) / 256, k.n), 256, 0, st>>>(w, lo, n, k.ps, k.ls);
   return cudaGetLastError();
 }
 
@@ -527,38 +546,40 @@ cudaError_t init_tc() {
 // Wlo: the precomputed lo part of W (tc_split_lo) => 3xTF32; NULL => plain TF32
 cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W, const float* Wlo, const float* bias,
                              const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat,
-                             const b2rl_wide_q_t* head, cudaStream_t st) {
+                             const b2rl_wide_q_t* head, const Stk& k, cudaStream_t st) {
   b2rl_wide_q_t q = {};
   if (head) q = *head;
   CUtensorMap ma, mb, ml;  // (the weight maps have boxes of HALF a slab: each CTA of a cluster loads one and multicasts it)
-  if (!make_map(&ma, X, M, HID, ldx, TCM) || !make_map(&mb, W, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
-  const dim3 grid(tc_grid(M)), block(TC_THREADS);
+  if (!make_map(&ma, X, M, HID, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map(&mb, W, HID, HID, HID, TCN / 2, k.n, k.ps))
+    return cudaErrorInvalidValue;
+  const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo) {
-    if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
+    if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
     return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
-                    st2, none, q);
+                    st2, none, q, k);
   }
   return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, bias, g, be, ln, relu, H, XH, st2,
-                  none, q);
+                  none, q, k);
 }
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
                                  const float* stat1, const float* g1, const float* be1, int ln, float* DZ1, float* part,
-                                 cudaStream_t st) {
+                                 const Stk& k, cudaStream_t st) {
   CUtensorMap ma, mb, ml;
-  if (!make_map(&ma, DZ2, M, HID, HID, TCM) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
-  const dim3 grid(tc_grid(M)), block(TC_THREADS);
+  if (!make_map(&ma, DZ2, M, HID, HID, TCM, k.n, (int64_t)M * HID) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2, k.n, k.ps))
+    return cudaErrorInvalidValue;
+  const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
   float* xh = const_cast<float*>(xh1);
   float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
   const float* none = nullptr;
   const b2rl_wide_q_t q = {};
   if (w2t_lo) {
-    if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2)) return cudaErrorInvalidValue;
+    if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
     return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, none, g1, be1, ln, 0, DZ1, xh, st1,
-                    part, q);
+                    part, q, k);
   }
-  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1, part, q);
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
 }
 
 }  // namespace b2rl

@@ -38,9 +38,10 @@ __device__ __forceinline__ void g_mbar_wait(uint64_t* b, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void g_tma_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(gs32(dst)),
-               "l"(map), "r"(c0), "r"(c1), "r"(gs32(bar))
+// rank-3 maps {column, batch row, agent}: rows beyond an agent's batch are zero-filled (they add nothing to the sum)
+__device__ __forceinline__ void g_tma_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(gs32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(gs32(bar))
                : "memory");
 }
 // MN-major, SWIZZLE_128B_BASE32B (layout type 1): LBO = 4 KB between 32-column chunks [16,30), SBO = 512 B between 4-row atoms [32,46)
@@ -72,8 +73,8 @@ __device__ __forceinline__ void g_split_lo(const float* src, float* dst, int n_f
   }
 }
 
-// grid (m tiles, splits): CTA (mt, sp) accumulates rows [sp * rows_per_split, ...) of the batch for output rows
-// [128 mt, 128 mt + 128) and writes its slice to part[sp][MA_pad][256].
+// grid (m tiles, splits, agents): CTA (mt, sp, ag) accumulates rows [sp * rows_per_split, ...) of agent ag's batch for
+// output rows [128 mt, 128 mt + 128) and writes its slice to part[ag][sp][MA_pad][256].
 template <int PREC>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Bn, int rows_per_split,
@@ -83,7 +84,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   constexpr int ST = Smem::STAGES;
   Smem& S = *reinterpret_cast<Smem*>(g_raw + ((1024u - (gs32(g_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GM, sp = blockIdx.y;
+  const int m0 = blockIdx.x * GM, sp = blockIdx.y, ag = blockIdx.z;
+  part += (size_t)ag * gridDim.y * MA_pad * GN;
   const int kb0 = sp * rows_per_split, kb1 = min(Bn, kb0 + rows_per_split);
   const int KB = (max(kb1 - kb0, 0) + GK - 1) / GK;
 
@@ -113,9 +115,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(G_A_BYTES + G_B_BYTES) : "memory");
         const int row = kb0 + kb * GK;  // (rows beyond the batch are zero-filled by TMA: they add nothing)
 #pragma unroll
-        for (int c = 0; c < GM / 32; ++c) g_tma_2d(S.a[s] + c * 1024, &mapA, m0 + 32 * c, row, &S.full[s]);
+        for (int c = 0; c < GM / 32; ++c) g_tma_3d(S.a[s] + c * 1024, &mapA, m0 + 32 * c, row, ag, &S.full[s]);
 #pragma unroll
-        for (int c = 0; c < GN / 32; ++c) g_tma_2d(S.b[s] + c * 1024, &mapB, 32 * c, row, &S.full[s]);
+        for (int c = 0; c < GN / 32; ++c) g_tma_3d(S.b[s] + c * 1024, &mapB, 32 * c, row, ag, &S.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -194,8 +196,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 // still has 8 warps sharing its 148 slices.
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(const float* __restrict__ part, int S, int MA, int MA_pad, float* __restrict__ C, float* __restrict__ Ct,
-                       unsigned long long* bump) {
+                       unsigned long long* bump, long long ps, long long cs) {
   __shared__ float red[8][8][33];  // [split lane][row][column]
+  {  // stacked agents: blockIdx.z = agent
+    const size_t ag = blockIdx.z;
+    part += ag * S * MA_pad * GN, C += ag * ps;
+    if (Ct) Ct += ag * ps;
+    if (bump) bump += ag * cs;
+  }
   if (bump && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *bump += 1ull;  // the step's update counter (wgrad.cu's bump CTA)
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int m0 = blockIdx.y * 8, n = blockIdx.x * 32 + tx;
@@ -238,15 +246,15 @@ static GEncodeFn g_encode() {
   }();
   return fn;
 }
-// [rows][cols] fp32, pitch ld floats; boxes of 32 columns x 32 rows
-static bool g_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+// [n_agents][rows][cols] fp32, pitch ld floats, agents rows * ld apart; boxes of 32 columns x 32 rows x 1 agent
+static bool g_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int n_agents) {
   GEncodeFn fn = g_encode();
   if (!fn) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  const cuuint32_t box[2] = {32, (cuuint32_t)GK};
-  const cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(n_agents < 1 ? 1 : n_agents)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)rows * ld * sizeof(float)};
+  const cuuint32_t box[3] = {32, (cuuint32_t)GK, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -259,26 +267,29 @@ cudaError_t init_tc_wgrad() {
   return e;
 }
 
-int tc_wgrad_splits(int Bn, int MA) {  // one wave of 148 CTAs over (m tiles x splits), at least 4 slabs per CTA
+// stacked = 0: one learner — one wave of 148 CTAs over (m tiles x splits), at least 4 slabs per CTA.
+// stacked = 1: a population — the agents fill the machine; the split depends on (Bn, MA) ONLY, never on how many agents a
+// launch holds, so that gradients are bitwise the same however a population is sharded: one split per 1024 batch rows.
+int tc_wgrad_splits(int Bn, int MA, int stacked) {
   const int mt = (MA + GM - 1) / GM;
   const int cap = (148 + mt - 1) / mt;
-  int s = (Bn + 4 * GK - 1) / (4 * GK);
+  int s = stacked ? (Bn + 1023) / 1024 : (Bn + 4 * GK - 1) / (4 * GK);
   return s < 1 ? 1 : (s > cap ? cap : s);
 }
 
 // A [Bn][lda] (columns 0..MA-1 used, a_cols columns exist), Bm [Bn][256] -> C [MA][256] (+ Ct [256][MA]); scratch >=
-// splits * MA_pad * 256 floats, MA_pad = MA rounded up to 128
+// n_agents * splits * MA_pad * 256 floats, MA_pad = MA rounded up to 128
 cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, const float* Bm, int Bn, float* C, float* Ct,
-                            float* scratch, int x3, unsigned long long* bump, cudaStream_t st) {
+                            float* scratch, int x3, unsigned long long* bump, const Stk& k, int stacked, cudaStream_t st) {
   CUtensorMap ma, mb;
-  if (!g_map(&ma, A, Bn, a_cols, lda) || !g_map(&mb, Bm, Bn, GN, GN)) return cudaErrorInvalidValue;
-  const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn, MA);
+  if (!g_map(&ma, A, Bn, a_cols, lda, k.n) || !g_map(&mb, Bm, Bn, GN, GN, k.n)) return cudaErrorInvalidValue;
+  const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn, MA, stacked);
   const int rps = (((Bn + S - 1) / S) + GK - 1) / GK * GK;
-  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
-  else tc_wgrad_kernel<0><<<dim3(mt, S), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
+  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
+  else tc_wgrad_kernel<0><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump);
+  tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8, k.n), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump, k.ps, k.cs);
   return cudaGetLastError();
 }
 

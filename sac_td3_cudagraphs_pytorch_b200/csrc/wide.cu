@@ -27,7 +27,14 @@ constexpr int WF_KC = 64;    // k chunk staged in shared memory
 __global__ void __launch_bounds__(256)
 wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const float* __restrict__ w1t,
                   const float* __restrict__ b, const float* __restrict__ g, const float* __restrict__ be, int ln,
-                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat) {
+                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, long long ps) {
+  {  // stacked agents: blockIdx.y = agent; its rows are M further, its parameters ps floats further
+    const size_t ag = blockIdx.y;
+    X += ag * M * ldx, H += ag * M * HID, w1t += ag * ps, b += ag * ps;
+    if (XH) XH += ag * M * HID;
+    if (stat) stat += ag * M;
+    if (ln) g += ag * ps, be += ag * ps;
+  }
   __shared__ __align__(16) float xs[WF_ROWS][WF_KC + 4];  // (k contiguous, 16-byte aligned rows: read as broadcast float4)
   __shared__ float zs[WF_ROWS][HID];
   __shared__ float2 st[WF_ROWS];
@@ -107,27 +114,32 @@ wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const 
 // ---- policy head: warp per row ----------------------------------------------------------------------------------------
 using WidePolicyArgs = b2rl_wide_policy_t;
 
-__global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_constant__ WidePolicyArgs P) {
+__global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_constant__ WidePolicyArgs P, const Stk K) {
   extern __shared__ float w3s[];  // [out][256]
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  for (int i = t; i < P.out_dim * HID; i += 256) w3s[i] = __ldg(P.w3 + i);
+  const size_t ag = blockIdx.y;                 // stacked agents: rows [ag * M, ag * M + M), parameters ps further
+  const float* w3g = P.w3 + ag * K.ps;
+  const float* b3g = P.b3 + ag * K.ps;
+  for (int i = t; i < P.out_dim * HID; i += 256) w3s[i] = __ldg(w3g + i);
   __syncthreads();
-  const int row = blockIdx.x * 8 + w;
+  const int row = blockIdx.x * 8 + w;           // row inside the agent's batch: the Philox key
   if (row >= P.M) return;
-  const uint64_t step = P.counters[P.counter_idx];
+  const size_t grow = ag * P.M + row;           // row of the stacked arrays
+  const uint32_t agent = P.agent + (uint32_t)ag;
+  const uint64_t step = P.counters[ag * K.cs + P.counter_idx];
   float h[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = __ldg(P.h2 + (size_t)row * HID + l + 32 * i);
+  for (int i = 0; i < 8; ++i) h[i] = __ldg(P.h2 + grow * HID + l + 32 * i);
   // the obs-part of the next network's input
-  const float* src = P.rows + (size_t)row * P.row_stride + P.src_off;
-  float* xr = P.xn + (size_t)row * P.ldn;
+  const float* src = P.rows + grow * P.row_stride + P.src_off;
+  float* xr = P.xn + grow * P.ldn;
   for (int k = l; k < P.O; k += 32) xr[k] = __ldg(src + k);
   float u_mu = 0.f, u_ls = 0.f;  // lane a < A keeps head outputs a and A + a
   for (int o = 0; o < P.out_dim; ++o) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
-    s = warp_sum(s) + __ldg(P.b3 + o);
+    s = warp_sum(s) + __ldg(b3g + o);
     if (o == l) u_mu = s;
     if (o == P.A + l) u_ls = s;
   }
@@ -135,27 +147,27 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
   if (l < P.A) {
     const float lo = __ldg(P.min_ac + l), hi = __ldg(P.max_ac + l);
     const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
-    const int64_t e = (int64_t)row * P.A + l;
+    const int64_t e = (int64_t)grow * P.A + l;
     float act_v;
     if (P.td3) {
       float th;
       act_v = td3_action(u_mu, scale, bias, th);
-      if (P.save) P.save[(size_t)row * 4 * P.A + 3 * P.A + l] = th;
+      if (P.save) P.save[grow * 4 * P.A + 3 * P.A + l] = th;
       if (P.smoothing) {
-        const float z = noise_at(P.eps, e, P.seed, row, l, step, P.agent, P.stream_id);
+        const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
         if (P.eps_out) P.eps_out[e] = z;
         float n = __fmul_rn(z, P.td3_std);
         n = fminf(fmaxf(n, -P.td3_c), P.td3_c);
         act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
       }
     } else {
-      const float z = noise_at(P.eps, e, P.seed, row, l, step, P.agent, P.stream_id);
+      const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
       if (P.eps_out) P.eps_out[e] = z;
       const GaussSample gs = gauss_sample(u_mu, u_ls, z, scale, bias);
       act_v = gs.action;
       lp = gs.logp;
       if (P.save) {  // what the head's backward pass needs: [M][4][A] = eps, sigma, tanh(x), tanh(raw log-std)
-        float* sv = P.save + (size_t)row * 4 * P.A;
+        float* sv = P.save + grow * 4 * P.A;
         sv[l] = z; sv[P.A + l] = gs.sigma; sv[2 * P.A + l] = gs.y; sv[3 * P.A + l] = gs.th;
       }
     }
@@ -163,36 +175,39 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
   }
   if (P.logp) {
     lp = warp_sum(lp);
-    if (l == 0) P.logp[row] = lp;
+    if (l == 0) P.logp[grow] = lp;
   }
 }
 
 // ---- critic head: warp per row ------------------------------------------------------------------------------------------
 using WideQArgs = b2rl_wide_q_t;
 
-__global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant__ WideQArgs Q) {
+__global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant__ WideQArgs Q, const Stk K) {
   __shared__ float sq_w[8], dq_w[8];
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int row = blockIdx.x * 8 + w;
+  const size_t ag = blockIdx.y;
+  const int lrow = blockIdx.x * 8 + w;
+  const size_t row = ag * Q.M + lrow;
+  const float* w3 = Q.w3 + ag * K.ps;
   float sq = 0.f, dqv = 0.f;
-  if (row < Q.M) {
+  if (lrow < Q.M) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(__ldg(Q.w3 + l + 32 * i), __ldg(Q.h2 + (size_t)row * HID + l + 32 * i), s);
-    const float q = warp_sum(s) + __ldg(Q.b3);
+    for (int i = 0; i < 8; ++i) s = fmaf(__ldg(w3 + l + 32 * i), __ldg(Q.h2 + row * HID + l + 32 * i), s);
+    const float q = warp_sum(s) + __ldg(Q.b3 + ag * K.ps);
     if (l == 0) {
       Q.q_out[row] = q;
       if (Q.mode == 1) {  // agents/agent.py:212-233
         const float q0 = Q.qn0[row], q1 = Q.qn1[row];
         const float qmin = fminf(q0, q1);
         float qp = Q.bcq_mix ? __fadd_rn(__fmul_rn(0.75f, qmin), __fmul_rn(0.25f, fmaxf(q0, q1))) : qmin;
-        if (!Q.td3) qp = __fsub_rn(qp, __fmul_rn(expf(Q.log_alpha[0]), Q.logp[row]));
-        const float* rr = Q.rows + (size_t)row * Q.row_stride + Q.rd_off;
+        if (!Q.td3) qp = __fsub_rn(qp, __fmul_rn(expf(Q.log_alpha[ag * K.as]), Q.logp[row]));
+        const float* rr = Q.rows + row * Q.row_stride + Q.rd_off;
         const float y = __fadd_rn(rr[0], __fmul_rn(__fmul_rn(1.0f - rr[1], Q.gamma), qp));
         if (Q.targ_out) Q.targ_out[row] = y;
         const float dlt = q - y;
         dqv = dlt * (2.0f / (float)Q.M);
-        Q.dz3[(size_t)row * MAX_OUT] = dqv;
+        Q.dz3[row * MAX_OUT] = dqv;
         sq = dlt * dlt;
       }
     }
@@ -204,8 +219,9 @@ __global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant_
       float s = 0.f, d = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s += sq_w[i]; d += dq_w[i]; }
-      Q.sq_part[2 * blockIdx.x] = s;
-      Q.sq_part[2 * blockIdx.x + 1] = d;
+      const size_t pi = ag * gridDim.x + blockIdx.x;
+      Q.sq_part[2 * pi] = s;
+      Q.sq_part[2 * pi + 1] = d;
     }
   }
 }
@@ -217,7 +233,13 @@ constexpr int WB_ROWS = 128;
 __global__ void __launch_bounds__(256)
 wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __restrict__ w3, const float* __restrict__ xh,
                    const float2* __restrict__ stat, const float* __restrict__ g, const float* __restrict__ be, int ln, int M,
-                   float* __restrict__ dz, float* __restrict__ part) {
+                   float* __restrict__ dz, float* __restrict__ part, long long ps) {
+  {  // stacked agents: blockIdx.y = agent
+    const size_t ag = blockIdx.y;
+    dz3 += ag * M * MAX_OUT, xh += ag * M * HID, dz += ag * M * HID, w3 += ag * ps;
+    part += ag * gridDim.x * 3 * HID;
+    if (ln) stat += ag * M, g += ag * ps, be += ag * ps;
+  }
   extern __shared__ float wsm[];          // w3 [n_out][256], then the cross-warp reduction buffer [8][3][256]
   float* w3s = wsm;
   float* red = wsm + n_out * HID;
@@ -294,7 +316,10 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
 // G[off[v] + j] = sum_p part[p][v][j], v < 3 (v >= 1 only when layer_norm). Grid (8 column chunks, 3 vectors); thread
 // (c = t & 31, s = t >> 5) sums partials s, s + 8, ... of column 32 * chunk + c; fixed-order combine over s.
 __global__ void __launch_bounds__(256)
-wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G, int64_t off_b, int64_t off_g, int64_t off_be, int ln) {
+wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
+                   long long ps) {
+  part += (size_t)blockIdx.z * P * 3 * HID;  // stacked agents: blockIdx.z = agent
+  G += (size_t)blockIdx.z * ps;
   __shared__ float red[8][32];
   const int v = blockIdx.y, t = threadIdx.x, c = t & 31, sl = t >> 5, j = blockIdx.x * 32 + c;
   if (v > 0 && !ln) return;
@@ -313,7 +338,9 @@ wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G,
 // {sum sq, sum dQ} written by wide_q_head (online mode), P of them per critic.
 __global__ void __launch_bounds__(256)
 wide_critic_scalars_kernel(const float* __restrict__ sq0, const float* __restrict__ sq1, int P, int M, float* __restrict__ G,
-                           int64_t off_b3_0, int64_t off_b3_1, float* __restrict__ out) {
+                           int64_t off_b3_0, int64_t off_b3_1, float* __restrict__ out, const Stk K) {
+  sq0 += (size_t)blockIdx.x * P * 2, sq1 += (size_t)blockIdx.x * P * 2;  // stacked agents: blockIdx.x = agent
+  G += (size_t)blockIdx.x * K.ps, out += (size_t)blockIdx.x * K.os;
   __shared__ float red[3][256];
   const int t = threadIdx.x;
   float a = 0.f, d0 = 0.f, d1 = 0.f;
@@ -338,7 +365,12 @@ wide_critic_scalars_kernel(const float* __restrict__ sq0, const float* __restric
 __global__ void __launch_bounds__(256)
 wide_actor_loss_kernel(const float* __restrict__ q0, const float* __restrict__ q1, const float* __restrict__ logp,
                        const float* __restrict__ log_alpha, int td3, int M, float* __restrict__ dzq0, float* __restrict__ dzq1,
-                       float* __restrict__ part) {
+                       float* __restrict__ part, long long as) {
+  {  // stacked agents: blockIdx.y = agent
+    const size_t ag = blockIdx.y;
+    q0 += ag * M, dzq0 += ag * M * MAX_OUT, part += ag * gridDim.x * 2;
+    if (!td3) q1 += ag * M, logp += ag * M, log_alpha += ag * as, dzq1 += ag * M * MAX_OUT;
+  }
   __shared__ float red[2][8];
   const int t = threadIdx.x, row = blockIdx.x * 256 + t;
   float lossr = 0.f, lp = 0.f;
@@ -374,7 +406,8 @@ wide_actor_loss_kernel(const float* __restrict__ q0, const float* __restrict__ q
 // dQ/da[row][a] = sum_j dz1[row][j] * w1t[O + a][j]  (first-layer dX, action columns only); warp per row
 __global__ void __launch_bounds__(256)
 wide_dqda_kernel(const float* __restrict__ dz1, const float* __restrict__ w1a /* w1t + O * 256: [A][256] */, int A, int M,
-                 float* __restrict__ dqda) {
+                 float* __restrict__ dqda, long long ps) {
+  dz1 += (size_t)blockIdx.y * M * HID, dqda += (size_t)blockIdx.y * M * A, w1a += (size_t)blockIdx.y * ps;  // blockIdx.y = agent
   extern __shared__ float was[];
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   for (int i = t; i < A * HID; i += 256) was[i] = __ldg(w1a + i);
@@ -398,7 +431,14 @@ wide_dqda_kernel(const float* __restrict__ dz1, const float* __restrict__ w1a /*
 __global__ void __launch_bounds__(256)
 wide_actor_head_bwd_kernel(const float* __restrict__ dqda0, const float* __restrict__ dqda1, const float* __restrict__ save,
                            const float* __restrict__ min_ac, const float* __restrict__ max_ac, const float* __restrict__ log_alpha,
-                           int td3, int A, int M, float* __restrict__ du /* [M][MAX_OUT] */, float* __restrict__ part_du) {
+                           int td3, int A, int M, float* __restrict__ du /* [M][MAX_OUT] */, float* __restrict__ part_du,
+                           long long as) {
+  {  // stacked agents: blockIdx.y = agent
+    const size_t ag = blockIdx.y;
+    dqda0 += ag * M * A, save += ag * M * 4 * A, du += ag * M * MAX_OUT, part_du += ag * gridDim.x * MAX_OUT;
+    if (dqda1) dqda1 += ag * M * A;
+    if (!td3) log_alpha += ag * as;
+  }
   __shared__ float red[8][MAX_OUT];
   const int t = threadIdx.x, row = blockIdx.x * 256 + t, out = td3 ? A : 2 * A;
   const bool live = row < M;
@@ -439,7 +479,13 @@ wide_actor_head_bwd_kernel(const float* __restrict__ dqda0, const float* __restr
 // actor_loss, mean logpi, alpha -> out; d head.bias -> G. part_s [P][2], part_du [P][MAX_OUT] from the two kernels above.
 __global__ void __launch_bounds__(256)
 wide_actor_scalars_kernel(const float* __restrict__ part_s, const float* __restrict__ part_du, int P, int M, int out_dim, int td3,
-                          const float* __restrict__ log_alpha, float* __restrict__ G, int64_t off_b3, float* __restrict__ out) {
+                          const float* __restrict__ log_alpha, float* __restrict__ G, int64_t off_b3, float* __restrict__ out,
+                          const Stk K) {
+  {  // stacked agents: blockIdx.x = agent
+    const size_t ag = blockIdx.x;
+    part_s += ag * P * 2, part_du += ag * P * MAX_OUT, G += ag * K.ps, out += ag * K.os;
+    if (!td3) log_alpha += ag * K.as;
+  }
   const int t = threadIdx.x;
   if (t < out_dim) {
     float s = 0.f;
@@ -457,7 +503,8 @@ wide_actor_scalars_kernel(const float* __restrict__ part_s, const float* __restr
 
 // temperature gradient (agents/agent.py:295-303): log_alpha state slot 1 <- alpha * mean(-logpi'' - targ_ent); one CTA
 __global__ void __launch_bounds__(256)
-wide_alpha_grad_kernel(const float* __restrict__ logp2, int M, float targ_ent, float* __restrict__ alpha_state) {
+wide_alpha_grad_kernel(const float* __restrict__ logp2, int M, float targ_ent, float* __restrict__ alpha_state, long long as) {
+  logp2 += (size_t)blockIdx.x * M, alpha_state += (size_t)blockIdx.x * as;  // stacked agents: blockIdx.x = agent
   __shared__ float red[256];
   const int t = threadIdx.x;
   float s = 0.f;
@@ -489,57 +536,59 @@ cudaError_t init_wide() {
   return e;
 }
 cudaError_t launch_wide_first(const float* X, int64_t ldx, int M, int K, const float* w1t, const float* b, const float* g,
-                              const float* be, int ln, float* H, float* XH, float* stat, cudaStream_t st) {
-  wide_first_kernel<<<(M + WF_ROWS - 1) / WF_ROWS, 256, 0, st>>>(X, ldx, M, K, w1t, b, g, be, ln, H, XH, reinterpret_cast<float2*>(stat));
+                              const float* be, int ln, float* H, float* XH, float* stat, const Stk& k, cudaStream_t st) {
+  wide_first_kernel<<<dim3((M + WF_ROWS - 1) / WF_ROWS, k.n), 256, 0, st>>>(X, ldx, M, K, w1t, b, g, be, ln, H, XH,
+                                                                            reinterpret_cast<float2*>(stat), k.ps);
   return cudaGetLastError();
 }
-cudaError_t launch_wide_policy_head(const WidePolicyArgs& p, cudaStream_t st) {
-  wide_policy_head_kernel<<<(p.M + 7) / 8, 256, (size_t)p.out_dim * HID * 4, st>>>(p);
+cudaError_t launch_wide_policy_head(const WidePolicyArgs& p, const Stk& k, cudaStream_t st) {
+  wide_policy_head_kernel<<<dim3((p.M + 7) / 8, k.n), 256, (size_t)p.out_dim * HID * 4, st>>>(p, k);
   return cudaGetLastError();
 }
-cudaError_t launch_wide_q_head(const WideQArgs& q, cudaStream_t st) {
-  wide_q_head_kernel<<<(q.M + 7) / 8, 256, 0, st>>>(q);
+cudaError_t launch_wide_q_head(const WideQArgs& q, const Stk& k, cudaStream_t st) {
+  wide_q_head_kernel<<<dim3((q.M + 7) / 8, k.n), 256, 0, st>>>(q, k);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_ln_bwd(const float* dz3, int n_out, const float* w3, const float* xh, const float* stat, const float* g,
-                               const float* be, int ln, int M, float* dz, float* part, cudaStream_t st) {
-  wide_ln_bwd_kernel<<<(M + WB_ROWS - 1) / WB_ROWS, 256, (size_t)(n_out + 24) * HID * 4, st>>>(
-      dz3, n_out, w3, xh, reinterpret_cast<const float2*>(stat), g, be, ln, M, dz, part);
+                               const float* be, int ln, int M, float* dz, float* part, const Stk& k, cudaStream_t st) {
+  wide_ln_bwd_kernel<<<dim3((M + WB_ROWS - 1) / WB_ROWS, k.n), 256, (size_t)(n_out + 24) * HID * 4, st>>>(
+      dz3, n_out, w3, xh, reinterpret_cast<const float2*>(stat), g, be, ln, M, dz, part, k.ps);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
-                               cudaStream_t st) {
-  wide_colsum_kernel<<<dim3(HID / 32, 3), 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln);
+                               const Stk& k, cudaStream_t st) {
+  wide_colsum_kernel<<<dim3(HID / 32, 3, k.n), 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln, k.ps);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float*, const float*, int M, float* G,
-                                       int64_t off0, int64_t off1, float* out, cudaStream_t st) {
-  wide_critic_scalars_kernel<<<1, 256, 0, st>>>(sq0, sq1, P, M, G, off0, off1, out);
+                                       int64_t off0, int64_t off1, float* out, const Stk& k, cudaStream_t st) {
+  wide_critic_scalars_kernel<<<k.n, 256, 0, st>>>(sq0, sq1, P, M, G, off0, off1, out, k);
   return cudaGetLastError();
 }
 
 cudaError_t launch_wide_actor_loss(const float* q0, const float* q1, const float* logp, const float* log_alpha, int td3, int M,
-                                   float* dzq0, float* dzq1, float* part, cudaStream_t st) {
-  wide_actor_loss_kernel<<<(M + 255) / 256, 256, 0, st>>>(q0, q1, logp, log_alpha, td3, M, dzq0, dzq1, part);
+                                   float* dzq0, float* dzq1, float* part, const Stk& k, cudaStream_t st) {
+  wide_actor_loss_kernel<<<dim3((M + 255) / 256, k.n), 256, 0, st>>>(q0, q1, logp, log_alpha, td3, M, dzq0, dzq1, part, k.as);
   return cudaGetLastError();
 }
-cudaError_t launch_wide_dqda(const float* dz1, const float* w1a, int A, int M, float* dqda, cudaStream_t st) {
-  wide_dqda_kernel<<<(M + 7) / 8, 256, (size_t)A * HID * 4, st>>>(dz1, w1a, A, M, dqda);
+cudaError_t launch_wide_dqda(const float* dz1, const float* w1a, int A, int M, float* dqda, const Stk& k, cudaStream_t st) {
+  wide_dqda_kernel<<<dim3((M + 7) / 8, k.n), 256, (size_t)A * HID * 4, st>>>(dz1, w1a, A, M, dqda, k.ps);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
                                        const float* max_ac, const float* log_alpha, int td3, int A, int M, float* du,
-                                       float* part_du, cudaStream_t st) {
-  wide_actor_head_bwd_kernel<<<(M + 255) / 256, 256, 0, st>>>(dqda0, dqda1, save, min_ac, max_ac, log_alpha, td3, A, M, du, part_du);
+                                       float* part_du, const Stk& k, cudaStream_t st) {
+  wide_actor_head_bwd_kernel<<<dim3((M + 255) / 256, k.n), 256, 0, st>>>(dqda0, dqda1, save, min_ac, max_ac, log_alpha, td3, A, M, du,
+                                                                         part_du, k.as);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_actor_scalars(const float* part_s, const float* part_du, int P, int M, int out_dim, int td3,
-                                      const float* log_alpha, float* G, int64_t off_b3, float* out, cudaStream_t st) {
-  wide_actor_scalars_kernel<<<1, 256, 0, st>>>(part_s, part_du, P, M, out_dim, td3, log_alpha, G, off_b3, out);
+                                      const float* log_alpha, float* G, int64_t off_b3, float* out, const Stk& k, cudaStream_t st) {
+  wide_actor_scalars_kernel<<<k.n, 256, 0, st>>>(part_s, part_du, P, M, out_dim, td3, log_alpha, G, off_b3, out, k);
   return cudaGetLastError();
 }
-cudaError_t launch_wide_alpha_grad(const float* logp2, int M, float targ_ent, float* alpha_state, cudaStream_t st) {
-  wide_alpha_grad_kernel<<<1, 256, 0, st>>>(logp2, M, targ_ent, alpha_state);
+cudaError_t launch_wide_alpha_grad(const float* logp2, int M, float targ_ent, float* alpha_state, const Stk& k, cudaStream_t st) {
+  wide_alpha_grad_kernel<<<k.n, 256, 0, st>>>(logp2, M, targ_ent, alpha_state, k.as);
   return cudaGetLastError();
 }
 

@@ -55,7 +55,12 @@ def init_agent_params(agent_id: int, seed: int, ob_dim: int, ac_dim: int, td3: b
 
 class Population:
     def __init__(self, agent_ids, ob_dim: int, ac_dim: int, min_ac, max_ac, hps, device, seed: int = 0,
-                 rb_capacity: int = 100_000, batch_size: Optional[int] = None, use_graphs: bool = True):
+                 rb_capacity: int = 100_000, batch_size: Optional[int] = None, use_graphs: bool = True,
+                 wide: Optional[str] = None):
+        """wide: None = the batch-256 row-group kernels with the agent in blockIdx.y (each agent's layers stream from L2
+        once per 8 rows: latency-optimal for ONE agent, ~10 TFLOP/s however many are stacked); "3xtf32" / "tf32" = the
+        layer-by-layer tensor-core path (wide.py) with the agents stacked along the row dimension — n_agents x batch rows
+        per launch, per-agent weights fetched by rank-3 TMA maps: what a population of hundreds of agents wants."""
         self.ids = list(agent_ids)
         assert self.ids == list(range(self.ids[0], self.ids[0] + len(self.ids))), "agent ids must be contiguous"
         self.N, self.base = len(self.ids), self.ids[0]
@@ -114,6 +119,13 @@ class Population:
             gamma=float(hps.gamma), td3_std=float(hps.td3_std) if self.td3 else 0.0,
             td3_c=float(hps.td3_c) if self.td3 else 0.0, targ_ent=float(-self.ac_dim), seed=self.seed)
         self.args = self._make_args()
+        self.wide = wide
+        self.wide_q = self.wide_pi = None
+        if wide:
+            from .wide import WideActor, WideCritic, _Owner
+            own = _Owner(self)
+            self.wide_q = WideCritic(own, self.B, wide)
+            self.wide_pi = WideActor(own, self.B, wide)
 
     # ------------------------------------------------------------------ replay
     def fill_replay(self, td: Mapping[str, torch.Tensor], agent: Optional[int] = None) -> None:
@@ -166,13 +178,16 @@ class Population:
         L.check(lib.b2rl_replay_sample_gather(
             self.storage.data_ptr(), self.storage[0].numel(), 0, self.fmt, self.B, self.N, None, self.idx.data_ptr(),
             self.rows.data_ptr(), C.c_uint64(self.seed), self.counters.data_ptr(), L.CTR_Q, 0, self.base, st), "gather")
+        delay = int(h.actor_update_delay) if do_actor else 0
+        extra = [seg(lay.actor.begin, lay.actor.end, 0.0, False, True)] if (self.td3 and do_polyak and delay == 0) else []
+        if self.wide_q is not None:  # the tensor-core path, agents stacked along the rows (launch counts: tools/bench_population.py)
+            self.wide_q.update_qnets(self.rows, polyak=do_polyak, extra_segs=extra)
+            for j in range(delay):
+                self.wide_pi.update_actor(self.rows, polyak=self.td3 and do_polyak and j == delay - 1)
+            return -1
         fn = lib.b2rl_critic_update_td3 if self.td3 else lib.b2rl_critic_update_sac
         L.check(fn(C.byref(self.args), st), "critic_update")
-        delay = int(h.actor_update_delay) if do_actor else 0
-        segs = [seg(lay.critic[0].begin, lay.critic[1].end, float(h.qnets_lr), True, do_polyak, L.CTR_Q)]
-        if self.td3 and do_polyak and delay == 0:
-            segs.append(seg(lay.actor.begin, lay.actor.end, 0.0, False, True))
-        self._adam(segs)
+        self._adam([seg(lay.critic[0].begin, lay.critic[1].end, float(h.qnets_lr), True, do_polyak, L.CTR_Q)] + extra)
         n += 4
         for j in range(delay):
             fn = lib.b2rl_actor_update_td3 if self.td3 else lib.b2rl_actor_update_sac

@@ -21,20 +21,66 @@ from . import _lib as L
 STREAM_CRITIC_EPS, STREAM_ACTOR_EPS, STREAM_ALPHA_EPS = 1, 2, 3  # csrc/rng.cuh
 
 
-def _tc_wgrads(lib, ag, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, dz3, bump, st):
+class _Owner:
+    """What the wide path needs from its owner, which is either an ``Agent`` (one learner: every array has M rows, the
+    C ABI's ``stack`` argument is NULL) or a ``population.Population`` (N stacked learners, BASELINE.json config 4: every
+    per-row array is [N][M][..], parameters / scalars are reached through the strides of ``b2rl_stack_t``)."""
+
+    def __init__(self, owner):
+        self.owner = owner
+        self.stacked = hasattr(owner, "N")  # a Population
+        self.lib, self.device, self.layout, self.arena = owner._lib, owner.device, owner.layout, owner.arena
+        self.fmt, self.hps, self.hyper, self.td3, self.ac_dim = owner.fmt, owner.hps, owner._hyper, owner.td3, owner.ac_dim
+        self.min_ac, self.max_ac, self.counters, self.out = owner.min_ac, owner.max_ac, owner.counters, owner.out
+        self.autotune = owner.autotune
+        if self.stacked:
+            self.n, self.base, self.alpha_state = owner.N, owner.base, owner.alpha_state
+            self.launch_adam = owner._adam
+        else:
+            self.n, self.base, self.alpha_state = 1, owner.agent_id, owner._alpha_state
+            self.launch_adam = owner._launch_adam
+        self._stk = None
+        self._ws = {}
+
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def stack(self, lo_stride: int = 0):
+        """The ``b2rl_stack_t*`` argument (None for a single learner)."""
+        if not self.stacked:
+            return None
+        s = L.Stack(self.n, self.base, self.arena.agent_stride, lo_stride, self.alpha_state.stride(0), self.counters.stride(0),
+                    self.out.stride(0))
+        return s
+
+    def workspace(self, M: int) -> torch.Tensor:
+        """H1 H2 DZ1 DZ2 [2][n*M][256] + DZ3 [2][n*M][MAX_OUT], shared by the critic and the actor step."""
+        if not self.stacked:
+            return self.owner.workspace(M)
+        if M not in self._ws:
+            nm = self.n * M
+            self._ws[M] = torch.zeros(8 * nm * 256 + 2 * nm * L.MAX_OUT, dtype=torch.float32, device=self.device)
+        return self._ws[M]
+
+    def seg(self, begin, end, lr, adam, polyak, counter=0, clip=False):
+        return L.Seg(begin, end, lr, int(adam), int(polyak), counter, 1.0, int(clip))
+
+
+def _tc_wgrads(lib, stk, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, dz3, bump, st):
     """dW1t = X0^T dZ1, dW2t = H1^T dZ2 (+ the w2n transposed shadow), dW3 = dZ3^T H2 of one network, on the tensor cores
     (tc_wgrad.cu) into the arena's gradient region at G."""
     o = net.off
     f = lambda off: G + 4 * off
     sc = scratch.data_ptr()
-    L.check(lib.b2rl_tc_wgrad(x0_ptr, ldx, ldx, net.in_dim, dz1, M, f(o["w1t"]), None, sc, x3, None, st), "tc_wgrad w1")
-    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), f(o["w2n"]), sc, x3, None, st), "tc_wgrad w2")
-    L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, st), "tc_wgrad w3")
+    L.check(lib.b2rl_tc_wgrad(x0_ptr, ldx, ldx, net.in_dim, dz1, M, f(o["w1t"]), None, sc, x3, None, stk, st), "tc_wgrad w1")
+    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), f(o["w2n"]), sc, x3, None, stk, st), "tc_wgrad w2")
+    L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, stk, st), "tc_wgrad w3")
 
 
-def _wgrad_scratch(lib, ag, M, dev):
-    dims = {1, 256} | {n.in_dim for n in [ag.layout.actor, *ag.layout.critic]}
-    return torch.empty(max(lib.b2rl_tc_wgrad_scratch_floats(d, M) for d in dims), dtype=torch.float32, device=dev)
+def _wgrad_scratch(own: "_Owner", M):
+    dims = {1, 256} | {n.in_dim for n in [own.layout.actor, *own.layout.critic]}
+    n = own.n if own.stacked else 0
+    return torch.empty(max(own.lib.b2rl_tc_wgrad_scratch_floats(d, M, n) for d in dims), dtype=torch.float32, device=own.device)
 
 
 class WideCritic:
@@ -43,57 +89,78 @@ class WideCritic:
         (single MMA, ~1e-3 per product, ~1e-2 on gradients because dLoss/dQ is a difference of Q and the TD target)."""
         assert precision in ("3xtf32", "tf32")
         self.x3 = precision == "3xtf32"
-        self.ag, self.M = agent, int(batch)
-        ag, M, dev = agent, self.M, agent.device
-        self._lib = ag._lib
+        own = self.ag = agent if isinstance(agent, _Owner) else _Owner(agent)  # an Agent, or a Population (M rows PER AGENT)
+        self.M = int(batch)
+        M, dev, n = self.M, own.device, own.n
+        NM = self.NM = n * M  # rows of the stacked arrays
+        self._lib = own.lib
         f32 = dict(dtype=torch.float32, device=dev)
-        O, A = ag.fmt.ob_dim, ag.ac_dim
+        O, A = own.fmt.ob_dim, own.ac_dim
         self.ldn = (O + A + 3) & ~3
-        self.t1, self.t2 = torch.empty(M, 256, **f32), torch.empty(M, 256, **f32)     # scratch activations
-        self.xn = torch.zeros(M, self.ldn, **f32)                                      # [next_obs | a']
-        self.logp, self.qn, self.q = torch.zeros(M, **f32), torch.zeros(2, M, **f32), torch.zeros(2, M, **f32)
-        self.xh1, self.xh2 = torch.empty(2, M, 256, **f32), torch.empty(2, M, 256, **f32)
-        self.st1, self.st2 = torch.zeros(2, M, 2, **f32), torch.zeros(2, M, 2, **f32)
-        self.P128, self.P8 = (M + 127) // 128, (M + 7) // 8
-        self.part1, self.part2 = torch.zeros(2, self.P128, 3, 256, **f32), torch.zeros(2, self.P128, 3, 256, **f32)
-        self.sq = torch.zeros(2, self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
-        self.ws = ag.workspace(M)
-        self.wlo = torch.zeros(2, ag.layout.region, **f32)  # lo parts (3xTF32) of the online and target regions, same offsets
-        self.gscratch = _wgrad_scratch(self._lib, ag, M, dev)
+        self.t1, self.t2 = torch.empty(NM, 256, **f32), torch.empty(NM, 256, **f32)     # scratch activations
+        self.xn = torch.zeros(NM, self.ldn, **f32)                                       # [next_obs | a']
+        self.logp, self.qn, self.q = torch.zeros(NM, **f32), torch.zeros(2, NM, **f32), torch.zeros(2, NM, **f32)
+        self.xh1, self.xh2 = torch.empty(2, NM, 256, **f32), torch.empty(2, NM, 256, **f32)
+        self.st1, self.st2 = torch.zeros(2, NM, 2, **f32), torch.zeros(2, NM, 2, **f32)
+        self.P128, self.P8 = (M + 127) // 128, (M + 7) // 8   # per agent
+        self.part1, self.part2 = torch.zeros(2, n * self.P128, 3, 256, **f32), torch.zeros(2, n * self.P128, 3, 256, **f32)
+        self.sq = torch.zeros(2, n * self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
+        self.ws = own.workspace(M)
+        # lo parts (3xTF32) of the online and target regions, same offsets; one [2][region] mirror per agent
+        self.wlo = torch.zeros(n, 2, own.layout.region, **f32)
+        self.stk = own.stack(lo_stride=2 * own.layout.region)
+        self.gscratch = _wgrad_scratch(own, M)
 
-    # pointers into the arena: region r, float offset o
+    # pointers into the arena (agent 0's copy): region r, float offset o
     def _p(self, region: int, off: int) -> int:
         return self.ag.arena.flat.data_ptr() + 4 * (region * self.ag.layout.region + off)
 
     def _ws(self, which: int, slot: int) -> int:  # H1 H2 DZ1 DZ2 of common.cuh::ws_carve
-        return self.ws.data_ptr() + 4 * ((which * 2 + slot) * self.M * 256)
+        return self.ws.data_ptr() + 4 * ((which * 2 + slot) * self.NM * 256)
 
     def _dz3(self, slot: int) -> int:
-        return self.ws.data_ptr() + 4 * (8 * self.M * 256 + slot * self.M * L.MAX_OUT)
+        return self.ws.data_ptr() + 4 * (8 * self.NM * 256 + slot * self.NM * L.MAX_OUT)
+
+    def _split_lo(self, base: int, lo_base: int, spans, whole: int, st) -> None:
+        """Refresh the lo parts (3xTF32) of the weights that changed. One learner: ONE launch over `whole` floats (the
+        regions are neighbours in the arena). Stacked: one launch per 256 x 256 matrix in `spans` (float offsets from
+        `base`) over all agents — splitting whole regions would move 6.7 MB per agent and step."""
+        lib, stk = self._lib, self.stk
+        if stk is None:
+            L.check(lib.b2rl_tc_split_lo(base, lo_base, whole, None, st), "tc_split_lo")
+            return
+        for off in spans:
+            L.check(lib.b2rl_tc_split_lo(base + 4 * off, lo_base + 4 * off, 256 * 256, C.byref(stk), st), "tc_split_lo")
 
     def update_qnets(self, rows: torch.Tensor, eps: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None,
-                     targ_out: Optional[torch.Tensor] = None, adam: bool = True) -> dict:
-        """rows: the sampled batch [M][row_stride] (replay.Batch.rows). Enqueue-only (graph-capturable).
-        adam=False: stop after the gradients (data parallel: all-reduce them, then step)."""
+                     targ_out: Optional[torch.Tensor] = None, adam: bool = True, polyak: bool = False, extra_segs=()) -> dict:
+        """rows: the sampled batch [M][row_stride] (replay.Batch.rows; stacked: [n_agents][M][row_stride]).
+        Enqueue-only (graph-capturable). adam=False: stop after the gradients (data parallel: all-reduce them, then step);
+        polyak / extra_segs: let the target average ride in the Adam launch (population.py)."""
         ag, lib, M = self.ag, self._lib, self.M
-        assert rows.shape == (M, ag.fmt.row_stride) and rows.is_contiguous()
-        lay, st = ag.layout, ag._stream()
+        assert rows.numel() == self.NM * ag.fmt.row_stride and rows.is_contiguous()
+        lay, st = ag.layout, ag.stream()
         O, A, rs = ag.fmt.ob_dim, ag.ac_dim, ag.fmt.row_stride
         ln = int(bool(ag.hps.layer_norm))
         RP, RT, RG = L.REGION_P, L.REGION_T, 4
         none = None
+        stk = C.byref(self.stk) if self.stk is not None else None
 
         def first(x_ptr, ldx, K, net, region, H, XH, stat):
             o = net.off
             L.check(lib.b2rl_wide_first(x_ptr, ldx, M, K, self._p(region, o["w1t"]), self._p(region, o["b1"]),
                                         self._p(region, o["g1"]) if ln else none, self._p(region, o["be1"]) if ln else none, ln,
-                                        H, XH, stat, st), "wide_first")
+                                        H, XH, stat, stk, st), "wide_first")
 
-        # the weights change every step: their lo parts are recomputed — ONE launch over the online + target regions
-        # (1.7 MB; they are neighbours in the arena), not one per matrix; every weight keeps its arena offset in the mirror
+        # the weights change every step: their lo parts are recomputed; every weight keeps its arena offset in the mirror
         base = self._p(RP, 0)
+        ra = RT if ag.td3 else RP  # next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor
+        act = lay.actor
         if self.x3:
-            L.check(lib.b2rl_tc_split_lo(base, self.wlo.data_ptr(), 2 * lay.region, st), "tc_split_lo")
+            R = lay.region
+            spans = [ra * R + act.off["w2n"]] + [RT * R + c.off["w2n"] for c in lay.critic] + \
+                    [RP * R + c.off[f] for c in lay.critic for f in ("w2n", "w2t")]
+            self._split_lo(base, self.wlo.data_ptr(), spans, 2 * R, st)
 
         def lo_of(slot, w_ptr):
             return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
@@ -103,14 +170,12 @@ class WideCritic:
             w = self._p(region, o["w2n"])
             b2, g2, be2 = self._p(region, o["b2"]), self._p(region, o["g2"]) if ln else none, self._p(region, o["be2"]) if ln else none
             if head is None:
-                L.check(lib.b2rl_tc_linear(x_ptr, 256, M, w, lo_of(slot, w), b2, g2, be2, ln, 1, H, XH, stat, st), "tc_linear")
+                L.check(lib.b2rl_tc_linear(x_ptr, 256, M, w, lo_of(slot, w), b2, g2, be2, ln, 1, H, XH, stat, stk, st), "tc_linear")
             else:  # the critic's scalar head in the same kernel's epilogue
-                L.check(lib.b2rl_tc_linear_q(x_ptr, 256, M, w, lo_of(slot, w), b2, g2, be2, ln, H, XH, stat, C.byref(head), st),
+                L.check(lib.b2rl_tc_linear_q(x_ptr, 256, M, w, lo_of(slot, w), b2, g2, be2, ln, H, XH, stat, C.byref(head), stk, st),
                         "tc_linear_q")
 
-        # ---- next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor (:194-202)
-        ra = RT if ag.td3 else RP
-        act = lay.actor
+        # ---- next action (agent.py:194-205)
         first(rows.data_ptr() + 4 * (O + A + 2), rs, O, act, ra, self.t1.data_ptr(), none, none)
         hidden(self.t1.data_ptr(), act, ra, self.t2.data_ptr(), none, none, 0)
         p = L.WidePolicy()
@@ -120,21 +185,21 @@ class WideCritic:
         p.logp = None if ag.td3 else self.logp.data_ptr()
         p.counters = ag.counters.data_ptr()
         p.M, p.O, p.A, p.out_dim, p.row_stride, p.ldn, p.src_off = M, O, A, act.out_dim, rs, self.ldn, O + A + 2
-        p.td3, p.smoothing = int(ag.td3), int(ag._hyper.targ_smoothing)
+        p.td3, p.smoothing = int(ag.td3), int(ag.hyper.targ_smoothing)
         p.counter_idx, p.stream_id = L.CTR_Q, STREAM_CRITIC_EPS
-        p.td3_std, p.td3_c, p.seed, p.agent = ag._hyper.td3_std, ag._hyper.td3_c, ag._hyper.seed, ag.agent_id
-        L.check(lib.b2rl_wide_policy_head(C.byref(p), st), "wide_policy_head")
+        p.td3_std, p.td3_c, p.seed, p.agent = ag.hyper.td3_std, ag.hyper.td3_c, ag.hyper.seed, ag.base
+        L.check(lib.b2rl_wide_policy_head(C.byref(p), stk, st), "wide_policy_head")
 
         def q_head(net, region, k, mode):
             q = L.WideQ()
             q.h2, q.w3, q.b3 = None, self._p(region, net.off["w3"]), self._p(region, net.off["b3"])
             q.q_out = (self.q if mode else self.qn)[k].data_ptr()
             q.qn0, q.qn1, q.logp = self.qn[0].data_ptr(), self.qn[1].data_ptr(), self.logp.data_ptr()
-            q.rows, q.log_alpha = rows.data_ptr(), ag._alpha_state.data_ptr()
+            q.rows, q.log_alpha = rows.data_ptr(), ag.alpha_state.data_ptr()
             q.dz3, q.sq_part = self._dz3(k), self.sq[k].data_ptr()
             q.targ_out = L.ptr(targ_out) if (mode and k == 0) else None
-            q.M, q.mode, q.row_stride, q.rd_off, q.td3, q.bcq_mix = M, mode, rs, O + A, int(ag.td3), int(ag._hyper.bcq_mix)
-            q.gamma = ag._hyper.gamma
+            q.M, q.mode, q.row_stride, q.rd_off, q.td3, q.bcq_mix = M, mode, rs, O + A, int(ag.td3), int(ag.hyper.bcq_mix)
+            q.gamma = ag.hyper.gamma
             return q
 
         # ---- twin target Q on (next_obs, a')  (agent.py:208-210)
@@ -151,25 +216,26 @@ class WideCritic:
                    head=q_head(net, RP, k, 1))
             L.check(lib.b2rl_wide_ln_bwd(self._dz3(k), 1, self._p(RP, o["w3"]), self.xh2[k].data_ptr(), self.st2[k].data_ptr(),
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
-                                         self._ws(3, k), self.part2[k].data_ptr(), st), "wide_ln_bwd")
+                                         self._ws(3, k), self.part2[k].data_ptr(), stk, st), "wide_ln_bwd")
             w2t = self._p(RP, o["w2t"])
             L.check(lib.b2rl_tc_linear_bwd(self._ws(3, k), M, w2t, lo_of(5 + k, w2t), self.xh1[k].data_ptr(), self.st1[k].data_ptr(),
                                            self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                           self._ws(2, k), self.part1[k].data_ptr(), st), "tc_linear_bwd")
+                                           self._ws(2, k), self.part1[k].data_ptr(), stk, st), "tc_linear_bwd")
             L.check(lib.b2rl_wide_colsum(self.part2[k].data_ptr(), self.P128, G, o["b2"], o["g2"] if ln else 0, o["be2"] if ln else 0,
-                                         ln, st), "wide_colsum")
+                                         ln, stk, st), "wide_colsum")
             L.check(lib.b2rl_wide_colsum(self.part1[k].data_ptr(), self.P128, G, o["b1"], o["g1"] if ln else 0, o["be1"] if ln else 0,
-                                         ln, st), "wide_colsum")
+                                         ln, stk, st), "wide_colsum")
         L.check(lib.b2rl_wide_critic_scalars(self.sq[0].data_ptr(), self.sq[1].data_ptr(), self.P8, self._dz3(0), self._dz3(1), M, G,
-                                             lay.critic[0].off["b3"], lay.critic[1].off["b3"], ag.out.data_ptr(), st),
+                                             lay.critic[0].off["b3"], lay.critic[1].off["b3"], ag.out.data_ptr(), stk, st),
                 "wide_critic_scalars")
         # ---- weight gradients (wgrad.cu reads rows / H1 / H2 / DZ1 / DZ2 / DZ3 of the workspace), then Adam
         for k in range(2):
-            _tc_wgrads(lib, ag, M, int(self.x3), self.gscratch, G, lay.critic[k], rows.data_ptr(), rs, self._ws(0, k), self._ws(1, k),
+            _tc_wgrads(lib, stk, M, int(self.x3), self.gscratch, G, lay.critic[k], rows.data_ptr(), rs, self._ws(0, k), self._ws(1, k),
                        self._ws(2, k), self._ws(3, k), self._dz3(k), ag.counters.data_ptr() + 8 * L.CTR_Q if k == 1 else None, st)
         if adam:
-            ag._launch_adam(ag.critic_segs(False))
-        return {"loss/qf_loss": ag.out[L.OUT_QF_LOSS]}
+            ag.launch_adam([ag.seg(lay.critic[0].begin, lay.critic[1].end, float(ag.hps.qnets_lr), True, polyak, L.CTR_Q)]
+                           + list(extra_segs))
+        return {"loss/qf_loss": ag.out[..., L.OUT_QF_LOSS]}
 
 
 class WideActor:
@@ -181,58 +247,64 @@ class WideActor:
 
     def __init__(self, agent, batch: int, precision: str = "3xtf32"):
         assert precision in ("3xtf32", "tf32")
-        assert not agent.hps.clip_norm > 0, "the wide actor step has no gradient clipping: use the row-group path"
+        own = self.ag = agent if isinstance(agent, _Owner) else _Owner(agent)
+        assert not own.hps.clip_norm > 0, "the wide actor step has no gradient clipping: use the row-group path"
         self.x3 = precision == "3xtf32"
-        self.ag, self.M = agent, int(batch)
-        ag, M, dev = agent, self.M, agent.device
-        self._lib = ag._lib
+        self.M = int(batch)
+        M, dev, n = self.M, own.device, own.n
+        NM = self.NM = n * M
+        self._lib = own.lib
         f32 = dict(dtype=torch.float32, device=dev)
-        O, A = ag.fmt.ob_dim, ag.ac_dim
+        O, A = own.fmt.ob_dim, own.ac_dim
         self.ldn = (O + A + 3) & ~3
-        self.nq = 1 if ag.td3 else 2  # TD3's loss uses critic 0 only (agent.py:274-275)
-        self.t1, self.t2 = torch.empty(M, 256, **f32), torch.empty(M, 256, **f32)
-        self.xq = torch.zeros(M, self.ldn, **f32)                       # [obs | a_pi]
-        self.save = torch.zeros(M, 4, A, **f32)
-        self.logp, self.logp2 = torch.zeros(M, **f32), torch.zeros(M, **f32)
-        self.q = torch.zeros(2, M, **f32)
-        self.xa1, self.xa2 = torch.empty(M, 256, **f32), torch.empty(M, 256, **f32)       # actor x-hat
-        self.sa1, self.sa2 = torch.zeros(M, 2, **f32), torch.zeros(M, 2, **f32)
-        self.xq1, self.xq2 = torch.empty(2, M, 256, **f32), torch.empty(2, M, 256, **f32)  # critics' x-hat
-        self.sq1, self.sq2 = torch.zeros(2, M, 2, **f32), torch.zeros(2, M, 2, **f32)
-        self.dzq = torch.zeros(2, M, L.MAX_OUT, **f32)
-        self.dqda = torch.zeros(2, M, A, **f32)
-        self.P128, self.P256 = (M + 127) // 128, (M + 255) // 256
-        self.part = torch.zeros(2, self.P128, 3, 256, **f32)
-        self.part_s, self.part_du = torch.zeros(self.P256, 2, **f32), torch.zeros(self.P256, L.MAX_OUT, **f32)
-        self.ws = ag.workspace(M)
-        self.wlo = torch.zeros(ag.layout.region, **f32)  # lo parts (3xTF32) of the online region, same offsets
-        self.gscratch = _wgrad_scratch(self._lib, ag, M, dev)
+        self.nq = 1 if own.td3 else 2  # TD3's loss uses critic 0 only (agent.py:274-275)
+        self.t1, self.t2 = torch.empty(NM, 256, **f32), torch.empty(NM, 256, **f32)
+        self.xq = torch.zeros(NM, self.ldn, **f32)                       # [obs | a_pi]
+        self.save = torch.zeros(NM, 4, A, **f32)
+        self.logp, self.logp2 = torch.zeros(NM, **f32), torch.zeros(NM, **f32)
+        self.q = torch.zeros(2, NM, **f32)
+        self.xa1, self.xa2 = torch.empty(NM, 256, **f32), torch.empty(NM, 256, **f32)       # actor x-hat
+        self.sa1, self.sa2 = torch.zeros(NM, 2, **f32), torch.zeros(NM, 2, **f32)
+        self.xq1, self.xq2 = torch.empty(2, NM, 256, **f32), torch.empty(2, NM, 256, **f32)  # critics' x-hat
+        self.sq1, self.sq2 = torch.zeros(2, NM, 2, **f32), torch.zeros(2, NM, 2, **f32)
+        self.dzq = torch.zeros(2, NM, L.MAX_OUT, **f32)
+        self.dqda = torch.zeros(2, NM, A, **f32)
+        self.P128, self.P256 = (M + 127) // 128, (M + 255) // 256  # per agent
+        self.part = torch.zeros(2, n * self.P128, 3, 256, **f32)
+        self.part_s, self.part_du = torch.zeros(n * self.P256, 2, **f32), torch.zeros(n * self.P256, L.MAX_OUT, **f32)
+        self.ws = own.workspace(M)
+        self.wlo = torch.zeros(n, own.layout.region, **f32)  # lo parts (3xTF32) of the online region, same offsets
+        self.stk = own.stack(lo_stride=own.layout.region)
+        self.gscratch = _wgrad_scratch(own, M)
 
     _p = WideCritic._p
     _ws = WideCritic._ws
     _dz3 = WideCritic._dz3
+    _split_lo = WideCritic._split_lo
 
     def update_actor(self, rows: torch.Tensor, eps: Optional[torch.Tensor] = None, eps_alpha: Optional[torch.Tensor] = None,
-                     adam: bool = True) -> dict:
+                     adam: bool = True, polyak: bool = False) -> dict:
         ag, lib, M = self.ag, self._lib, self.M
-        assert rows.shape == (M, ag.fmt.row_stride) and rows.is_contiguous()
-        lay, st = ag.layout, ag._stream()
+        assert rows.numel() == self.NM * ag.fmt.row_stride and rows.is_contiguous()
+        lay, st = ag.layout, ag.stream()
         O, A, rs = ag.fmt.ob_dim, ag.ac_dim, ag.fmt.row_stride
         ln = int(bool(ag.hps.layer_norm))
         RP, RG = L.REGION_P, 4
         none = None
         act, ao = lay.actor, lay.actor.off
-        la = ag._alpha_state.data_ptr()
+        la = ag.alpha_state.data_ptr()
+        stk = C.byref(self.stk) if self.stk is not None else None
 
         def first(x_ptr, ldx, K, net, H, XH, stat):
             o = net.off
             L.check(lib.b2rl_wide_first(x_ptr, ldx, M, K, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
                                         self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                        H, XH, stat, st), "wide_first")
+                                        H, XH, stat, stk, st), "wide_first")
 
         base = self._p(RP, 0)
-        if self.x3:  # one launch over the online region (the critic step's Adam has just changed the critics)
-            L.check(lib.b2rl_tc_split_lo(base, self.wlo.data_ptr(), lay.region, st), "tc_split_lo")
+        if self.x3:  # the online region's matrices (the critic step's Adam has just changed the critics)
+            spans = [n_.off[f] for n_ in [act, *lay.critic[:self.nq]] for f in ("w2n", "w2t")]
+            self._split_lo(base, self.wlo.data_ptr(), spans, lay.region, st)
 
         def lo_of(slot, w_ptr):
             return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
@@ -242,7 +314,7 @@ class WideActor:
             w = self._p(RP, o["w2n"])
             L.check(lib.b2rl_tc_linear(x_ptr, 256, M, w, lo_of(slot, w), self._p(RP, o["b2"]),
                                        self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, 1,
-                                       H, XH, stat, st), "tc_linear")
+                                       H, XH, stat, stk, st), "tc_linear")
 
         def policy(h2_ptr, eps_t, stream_id, xn, logp, save):
             p = L.WidePolicy()
@@ -252,18 +324,18 @@ class WideActor:
             p.counters = ag.counters.data_ptr()
             p.M, p.O, p.A, p.out_dim, p.row_stride, p.ldn, p.src_off = M, O, A, act.out_dim, rs, self.ldn, 0
             p.td3, p.smoothing, p.counter_idx, p.stream_id = int(ag.td3), 0, L.CTR_PI, stream_id
-            p.td3_std, p.td3_c, p.seed, p.agent = 0.0, 0.0, ag._hyper.seed, ag.agent_id
-            L.check(lib.b2rl_wide_policy_head(C.byref(p), st), "wide_policy_head")
+            p.td3_std, p.td3_c, p.seed, p.agent = 0.0, 0.0, ag.hyper.seed, ag.base
+            L.check(lib.b2rl_wide_policy_head(C.byref(p), stk, st), "wide_policy_head")
 
         def bwd_layers(dz3_ptr, n_out, net, xh2, st2, xh1, st1, dz2_out, dz1_out, part, slot):
             o = net.off
             L.check(lib.b2rl_wide_ln_bwd(dz3_ptr, n_out, self._p(RP, o["w3"]), xh2, st2,
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
-                                         dz2_out, part[0].data_ptr(), st), "wide_ln_bwd")
+                                         dz2_out, part[0].data_ptr(), stk, st), "wide_ln_bwd")
             w2t = self._p(RP, o["w2t"])
             L.check(lib.b2rl_tc_linear_bwd(dz2_out, M, w2t, lo_of(slot, w2t), xh1, st1,
                                            self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                           dz1_out, part[1].data_ptr(), st), "tc_linear_bwd")
+                                           dz1_out, part[1].data_ptr(), stk, st), "tc_linear_bwd")
 
         # ---- actor forward on obs, sample (agent.py:251 / :254-255): H1 / H2 go to workspace slot 0 for wgrad
         first(rows.data_ptr(), rs, O, act, self._ws(0, 0), self.xa1.data_ptr(), self.sa1.data_ptr())
@@ -281,68 +353,69 @@ class WideActor:
             w2 = self._p(RP, o["w2n"])
             L.check(lib.b2rl_tc_linear_q(self.t1.data_ptr(), 256, M, w2, lo_of(1 + k, w2), self._p(RP, o["b2"]),
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, None,
-                                         self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), C.byref(q), st), "tc_linear_q")
+                                         self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), C.byref(q), stk, st), "tc_linear_q")
         L.check(lib.b2rl_wide_actor_loss(self.q[0].data_ptr(), None if ag.td3 else self.q[1].data_ptr(),
                                          None if ag.td3 else self.logp.data_ptr(), None if ag.td3 else la, int(ag.td3), M,
                                          self.dzq[0].data_ptr(), None if ag.td3 else self.dzq[1].data_ptr(),
-                                         self.part_s.data_ptr(), st), "wide_actor_loss")
+                                         self.part_s.data_ptr(), stk, st), "wide_actor_loss")
         # ---- backward through critic k down to its action inputs
         for k in range(self.nq):
             net = lay.critic[k]
             bwd_layers(self.dzq[k].data_ptr(), 1, net, self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), self.xq1[k].data_ptr(),
                        self.sq1[k].data_ptr(), self.t1.data_ptr(), self.t2.data_ptr(), self.part, 3 + k)
             L.check(lib.b2rl_wide_dqda(self.t2.data_ptr(), self._p(RP, net.off["w1t"]) + 4 * O * 256, A, M,
-                                       self.dqda[k].data_ptr(), st), "wide_dqda")
+                                       self.dqda[k].data_ptr(), stk, st), "wide_dqda")
         # ---- backward through the action head and the actor
         G = self._p(RG, 0)
         L.check(lib.b2rl_wide_actor_head_bwd(self.dqda[0].data_ptr(), None if ag.td3 else self.dqda[1].data_ptr(),
                                              self.save.data_ptr(), ag.min_ac.data_ptr(), ag.max_ac.data_ptr(),
-                                             None if ag.td3 else la, int(ag.td3), A, M, self._dz3(0), self.part_du.data_ptr(), st),
+                                             None if ag.td3 else la, int(ag.td3), A, M, self._dz3(0), self.part_du.data_ptr(), stk, st),
                 "wide_actor_head_bwd")
         bwd_layers(self._dz3(0), act.out_dim, act, self.xa2.data_ptr(), self.sa2.data_ptr(), self.xa1.data_ptr(),
                    self.sa1.data_ptr(), self._ws(3, 0), self._ws(2, 0), self.part, 5)
         L.check(lib.b2rl_wide_colsum(self.part[0].data_ptr(), self.P128, G, ao["b2"], ao["g2"] if ln else 0,
-                                     ao["be2"] if ln else 0, ln, st), "wide_colsum")
+                                     ao["be2"] if ln else 0, ln, stk, st), "wide_colsum")
         L.check(lib.b2rl_wide_colsum(self.part[1].data_ptr(), self.P128, G, ao["b1"], ao["g1"] if ln else 0,
-                                     ao["be1"] if ln else 0, ln, st), "wide_colsum")
+                                     ao["be1"] if ln else 0, ln, stk, st), "wide_colsum")
         L.check(lib.b2rl_wide_actor_scalars(self.part_s.data_ptr(), self.part_du.data_ptr(), self.P256, M, act.out_dim,
-                                            int(ag.td3), None if ag.td3 else la, G, ao["b3"], ag.out.data_ptr(), st),
+                                            int(ag.td3), None if ag.td3 else la, G, ao["b3"], ag.out.data_ptr(), stk, st),
                 "wide_actor_scalars")
-        _tc_wgrads(lib, ag, M, int(self.x3), self.gscratch, G, act, rows.data_ptr(), rs, self._ws(0, 0), self._ws(1, 0),
+        _tc_wgrads(lib, stk, M, int(self.x3), self.gscratch, G, act, rows.data_ptr(), rs, self._ws(0, 0), self._ws(1, 0),
                    self._ws(2, 0), self._ws(3, 0), self._dz3(0), ag.counters.data_ptr() + 8 * L.CTR_PI, st)
         if not adam:
             return {}
-        ag._launch_adam(ag.actor_segs(False))
-        out = {"loss/actor_loss": ag.out[L.OUT_ACTOR_LOSS]}
+        ag.launch_adam([ag.seg(act.begin, act.end, float(ag.hps.actor_lr), True, polyak, L.CTR_PI)])
+        out = {"loss/actor_loss": ag.out[..., L.OUT_ACTOR_LOSS]}
         if ag.td3:
             return out
         if ag.autotune:
             self.alpha_grad(rows, eps_alpha)
-            L.check(lib.b2rl_alpha_adam(la, ag.counters.data_ptr(), 1, float(ag.hps.log_alpha_lr), 1.0, ag.out.data_ptr(), st),
+            L.check(lib.b2rl_alpha_adam(la, ag.counters.data_ptr(), ag.n, float(ag.hps.log_alpha_lr), 1.0, ag.out.data_ptr(), st),
                     "alpha_adam")
-            out["loss/alpha_loss"] = ag.out[L.OUT_ALPHA_LOSS]
-        out["vitals/alpha"] = ag.out[L.OUT_ALPHA]
+            out["loss/alpha_loss"] = ag.out[..., L.OUT_ALPHA_LOSS]
+        out["vitals/alpha"] = ag.out[..., L.OUT_ALPHA]
         return out
 
     def alpha_grad(self, rows: torch.Tensor, eps_alpha: Optional[torch.Tensor] = None) -> None:
         """agents/agent.py:295-300: log-prob of a fresh sample from the UPDATED actor; leaves the temperature's
         gradient in its state slot 1 (finish with b2rl_alpha_adam, after an all-reduce when data parallel)."""
         ag, lib, M = self.ag, self._lib, self.M
-        st, lay = ag._stream(), ag.layout
+        st, lay = ag.stream(), ag.layout
         O, rs = ag.fmt.ob_dim, ag.fmt.row_stride
         ln = int(bool(ag.hps.layer_norm))
         act, o, RP = lay.actor, lay.actor.off, L.REGION_P
         none = None
+        stk = C.byref(self.stk) if self.stk is not None else None
         L.check(lib.b2rl_wide_first(rows.data_ptr(), rs, M, O, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
                                     self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                    self.t1.data_ptr(), none, none, st), "wide_first")
+                                    self.t1.data_ptr(), none, none, stk, st), "wide_first")
         w = self._p(RP, o["w2n"])
         wl = none
         if self.x3:  # (the actor's Adam step has just changed this matrix)
             wl = self.wlo.data_ptr() + (w - self._p(RP, 0))
-            L.check(lib.b2rl_tc_split_lo(w, wl, 256 * 256, st), "tc_split_lo")
+            L.check(lib.b2rl_tc_split_lo(w, wl, 256 * 256, stk, st), "tc_split_lo")
         L.check(lib.b2rl_tc_linear(self.t1.data_ptr(), 256, M, w, wl, self._p(RP, o["b2"]), self._p(RP, o["g2"]) if ln else none,
-                                   self._p(RP, o["be2"]) if ln else none, ln, 1, self.t2.data_ptr(), none, none, st), "tc_linear")
+                                   self._p(RP, o["be2"]) if ln else none, ln, 1, self.t2.data_ptr(), none, none, stk, st), "tc_linear")
         p = L.WidePolicy()
         p.h2, p.w3, p.b3 = self.t2.data_ptr(), self._p(RP, o["w3"]), self._p(RP, o["b3"])
         p.rows, p.min_ac, p.max_ac = rows.data_ptr(), ag.min_ac.data_ptr(), ag.max_ac.data_ptr()
@@ -350,7 +423,7 @@ class WideActor:
         p.counters = ag.counters.data_ptr()
         p.M, p.O, p.A, p.out_dim, p.row_stride, p.ldn, p.src_off = M, O, ag.ac_dim, act.out_dim, rs, self.ldn, 0
         p.td3, p.smoothing, p.counter_idx, p.stream_id = 0, 0, L.CTR_PI, STREAM_ALPHA_EPS
-        p.td3_std, p.td3_c, p.seed, p.agent = 0.0, 0.0, ag._hyper.seed, ag.agent_id
-        L.check(lib.b2rl_wide_policy_head(C.byref(p), st), "wide_policy_head")
-        L.check(lib.b2rl_wide_alpha_grad(self.logp2.data_ptr(), M, float(ag._hyper.targ_ent), ag._alpha_state.data_ptr(), st),
+        p.td3_std, p.td3_c, p.seed, p.agent = 0.0, 0.0, ag.hyper.seed, ag.base
+        L.check(lib.b2rl_wide_policy_head(C.byref(p), stk, st), "wide_policy_head")
+        L.check(lib.b2rl_wide_alpha_grad(self.logp2.data_ptr(), M, float(ag.hyper.targ_ent), ag.alpha_state.data_ptr(), stk, st),
                 "wide_alpha_grad")

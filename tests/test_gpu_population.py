@@ -70,3 +70,68 @@ def test_population_is_invariant_to_sharding():
     got = torch.cat([p.arena.flat for p in parts])
     assert torch.equal(whole.arena.flat, got)
     assert torch.equal(whole.idx, torch.cat([p.idx for p in parts]))  # same index draws per global agent id
+
+
+# ---- the population on the tensor-core (wide) path: agents stacked along the rows ----------------------------------------------
+def _wide_population(ids, algo, B, use_graphs=True, wide="3xtf32"):
+    from sac_td3_cudagraphs_pytorch_b200 import sac_hps, td3_hps
+    from sac_td3_cudagraphs_pytorch_b200.population import Population
+    hps = (sac_hps if algo == "sac" else td3_hps)(batch_size=B)
+    pop = Population(ids, 11, 3, [-1.0] * 3, [1.0] * 3, hps, "cuda", seed=42, rb_capacity=1000, use_graphs=use_graphs, wide=wide)
+    for g, aid in enumerate(ids):
+        pop.fill_replay(_data(aid), agent=g)
+    return pop
+
+
+@pytest.mark.parametrize("algo,B", [("sac", 256), ("td3", 200)])
+def test_wide_population_is_invariant_to_sharding(algo, B):
+    """Bitwise: [0,1,2,3] on one GPU == [0,1] + [2] + [3] (graph replay and eager launches) — the multi-GPU contract of
+    BASELINE.json config 4 (a partition of the agent ids, no collective) on the tcgen05 path. B = 200 is ragged against
+    the 128-row tiles: an agent's tail rows are zero-filled by TMA, never read from its neighbour."""
+    whole = _wide_population([0, 1, 2, 3], algo, B)
+    parts = [_wide_population([0, 1], algo, B), _wide_population([2], algo, B, use_graphs=False), _wide_population([3], algo, B)]
+    for i in range(7):
+        whole.iteration()
+        for p in parts:
+            p.iteration()
+    torch.cuda.synchronize()
+    assert torch.isfinite(whole.out).all()
+    assert torch.equal(whole.arena.flat, torch.cat([p.arena.flat for p in parts]))
+    assert torch.equal(whole.counters[:, :3], torch.cat([p.counters[:, :3] for p in parts]))
+    assert torch.equal(whole.out, torch.cat([p.out for p in parts]))
+    assert torch.equal(whole.alpha_state[:, [0, 2, 3]], torch.cat([p.alpha_state[:, [0, 2, 3]] for p in parts]))
+    assert not torch.equal(whole.arena.flat[0], whole.arena.flat[1])
+
+
+@pytest.mark.parametrize("algo", ["sac", "td3"])
+def test_wide_population_matches_the_fp32_row_path(algo):
+    """Same agents, data, index draws and noise on the row-group fp32 kernels and on the stacked 3xTF32 tensor-core path:
+    after the first iteration (critic step + two actor steps from identical state) the losses agree to 2e-5, the critics'
+    gradients to 5e-5 of each agent's largest entry (stated 3xTF32 bound; a ReLU unit within ~1e-6 of its kink may flip
+    between two correct evaluations — seeds are fixed, and none does here), and after 6 iterations the parameters to 2e-3
+    (Adam's first steps move every weight by lr whatever the gradient's size, which amplifies rounding-level differences)."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    ids = [3, 4, 5]
+    wide, row = _wide_population(ids, algo, 256), _wide_population(ids, algo, 256, wide=None)
+    wide.iteration()
+    row.iteration()
+    torch.cuda.synchronize()
+    assert torch.equal(wide.idx, row.idx)
+    lay = wide.layout
+    for g in range(len(ids)):
+        for k in (L.OUT_QF_LOSS, L.OUT_ACTOR_LOSS):
+            a, b = float(wide.out[g, k]), float(row.out[g, k])
+            assert abs(a - b) <= 2e-5 * max(abs(b), 1e-3), (g, k, a, b)
+        gw = wide.arena.flat[g, L.REGION_G, lay.critic[0].begin:lay.critic[1].end]
+        gr = row.arena.flat[g, L.REGION_G, lay.critic[0].begin:lay.critic[1].end]
+        d = float((gw - gr).abs().max()) / float(gr.abs().max())
+        assert d <= 5e-5, f"agent {ids[g]}: critic gradients differ by {d:.2e}"
+    for i in range(5):
+        wide.iteration()
+        row.iteration()
+    torch.cuda.synchronize()
+    for r in (L.REGION_P, L.REGION_T):
+        pw, pr = wide.arena.flat[:, r], row.arena.flat[:, r]
+        d = float((pw - pr).abs().max()) / float(pr.abs().max())
+        assert d <= 2e-3, f"region {r}: parameters differ by {d:.2e} after 6 iterations"
+    assert torch.equal(wide.counters[:, :3], row.counters[:, :3])

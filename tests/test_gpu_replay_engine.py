@@ -354,10 +354,10 @@ def test_bad_sampling_and_tensor_core_arguments_are_refused():
     x = torch.zeros(256, 64, device="cuda")
     y = torch.zeros(256, 256, device="cuda")
     c = torch.zeros(64, 256, device="cuda")
-    sc = torch.zeros(lib.b2rl_tc_wgrad_scratch_floats(64, 256), device="cuda")
-    assert lib.b2rl_tc_wgrad(x.data_ptr(), 64, 32, 64, y.data_ptr(), 256, c.data_ptr(), None, sc.data_ptr(), 0, None, st) < 0
-    assert lib.b2rl_tc_wgrad(x.data_ptr() + 4, 64, 64, 64, y.data_ptr(), 256, c.data_ptr(), None, sc.data_ptr(), 0, None, st) < 0
-    assert lib.b2rl_tc_wgrad_scratch_floats(0, 256) < 0
+    sc = torch.zeros(lib.b2rl_tc_wgrad_scratch_floats(64, 256, 0), device="cuda")
+    assert lib.b2rl_tc_wgrad(x.data_ptr(), 64, 32, 64, y.data_ptr(), 256, c.data_ptr(), None, sc.data_ptr(), 0, None, None, st) < 0
+    assert lib.b2rl_tc_wgrad(x.data_ptr() + 4, 64, 64, 64, y.data_ptr(), 256, c.data_ptr(), None, sc.data_ptr(), 0, None, None, st) < 0
+    assert lib.b2rl_tc_wgrad_scratch_floats(0, 256, 0) < 0
     # fused critic head without a head
-    assert lib.b2rl_tc_linear_q(y.data_ptr(), 256, 256, y.data_ptr(), None, y.data_ptr(), None, None, 0, None, None, None, None, st) < 0
+    assert lib.b2rl_tc_linear_q(y.data_ptr(), 256, 256, y.data_ptr(), None, y.data_ptr(), None, None, 0, None, None, None, None, None, st) < 0
     torch.cuda.synchronize()  # (nothing was launched: no sticky error)

@@ -27,10 +27,10 @@ def test_tc_linear_matches_torch(M, ln, relu, x3):
     st = torch.cuda.current_stream().cuda_stream
     Wlo = torch.empty_like(W)
     if x3:
-        L.check(lib.b2rl_tc_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), st), "split")
+        L.check(lib.b2rl_tc_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), None, st), "split")
     L.check(lib.b2rl_tc_linear(X.data_ptr(), 256, M, W.data_ptr(), Wlo.data_ptr() if x3 else None, b.data_ptr(), gam.data_ptr(),
                                bet.data_ptr(), int(ln),
-                               int(relu), H.data_ptr(), XH.data_ptr(), stat.data_ptr(), st), "tc_linear")
+                               int(relu), H.data_ptr(), XH.data_ptr(), stat.data_ptr(), None, st), "tc_linear")
     torch.cuda.synchronize()
     z = X.double() @ W.double().T + b.double()
     if ln:
@@ -63,9 +63,9 @@ def test_tc_wgrad_matches_torch(Bn, MA, lda, transpose, x3):
     Bm = torch.randn(Bn, 256, device="cuda", generator=g)
     Cc = torch.full((MA, 256), float("nan"), device="cuda")
     Ct = torch.full((256, MA), float("nan"), device="cuda") if transpose else None
-    scratch = torch.empty(lib.b2rl_tc_wgrad_scratch_floats(MA, Bn), device="cuda")
+    scratch = torch.empty(lib.b2rl_tc_wgrad_scratch_floats(MA, Bn, 0), device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    L.check(lib.b2rl_tc_wgrad(A.data_ptr(), lda, lda, MA, Bm.data_ptr(), Bn, Cc.data_ptr(), L.ptr(Ct), scratch.data_ptr(), int(x3), None, st),
+    L.check(lib.b2rl_tc_wgrad(A.data_ptr(), lda, lda, MA, Bm.data_ptr(), Bn, Cc.data_ptr(), L.ptr(Ct), scratch.data_ptr(), int(x3), None, None, st),
             "tc_wgrad")
     torch.cuda.synchronize()
     want = A[:, :MA].double().T @ Bm.double()
@@ -75,3 +75,91 @@ def test_tc_wgrad_matches_torch(Bn, MA, lda, transpose, x3):
     assert err <= ((4e-6 if Bn <= 4096 else 2e-5) if x3 else 3e-3)
     if transpose:
         assert torch.equal(Ct, Cc.T.contiguous())
+
+
+# ---- stacked agents (include/b2rl.h b2rl_stack_t): per-agent weights through rank-3 TMA maps ---------------------------------
+@pytest.mark.parametrize("x3", [False, True])
+@pytest.mark.parametrize("n_agents,M", [(3, 256), (5, 200), (2, 640), (4, 72)])
+def test_tc_linear_stacked_agents_match_torch(n_agents, M, x3):
+    """Agent g's rows [g*M, g*M + M) are multiplied by agent g's own matrix / bias / LayerNorm affine (param_stride apart,
+    as in the population arena); ragged per-agent batches (200, 72: the tail of an agent's last tile is zero-filled by TMA,
+    never read from the next agent's rows) and the single-learner entry give the same bits per agent."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(100 * n_agents + M)
+    ps = 4 * 256 * 256 + 1024  # floats between agents' parameter blocks: [W | bias | gamma | beta | pad]
+    P = torch.zeros(n_agents, ps, device="cuda")
+    P[:, :65536] = torch.randn(n_agents, 65536, device="cuda", generator=g) / 16.0
+    P[:, 65536:65792] = torch.randn(n_agents, 256, device="cuda", generator=g) * 0.1
+    P[:, 65792:66048] = 1.0 + 0.1 * torch.randn(n_agents, 256, device="cuda", generator=g)
+    P[:, 66048:66304] = 0.1 * torch.randn(n_agents, 256, device="cuda", generator=g)
+    Plo = torch.zeros_like(P)
+    X = torch.randn(n_agents * M, 256, device="cuda", generator=g)
+    H = torch.full((n_agents * M, 256), float("nan"), device="cuda")
+    XH = torch.full((n_agents * M, 256), float("nan"), device="cuda")
+    stat = torch.zeros(n_agents * M, 2, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    stk = L.Stack(n_agents, 0, ps, ps, 0, 0, 0)
+    base = P.data_ptr()
+    if x3:
+        L.check(lib.b2rl_tc_split_lo(base, Plo.data_ptr(), 65536, C.byref(stk), st), "split")
+    L.check(lib.b2rl_tc_linear(X.data_ptr(), 256, M, base, Plo.data_ptr() if x3 else None, base + 4 * 65536, base + 4 * 65792,
+                               base + 4 * 66048, 1, 1, H.data_ptr(), XH.data_ptr(), stat.data_ptr(), C.byref(stk), st), "tc_linear")
+    # the same through the single-learner entry, agent by agent
+    H1, XH1 = torch.empty(M, 256, device="cuda"), torch.empty(M, 256, device="cuda")
+    st1 = torch.zeros(M, 2, device="cuda")
+    tol = 4e-6 if x3 else 3e-3
+    for a in range(n_agents):
+        Xa = X[a * M:(a + 1) * M]
+        pa = base + 4 * a * ps
+        L.check(lib.b2rl_tc_linear(Xa.data_ptr(), 256, M, pa, (Plo.data_ptr() + 4 * a * ps) if x3 else None, pa + 4 * 65536,
+                                   pa + 4 * 65792, pa + 4 * 66048, 1, 1, H1.data_ptr(), XH1.data_ptr(), st1.data_ptr(), None, st), "tc1")
+        torch.cuda.synchronize()
+        assert torch.equal(H[a * M:(a + 1) * M], H1) and torch.equal(XH[a * M:(a + 1) * M], XH1), f"agent {a}"
+        assert torch.equal(stat[a * M:(a + 1) * M], st1)
+        W = P[a, :65536].view(256, 256).double()
+        z = Xa.double() @ W.T + P[a, 65536:65792].double()
+        xh = (z - z.mean(1, keepdim=True)) / torch.sqrt(z.var(1, unbiased=False, keepdim=True) + 1e-5)
+        want = torch.relu(xh * P[a, 65792:66048].double() + P[a, 66048:66304].double())
+        assert float((H1.double() - want).abs().max()) / float(want.abs().max()) <= tol
+
+
+@pytest.mark.parametrize("x3", [False, True])
+@pytest.mark.parametrize("n_agents,Bn,MA,lda", [(3, 256, 256, 256), (4, 200, 14, 28), (2, 256, 1, 64), (2, 2500, 256, 256)])
+def test_tc_wgrad_stacked_agents_match_torch(n_agents, Bn, MA, lda, x3):
+    """Per-agent C_g = A_g[:, :MA]^T . B_g over the agent's own Bn rows, written into per-agent gradient tensors
+    param_stride apart (+ the transposed shadow); the per-agent update counters advance by one."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(Bn + MA + n_agents)
+    A = torch.randn(n_agents * Bn, lda, device="cuda", generator=g)
+    Bm = torch.randn(n_agents * Bn, 256, device="cuda", generator=g)
+    ps = 2 * 256 * 256 + 64
+    G = torch.full((n_agents, ps), float("nan"), device="cuda")
+    ctr = torch.zeros(n_agents, 8, dtype=torch.int64, device="cuda")
+    transpose = MA == 256
+    scratch = torch.empty(lib.b2rl_tc_wgrad_scratch_floats(MA, Bn, n_agents), device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    stk = L.Stack(n_agents, 0, ps, 0, 0, 8, 0)
+    L.check(lib.b2rl_tc_wgrad(A.data_ptr(), lda, lda, MA, Bm.data_ptr(), Bn, G.data_ptr(), (G.data_ptr() + 4 * 65536) if transpose else None,
+                              scratch.data_ptr(), int(x3), ctr.data_ptr() + 8 * 1, C.byref(stk), st), "tc_wgrad")
+    torch.cuda.synchronize()
+    assert ctr[:, 1].tolist() == [1] * n_agents and int(ctr.sum()) == n_agents
+    for a in range(n_agents):
+        want = A[a * Bn:(a + 1) * Bn, :MA].double().T @ Bm[a * Bn:(a + 1) * Bn].double()
+        got = G[a, :MA * 256].view(MA, 256)
+        err = float((got.double() - want).abs().max()) / float(want.abs().max())
+        # (a 1024-row slice chains 128 fp32 accumulations per TMEM element: 7e-6 measured at Bn = 2500)
+        assert err <= ((4e-6 if Bn <= 1024 else 1.5e-5) if x3 else 3e-3), (a, err)
+        if transpose:
+            assert torch.equal(G[a, 65536:2 * 65536].view(256, 256), got.T.contiguous())
+    # a shard holding one agent gives the same bits (the split never depends on the number of agents)
+    G1 = torch.full((1, ps), float("nan"), device="cuda")
+    stk1 = L.Stack(1, 0, ps, 0, 0, 8, 0)
+    a = n_agents - 1
+    L.check(lib.b2rl_tc_wgrad(A[a * Bn:].data_ptr(), lda, lda, MA, Bm[a * Bn:].data_ptr(), Bn, G1.data_ptr(), None, scratch.data_ptr(),
+                              int(x3), None, C.byref(stk1), st), "tc_wgrad")
+    torch.cuda.synchronize()
+    assert torch.equal(G1[0, :MA * 256], G[a, :MA * 256])

@@ -13,11 +13,11 @@ for M in [int(x) for x in sys.argv[1:]] or [4096, 65536, 262144]:
     H = torch.empty(M, 256, device="cuda"); XH = torch.empty(M, 256, device="cuda"); stat = torch.empty(M, 2, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     Wlo = torch.empty_like(W)
-    L.check(lib.b2rl_tc_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), st), "split")
+    L.check(lib.b2rl_tc_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), None, st), "split")
     x3 = False
     def ours(xh=True):
         L.check(lib.b2rl_tc_linear(X.data_ptr(), 256, M, W.data_ptr(), Wlo.data_ptr() if x3 else None, b.data_ptr(), g.data_ptr(), be.data_ptr(), 1, 1,
-                                   H.data_ptr(), XH.data_ptr() if xh else None, stat.data_ptr(), st), "tc")
+                                   H.data_ptr(), XH.data_ptr() if xh else None, stat.data_ptr(), None, st), "tc")
     def ref():
         return torch.relu(torch.nn.functional.layer_norm(torch.addmm(b, X, W.t()), (256,), g, be))
     def timeit(fn, n=30):
