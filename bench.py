@@ -197,7 +197,7 @@ def run_b2rl(args, rank, world, device):
     #      step, one step late; "sync": it reads step t's losses before preparing step t + 1.
     n_env = 4
     src_rows = torch.randn(n_env, fmt.row_stride)           # "what the envs just produced" (pageable host memory)
-    Ke = max(30, min(K, 3000))
+    Ke = max(300, min(K, 3000))  # (>= 300 steps: ~20 ms of wall clock even at the driver's --steps 20)
     step_no = [W + K]
 
     def e2e_loop(n, pipelined):
@@ -279,7 +279,9 @@ def run_b2rl(args, rank, world, device):
     fl = C.c_double(0.0)
     t_probe = time_kernel(lambda: L.check(lib.b2rl_ffma_probe(sink.data_ptr(), 4096, C.byref(fl), st())), iters=20, warm=3)
     ffma_peak = fl.value / t_probe / 1e12
-    tr = REPO / "profiles" / "r1_traffic.json"  # DRAM bytes per launch from the committed ncu --set full capture
+    tr = REPO / "profiles" / "r2_traffic.json"  # DRAM bytes per launch from the committed ncu --set full captures
+    if not tr.exists():
+        tr = REPO / "profiles" / "r1_traffic.json"
     traffic = None
     if tr.exists() and args.workload == "td3_hopper":
         t_ = json.loads(tr.read_text())["critic_fused_kernel"]
@@ -291,12 +293,19 @@ def run_b2rl(args, rank, world, device):
     # replay gather alone at a bandwidth-relevant size (HBM roofline): 65536 rows per launch
     peaks = json.loads((REPO / "MEASURED_PEAKS.json").read_text()) if (REPO / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    GB = 65536
-    t_g = time_kernel(lambda: rb.sample(GB), iters=50, warm=5)
+    GB = min(1 << 20, cap)  # >= 117 MB read at random + 117 MB written per launch (Hopper): out of L2, launch cost < 2 %
+    t_g = time_kernel(lambda: rb.sample(GB), iters=40, warm=10, per_graph=10)
     g_bytes = GB * (2 * fmt.row_stride * 4 + 8)
+    tg_ = None
+    if tr.exists() and args.workload != "sac_humanoid" and "gather_kernel" in json.loads(tr.read_text()):
+        t_ = json.loads(tr.read_text())["gather_kernel"]
+        tg_ = t_["dram_bytes_read"] + t_["dram_bytes_write"]
     roof_g = {"bound": "hbm", "kernel": "gather_kernel", "achieved": g_bytes / t_g / 1e9, "peak": hbm_peak, "unit": "GB/s",
-              "frac": g_bytes / t_g / 1e9 / hbm_peak, "traffic": None, "rows_per_launch": GB,
+              "frac": g_bytes / t_g / 1e9 / hbm_peak, "traffic": tg_, "rows_per_launch": GB, "us_per_launch": t_g * 1e6,
+              "bytes_per_row": 2 * fmt.row_stride * 4 + 8,
               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}
+    rb._rows.pop(GB, None)
+    rb._idx.pop(GB, None)
 
     # the tensor-core hidden layer of the large-batch path (BASELINE.json config 5: batch 65 536) on its own: HBM-bound
     # (X in, H and x-hat out: 3 x 4 bytes per element moved, 512 flops per element)
@@ -331,12 +340,24 @@ def run_b2rl(args, rank, world, device):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def make_cpu_reference(workload, device="cpu", n_rows=100_000):
+_CPU_DATA = {}
+
+
+def make_cpu_reference(workload, device="cpu", n_rows=None):
+    """The reference's CPU update path on the SAME configuration as the GPU arm: same shapes, batch 256, and a replay
+    buffer of the same number of rows (2 M Hopper / 1 M Humanoid transitions, six [cap, d] tensors as torchrl stores them)."""
     from oracle import OracleAgent, make_synthetic_transitions, sac_defaults, td3_defaults
-    algo, O, A, bound, _ = WORKLOADS[workload]
+    algo, O, A, bound, cap = WORKLOADS[workload]
+    n_rows = n_rows or cap
     hps = sac_defaults() if algo == "sac" else td3_defaults()
     hps.adam_capturable = False
-    td = make_synthetic_transitions(n_rows, O, A, [-bound] * A, [bound] * A, seed=1234, device=device)
+    key = (O, A, n_rows, device)
+    if key not in _CPU_DATA:  # (generated in chunks: one 1 M x 376 randn needs 3 GB of temporaries)
+        parts = [make_synthetic_transitions(min(250_000, n_rows - c0), O, A, [-bound] * A, [bound] * A, seed=1234 + c0, device=device)
+                 for c0 in range(0, n_rows, 250_000)]
+        _CPU_DATA.clear()
+        _CPU_DATA[key] = {k: torch.cat([p_[k] for p_ in parts]) for k in parts[0]}
+    td = _CPU_DATA[key]
     ag = OracleAgent(O, A, [-bound] * A, [bound] * A, hps, device=device, seed=0)
     gen = torch.Generator(device=device).manual_seed(4321)
 
@@ -367,7 +388,8 @@ def cpu_baseline(workload, budget_s=12.0):
     best, used = (r1, 1) if r1 >= rN else (rN, cores)
     return {"value": best, "unit": "updates/s", "cores": used, "kind": "port",
             "sample": f"{n1} iterations at 1 thread ({r1:.1f}/s) and {nN} at {cores} threads ({rN:.1f}/s) of the same "
-                      f"workload (replay 1e5 rows) on the host CPU; oracle = bit-exact restatement of the reference"}
+                      f"workload (same replay size as the GPU arm: {WORKLOADS[workload][4]} rows) on the host CPU; oracle = "
+                      f"bit-exact restatement of the reference"}
 
 
 def run_reference(args, rank):
@@ -396,7 +418,7 @@ def run_reference(args, rank):
             "unit": "updates/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": el / n * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "algo": algo, "ob_dim": O, "ac_dim": A, "batch": 256,
-                       "device": "host cpu", "replay_rows": 100_000,
+                       "device": "host cpu", "replay_rows": cap, "hidden": "2x256+LN",
                        "cadence": "sample + critic update + 2 actor updates every 3rd iteration + polyak"},
             "cpu_baseline": {"value": v, "unit": "updates/s", "cores": threads, "kind": "port",
                              "sample": f"{n} iterations (asked {K}, budget {budget:.0f}s); 1 thread {r1:.1f}/s vs "
@@ -406,19 +428,25 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def run_reference_cuda(args):
-    """The reference's GPU arrangement (orchestrator.py:308-315, :338, :352) on the torch oracle: update_qnets and
-    update_actor each in a CUDA graph with static input copies, eager sampling and eager Polyak."""
+def time_reference_cuda(workload, steps, warmup, device="cuda"):
+    """The reference's own GPU arrangement (orchestrator.py:308-315, :338, :352) on this GPU: the torch-op update of the
+    oracle (bit-exact restatement of agents/agent.py) with update_qnets and update_actor each captured in a CUDA graph the
+    way tensordict's CudaGraphModule does it (static input copies per call), eager torchrl-style sampling (randint +
+    one gather per key) and the eager Polyak lerp — same shapes, batch 256 and replay size as the b2rl arm, TF32 off.
+    This is the "beat the reference's CUDA-graph torch path on one B200" yardstick of the north star."""
     from oracle import OracleAgent, make_synthetic_transitions, sac_defaults, td3_defaults
-    algo, O, A, bound, _ = WORKLOADS[args.workload]
-    dev = "cuda"
+    algo, O, A, bound, n_rows = WORKLOADS[workload]
+    dev = device
+    tf32_was = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     hps = sac_defaults() if algo == "sac" else td3_defaults()
-    n_rows = 1_000_000
-    td = make_synthetic_transitions(n_rows, O, A, [-bound] * A, [bound] * A, seed=1234, device=dev)
+    parts = [make_synthetic_transitions(min(250_000, n_rows - c0), O, A, [-bound] * A, [bound] * A, seed=1234 + c0, device=dev)
+             for c0 in range(0, n_rows, 250_000)]
+    td = {k: torch.cat([p_[k] for p_ in parts]) for k in parts[0]}
+    del parts
     ag = OracleAgent(O, A, [-bound] * A, [bound] * A, hps, device=dev, seed=0, torch_adam=True)
     static = {k: v[:256].clone() for k, v in td.items()}
-    graphs = {}
+    graphs, kernels = {}, {}
 
     def graphed(name, fn):
         s = torch.cuda.Stream()
@@ -427,6 +455,14 @@ def run_reference_cuda(args):
             for _ in range(3):
                 fn(static)
         torch.cuda.current_stream().wait_stream(s)
+        try:  # device kernels of one eager call = the kernel nodes the graph replays
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fn(static)
+                torch.cuda.synchronize()
+            kernels[name] = sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA)
+        except Exception:
+            kernels[name] = None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = fn(static)
@@ -447,22 +483,138 @@ def run_reference_cuda(args):
                 graphs["pi"][0].replay()
         ag.update_targ_nets()
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    K = args.steps
     e0.record()
-    for i in range(K):
-        step(args.warmup + i)
+    for i in range(steps):
+        step(warmup + i)
     e1.record()
     torch.cuda.synchronize()
     el = e0.elapsed_time(e1) * 1e-3
+    torch.backends.cuda.matmul.allow_tf32 = tf32_was
+    del td, ag, graphs
+    torch.cuda.empty_cache()
+    return {"value": steps / el, "unit": "updates/s", "ms_per_step": el / steps * 1e3, "steps": steps,
+            "kernels_per_graph": kernels, "replay_rows": n_rows, "tf32": False,
+            "what": "reference arrangement: torch ops, update_qnets / update_actor each in a CUDA graph with static-input "
+                    "copies, eager sampling + Polyak (orchestrator.py:308-315, :338, :352), same GPU, same config"}
+
+
+def run_reference_cuda(args):
+    r = time_reference_cuda(args.workload, args.steps, args.warmup)
     print(json.dumps({"impl": "reference", "variant": "torch ops in CUDA graphs on the GPU (orchestrator.py:308-315)",
-                      "metric": "gradient updates/sec (batch 256, Hopper shapes)", "value": K / el, "unit": "updates/s",
-                      "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": el / K * 1e3,
-                      "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": args.workload, "device": "cuda", "tf32": False}}))
+                      "metric": "gradient updates/sec (batch 256, Hopper shapes)", "value": r["value"], "unit": "updates/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "kernels_per_graph": r["kernels_per_graph"],
+                      "config": {"workload": args.workload, "device": "cuda", "tf32": False, "replay_rows": r["replay_rows"]}}))
+
+
+# ------------------------------------------------------------------------------------------ configs 4 and 5 (every N)
+def _max_over_ranks(x, world, device):
+    if world > 1:
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t)
+    return x
+
+
+def run_dp_leg(rank, world, device, B=65536, rows=1_000_000, iters=30):
+    """BASELINE.json configs[4]: SAC Hopper, batch 65 536 PER GPU from a 1 M-transition replay per GPU, data-parallel
+    learner (dp.DataParallelLearner on the tcgen05 wide path, 3xTF32) with one NCCL gradient all-reduce per optimizer step.
+    Weak scaling: transitions/s summed over ranks; time = CUDA events, max over ranks."""
+    from oracle import make_synthetic_transitions
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L, sac_hps
+    from sac_td3_cudagraphs_pytorch_b200.agents.agent import Agent
+    from sac_td3_cudagraphs_pytorch_b200.dp import DataParallelLearner, GradComm
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    O, A = 11, 3
+    hps = sac_hps(batch_size=B)
+    rb = ReplayBuffer(rows, device, seed=77 + rank, agent_id=rank)
+    for c0 in range(0, rows, 250_000):
+        td = make_synthetic_transitions(min(250_000, rows - c0), O, A, [-1.0] * A, [1.0] * A, seed=4321 + c0 + 17 * rank)
+        rb.extend({k: v.to(device) for k, v in td.items()})
+    torch.manual_seed(0)  # identical initial parameters on every rank
+    ag = Agent({"ob_shape": (O,), "ac_shape": (A,)}, np.full(A, -1.0, np.float32), np.full(A, 1.0, np.float32),
+               torch.device(device), hps, rb=rb, seed=5, agent_id=rank)
+    dp = DataParallelLearner(ag, rb, B, GradComm(), wide="3xtf32")
+    for i in range(9):  # every (actor?, polyak?) variant: first occurrence eager, second captured, third replayed
+        dp.iteration(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(9, 9 + iters):
+        dp.iteration(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / iters, world, device)
+    # the gradient all-reduce alone (the critic bucket: both critics' gradient span)
+    lay = ag.layout
+    bucket = ag.arena.flat[0, L.REGION_G, lay.critic[0].begin:lay.critic[1].core_end]
+    ar_us = None
+    if world > 1:
+        for _ in range(5):
+            torch.distributed.all_reduce(bucket)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            torch.distributed.all_reduce(bucket)
+        e1.record()
+        torch.cuda.synchronize()
+        ar_us = _max_over_ranks(e0.elapsed_time(e1) / 50 * 1e3, world, device)
+    finite = bool(torch.isfinite(ag.out).all())
+    out = {"ms_per_iteration": ms, "transitions_per_s": world * B / ms * 1e3, "batch_per_gpu": B, "replay_rows_per_gpu": rows,
+           "precision": "3xtf32 (fp32-class gradients on tcgen05)", "graph_replay": bool(dp.graphs), "n_gpus": world,
+           "allreduce_bucket_bytes": int(bucket.numel() * 4), "allreduce_us": ar_us, "scaling": "weak", "outputs_finite": finite,
+           "what": "SAC Hopper, reference cadence (critic step + 2 actor/alpha steps every 3rd iteration + Polyak), gradients "
+                   "all-reduced (NCCL, sum) once per optimizer step, 1/W folded into Adam"}
+    del dp, ag, rb
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_population_leg(rank, world, device, n_total=1024, iters=30, rb_rows=20_000, weak=False):
+    """BASELINE.json configs[3]: a population of independent SAC Hopper agents (own parameters, optimizer state, replay
+    slice, Philox streams), stacked on the tcgen05 wide path, sharded over the ranks as a partition of the agent ids with
+    NO cross-GPU traffic. weak=False: 1024 agents in total (shard(1024, W, rank)); weak=True: 1024 agents per GPU."""
+    from oracle import make_synthetic_transitions
+    from sac_td3_cudagraphs_pytorch_b200 import sac_hps
+    from sac_td3_cudagraphs_pytorch_b200.population import Population, shard
+    ids = range(rank * n_total, (rank + 1) * n_total) if weak else shard(n_total, world, rank)
+    td = make_synthetic_transitions(rb_rows, 11, 3, [-1.0] * 3, [1.0] * 3, seed=99)
+    pop = Population(ids, 11, 3, [-1.0] * 3, [1.0] * 3, sac_hps(), device, seed=1, rb_capacity=rb_rows, wide="3xtf32")
+    pop.fill_replay(td)
+    for i in range(6):
+        pop.iteration()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        pop.iteration()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(e0.elapsed_time(e1) / iters, world, device)
+    peaks = json.loads((REPO / "MEASURED_PEAKS.json").read_text()) if (REPO / "MEASURED_PEAKS.json").exists() else {}
+    hbm, tens = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops_sustained", 1351.5)
+    n_all = n_total * world if weak else n_total
+    n_local = len(ids)
+    # SURVEY §8(d): 8.6 GB of unavoidable optimizer / weight traffic and 515.6 GFLOP per iteration of 1024 agents
+    floor_gb, gflop = 8.6 * n_local / 1024, 515.6 * n_local / 1024
+    out = {"ms_per_iteration": ms, "agent_updates_per_s": n_all / ms * 1e3, "agent_updates_per_s_per_gpu": n_all / ms * 1e3 / world,
+           "agents_total": n_all, "agents_this_rank": n_local, "n_gpus": world, "scaling": "weak" if weak else "strong",
+           "hbm_floor_frac": floor_gb / (ms * 1e-3) / hbm, "tensor_frac_of_bf16_sustained": gflop / ms / tens,
+           "hbm_floor": "8.6 GB per iteration of 1024 agents (Adam 28 B/param, Polyak 12 B/param, one read of the weights; SURVEY 8(d)) "
+                        "/ time / MEASURED_PEAKS hbm_gbs", "precision": "3xtf32", "batch": 256, "replay_rows_per_agent": rb_rows,
+           "outputs_finite": bool(torch.isfinite(pop.out).all()),
+           "what": "SAC Hopper agents, batch 256 each, reference cadence; one CUDA graph replay advances every agent of the shard"}
+    del pop
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -476,6 +628,8 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--also", default="sac_hopper,sac_humanoid", help="extra workloads measured after the main one (N=1)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the config-4 (population) and config-5 (data-parallel) legs")
+    ap.add_argument("--no-torch-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -501,6 +655,18 @@ def main():
             extra[w] = {"updates_per_s": r2["value"], "ms_per_step": r2["elapsed"] / a2.steps * 1e3,
                         "e2e_updates_per_s": r2["e2e"]["value"], "critic_fused_frac_of_ffma_peak": r2["roofline"]["frac"],
                         "per_kernel_us": r2["per_kernel_us"]}
+            torch.cuda.empty_cache()
+            if not args.no_torch_baseline:
+                extra[w]["torch_cudagraph_baseline"] = time_reference_cuda(w, 300, 20, device)
+            if not args.no_cpu_baseline:
+                extra[w]["cpu_baseline"] = cpu_baseline(w, budget_s=8.0)
+    legs = {}
+    if not args.no_legs:  # BASELINE.json configs[3] and [4], at every N
+        torch.cuda.empty_cache()
+        legs["dp_b65536"] = run_dp_leg(rank, world, device)
+        legs["population_1024"] = run_population_leg(rank, world, device)
+        if world > 1:
+            legs["population_1024_per_gpu"] = run_population_leg(rank, world, device, weak=True)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -521,8 +687,10 @@ def main():
         "roofline": res["roofline"], "roofline_gather": res["roofline_gather"], "roofline_tc_linear": res["roofline_tc_linear"], "per_kernel_us": res["per_kernel_us"],
         "outputs_finite": res["finite"],
     }
-    if extra:
-        line["also"] = extra
+    if extra or legs:
+        line["also"] = {**extra, **legs}
+    if world == 1 and not args.no_torch_baseline:
+        line["torch_cudagraph_baseline"] = time_reference_cuda(args.workload, 300, 20, device)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload)
     print(json.dumps(line))

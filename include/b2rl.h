@@ -178,6 +178,21 @@ typedef struct b2rl_adam_args {
   float* arena;                /* dev */
   const uint64_t* counters;    /* dev uint64[8] per agent */
   const float* grad_sumsq;     /* dev float per agent (from b2rl_grad_sumsq) or NULL */
+  /* 3xTF32 mirror (wide path): when not NULL, every parameter this launch writes also leaves its "lo part"
+   * p - tf32_truncate(p) (what b2rl_tc_split_lo computes) at the same region offset of the mirror
+   * lo[agent][0 = online | 1 = target][region_stride], so the tensor-core kernels never need a split pass over weights
+   * that an optimizer step has just changed. */
+  float* lo;                   /* dev or NULL */
+  int64_t lo_agent_stride;     /* floats between agents' mirrors (>= 2 * region_stride) */
+  /* Shadow pairs: shadow_src[i] / shadow_dst[i] are the region offsets of a net's w2t [256][256] and of its natural-layout
+   * shadow w2n (= w2t transposed, see "parameter arena"). For a pair whose w2t lies inside one of the segments, the launch
+   * steps w2t from ITS gradient and writes the new parameter / exp_avg / exp_avg_sq / target (and lo parts) to BOTH
+   * layouts through a 32 x 32 transposing tile; the shadow's own gradient, exp_avg and exp_avg_sq are never read. Same
+   * values as stepping the shadow with the transposed gradient (it stays bit-identical to w2t^T), 20 bytes per shadow
+   * element less traffic, and no transposed gradient copy is needed (weight-gradient kernels, data-parallel all-reduce). */
+  int64_t shadow_src[3], shadow_dst[3];
+  int32_t n_shadow;            /* 0..3 */
+  int32_t reserved2;
 } b2rl_adam_args_t;
 
 /* ---- entry points ---------------------------------------------------------------------- */

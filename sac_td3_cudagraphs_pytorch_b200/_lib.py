@@ -56,7 +56,8 @@ class AdamArgs(C.Structure):
                 ("polyak", C.c_float), ("clip_norm", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("reserved", C.c_int32),
                 ("region_stride", C.c_int64), ("arena_agent_stride", C.c_int64),
-                ("arena", C.c_void_p), ("counters", C.c_void_p), ("grad_sumsq", C.c_void_p)]
+                ("arena", C.c_void_p), ("counters", C.c_void_p), ("grad_sumsq", C.c_void_p), ("lo", C.c_void_p), ("lo_agent_stride", C.c_int64),
+                ("shadow_src", C.c_int64 * 3), ("shadow_dst", C.c_int64 * 3), ("n_shadow", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class WidePolicy(C.Structure):

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from ..arena import Arena, NetLayout, TENSOR_NAMES, make_layout
+from ..arena import Arena, NetLayout, TENSOR_NAMES, make_layout, set_shadow_pairs
 from ..hps import hp_get
 from ..replay import Batch, pack_rows, row_format
 from .nets import Actor, Critic, TanhGaussActor, log_module_info
@@ -163,6 +163,7 @@ class Agent:
         self._ws: dict[int, torch.Tensor] = {}
         self._staging: dict[int, torch.Tensor] = {}
         self._predict_draw = 0
+        self._lo: Optional[torch.Tensor] = None  # 3xTF32 mirror of the online / target regions (wide path), see lo_mirror()
         self.autotune = False
         if not self.td3:
             self._alpha_state[0] = math.log(hps.alpha_init)
@@ -253,7 +254,24 @@ class Agent:
         a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-8
         a.region_stride, a.arena_agent_stride = self.layout.region, self.arena.agent_stride
         a.arena, a.counters, a.grad_sumsq = self.arena.flat.data_ptr(), self.counters.data_ptr(), self._sumsq.data_ptr()
+        a.lo, a.lo_agent_stride = L.ptr(self._lo), 2 * self.layout.region  # (NULL unless the wide 3xTF32 path is in use)
+        set_shadow_pairs(a, self.layout)
         return a
+
+    def lo_mirror(self) -> torch.Tensor:
+        """[1][2][region]: the "lo parts" p - tf32(p) of the online and target regions, at the parameters' own offsets —
+        the second operand of the 3xTF32 tensor-core products (wide.py). Created on first use; from then on every
+        Adam / Polyak launch of this agent keeps it current (b2rl_adam_args_t.lo). Host-side writes to the parameters
+        (load_params, load_from_disk do it themselves; module.load_state_dict does not) need refresh_lo()."""
+        if self._lo is None:
+            self._lo = torch.zeros(1, 2, self.layout.region, dtype=torch.float32, device=self.device)
+            self.refresh_lo()
+        return self._lo
+
+    def refresh_lo(self) -> None:
+        if self._lo is not None:
+            L.check(self._lib.b2rl_tc_split_lo(self.arena.flat.data_ptr(), self._lo.data_ptr(), 2 * self.layout.region, None,
+                                               self._stream()), "tc_split_lo")
 
     def _launch_adam(self, segs: list) -> None:
         a = self._adam_args(segs)
@@ -443,6 +461,7 @@ class Agent:
             if self.autotune and "alpha_optimizer" in ckpt:
                 self.alpha_optimizer.load_state_dict(ckpt["alpha_optimizer"])
         self.arena.sync_shadows()
+        self.refresh_lo()
 
     def load(self, wandb_run_path: str, model_name: str = "ckpt_best.pth"):
         """agents/agent.py:403-425 downloads the file from wandb; network I/O is out of scope here —
@@ -461,3 +480,4 @@ class Agent:
         if sync_targets:
             ar.region(L.REGION_T).copy_(ar.region(L.REGION_P))
         ar.sync_shadows()
+        self.refresh_lo()

@@ -83,6 +83,15 @@ def make_layout(ob_dim: int, ac_dim: int, td3: bool, layer_norm: bool) -> ArenaL
     return ArenaLayout([c0, c1], a, _up4(cur))
 
 
+def set_shadow_pairs(adam_args, layout: ArenaLayout) -> None:
+    """Tell an Adam / Polyak launch where every net's (w2t, w2n) pair lives (b2rl_adam_args_t.shadow_*): the step is
+    computed at w2t and written to both layouts, the shadow's own gradient / moments are never read."""
+    nets = (*layout.critic, layout.actor)
+    for i, net in enumerate(nets):
+        adam_args.shadow_src[i], adam_args.shadow_dst[i] = net.off["w2t"], net.off["w2n"]
+    adam_args.n_shadow = len(nets)
+
+
 class Arena:
     """The device allocation + view helpers. ``n_agents`` > 1 stacks independent learners."""
 

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   float* V = P + 3 * A.region_stride;
   float* G = P + 4 * A.region_stride;
   const uint64_t* ctr = A.counters + (size_t)agent * 8;
+  float* LO = A.lo ? A.lo + (size_t)agent * A.lo_agent_stride : nullptr;  // 3xTF32 mirror: lo parts of what is written here
 
   __shared__ SegScalars sc[B2RL_MAX_SEG];
   if (threadIdx.x < A.n_seg) {
@@ -43,12 +44,79 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   }
   __syncthreads();
 
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  const float omb1 = 1.0f - A.beta1, omb2 = 1.0f - A.beta2;
+  const int main_ctas = (int)gridDim.x - 64 * A.n_shadow;
+  if ((int)blockIdx.x >= main_ctas) {
+    // ---- shadow pairs: one 32 x 32 tile of a net's w2t per CTA; the step is computed once, at the w2t position, and
+    // the results go to w2t (as they are read: rows of 128 bytes) and, transposed through shared memory, to w2n.
+    __shared__ float tr[32][33];
+    const int tile = (int)blockIdx.x - main_ctas, pr = tile >> 6, tin = tile & 63;
+    const int64_t src = A.shadow_src[pr], dst = A.shadow_dst[pr];
+    int si = -1;
+    for (int q = 0; q < A.n_seg; ++q)
+      if (src >= A.seg[q].begin && src < A.seg[q].end) si = q;
+    if (si < 0) return;  // (this launch does not touch that net)
+    const b2rl_seg_t& s = A.seg[si];
+    const SegScalars k = sc[si];
+    const int k0 = (tin >> 3) * 32, j0 = (tin & 7) * 32, r = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
+    const int64_t i = src + (int64_t)(k0 + r) * HID + j0 + c4;        // w2t[k0 + r][j0 + c4 ..]
+    const int64_t it = dst + (int64_t)(j0 + r) * HID + k0 + c4;       // w2n[j0 + r][k0 + c4 ..]
+    auto put_t = [&](float* base, const float4& x) {  // x (held for w2t[k0 + r][j0 + c4..]) -> base[w2n tile], transposed
+      __syncthreads();
+      tr[r][c4] = x.x, tr[r][c4 + 1] = x.y, tr[r][c4 + 2] = x.z, tr[r][c4 + 3] = x.w;
+      __syncthreads();
+      *reinterpret_cast<float4*>(base + it) = make_float4(tr[c4][r], tr[c4 + 1][r], tr[c4 + 2][r], tr[c4 + 3][r]);
+    };
+    float4 p = *reinterpret_cast<const float4*>(P + i);
+    if (s.do_adam) {
+      float4 g = *reinterpret_cast<const float4*>(G + i);
+      float4 m = *reinterpret_cast<const float4*>(M1 + i);
+      float4 v = *reinterpret_cast<const float4*>(V + i);
+      float* pp = &p.x; float* gp = &g.x; float* mp = &m.x; float* vp = &v.x;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float gg = __fmul_rn(gp[c], k.gscale);
+        gp[c] = gg;
+        adam_elem(pp[c], gg, mp[c], vp[c], k, A.beta2, omb1, omb2, A.eps);
+      }
+      if (s.clip) *reinterpret_cast<float4*>(G + i) = g;
+      *reinterpret_cast<float4*>(P + i) = p;
+      *reinterpret_cast<float4*>(M1 + i) = m;
+      *reinterpret_cast<float4*>(V + i) = v;
+      put_t(P, p);
+      put_t(M1, m);
+      put_t(V, v);
+      if (LO) {
+        const float4 l = tf32_lo4(p);
+        *reinterpret_cast<float4*>(LO + i) = l;
+        put_t(LO, l);
+      }
+    }
+    if (s.do_polyak) {
+      float4 tg = *reinterpret_cast<const float4*>(T + i);
+      tg.x = polyak_elem(tg.x, p.x, A.polyak);
+      tg.y = polyak_elem(tg.y, p.y, A.polyak);
+      tg.z = polyak_elem(tg.z, p.z, A.polyak);
+      tg.w = polyak_elem(tg.w, p.w, A.polyak);
+      *reinterpret_cast<float4*>(T + i) = tg;
+      put_t(T, tg);
+      if (LO) {
+        const float4 l = tf32_lo4(tg);
+        *reinterpret_cast<float4*>(LO + A.region_stride + i) = l;
+        put_t(LO + A.region_stride, l);
+      }
+    }
+    return;
+  }
+  const int64_t stride = (int64_t)main_ctas * blockDim.x * 4;
   for (int si = 0; si < A.n_seg; ++si) {
     const b2rl_seg_t& s = A.seg[si];
     const SegScalars k = sc[si];
-    const float omb1 = 1.0f - A.beta1, omb2 = 1.0f - A.beta2;
     for (int64_t i = s.begin + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < s.end; i += stride) {
+      bool paired = false;  // w2t / w2n of a shadow pair: stepped by the tile CTAs above
+      for (int q = 0; q < A.n_shadow; ++q)
+        paired |= (i >= A.shadow_src[q] && i < A.shadow_src[q] + HID * HID) || (i >= A.shadow_dst[q] && i < A.shadow_dst[q] + HID * HID);
+      if (paired) continue;
       float4 p = *reinterpret_cast<const float4*>(P + i);
       if (s.do_adam) {
         float4 g = *reinterpret_cast<const float4*>(G + i);
@@ -64,6 +132,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
         // clip_grad_norm_ scales .grad in place (agent.py:284-285): keep region 4 what torch would show
         if (s.clip) *reinterpret_cast<float4*>(G + i) = g;
         *reinterpret_cast<float4*>(P + i) = p;
+        if (LO) *reinterpret_cast<float4*>(LO + i) = tf32_lo4(p);
         *reinterpret_cast<float4*>(M1 + i) = m;
         *reinterpret_cast<float4*>(V + i) = v;
       }
@@ -74,6 +143,7 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
         tg.z = polyak_elem(tg.z, p.z, A.polyak);
         tg.w = polyak_elem(tg.w, p.w, A.polyak);
         *reinterpret_cast<float4*>(T + i) = tg;
+        if (LO) *reinterpret_cast<float4*>(LO + A.region_stride + i) = tf32_lo4(tg);
       }
     }
   }
@@ -128,13 +198,24 @@ cudaError_t init_adam() {
   return e;
 }
 
-cudaError_t launch_adam(const b2rl_adam_args_t& a, cudaStream_t st) {
+cudaError_t launch_adam(const b2rl_adam_args_t& a_in, cudaStream_t st) {
+  b2rl_adam_args_t a = a_in;  // keep only the shadow pairs this launch touches (w2t inside one of its segments)
+  a.n_shadow = 0;
   int64_t total = 0;
   for (int i = 0; i < a.n_seg; ++i) total += a.seg[i].end - a.seg[i].begin;
+  for (int q = 0; q < a_in.n_shadow; ++q)
+    for (int i = 0; i < a.n_seg; ++i)
+      if (a_in.shadow_src[q] >= a.seg[i].begin && a_in.shadow_src[q] < a.seg[i].end) {
+        a.shadow_src[a.n_shadow] = a_in.shadow_src[q];
+        a.shadow_dst[a.n_shadow++] = a_in.shadow_dst[q];
+        total -= 2 * (int64_t)HID * HID;  // (both layouts are stepped by the pair's 64 tile CTAs)
+        break;
+      }
   int ctas = (int)((total / 4 + 255) / 256);
   if (ctas < 1) ctas = 1;
   if (ctas > 148 * 4) ctas = 148 * 4;  // grid-stride beyond four CTAs per SM
-  return launch_k(adam_polyak_kernel, dim3(ctas, a.n_agents), dim3(256), 1, 0, st, a);
+  // + 64 tile CTAs per shadow pair (blockIdx.x >= ctas)
+  return launch_k(adam_polyak_kernel, dim3(ctas + 64 * a.n_shadow, a.n_agents), dim3(256), 1, 0, st, a);
 }
 
 cudaError_t launch_sumsq(const float* arena, int64_t region_stride, int64_t agent_stride, int64_t begin, int64_t end,

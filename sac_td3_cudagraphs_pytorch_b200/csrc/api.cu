@@ -232,7 +232,7 @@ int b2rl_replay_extend_dev(float* storage, int64_t capacity, b2rl_rowfmt_t fmt, 
 }
 
 int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, const b2rl_stack_t* stack, void* stream) {
-  if (!W || !W_lo || n < 1) return fail(B2RL_E_INVALID, "tc_split_lo: bad arguments");
+  if (!W || !W_lo || n < 1 || !aligned16(W) || !aligned16(W_lo)) return fail(B2RL_E_INVALID, "tc_split_lo: bad arguments (16-byte aligned tensors)");
   if (int rc = check_stack(stack, "tc_split_lo")) return rc;
   return check_launch(b2rl::launch_tc_split_lo(W, W_lo, n, make_stk(stack), (cudaStream_t)stream), "tc_split_lo");
 }
@@ -451,6 +451,21 @@ int b2rl_adam_polyak_multi(const b2rl_adam_args_t* a, void* stream) {
   if (a->n_agents < 1 || a->n_agents > 65535) return fail(B2RL_E_INVALID, "adam: bad n_agents");
   if (!aligned16(a->arena) || (a->region_stride & 3) || (a->arena_agent_stride & 3))
     return fail(B2RL_E_INVALID, "adam: arena must be 16-byte aligned, strides multiples of 4 floats");
+  if (a->lo && (!aligned16(a->lo) || (a->lo_agent_stride & 3) || a->lo_agent_stride < 2 * a->region_stride))
+    return fail(B2RL_E_INVALID, "adam: the lo mirror must be 16-byte aligned, its agent stride >= 2 regions and a multiple of 4 floats");
+  if (a->n_shadow < 0 || a->n_shadow > 3) return fail(B2RL_E_INVALID, "adam: n_shadow %d out of range", a->n_shadow);
+  for (int q = 0; q < a->n_shadow; ++q) {
+    const int64_t src = a->shadow_src[q], dst = a->shadow_dst[q], n = (int64_t)B2RL_HID * B2RL_HID;
+    if (src < 0 || dst < 0 || (src & 3) || (dst & 3) || src + n > a->region_stride || dst + n > a->region_stride ||
+        (src < dst + n && dst < src + n))
+      return fail(B2RL_E_INVALID, "adam: shadow pair %d must be two disjoint, 4-float aligned 256x256 spans of a region", q);
+    for (int i = 0; i < a->n_seg; ++i) {  // a segment holds a pair's two spans entirely or not at all
+      const b2rl_seg_t& s = a->seg[i];
+      const bool in_src = src >= s.begin && src + n <= s.end, in_dst = dst >= s.begin && dst + n <= s.end;
+      const bool cut = (src < s.end && src + n > s.begin && !in_src) || (dst < s.end && dst + n > s.begin && !in_dst);
+      if (cut || in_src != in_dst) return fail(B2RL_E_INVALID, "adam: segment %d splits shadow pair %d", i, q);
+    }
+  }
   for (int i = 0; i < a->n_seg; ++i) {
     const b2rl_seg_t& s = a->seg[i];
     if (s.begin < 0 || s.end < s.begin || (s.begin & 3) || (s.end & 3) || s.end > a->region_stride)

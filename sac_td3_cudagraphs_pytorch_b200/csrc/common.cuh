@@ -138,6 +138,10 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                "f"(v.z), "f"(v.w));
 }
 
+// "lo part" of an fp32 value for the 3xTF32 products: x - (x truncated to TF32's 10 mantissa bits, as the tensor core reads it)
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_lo4(float4 x) { return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

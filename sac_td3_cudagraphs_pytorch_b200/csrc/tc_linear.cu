@@ -521,11 +521,15 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t co
 // lo part of a weight matrix for the 3xTF32 mode: lo = w - tf32_truncate(w)
 __global__ void tc_split_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, int n, long long ps, long long ls) {
   w += (size_t)blockIdx.y * ps, lo += (size_t)blockIdx.y * ls;  // stacked agents: blockIdx.y = agent
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) lo[i] = w[i] - __uint_as_float(__float_as_uint(w[i]) & 0xFFFFE000u);
+  const int n4 = n >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(lo)[i] = tf32_lo4(__ldg(reinterpret_cast<const float4*>(w) + i));
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) lo[4 * n4 + threadIdx.x] = tf32_lo(w[4 * n4 + threadIdx.x]);
 }
 cudaError_t launch_tc_split_lo(const float* w, float* lo, int n, const Stk& k, cudaStream_t st) {
-  tc_split_lo_kernel<<<dim3((n + 255) / 256, k.n), 256, 0, st>>>(w, lo, n, k.ps, k.ls);
+  int ctas = (n / 4 + 255) / 256;
+  ctas = ctas < 1 ? 1 : (ctas > 592 ? 592 : ctas);
+  tc_split_lo_kernel<<<dim3(ctas, k.n), 256, 0, st>>>(w, lo, n, k.ps, k.ls);
   return cudaGetLastError();
 }
 

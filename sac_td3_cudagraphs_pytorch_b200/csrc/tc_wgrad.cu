@@ -78,7 +78,8 @@ __device__ __forceinline__ void g_split_lo(const float* src, float* dst, int n_f
 template <int PREC>
 __global__ void __launch_bounds__(G_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Bn, int rows_per_split,
-                int MA_pad, int MA, float* __restrict__ part) {
+                int MA_pad, int MA, float* __restrict__ part, float* __restrict__ Cd, float* __restrict__ Ctd,
+                unsigned long long* bump, long long ps, long long cs) {
   extern __shared__ unsigned char g_raw[];
   using Smem = GSmemT<PREC>;
   constexpr int ST = Smem::STAGES;
@@ -154,8 +155,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.lo_ready[s])) : "memory");
       }
     }
-    float* dst = part + ((size_t)sp * MA_pad + m0 + 32 * lg + lane) * GN;
-    const bool live = m0 + 32 * lg + lane < MA;  // only rows that exist are written (dW1: 14 of 128, a critic's dW3: 1)
+    // Cd != NULL (one split: nothing to add up): the tile goes straight to the gradient tensor C [MA][256] of this agent
+    // (thread <-> row m: 128 contiguous bytes per chunk) and to its transpose Ct [256][MA] (lanes <-> consecutive m:
+    // coalesced), and CTA (0, 0, agent) advances the agent's update counter — no reduce launch, no scratch round trip.
+    const int mrow = m0 + 32 * lg + lane;
+    float* dst = Cd ? Cd + (size_t)ag * ps + (size_t)mrow * GN : part + ((size_t)sp * MA_pad + mrow) * GN;
+    float* dstT = (Cd && Ctd) ? Ctd + (size_t)ag * ps + mrow : nullptr;
+    if (Cd && bump && blockIdx.x == 0 && et == 0) bump[(size_t)ag * cs] += 1ull;
+    const bool live = mrow < MA;  // only rows that exist are written (dW1: 14 of 128, a critic's dW3: 1)
     if (m0 + 32 * lg >= MA) {
       // none of this warp's 32 rows exists: nothing to read back or write
     } else if (KB > 0) {
@@ -178,10 +185,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         if (live) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) d4[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+          if (dstT) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dstT[(size_t)(c * 32 + i) * MA] = __uint_as_float(r[i]);
+          }
         }
       }
     } else if (live) {  // an empty slice (more splits than slabs): zeros
       for (int c = 0; c < GN / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dstT)
+        for (int n = 0; n < GN; ++n) dstT[(size_t)n * MA] = 0.f;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -285,10 +298,13 @@ cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, con
   if (!g_map(&ma, A, Bn, a_cols, lda, k.n) || !g_map(&mb, Bm, Bn, GN, GN, k.n)) return cudaErrorInvalidValue;
   const int mt = (MA + GM - 1) / GM, MA_pad = mt * GM, S = tc_wgrad_splits(Bn, MA, stacked);
   const int rps = (((Bn + S - 1) / S) + GK - 1) / GK * GK;
-  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
-  else tc_wgrad_kernel<0><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch);
+  const bool direct = stacked && S == 1;  // one split per agent: the epilogue writes C / Ct itself (and bumps the counter)
+  float* cd = direct ? C : nullptr;
+  float* ctd = direct ? Ct : nullptr;
+  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs);
+  else tc_wgrad_kernel<0><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess || direct) return e;
   tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8, k.n), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump, k.ps, k.cs);
   return cudaGetLastError();
 }

@@ -114,6 +114,7 @@ wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const 
 // ---- policy head: warp per row ----------------------------------------------------------------------------------------
 using WidePolicyArgs = b2rl_wide_policy_t;
 
+constexpr int WP_ROWS = 64;  // rows per CTA (8 per warp): the head's weights are staged once per 64 rows, not once per 8
 __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_constant__ WidePolicyArgs P, const Stk K) {
   extern __shared__ float w3s[];  // [out][256]
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
@@ -122,60 +123,63 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
   const float* b3g = P.b3 + ag * K.ps;
   for (int i = t; i < P.out_dim * HID; i += 256) w3s[i] = __ldg(w3g + i);
   __syncthreads();
-  const int row = blockIdx.x * 8 + w;           // row inside the agent's batch: the Philox key
-  if (row >= P.M) return;
-  const size_t grow = ag * P.M + row;           // row of the stacked arrays
   const uint32_t agent = P.agent + (uint32_t)ag;
   const uint64_t step = P.counters[ag * K.cs + P.counter_idx];
-  float h[8];
+  float lo = 0.f, hi = 0.f;
+  if (l < P.A) lo = __ldg(P.min_ac + l), hi = __ldg(P.max_ac + l);
+  const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+  for (int rr = 0; rr < WP_ROWS / 8; ++rr) {
+    const int row = blockIdx.x * WP_ROWS + rr * 8 + w;  // row inside the agent's batch: the Philox key
+    if (row >= P.M) break;
+    const size_t grow = ag * P.M + row;         // row of the stacked arrays
+    float h[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = __ldg(P.h2 + grow * HID + l + 32 * i);
-  // the obs-part of the next network's input
-  const float* src = P.rows + grow * P.row_stride + P.src_off;
-  float* xr = P.xn + grow * P.ldn;
-  for (int k = l; k < P.O; k += 32) xr[k] = __ldg(src + k);
-  float u_mu = 0.f, u_ls = 0.f;  // lane a < A keeps head outputs a and A + a
-  for (int o = 0; o < P.out_dim; ++o) {
-    float s = 0.f;
+    for (int i = 0; i < 8; ++i) h[i] = __ldg(P.h2 + grow * HID + l + 32 * i);
+    // the obs-part of the next network's input
+    const float* src = P.rows + grow * P.row_stride + P.src_off;
+    float* xr = P.xn + grow * P.ldn;
+    for (int k = l; k < P.O; k += 32) xr[k] = __ldg(src + k);
+    float u_mu = 0.f, u_ls = 0.f;  // lane a < A keeps head outputs a and A + a
+    for (int o = 0; o < P.out_dim; ++o) {
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
-    s = warp_sum(s) + __ldg(b3g + o);
-    if (o == l) u_mu = s;
-    if (o == P.A + l) u_ls = s;
-  }
-  float lp = 0.f;
-  if (l < P.A) {
-    const float lo = __ldg(P.min_ac + l), hi = __ldg(P.max_ac + l);
-    const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
-    const int64_t e = (int64_t)grow * P.A + l;
-    float act_v;
-    if (P.td3) {
-      float th;
-      act_v = td3_action(u_mu, scale, bias, th);
-      if (P.save) P.save[grow * 4 * P.A + 3 * P.A + l] = th;
-      if (P.smoothing) {
+      for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
+      s = warp_sum(s) + __ldg(b3g + o);
+      if (o == l) u_mu = s;
+      if (o == P.A + l) u_ls = s;
+    }
+    float lp = 0.f;
+    if (l < P.A) {
+      const int64_t e = (int64_t)grow * P.A + l;
+      float act_v;
+      if (P.td3) {
+        float th;
+        act_v = td3_action(u_mu, scale, bias, th);
+        if (P.save) P.save[grow * 4 * P.A + 3 * P.A + l] = th;
+        if (P.smoothing) {
+          const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
+          if (P.eps_out) P.eps_out[e] = z;
+          float n = __fmul_rn(z, P.td3_std);
+          n = fminf(fmaxf(n, -P.td3_c), P.td3_c);
+          act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
+        }
+      } else {
         const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
         if (P.eps_out) P.eps_out[e] = z;
-        float n = __fmul_rn(z, P.td3_std);
-        n = fminf(fmaxf(n, -P.td3_c), P.td3_c);
-        act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
+        const GaussSample gs = gauss_sample(u_mu, u_ls, z, scale, bias);
+        act_v = gs.action;
+        lp = gs.logp;
+        if (P.save) {  // what the head's backward pass needs: [M][4][A] = eps, sigma, tanh(x), tanh(raw log-std)
+          float* sv = P.save + grow * 4 * P.A;
+          sv[l] = z; sv[P.A + l] = gs.sigma; sv[2 * P.A + l] = gs.y; sv[3 * P.A + l] = gs.th;
+        }
       }
-    } else {
-      const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
-      if (P.eps_out) P.eps_out[e] = z;
-      const GaussSample gs = gauss_sample(u_mu, u_ls, z, scale, bias);
-      act_v = gs.action;
-      lp = gs.logp;
-      if (P.save) {  // what the head's backward pass needs: [M][4][A] = eps, sigma, tanh(x), tanh(raw log-std)
-        float* sv = P.save + grow * 4 * P.A;
-        sv[l] = z; sv[P.A + l] = gs.sigma; sv[2 * P.A + l] = gs.y; sv[3 * P.A + l] = gs.th;
-      }
+      xr[P.O + l] = act_v;
     }
-    xr[P.O + l] = act_v;
-  }
-  if (P.logp) {
-    lp = warp_sum(lp);
-    if (l == 0) P.logp[grow] = lp;
+    if (P.logp) {
+      lp = warp_sum(lp);
+      if (l == 0) P.logp[grow] = lp;
+    }
   }
 }
 
@@ -542,7 +546,7 @@ cudaError_t launch_wide_first(const float* X, int64_t ldx, int M, int K, const f
   return cudaGetLastError();
 }
 cudaError_t launch_wide_policy_head(const WidePolicyArgs& p, const Stk& k, cudaStream_t st) {
-  wide_policy_head_kernel<<<dim3((p.M + 7) / 8, k.n), 256, (size_t)p.out_dim * HID * 4, st>>>(p, k);
+  wide_policy_head_kernel<<<dim3((p.M + WP_ROWS - 1) / WP_ROWS, k.n), 256, (size_t)p.out_dim * HID * 4, st>>>(p, k);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_q_head(const WideQArgs& q, const Stk& k, cudaStream_t st) {

@@ -6,8 +6,8 @@ torch.distributed anywhere); the parity oracle is a single rank ru
 the W local batches (mean of equal-sized means = global mean).
 
 Replicas stay bit-identical: every rank applies the same reduced gradient with the same arithmetic. The
-natural-layout shadow gradients (`w2n`) are not reduced — a ring all-reduce may sum two positions of the
-buffer in different orders — but re-derived from the reduced primary gradient by a transposed copy.
+natural-layout shadows (`w2n`) never see a gradient of their own — a ring all-reduce may sum two positions of the
+buffer in different orders — the Adam launch steps `w2t` and writes the result to both layouts (adam.cu).
 """
 from __future__ import annotations
 
@@ -40,10 +40,9 @@ def reduce_grad_span(arena: Arena, layout: ArenaLayout, comm: GradComm, which: s
         return
     nets = layout.critic if which == "critic" else [layout.actor]
     g = arena.flat[agent, L.REGION_G]
-    comm.all_reduce_sum(g[nets[0].begin:nets[-1].core_end])  # one contiguous bucket (shadows in between ride along)
-    with torch.no_grad():
-        for net in nets:
-            arena.tensor(net, "w2n", L.REGION_G, agent).copy_(arena.tensor(net, "w2t", L.REGION_G, agent))
+    # one contiguous bucket (a shadow's gradient slot in between rides along unused: the Adam launch derives the w2n
+    # shadows from the reduced w2t gradient through its transposing tiles, so replicas stay bit-identical with no copy)
+    comm.all_reduce_sum(g[nets[0].begin:nets[-1].core_end])
 
 
 class DataParallelLearner:
@@ -66,10 +65,13 @@ class DataParallelLearner:
         self.rows = torch.zeros(self.B, agent.fmt.row_stride, dtype=torch.float32, device=dev)
         self.idx = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.launches = 0
-        # One CUDA graph per iteration variant (actor updates? Polyak?) when the batch is sampled on the device and there
-        # is no collective to capture (one rank): the wide path is ~110 launches per iteration, ~0.9 ms of host time to
-        # enqueue — all of a batch-16 384 iteration (tools/dp_cpu_time.py). With W > 1 the iteration stays eager.
-        self.graphs = (self.comm.world == 1 and rb is not None and bool(agent.hps.cudagraphs)) if graphs is None else bool(graphs)
+        # One CUDA graph per iteration variant (actor updates? Polyak?) when the batch is sampled on the device: the wide
+        # path is ~100 launches per iteration, ~0.9 ms of host time to enqueue — all of a batch-16 384 iteration
+        # (tools/dp_cpu_time.py). With W > 1 the NCCL all-reduces are captured INSIDE the iteration graph (NCCL collectives
+        # are stream-capturable; every rank replays the same sequence), so the multi-rank iteration is one graph launch
+        # too; other backends (gloo in the CPU-side tests) stay eager.
+        capturable = self.comm.world == 1 or (dist.is_initialized() and dist.get_backend(self.comm.group) == "nccl")
+        self.graphs = (capturable and rb is not None and bool(agent.hps.cudagraphs)) if graphs is None else bool(graphs)
         self._graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
         self._size_on_device = -1
         self._warm: set = set()

@@ -20,7 +20,7 @@ import torch
 from . import _lib as L
 from .agents.agent import HID_DIMS
 from .agents.nets import Actor, Critic, TanhGaussActor
-from .arena import Arena, make_layout
+from .arena import Arena, make_layout, set_shadow_pairs
 from .replay import pack_rows, row_format
 
 
@@ -119,6 +119,7 @@ class Population:
             gamma=float(hps.gamma), td3_std=float(hps.td3_std) if self.td3 else 0.0,
             td3_c=float(hps.td3_c) if self.td3 else 0.0, targ_ent=float(-self.ac_dim), seed=self.seed)
         self.args = self._make_args()
+        self._lo: Optional[torch.Tensor] = None
         self.wide = wide
         self.wide_q = self.wide_pi = None
         if wide:
@@ -169,7 +170,23 @@ class Population:
         a.beta1, a.beta2, a.eps = 0.9, 0.999, 1e-8
         a.region_stride, a.arena_agent_stride = self.layout.region, self.arena.agent_stride
         a.arena, a.counters, a.grad_sumsq = self.arena.flat.data_ptr(), self.counters.data_ptr(), self.sumsq.data_ptr()
+        a.lo, a.lo_agent_stride = L.ptr(self._lo), 2 * self.layout.region
+        set_shadow_pairs(a, self.layout)
         L.check(self._lib.b2rl_adam_polyak_multi(C.byref(a), self._stream()), "adam_polyak_multi")
+
+    def lo_mirror(self) -> torch.Tensor:
+        """[N][2][region] lo parts of every agent's online / target regions for the 3xTF32 products (Agent.lo_mirror);
+        kept current by every Adam / Polyak launch of the population."""
+        if self._lo is None:
+            self._lo = torch.zeros(self.N, 2, self.layout.region, dtype=torch.float32, device=self.device)
+            self.refresh_lo()
+        return self._lo
+
+    def refresh_lo(self) -> None:
+        if self._lo is not None:
+            stk = L.Stack(self.N, self.base, self.arena.agent_stride, 2 * self.layout.region, 0, 0, 0)
+            L.check(self._lib.b2rl_tc_split_lo(self.arena.flat.data_ptr(), self._lo.data_ptr(), 2 * self.layout.region,
+                                               C.byref(stk), self._stream()), "tc_split_lo")
 
     def _enqueue(self, do_actor: bool, do_polyak: bool) -> int:
         lib, st, lay, h = self._lib, self._stream(), self.layout, self.hps

@@ -62,6 +62,10 @@ class _Owner:
             self._ws[M] = torch.zeros(8 * nm * 256 + 2 * nm * L.MAX_OUT, dtype=torch.float32, device=self.device)
         return self._ws[M]
 
+    def lo_mirror(self) -> torch.Tensor:
+        """[n][2][region] lo parts of the online / target regions (3xTF32), maintained by the owner's Adam launches."""
+        return self.owner.lo_mirror()
+
     def seg(self, begin, end, lr, adam, polyak, counter=0, clip=False):
         return L.Seg(begin, end, lr, int(adam), int(polyak), counter, 1.0, int(clip))
 
@@ -73,7 +77,8 @@ def _tc_wgrads(lib, stk, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, 
     f = lambda off: G + 4 * off
     sc = scratch.data_ptr()
     L.check(lib.b2rl_tc_wgrad(x0_ptr, ldx, ldx, net.in_dim, dz1, M, f(o["w1t"]), None, sc, x3, None, stk, st), "tc_wgrad w1")
-    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), f(o["w2n"]), sc, x3, None, stk, st), "tc_wgrad w2")
+    # (no transposed copy into the w2n shadow's gradient: the Adam launch derives the shadow from w2t, adam.cu)
+    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), None, sc, x3, None, stk, st), "tc_wgrad w2")
     L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, stk, st), "tc_wgrad w3")
 
 
@@ -106,8 +111,9 @@ class WideCritic:
         self.part1, self.part2 = torch.zeros(2, n * self.P128, 3, 256, **f32), torch.zeros(2, n * self.P128, 3, 256, **f32)
         self.sq = torch.zeros(2, n * self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
         self.ws = own.workspace(M)
-        # lo parts (3xTF32) of the online and target regions, same offsets; one [2][region] mirror per agent
-        self.wlo = torch.zeros(n, 2, own.layout.region, **f32)
+        # lo parts (3xTF32) of the online and target regions, same offsets: one [2][region] mirror per agent, created (and
+        # filled) here, kept current from now on by the owner's Adam / Polyak launches — no split pass per step
+        self.wlo = own.lo_mirror() if self.x3 else None
         self.stk = own.stack(lo_stride=2 * own.layout.region)
         self.gscratch = _wgrad_scratch(own, M)
 
@@ -120,17 +126,6 @@ class WideCritic:
 
     def _dz3(self, slot: int) -> int:
         return self.ws.data_ptr() + 4 * (8 * self.NM * 256 + slot * self.NM * L.MAX_OUT)
-
-    def _split_lo(self, base: int, lo_base: int, spans, whole: int, st) -> None:
-        """Refresh the lo parts (3xTF32) of the weights that changed. One learner: ONE launch over `whole` floats (the
-        regions are neighbours in the arena). Stacked: one launch per 256 x 256 matrix in `spans` (float offsets from
-        `base`) over all agents — splitting whole regions would move 6.7 MB per agent and step."""
-        lib, stk = self._lib, self.stk
-        if stk is None:
-            L.check(lib.b2rl_tc_split_lo(base, lo_base, whole, None, st), "tc_split_lo")
-            return
-        for off in spans:
-            L.check(lib.b2rl_tc_split_lo(base + 4 * off, lo_base + 4 * off, 256 * 256, C.byref(stk), st), "tc_split_lo")
 
     def update_qnets(self, rows: torch.Tensor, eps: Optional[torch.Tensor] = None, eps_out: Optional[torch.Tensor] = None,
                      targ_out: Optional[torch.Tensor] = None, adam: bool = True, polyak: bool = False, extra_segs=()) -> dict:
@@ -152,15 +147,10 @@ class WideCritic:
                                         self._p(region, o["g1"]) if ln else none, self._p(region, o["be1"]) if ln else none, ln,
                                         H, XH, stat, stk, st), "wide_first")
 
-        # the weights change every step: their lo parts are recomputed; every weight keeps its arena offset in the mirror
+        # every weight keeps its arena offset in the lo mirror (3xTF32), which the optimizer launches keep current
         base = self._p(RP, 0)
         ra = RT if ag.td3 else RP  # next action: SAC samples from the ONLINE actor (agent.py:205), TD3 uses the TARGET actor
         act = lay.actor
-        if self.x3:
-            R = lay.region
-            spans = [ra * R + act.off["w2n"]] + [RT * R + c.off["w2n"] for c in lay.critic] + \
-                    [RP * R + c.off[f] for c in lay.critic for f in ("w2n", "w2t")]
-            self._split_lo(base, self.wlo.data_ptr(), spans, 2 * R, st)
 
         def lo_of(slot, w_ptr):
             return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
@@ -273,14 +263,13 @@ class WideActor:
         self.part = torch.zeros(2, n * self.P128, 3, 256, **f32)
         self.part_s, self.part_du = torch.zeros(n * self.P256, 2, **f32), torch.zeros(n * self.P256, L.MAX_OUT, **f32)
         self.ws = own.workspace(M)
-        self.wlo = torch.zeros(n, own.layout.region, **f32)  # lo parts (3xTF32) of the online region, same offsets
-        self.stk = own.stack(lo_stride=own.layout.region)
+        self.wlo = own.lo_mirror() if self.x3 else None  # (shared with WideCritic; see there)
+        self.stk = own.stack(lo_stride=2 * own.layout.region)
         self.gscratch = _wgrad_scratch(own, M)
 
     _p = WideCritic._p
     _ws = WideCritic._ws
     _dz3 = WideCritic._dz3
-    _split_lo = WideCritic._split_lo
 
     def update_actor(self, rows: torch.Tensor, eps: Optional[torch.Tensor] = None, eps_alpha: Optional[torch.Tensor] = None,
                      adam: bool = True, polyak: bool = False) -> dict:
@@ -302,9 +291,6 @@ class WideActor:
                                         H, XH, stat, stk, st), "wide_first")
 
         base = self._p(RP, 0)
-        if self.x3:  # the online region's matrices (the critic step's Adam has just changed the critics)
-            spans = [n_.off[f] for n_ in [act, *lay.critic[:self.nq]] for f in ("w2n", "w2t")]
-            self._split_lo(base, self.wlo.data_ptr(), spans, lay.region, st)
 
         def lo_of(slot, w_ptr):
             return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
@@ -410,10 +396,7 @@ class WideActor:
                                     self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
                                     self.t1.data_ptr(), none, none, stk, st), "wide_first")
         w = self._p(RP, o["w2n"])
-        wl = none
-        if self.x3:  # (the actor's Adam step has just changed this matrix)
-            wl = self.wlo.data_ptr() + (w - self._p(RP, 0))
-            L.check(lib.b2rl_tc_split_lo(w, wl, 256 * 256, stk, st), "tc_split_lo")
+        wl = self.wlo.data_ptr() + (w - self._p(RP, 0)) if self.x3 else none  # (current: the actor's Adam launch wrote it)
         L.check(lib.b2rl_tc_linear(self.t1.data_ptr(), 256, M, w, wl, self._p(RP, o["b2"]), self._p(RP, o["g2"]) if ln else none,
                                    self._p(RP, o["be2"]) if ln else none, ln, 1, self.t2.data_ptr(), none, none, stk, st), "tc_linear")
         p = L.WidePolicy()

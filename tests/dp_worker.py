@@ -24,9 +24,17 @@ def make_agent(hps, agent_id, dev):
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # B2RL_DP_BACKEND=gloo: all ranks share GPU 0 and reduce through gloo (CUDA tensors staged through the host) — the same
+    # kernels, grad_scale = 1/W and deferred alpha step as under NCCL, runnable on a one-GPU box (NCCL refuses two ranks
+    # on one device)
+    backend = os.environ.get("B2RL_DP_BACKEND", "nccl")
+    local = local % torch.cuda.device_count() if backend == "gloo" else local
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
     B, n_it = 64, 4
     # row-group kernels (fp32, tight bound) and the tensor-core wide path (3xTF32: fp32-class gradients, but a ReLU mask
     # may flip where a pre-activation is within 1e-6 of zero, and Adam's first steps amplify: looser stated bound)
@@ -70,10 +78,43 @@ def main():
             print(f"DP_RESULT {algo} wide={wide} world={world} worst_rel_dev_vs_single_rank={worst:.3e}", flush=True)
             assert worst <= tol, worst
             assert ag.counters[:3].tolist() == ref.counters[:3].tolist()
+    if backend == "nccl":
+        graph_replay_equals_eager(rank, world, dev)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
         print("DP_OK", flush=True)
+
+
+def graph_replay_equals_eager(rank, world, dev):
+    """W ranks, device-side sampling: the iteration graphs (NCCL all-reduces captured inside) replay the same launches as
+    the eager loop — parameters, optimizer state and counters bitwise equal after 9 iterations, replicas identical."""
+    from sac_td3_cudagraphs_pytorch_b200.replay import ReplayBuffer
+    for algo, wide in (("sac", "3xtf32"), ("td3", None)):
+        mk = sac_hps if algo == "sac" else td3_hps
+        agents, dps = [], []
+        for graphs in (True, False):
+            ag = make_agent(mk(batch_size=256), rank, dev)
+            rb = ReplayBuffer(2000, dev, seed=9, agent_id=rank)
+            td = make_synthetic_transitions(1500, 11, 3, [-1.0] * 3, [1.0] * 3, seed=40 + rank)
+            rb.extend({k: v.to(dev) for k, v in td.items()})
+            agents.append(ag)
+            dps.append(DataParallelLearner(ag, rb, 256, GradComm(), wide=wide, graphs=graphs))
+        assert dps[0].graphs and not dps[1].graphs
+        for i in range(9):
+            for dp in dps:
+                dp.iteration(i)
+        torch.cuda.synchronize()
+        assert len(dps[0]._graphs) >= 2
+        assert torch.equal(agents[0].arena.flat[:, :4], agents[1].arena.flat[:, :4]), f"{algo}: graph != eager"
+        assert torch.equal(agents[0].counters[:4], agents[1].counters[:4])
+        assert torch.equal(agents[0]._alpha_state[[0, 2, 3]], agents[1]._alpha_state[[0, 2, 3]])
+        mine = agents[0].arena.flat[0, :4].double().sum().reshape(1)
+        got = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(got, mine)
+        assert all(torch.equal(g, got[0]) for g in got), f"{algo}: replicas diverged {got}"
+        if rank == 0:
+            print(f"DP_GRAPH_OK {algo} wide={wide} world={world} graphs={len(dps[0]._graphs)}", flush=True)
 
 
 if __name__ == "__main__":

@@ -361,3 +361,53 @@ def test_bad_sampling_and_tensor_core_arguments_are_refused():
     # fused critic head without a head
     assert lib.b2rl_tc_linear_q(y.data_ptr(), 256, 256, y.data_ptr(), None, y.data_ptr(), None, None, 0, None, None, None, None, None, st) < 0
     torch.cuda.synchronize()  # (nothing was launched: no sticky error)
+
+
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper"])
+def test_update_functions_can_be_wrapped_like_cudagraphmodule(name):
+    """`update_*` must be wrappable by tensordict's CudaGraphModule (orchestrator.py:313-315) — warm-up calls
+    run eagerly, then ONE call on a static six-key input dict is captured, and every later call copies the new batch
+    into the static inputs and replays. Emulated with torch.cuda.CUDAGraph (tensordict is not in this image): the wrapped
+    agent ends bitwise equal to an unwrapped twin fed the same batches, and the returned loss tensors are refreshed."""
+    from tests.golden.cases import case_inputs
+    from tests.helpers import batch_of, make_agent
+    inp = case_inputs(name)
+    wrapped, plain = make_agent(inp, seed=4), make_agent(inp, seed=4)
+    dev = lambda d: {k: v.cuda() for k, v in d.items()}
+    static = dev(batch_of(inp, 0))
+    graphs, outs = {}, {}
+
+    def call(fn_name, batch):
+        for k in static:
+            static[k].copy_(batch[k])                       # CudaGraphModule: tree-copy into the static inputs
+        fn = getattr(wrapped, fn_name)
+        n = call.count[fn_name] = call.count.get(fn_name, 0) + 1
+        if n <= 2:                                          # warm-up calls
+            return dict(fn(static))
+        if fn_name not in graphs:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                outs[fn_name] = dict(fn(static))
+            graphs[fn_name] = g
+        graphs[fn_name].replay()
+        return {k: v.clone() for k, v in outs[fn_name].items()}
+    call.count = {}
+
+    for i in range(6):
+        b = dev(batch_of(inp, i))
+        got = call("update_qnets", b)
+        want = dict(plain.update_qnets(b))
+        for a in (wrapped, plain):
+            a.qnet_updates_so_far += 1
+        assert torch.equal(got["loss/qf_loss"], want["loss/qf_loss"]), i
+        for j in range(2):
+            got = call("update_actor", b)
+            want = dict(plain.update_actor(b))
+            assert torch.equal(got["loss/actor_loss"], want["loss/actor_loss"]), (i, j)
+        for a in (wrapped, plain):
+            a.update_targ_nets()
+    torch.cuda.synchronize()
+    assert len(graphs) == 2
+    assert torch.equal(wrapped.arena.flat[:, :4], plain.arena.flat[:, :4])
+    assert torch.equal(wrapped.counters[:3], plain.counters[:3])
