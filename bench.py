@@ -654,7 +654,7 @@ def main():
             r2 = run_b2rl(a2, 0, 1, device)
             extra[w] = {"updates_per_s": r2["value"], "ms_per_step": r2["elapsed"] / a2.steps * 1e3,
                         "e2e_updates_per_s": r2["e2e"]["value"], "critic_fused_frac_of_ffma_peak": r2["roofline"]["frac"],
-                        "per_kernel_us": r2["per_kernel_us"]}
+                        "per_kernel_us": r2["per_kernel_us"], "roofline_gather": r2["roofline_gather"]}
             torch.cuda.empty_cache()
             if not args.no_torch_baseline:
                 extra[w]["torch_cudagraph_baseline"] = time_reference_cuda(w, 300, 20, device)

@@ -15,7 +15,10 @@ namespace b2rl {
 
 using SegScalars = AdamScalars;
 
-__global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ b2rl_adam_args_t A) {
+// PS.seg[q]: the segment whose scalars (lr, step count, clip, Polyak) govern shadow pair q. launch_adam has already cut
+// the pairs' spans out of the segment list, so the element-wise loop below never meets them.
+struct PairSeg { int seg[3]; };
+__global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant__ b2rl_adam_args_t A, const __grid_constant__ PairSeg PS) {
   pdl_enter();
   const int agent = blockIdx.y;
   float* P = A.arena + (size_t)agent * A.arena_agent_stride;
@@ -49,26 +52,26 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
   if ((int)blockIdx.x >= main_ctas) {
     // ---- shadow pairs: one 32 x 32 tile of a net's w2t per CTA; the step is computed once, at the w2t position, and
     // the results go to w2t (as they are read: rows of 128 bytes) and, transposed through shared memory, to w2n.
-    __shared__ float tr[32][33];
+    __shared__ float tr[6][32][33];  // p, m, v, lo(p), target, lo(target)
     const int tile = (int)blockIdx.x - main_ctas, pr = tile >> 6, tin = tile & 63;
     const int64_t src = A.shadow_src[pr], dst = A.shadow_dst[pr];
-    int si = -1;
-    for (int q = 0; q < A.n_seg; ++q)
-      if (src >= A.seg[q].begin && src < A.seg[q].end) si = q;
-    if (si < 0) return;  // (this launch does not touch that net)
+    const int si = PS.seg[pr];
     const b2rl_seg_t& s = A.seg[si];
     const SegScalars k = sc[si];
     const int k0 = (tin >> 3) * 32, j0 = (tin & 7) * 32, r = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
     const int64_t i = src + (int64_t)(k0 + r) * HID + j0 + c4;        // w2t[k0 + r][j0 + c4 ..]
     const int64_t it = dst + (int64_t)(j0 + r) * HID + k0 + c4;       // w2n[j0 + r][k0 + c4 ..]
-    auto put_t = [&](float* base, const float4& x) {  // x (held for w2t[k0 + r][j0 + c4..]) -> base[w2n tile], transposed
-      __syncthreads();
-      tr[r][c4] = x.x, tr[r][c4 + 1] = x.y, tr[r][c4 + 2] = x.z, tr[r][c4 + 3] = x.w;
-      __syncthreads();
-      *reinterpret_cast<float4*>(base + it) = make_float4(tr[c4][r], tr[c4 + 1][r], tr[c4 + 2][r], tr[c4 + 3][r]);
+    auto stage = [&](int b, const float4& x) {  // x is held for w2t[k0 + r][j0 + c4 ..]
+      tr[b][r][c4] = x.x, tr[b][r][c4 + 1] = x.y, tr[b][r][c4 + 2] = x.z, tr[b][r][c4 + 3] = x.w;
     };
+    auto out_t = [&](int b, float* base) {      // -> base[w2n tile], transposed
+      *reinterpret_cast<float4*>(base + it) = make_float4(tr[b][c4][r], tr[b][c4 + 1][r], tr[b][c4 + 2][r], tr[b][c4 + 3][r]);
+    };
+    const bool da = s.do_adam != 0, dp = s.do_polyak != 0;
     float4 p = *reinterpret_cast<const float4*>(P + i);
-    if (s.do_adam) {
+    float4 tg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dp) tg = *reinterpret_cast<const float4*>(T + i);  // (requested before the Adam arithmetic)
+    if (da) {
       float4 g = *reinterpret_cast<const float4*>(G + i);
       float4 m = *reinterpret_cast<const float4*>(M1 + i);
       float4 v = *reinterpret_cast<const float4*>(V + i);
@@ -83,40 +86,64 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(const __grid_constant_
       *reinterpret_cast<float4*>(P + i) = p;
       *reinterpret_cast<float4*>(M1 + i) = m;
       *reinterpret_cast<float4*>(V + i) = v;
-      put_t(P, p);
-      put_t(M1, m);
-      put_t(V, v);
+      stage(0, p);
+      stage(1, m);
+      stage(2, v);
       if (LO) {
         const float4 l = tf32_lo4(p);
         *reinterpret_cast<float4*>(LO + i) = l;
-        put_t(LO, l);
+        stage(3, l);
       }
     }
-    if (s.do_polyak) {
-      float4 tg = *reinterpret_cast<const float4*>(T + i);
+    if (dp) {
       tg.x = polyak_elem(tg.x, p.x, A.polyak);
       tg.y = polyak_elem(tg.y, p.y, A.polyak);
       tg.z = polyak_elem(tg.z, p.z, A.polyak);
       tg.w = polyak_elem(tg.w, p.w, A.polyak);
       *reinterpret_cast<float4*>(T + i) = tg;
-      put_t(T, tg);
+      stage(4, tg);
       if (LO) {
         const float4 l = tf32_lo4(tg);
         *reinterpret_cast<float4*>(LO + A.region_stride + i) = l;
-        put_t(LO + A.region_stride, l);
+        stage(5, l);
       }
+    }
+    __syncthreads();
+    if (da) {
+      out_t(0, P);
+      out_t(1, M1);
+      out_t(2, V);
+      if (LO) out_t(3, LO);
+    }
+    if (dp) {
+      out_t(4, T);
+      if (LO) out_t(5, LO + A.region_stride);
     }
     return;
   }
+  // ---- everything else, element-wise: the segments (pieces between the pairs' spans) form ONE flat index space, so that
+  // a thread's elements are independent loads in flight instead of one dependent round trip per segment
+  __shared__ int64_t sbeg[B2RL_MAX_SEG], slen[B2RL_MAX_SEG];
+  if (threadIdx.x < B2RL_MAX_SEG) {
+    const bool on = (int)threadIdx.x < A.n_seg;
+    sbeg[threadIdx.x] = on ? A.seg[threadIdx.x].begin : 0;
+    slen[threadIdx.x] = on ? A.seg[threadIdx.x].end - A.seg[threadIdx.x].begin : 0;
+  }
+  __syncthreads();
+  int64_t total = 0;
+#pragma unroll
+  for (int q = 0; q < B2RL_MAX_SEG; ++q) total += slen[q];
   const int64_t stride = (int64_t)main_ctas * blockDim.x * 4;
-  for (int si = 0; si < A.n_seg; ++si) {
+  for (int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; f < total; f += stride) {
+    int si = 0;
+    int64_t off = f;
+#pragma unroll
+    for (int q = 0; q < B2RL_MAX_SEG - 1; ++q)
+      if (si == q && off >= slen[q]) { off -= slen[q]; si = q + 1; }
+    const int64_t i = sbeg[si] + off;
     const b2rl_seg_t& s = A.seg[si];
     const SegScalars k = sc[si];
-    for (int64_t i = s.begin + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < s.end; i += stride) {
-      bool paired = false;  // w2t / w2n of a shadow pair: stepped by the tile CTAs above
-      for (int q = 0; q < A.n_shadow; ++q)
-        paired |= (i >= A.shadow_src[q] && i < A.shadow_src[q] + HID * HID) || (i >= A.shadow_dst[q] && i < A.shadow_dst[q] + HID * HID);
-      if (paired) continue;
+    {
       float4 p = *reinterpret_cast<const float4*>(P + i);
       if (s.do_adam) {
         float4 g = *reinterpret_cast<const float4*>(G + i);
@@ -199,23 +226,55 @@ cudaError_t init_adam() {
 }
 
 cudaError_t launch_adam(const b2rl_adam_args_t& a_in, cudaStream_t st) {
-  b2rl_adam_args_t a = a_in;  // keep only the shadow pairs this launch touches (w2t inside one of its segments)
+  // Keep only the shadow pairs this launch touches (w2t inside one of its segments) and CUT their two spans out of the
+  // segment list: the element-wise CTAs then walk plain spans (a per-element "is this a pair's span?" test made of
+  // dependent constant-bank loads cost 8 us per launch), the pairs go to 64 tile CTAs each. A pair's tiles take their
+  // scalars from any piece of the segment the pair was cut from (or from a zero-length piece if nothing is left of it).
+  b2rl_adam_args_t a = a_in;
+  PairSeg ps = {{0, 0, 0}};
   a.n_shadow = 0;
+  a.n_seg = 0;
+  const int64_t n = (int64_t)HID * HID;
   int64_t total = 0;
-  for (int i = 0; i < a.n_seg; ++i) total += a.seg[i].end - a.seg[i].begin;
-  for (int q = 0; q < a_in.n_shadow; ++q)
-    for (int i = 0; i < a.n_seg; ++i)
-      if (a_in.shadow_src[q] >= a.seg[i].begin && a_in.shadow_src[q] < a.seg[i].end) {
+  for (int i = 0; i < a_in.n_seg; ++i) {
+    const b2rl_seg_t& s = a_in.seg[i];
+    int64_t cuts[6][2];
+    int nc = 0;
+    const int first_pair = a.n_shadow;
+    for (int q = 0; q < a_in.n_shadow; ++q)
+      if (a_in.shadow_src[q] >= s.begin && a_in.shadow_src[q] < s.end) {
         a.shadow_src[a.n_shadow] = a_in.shadow_src[q];
         a.shadow_dst[a.n_shadow++] = a_in.shadow_dst[q];
-        total -= 2 * (int64_t)HID * HID;  // (both layouts are stepped by the pair's 64 tile CTAs)
-        break;
+        cuts[nc][0] = a_in.shadow_src[q], cuts[nc++][1] = a_in.shadow_src[q] + n;
+        cuts[nc][0] = a_in.shadow_dst[q], cuts[nc++][1] = a_in.shadow_dst[q] + n;
       }
+    for (int x = 0; x < nc; ++x)  // sort the cuts by start
+      for (int y = x + 1; y < nc; ++y)
+        if (cuts[y][0] < cuts[x][0]) {
+          const int64_t t0 = cuts[x][0], t1 = cuts[x][1];
+          cuts[x][0] = cuts[y][0], cuts[x][1] = cuts[y][1], cuts[y][0] = t0, cuts[y][1] = t1;
+        }
+    const int first_piece = a.n_seg;
+    int64_t cur = s.begin;
+    for (int x = 0; x <= nc; ++x) {
+      const int64_t stop = x < nc ? cuts[x][0] : s.end;
+      if (stop > cur || (x == nc && a.n_seg == first_piece)) {  // (at least one piece per segment: it carries the scalars)
+        if (a.n_seg >= B2RL_MAX_SEG) return cudaErrorInvalidValue;
+        a.seg[a.n_seg] = s;
+        a.seg[a.n_seg].begin = cur;
+        a.seg[a.n_seg].end = stop > cur ? stop : cur;
+        total += a.seg[a.n_seg].end - cur;
+        ++a.n_seg;
+      }
+      if (x < nc) cur = cuts[x][1];
+    }
+    for (int q = first_pair; q < a.n_shadow; ++q) ps.seg[q] = first_piece;
+  }
   int ctas = (int)((total / 4 + 255) / 256);
   if (ctas < 1) ctas = 1;
   if (ctas > 148 * 4) ctas = 148 * 4;  // grid-stride beyond four CTAs per SM
   // + 64 tile CTAs per shadow pair (blockIdx.x >= ctas)
-  return launch_k(adam_polyak_kernel, dim3(ctas + 64 * a.n_shadow, a.n_agents), dim3(256), 1, 0, st, a);
+  return launch_k(adam_polyak_kernel, dim3(ctas + 64 * a.n_shadow, a.n_agents), dim3(256), 1, 0, st, a, ps);
 }
 
 cudaError_t launch_sumsq(const float* arena, int64_t region_stride, int64_t agent_stride, int64_t begin, int64_t end,

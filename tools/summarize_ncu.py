@@ -6,7 +6,9 @@ import csv, io, subprocess, sys, collections
 METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__cluster_size", "launch__registers_per_thread",
            "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
-           "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_tmem_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum", "sm__inst_executed_pipe_tma.sum",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct",
            "smsp__pcsamp_warps_issue_stalled_no_instructions", "smsp__pcsamp_warps_issue_stalled_long_scoreboard",
            "smsp__pcsamp_warps_issue_stalled_short_scoreboard", "smsp__pcsamp_warps_issue_stalled_barrier",
            "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_selected", "smsp__pcsamp_sample_count"]
@@ -39,6 +41,9 @@ def full(path):
     for m in METRICS:
         if m in hdr:
             i = hdr.index(m)
+            w.writerow([m, units[i]] + [r[i] for r in data])
+    for i, m in enumerate(hdr):  # every tensor-pipe counter the report holds, whatever this ncu version calls them
+        if "pipe_tensor" in m and m not in METRICS:
             w.writerow([m, units[i]] + [r[i] for r in data])
 
 
