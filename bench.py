@@ -41,6 +41,7 @@ WORKLOADS = {
     "sac_humanoid": ("sac", 376, 17, 0.4, 1_000_000),
 }
 HID = 256
+CADENCE = "sample + critic update + 2 actor updates every 3rd iteration + polyak"
 
 
 def flops_per_iteration(algo, O, A, B=256, delay=2):
@@ -417,9 +418,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "gradient updates/sec (batch 256, Hopper shapes)", "value": v,
             "unit": "updates/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": el / n * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "algo": algo, "ob_dim": O, "ac_dim": A, "batch": 256,
-                       "device": "host cpu", "replay_rows": cap, "hidden": "2x256+LN",
-                       "cadence": "sample + critic update + 2 actor updates every 3rd iteration + polyak"},
+            "config": {"workload": args.workload, "algo": algo, "ob_dim": O, "ac_dim": A, "batch": 256, "hidden": "2x256+LN",
+                       "replay_rows": cap, "replay_bytes": cap * 4 * ((2 * O + A + 2 + 3) & ~3), "cadence": CADENCE,
+                       "execution": "torch ops on the host CPU (the reference's cuda: false path)", "device": "host cpu"},
             "cpu_baseline": {"value": v, "unit": "updates/s", "cores": threads, "kind": "port",
                              "sample": f"{n} iterations (asked {K}, budget {budget:.0f}s); 1 thread {r1:.1f}/s vs "
                                        f"{cores} threads {rN:.1f}/s in calibration"},
@@ -681,7 +682,7 @@ def main():
                    "replay_rows": res["rb_rows"], "replay_bytes": res["rb_rows"] * res["row_bytes"],
                    "l2": "inputs larger than L2: sampled rows come from a replay buffer > 126 MB; parameters/optimizer "
                          "state (8 MB) are reused every step by the nature of the loop",
-                   "cadence": "sample + critic update + 2 actor updates every 3rd iteration + polyak, one CUDA graph replay per step",
+                   "cadence": CADENCE, "execution": "one CUDA graph replay per step",
                    "parallelism": f"{world} independent learner(s), one per GPU, no collective"},
         "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["launches"],
         "roofline": res["roofline"], "roofline_gather": res["roofline_gather"], "roofline_tc_linear": res["roofline_tc_linear"], "per_kernel_us": res["per_kernel_us"],

@@ -243,9 +243,11 @@ __device__ __forceinline__ void first_smem(const float* __restrict__ Ws, int K, 
     fma_k(acc, *reinterpret_cast<const float4*>(Ws + k * CW + 4 * l), X[k], X[ldx + k]);
   store_partials(acc, red);
 }
-// First layers read from global memory (any K; Humanoid: 376 / 393): chunks of 8 k, two chunks in flight, tails
-// clamped (x = 0).
-constexpr int CH = 8;
+// First layers read from global memory (any K; Humanoid: 376 / 393): the hidden layers' four-set register rotation
+// (three groups of 4 k always in flight, no register moves) over this warp's slice of K. The slice is padded to a whole
+// number of 4-group trips: padded k re-request the slice's last weight row (an L1 hit) and multiply x = 0. (The first
+// version — chunks of 8 k, two chunks in flight — ran the same bytes 1.3-1.6x slower than the hidden layers' pipeline:
+// 8-10 k cycles per Humanoid first layer, 35 % of its critic kernel.)
 static __device__ __noinline__ void first_global(const float* __restrict__ W, int K, const float4* __restrict__ X, int ldx,
                                                  int j0, float* __restrict__ red) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -258,25 +260,33 @@ static __device__ __noinline__ void first_global(const float* __restrict__ W, in
     const float4* xa = X + k0;
     const float4* xb = xa + ldx;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 A[CH], Bf[CH];
-#define B2RL_LOADC(buf, kk) \
-  _Pragma("unroll") for (int u = 0; u < CH; ++u) buf[u] = ldg4(wp + (size_t)min((kk) + u, n - 1) * HID);
-#define B2RL_FMAC(buf, kk)                                                        \
-  _Pragma("unroll") for (int u = 0; u < CH; ++u) {                                \
-    const int kc = min((kk) + u, n - 1);                                          \
-    const bool on = (kk) + u < n;                                                 \
-    fma_k(acc, buf[u], on ? xa[kc] : zero, on ? xb[kc] : zero);                   \
+    const int ng = (n + 3) >> 2;  // groups of 4 k
+    float4 s0[4], s1[4], s2[4], s3[4];
+#define B2RL_LOADG(set, g) \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) set[u] = ldg4(wp + (size_t)min(4 * (g) + u, n - 1) * HID);
+#define B2RL_FMAG(set, g)                                          \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                  \
+    const int kk = 4 * (g) + u;                                    \
+    const int kc = min(kk, n - 1);                                 \
+    const bool on = kk < n;                                        \
+    fma_k(acc, set[u], on ? xa[kc] : zero, on ? xb[kc] : zero);    \
   }
-    B2RL_LOADC(A, 0)
+    B2RL_LOADG(s0, 0)
+    B2RL_LOADG(s1, 1)
+    B2RL_LOADG(s2, 2)
 #pragma unroll 1
-    for (int kk = 0; kk < n; kk += 2 * CH) {
-      B2RL_LOADC(Bf, kk + CH)
-      B2RL_FMAC(A, kk)
-      B2RL_LOADC(A, kk + 2 * CH)
-      B2RL_FMAC(Bf, kk + CH)
+    for (int g = 0; g < ng; g += 4) {
+      B2RL_LOADG(s3, g + 3)
+      B2RL_FMAG(s0, g)
+      B2RL_LOADG(s0, g + 4)
+      B2RL_FMAG(s1, g + 1)
+      B2RL_LOADG(s1, g + 5)
+      B2RL_FMAG(s2, g + 2)
+      B2RL_LOADG(s2, g + 6)
+      B2RL_FMAG(s3, g + 3)
     }
-#undef B2RL_LOADC
-#undef B2RL_FMAC
+#undef B2RL_LOADG
+#undef B2RL_FMAG
   }
   store_partials(acc, red);
 }

@@ -19,11 +19,17 @@
 
 namespace b2rl {
 
-constexpr int WF_ROWS = 32;  // rows per CTA of wide_first
-constexpr int WF_KC = 64;    // k chunk staged in shared memory
+constexpr int WF_ROWS = 64;  // rows per CTA of wide_first: 8 per warp
+constexpr int WF_KC = 32;    // k chunk of weights / inputs staged in shared memory
 
 // ---- first layer -------------------------------------------------------------------------------------------------
-// thread j <-> output column j; 32 rows per CTA. z[r][j] = b[j] + sum_k X[r][k] * w1t[k][j].
+// z[r][j] = b[j] + sum_k X[r][k] * w1t[k][j], then LayerNorm / ReLU. A WARP owns 8 rows and all 256 columns (lane l:
+// columns 4l..4l+3 and 128+4l..+3), so a row's LayerNorm statistics are two warp reductions over registers — no staging
+// of z in shared memory, no CTA barrier between the product and the row-wise part (the first version, thread <-> column
+// over 32 rows with z staged through shared memory, ran at 1.4-2.9 TB/s: 187 us for 268-536 MB of output at
+// n_agents x M = 262 144 rows) — and every store is a full 512-byte row segment per warp instruction. The weight chunk
+// [k][256] and the rows' inputs are staged once per CTA; per four k a lane issues 8 LDS.128 of weights (16-byte lane
+// stride: conflict-free) and 8 broadcast LDS.128 of inputs for 256 FMAs.
 __global__ void __launch_bounds__(256)
 wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const float* __restrict__ w1t,
                   const float* __restrict__ b, const float* __restrict__ g, const float* __restrict__ be, int ln,
@@ -35,79 +41,93 @@ wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const 
     if (stat) stat += ag * M;
     if (ln) g += ag * ps, be += ag * ps;
   }
-  __shared__ __align__(16) float xs[WF_ROWS][WF_KC + 4];  // (k contiguous, 16-byte aligned rows: read as broadcast float4)
-  __shared__ float zs[WF_ROWS][HID];
-  __shared__ float2 st[WF_ROWS];
-  const int t = threadIdx.x, j = t, w = t >> 5, l = t & 31;
-  const int m0 = blockIdx.x * WF_ROWS;
-  float acc[WF_ROWS];
+  __shared__ __align__(16) float ws[WF_KC][HID];      // weight chunk, forward layout [k][j]
+  __shared__ __align__(16) float xs[WF_ROWS][WF_KC];  // the rows' inputs for the chunk
+  const int t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int m0 = blockIdx.x * WF_ROWS, r0 = m0 + 8 * w;
+  float acc[8][8];
 #pragma unroll
-  for (int r = 0; r < WF_ROWS; ++r) acc[r] = 0.f;
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
   for (int k0 = 0; k0 < K; k0 += WF_KC) {
     const int kc = min(WF_KC, K - k0), kc4 = (kc + 3) & ~3;
-    for (int i = t; i < WF_ROWS * kc4; i += 256) {
-      const int r = i / kc4, k = i - r * kc4;
+    for (int i = t; i < kc4 * (HID / 4); i += 256) {  // (rows kc..kc4-1 are zero: they meet zero inputs, but must be finite)
+      const int k = i >> 6, q = i & 63;
+      reinterpret_cast<float4*>(ws[k])[q] = k < kc ? ldg4(w1t + (size_t)(k0 + k) * HID + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = t; i < WF_ROWS * WF_KC; i += 256) {
+      const int r = i >> 5, k = i & 31;
       const int row = min(m0 + r, M - 1);  // (rows beyond M repeat the last one; their outputs are not stored)
-      xs[r][k] = k < kc ? __ldg(X + (size_t)row * ldx + k0 + k) : 0.f;  // (zero padding up to a multiple of 4)
+      xs[r][k] = k < kc ? __ldg(X + (size_t)row * ldx + k0 + k) : 0.f;
     }
     __syncthreads();
-    // four k per step: one broadcast LDS.128 of the row's inputs feeds four FMAs (one LDS.32 per FMA made this kernel
-    // issue-bound: 63 % issue-slot utilisation, 45 us at M = 65 536 for 134 MB of output)
     for (int k = 0; k < kc4; k += 4) {
-      float wv[4];
+      float4 wa[4], wb[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) wv[u] = k + u < kc ? __ldg(w1t + (size_t)(k0 + k + u) * HID + j) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        wa[u] = *reinterpret_cast<const float4*>(&ws[k + u][4 * l]);
+        wb[u] = *reinterpret_cast<const float4*>(&ws[k + u][128 + 4 * l]);
+      }
 #pragma unroll
-      for (int r = 0; r < WF_ROWS; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(&xs[r][k]);
-        acc[r] = fmaf(x.w, wv[3], fmaf(x.z, wv[2], fmaf(x.y, wv[1], fmaf(x.x, wv[0], acc[r]))));
+      for (int r = 0; r < 8; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(&xs[8 * w + r][k]);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc[r][0] = fmaf(xv[u], wa[u].x, acc[r][0]); acc[r][1] = fmaf(xv[u], wa[u].y, acc[r][1]);
+          acc[r][2] = fmaf(xv[u], wa[u].z, acc[r][2]); acc[r][3] = fmaf(xv[u], wa[u].w, acc[r][3]);
+          acc[r][4] = fmaf(xv[u], wb[u].x, acc[r][4]); acc[r][5] = fmaf(xv[u], wb[u].y, acc[r][5]);
+          acc[r][6] = fmaf(xv[u], wb[u].z, acc[r][6]); acc[r][7] = fmaf(xv[u], wb[u].w, acc[r][7]);
+        }
       }
     }
     __syncthreads();
   }
-  const float bj = b[j];
+  const float4 ba = ldg4(b + 4 * l), bb = ldg4(b + 128 + 4 * l);
+  const float bj[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+  float gj[8], bej[8];
 #pragma unroll
-  for (int r = 0; r < WF_ROWS; ++r) {
-    acc[r] += bj;
-    zs[r][j] = acc[r];
-  }
-  float gj = 1.f, bej = 0.f;
+  for (int c = 0; c < 8; ++c) gj[c] = 1.f, bej[c] = 0.f;
   if (ln) {
-    gj = g[j];
-    bej = be[j];
-    __syncthreads();
+    const float4 ga = ldg4(g + 4 * l), gb = ldg4(g + 128 + 4 * l), ea = ldg4(be + 4 * l), eb = ldg4(be + 128 + 4 * l);
+    gj[0] = ga.x, gj[1] = ga.y, gj[2] = ga.z, gj[3] = ga.w, gj[4] = gb.x, gj[5] = gb.y, gj[6] = gb.z, gj[7] = gb.w;
+    bej[0] = ea.x, bej[1] = ea.y, bej[2] = ea.z, bej[3] = ea.w, bej[4] = eb.x, bej[5] = eb.y, bej[6] = eb.z, bej[7] = eb.w;
+  }
 #pragma unroll
-    for (int rr = 0; rr < WF_ROWS / 8; ++rr) {  // warp w: rows w, w+8, ... (two-pass mean / variance)
-      const int r = w + 8 * rr;
-      float v[8];
+  for (int r = 0; r < 8; ++r) {
+    const int row = r0 + r;
+    if (row >= M) break;  // (warp-uniform)
+    float z[8], h[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = zs[r][l + 32 * i];
-      float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    for (int c = 0; c < 8; ++c) z[c] = acc[r][c] + bj[c];
+    if (ln) {  // two-pass mean / variance over the row's 256 values (8 per lane + shuffles)
+      float s = ((z[0] + z[1]) + (z[2] + z[3])) + ((z[4] + z[5]) + (z[6] + z[7]));
       s = warp_sum(s);
       const float mean = s * (1.0f / HID);
       float q = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+      for (int c = 0; c < 8; ++c) { const float d = z[c] - mean; q = fmaf(d, d, q); }
       q = warp_sum(q);
-      if (l == 0) st[r] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / HID) + LN_EPS));
-    }
-    __syncthreads();
-  }
+      const float rstd = 1.0f / sqrtf(q * (1.0f / HID) + LN_EPS);
+      if (stat && l == 0) stat[row] = make_float2(mean, rstd);
 #pragma unroll
-  for (int r = 0; r < WF_ROWS; ++r) {
-    const int row = m0 + r;
-    if (row >= M) break;
-    float x = acc[r], h;
-    if (ln) {
-      const float2 s = st[r];
-      x = (x - s.x) * s.y;
-      h = fmaxf(fmaf(x, gj, bej), 0.f);
-      if (stat && j == 0) stat[row] = s;
+      for (int c = 0; c < 8; ++c) {
+        z[c] = (z[c] - mean) * rstd;  // x-hat
+        h[c] = fmaxf(fmaf(z[c], gj[c], bej[c]), 0.f);
+      }
     } else {
-      h = fmaxf(x, 0.f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) h[c] = fmaxf(z[c], 0.f);
     }
-    H[(size_t)row * HID + j] = h;
-    if (XH) XH[(size_t)row * HID + j] = x;
+    float* hp = H + (size_t)row * HID;
+    *reinterpret_cast<float4*>(hp + 4 * l) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(hp + 128 + 4 * l) = make_float4(h[4], h[5], h[6], h[7]);
+    if (XH) {
+      float* xp = XH + (size_t)row * HID;
+      *reinterpret_cast<float4*>(xp + 4 * l) = make_float4(z[0], z[1], z[2], z[3]);
+      *reinterpret_cast<float4*>(xp + 128 + 4 * l) = make_float4(z[4], z[5], z[6], z[7]);
+    }
   }
 }
 
@@ -115,70 +135,92 @@ wide_first_kernel(const float* __restrict__ X, int64_t ldx, int M, int K, const 
 using WidePolicyArgs = b2rl_wide_policy_t;
 
 constexpr int WP_ROWS = 64;  // rows per CTA (8 per warp): the head's weights are staged once per 64 rows, not once per 8
+// Two phases per CTA of 64 rows. (1) WARP <-> row: the head's dot products (lanes over the 256 inputs), results to shared
+// memory. (2) THREAD <-> (row, action dimension): noise, tanh-Gaussian sample / TD3 smoothing, log-prob terms — the
+// transcendental part (Philox, Box-Muller, 2 tanh, exp, 2 log, a division: ~450 instructions) now runs once per 32
+// (row, dimension) pairs instead of once per row with 3 lanes alive: the one-phase version issued 669 warp instructions
+// per row and was issue-bound (74 % issue-slot utilisation, 1.5 TB/s of its 6.5: profiles/r2_ncu_full_pop256_summary.csv).
 __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_constant__ WidePolicyArgs P, const Stk K) {
-  extern __shared__ float w3s[];  // [out][256]
+  extern __shared__ float w3s[];            // [out][256], then us [64][out] head outputs, then lps [64][A] log-prob terms
+  float* us = w3s + P.out_dim * HID;
+  float* lps = us + WP_ROWS * P.out_dim;
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   const size_t ag = blockIdx.y;                 // stacked agents: rows [ag * M, ag * M + M), parameters ps further
   const float* w3g = P.w3 + ag * K.ps;
   const float* b3g = P.b3 + ag * K.ps;
   for (int i = t; i < P.out_dim * HID; i += 256) w3s[i] = __ldg(w3g + i);
   __syncthreads();
-  const uint32_t agent = P.agent + (uint32_t)ag;
-  const uint64_t step = P.counters[ag * K.cs + P.counter_idx];
-  float lo = 0.f, hi = 0.f;
-  if (l < P.A) lo = __ldg(P.min_ac + l), hi = __ldg(P.max_ac + l);
-  const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
-  for (int rr = 0; rr < WP_ROWS / 8; ++rr) {
-    const int row = blockIdx.x * WP_ROWS + rr * 8 + w;  // row inside the agent's batch: the Philox key
-    if (row >= P.M) break;
-    const size_t grow = ag * P.M + row;         // row of the stacked arrays
+  const int row0 = blockIdx.x * WP_ROWS;        // first row of this CTA inside the agent's batch
+  const int nrows = min(WP_ROWS, P.M - row0);
+  float hn[8];  // the next row's activations are requested before this row's head is computed (one round trip hidden)
+  if (w < nrows) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hn[i] = __ldg(P.h2 + (ag * P.M + row0 + w) * HID + l + 32 * i);
+  }
+  for (int rr = w; rr < nrows; rr += 8) {
+    const size_t grow = ag * P.M + row0 + rr;   // row of the stacked arrays
     float h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = __ldg(P.h2 + grow * HID + l + 32 * i);
+    for (int i = 0; i < 8; ++i) h[i] = hn[i];
+    if (rr + 8 < nrows) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hn[i] = __ldg(P.h2 + (grow + 8) * HID + l + 32 * i);
+    }
     // the obs-part of the next network's input
     const float* src = P.rows + grow * P.row_stride + P.src_off;
     float* xr = P.xn + grow * P.ldn;
     for (int k = l; k < P.O; k += 32) xr[k] = __ldg(src + k);
-    float u_mu = 0.f, u_ls = 0.f;  // lane a < A keeps head outputs a and A + a
     for (int o = 0; o < P.out_dim; ++o) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
-      s = warp_sum(s) + __ldg(b3g + o);
-      if (o == l) u_mu = s;
-      if (o == P.A + l) u_ls = s;
+      s = warp_sum(s);
+      if (l == 0) us[rr * P.out_dim + o] = s + __ldg(b3g + o);
     }
-    float lp = 0.f;
-    if (l < P.A) {
-      const int64_t e = (int64_t)grow * P.A + l;
-      float act_v;
-      if (P.td3) {
-        float th;
-        act_v = td3_action(u_mu, scale, bias, th);
-        if (P.save) P.save[grow * 4 * P.A + 3 * P.A + l] = th;
-        if (P.smoothing) {
-          const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
-          if (P.eps_out) P.eps_out[e] = z;
-          float n = __fmul_rn(z, P.td3_std);
-          n = fminf(fmaxf(n, -P.td3_c), P.td3_c);
-          act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
-        }
-      } else {
-        const float z = noise_at(P.eps, e, P.seed, row, l, step, agent, P.stream_id);
+  }
+  __syncthreads();
+  const uint32_t agent = P.agent + (uint32_t)ag;
+  const uint64_t step = P.counters[ag * K.cs + P.counter_idx];
+  for (int i = t; i < nrows * P.A; i += 256) {
+    const int rr = i / P.A, a = i - rr * P.A;
+    const int row = row0 + rr;                  // row inside the agent's batch: the Philox key
+    const size_t grow = ag * P.M + row;
+    const float lo = __ldg(P.min_ac + a), hi = __ldg(P.max_ac + a);
+    const float scale = (hi - lo) * 0.5f, bias = (hi + lo) * 0.5f;
+    const float u_mu = us[rr * P.out_dim + a];
+    const int64_t e = (int64_t)grow * P.A + a;
+    float act_v, lp = 0.f;
+    if (P.td3) {
+      float th;
+      act_v = td3_action(u_mu, scale, bias, th);
+      if (P.save) P.save[grow * 4 * P.A + 3 * P.A + a] = th;
+      if (P.smoothing) {
+        const float z = noise_at(P.eps, e, P.seed, row, a, step, agent, P.stream_id);
         if (P.eps_out) P.eps_out[e] = z;
-        const GaussSample gs = gauss_sample(u_mu, u_ls, z, scale, bias);
-        act_v = gs.action;
-        lp = gs.logp;
-        if (P.save) {  // what the head's backward pass needs: [M][4][A] = eps, sigma, tanh(x), tanh(raw log-std)
-          float* sv = P.save + grow * 4 * P.A;
-          sv[l] = z; sv[P.A + l] = gs.sigma; sv[2 * P.A + l] = gs.y; sv[3 * P.A + l] = gs.th;
-        }
+        float n = __fmul_rn(z, P.td3_std);
+        n = fminf(fmaxf(n, -P.td3_c), P.td3_c);
+        act_v = fminf(fmaxf(__fadd_rn(act_v, n), lo), hi);
       }
-      xr[P.O + l] = act_v;
+    } else {
+      const float z = noise_at(P.eps, e, P.seed, row, a, step, agent, P.stream_id);
+      if (P.eps_out) P.eps_out[e] = z;
+      const GaussSample gs = gauss_sample(u_mu, us[rr * P.out_dim + P.A + a], z, scale, bias);
+      act_v = gs.action;
+      lp = gs.logp;
+      if (P.save) {  // what the head's backward pass needs: [M][4][A] = eps, sigma, tanh(x), tanh(raw log-std)
+        float* sv = P.save + grow * 4 * P.A;
+        sv[a] = z; sv[P.A + a] = gs.sigma; sv[2 * P.A + a] = gs.y; sv[3 * P.A + a] = gs.th;
+      }
     }
-    if (P.logp) {
-      lp = warp_sum(lp);
-      if (l == 0) P.logp[grow] = lp;
+    P.xn[grow * P.ldn + P.O + a] = act_v;
+    lps[i] = lp;
+  }
+  if (P.logp) {
+    __syncthreads();
+    if (t < nrows) {  // log pi(a|s) = sum over the action dimensions, in index order
+      float s = 0.f;
+      for (int a = 0; a < P.A; ++a) s += lps[t * P.A + a];
+      P.logp[ag * P.M + row0 + t] = s;
     }
   }
 }
@@ -524,7 +566,8 @@ wide_alpha_grad_kernel(const float* __restrict__ logp2, int M, float targ_ent, f
 
 // ---- launches ----------------------------------------------------------------------------------------------------------------
 cudaError_t init_wide() {
-  cudaError_t e = cudaFuncSetAttribute(wide_policy_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_OUT * HID * 4);
+  cudaError_t e = cudaFuncSetAttribute(wide_policy_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (MAX_OUT * HID + WP_ROWS * (MAX_OUT + MAX_OUT / 2)) * 4);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(wide_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_OUT + 24) * HID * 4);
   cudaFuncAttributes fa;
@@ -546,7 +589,8 @@ cudaError_t launch_wide_first(const float* X, int64_t ldx, int M, int K, const f
   return cudaGetLastError();
 }
 cudaError_t launch_wide_policy_head(const WidePolicyArgs& p, const Stk& k, cudaStream_t st) {
-  wide_policy_head_kernel<<<dim3((p.M + WP_ROWS - 1) / WP_ROWS, k.n), 256, (size_t)p.out_dim * HID * 4, st>>>(p, k);
+  const size_t smem = ((size_t)p.out_dim * HID + (size_t)WP_ROWS * (p.out_dim + p.A)) * sizeof(float);
+  wide_policy_head_kernel<<<dim3((p.M + WP_ROWS - 1) / WP_ROWS, k.n), 256, smem, st>>>(p, k);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_q_head(const WideQArgs& q, const Stk& k, cudaStream_t st) {

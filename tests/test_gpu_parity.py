@@ -120,7 +120,9 @@ def test_protocol_matches_reference_fixture(name):
     # several Adam steps amplify summation-order noise (the first steps move every weight by ~lr*sign(g), so
     # a gradient that is pure rounding noise flips whole steps): allow 25x the reference's own
     # fp32-vs-float64 gap on the same trajectory (recorded in the fixture); single-step tests are tight
-    tol = max(2e-5, 25 * meta["reference_fp32_vs_fp64_oracle"])
+    # — capped at 2e-3 so that the bound can fail on the ill-conditioned cases too (sac_saturated's own gap is 2e-2);
+    # achieved deviations: profiles/r2_parity_report.txt (worst 6e-4, sac_clip_targfreq2; sac_saturated 2e-5)
+    tol = min(max(2e-5, 25 * meta["reference_fp32_vs_fp64_oracle"]), 2e-3)
     want = z["logs"]
     m = ~np.isnan(want)
     assert (np.isnan(rec["logs"]) == np.isnan(want)).all()
@@ -138,6 +140,15 @@ def test_protocol_matches_reference_fixture(name):
             assert ok, f"{name}: {g}/{n} off by {e:.3e} (tol {tol:.1e})"
     print(f"\n[{name}] worst deviation from the reference fixture {worst:.3e} "
           f"(reference fp32-vs-fp64 {meta['reference_fp32_vs_fp64_oracle']:.3e})")
+    if name == "sac_saturated":
+        # float64-anchored: on the deliberately ill-conditioned case the CUDA trajectory must be as close to the
+        # float64 oracle as the reference's own fp32 evaluation is, tensor group by tensor group (1.5x + 1e-4)
+        from tests.golden.make_golden import run_oracle
+        r32, r64 = run_oracle(inp, torch.float32, capturable=True), run_oracle(inp, torch.float64, capturable=True)
+        for g in GROUPS:
+            for n, t in rec.get(g, {}).items():
+                d_cuda, d_ref = rel_dev(t, r64[g][n]), rel_dev(r32[g][n], r64[g][n])
+                assert d_cuda <= 1.5 * d_ref + 1e-4, f"{g}/{n}: cuda-vs-fp64 {d_cuda:.3e} vs reference-fp32-vs-fp64 {d_ref:.3e}"
 
 
 @pytest.mark.parametrize("name,n_iter", [("sac_hopper", 1), ("sac_hopper", 10), ("sac_hopper", 100),

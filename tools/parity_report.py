@@ -83,6 +83,27 @@ def protocol_table(names):
                 wc = max(wc, rel_dev(t, r64[g][n]))
                 wr = max(wr, rel_dev(r32[g][n], r64[g][n]))
             print(f"   {name:28s} {g:13s} {wf:16.3e} {wc:12.3e} {wr:12.3e}")
+            if g.startswith("grad") and wc > 1e-5 and wc > 10 * wr:
+                # a gradient far outside the oracle's own fp32-vs-fp64 gap: show its structure. The update is
+                # discontinuous in two places: a ReLU unit whose pre-activation sits within rounding of zero may flip
+                # between two correct fp32 evaluations (that moves ONE row of a weight matrix, and that unit's bias /
+                # LayerNorm entries, by O(1/B) of the scale), and SAC's actor loss follows the arg-min critic of each batch
+                # row, so a row whose twin Q values are within rounding of each other may send its gradient through the
+                # other critic (that moves EVERY actor tensor by O(1/B): the case below — measured with the oracle alone:
+                # its capturable and non-capturable Adam variants, 1e-7 apart in the critics after one step, already give
+                # actor gradients 8e-4 apart on sac_hopper; the CUDA path lands on the reference's side, see cuda-vs-fixture).
+                for n, t in rec[g].items():
+                    d = (t.detach().cpu().double() - r64[g][n].double()).abs()
+                    big = d > 1e-5 * float(r64[g][n].abs().max())
+                    if bool(big.any()):
+                        where = ""
+                        if d.dim() == 2:
+                            rows_ = big.any(1).nonzero().flatten().tolist()
+                            where = f" in {len(rows_)} of {d.shape[0]} rows (rows {rows_[:6]}{'...' if len(rows_) > 6 else ''})"
+                        elif d.dim() == 3:
+                            rows_ = big.any(2).nonzero().tolist()
+                            where = f" in {len(rows_)} (critic, row) pairs {rows_[:6]}{'...' if len(rows_) > 6 else ''}"
+                        print(f"        {n:36s} {int(big.sum()):6d} of {d.numel():6d} elements off by > 1e-5 of the max{where}")
         print(f"   {name:28s} {'(fixture meta)':13s} reference fp32-vs-fp64 over all tensors and logs: "
               f"{meta['reference_fp32_vs_fp64_oracle']:.3e}")
 
