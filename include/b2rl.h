@@ -336,9 +336,12 @@ int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, con
                      const b2rl_stack_t* stack, void* stream);
 
 /* Head backward + ReLU mask + LayerNorm backward of layer 2: dz = LNbwd(ReLU'(dz3[:, :n_out] . w3)); part
- * [ceil(M/128)][3][256] per-CTA column sums. */
+ * [ceil(M/128)][3][256] per-CTA column sums. dw3_part (NULL, or [ceil(M/128)][3][256] with n_out == 1): per-CTA partials
+ * (slot 0) of the scalar head's weight gradient dW3[j] = sum_b dz3[b] * h2[b][j], h2 recomputed from x-hat — finish with
+ * b2rl_wide_colsum(dw3_part, P, G, off_w3, 0, 0, 0, ...): the critics then need no b2rl_tc_wgrad launch for w3. */
 int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,
-                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, const b2rl_stack_t* stack, void* stream);
+                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, float* dw3_part,
+                     const b2rl_stack_t* stack, void* stream);
 /* Column-sum partials -> gradients of bias / ln.weight / ln.bias at float offsets off_* of the gradient region G. */
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
                      const b2rl_stack_t* stack, void* stream);

@@ -42,7 +42,7 @@ cudaError_t launch_tc_linear_bwd(const float*, int, const float*, const float*, 
 cudaError_t launch_wide_policy_head(const b2rl_wide_policy_t&, const Stk&, cudaStream_t);
 cudaError_t launch_wide_q_head(const b2rl_wide_q_t&, const Stk&, cudaStream_t);
 cudaError_t launch_wide_ln_bwd(const float*, int, const float*, const float*, const float*, const float*, const float*, int, int,
-                               float*, float*, const Stk&, cudaStream_t);
+                               float*, float*, float*, const Stk&, cudaStream_t);
 cudaError_t launch_wide_actor_loss(const float*, const float*, const float*, const float*, int, int, float*, float*, float*,
                                    const Stk&, cudaStream_t);
 cudaError_t launch_wide_dqda(const float*, const float*, int, int, float*, const Stk&, cudaStream_t);
@@ -296,11 +296,13 @@ int b2rl_wide_q_head(const b2rl_wide_q_t* q, const b2rl_stack_t* stack, void* st
   return check_launch(b2rl::launch_wide_q_head(*q, make_stk(stack), (cudaStream_t)stream), "wide_q_head");
 }
 int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,
-                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, const b2rl_stack_t* stack, void* stream) {
+                     const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, float* dw3_part,
+                     const b2rl_stack_t* stack, void* stream) {
   if (int rc = check_stack(stack, "wide_ln_bwd")) return rc;
+  if (dw3_part && n_out != 1) return fail(B2RL_E_INVALID, "wide_ln_bwd: dw3_part is for scalar heads (n_out == 1)");
   if (!dz3 || !w3 || !xh || !dz || !part || M < 1 || n_out < 1 || n_out > B2RL_MAX_OUT) return fail(B2RL_E_INVALID, "wide_ln_bwd: bad arguments");
   if (layer_norm && (!g || !be || !stat)) return fail(B2RL_E_INVALID, "wide_ln_bwd: LayerNorm needs weight, bias and statistics");
-  return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, make_stk(stack), (cudaStream_t)stream), "wide_ln_bwd");
+  return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, dw3_part, make_stk(stack), (cudaStream_t)stream), "wide_ln_bwd");
 }
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
                      const b2rl_stack_t* stack, void* stream) {

@@ -274,16 +274,20 @@ __global__ void __launch_bounds__(256) wide_q_head_kernel(const __grid_constant_
 
 // ---- backward of the head and of layer 2's row-wise step: warp per row, 16 rows per warp, 128 per CTA -----------------
 // dh2[j] = sum_o dz3[row][o] * w3[o][j]; ReLU mask (recomputed from x-hat), LayerNorm backward -> dz2; per-CTA column
-// sums {sum dz, sum dn*xhat, sum dn} -> part[cta][3][256].
+// sums {sum dz, sum dn*xhat, sum dn} -> part[cta][3][256]. dw3_part (scalar heads only, n_out == 1: the critics): the
+// head's weight gradient dW3[j] = sum_b dz3[b] * h2[b][j] rides along — h2 is recomputed from x-hat, which this kernel
+// reads anyway — as a fourth column sum -> dw3_part[cta][3][256] (slot 0), so the critics need no tc_wgrad launch (a
+// 268 MB re-read of h2 per critic at 1 024 agents, 34 + 15 us per critic at batch 65 536) for a 256-float gradient.
 constexpr int WB_ROWS = 128;
 __global__ void __launch_bounds__(256)
 wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __restrict__ w3, const float* __restrict__ xh,
                    const float2* __restrict__ stat, const float* __restrict__ g, const float* __restrict__ be, int ln, int M,
-                   float* __restrict__ dz, float* __restrict__ part, long long ps) {
+                   float* __restrict__ dz, float* __restrict__ part, float* __restrict__ dw3_part, long long ps) {
   {  // stacked agents: blockIdx.y = agent
     const size_t ag = blockIdx.y;
     dz3 += ag * M * MAX_OUT, xh += ag * M * HID, dz += ag * M * HID, w3 += ag * ps;
     part += ag * gridDim.x * 3 * HID;
+    if (dw3_part) dw3_part += ag * gridDim.x * 3 * HID;
     if (ln) stat += ag * M, g += ag * ps, be += ag * ps;
   }
   extern __shared__ float wsm[];          // w3 [n_out][256], then the cross-warp reduction buffer [8][3][256]
@@ -292,12 +296,12 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   for (int i = t; i < n_out * HID; i += 256) w3s[i] = __ldg(w3 + i);
   __syncthreads();
-  float gj[8], bj[8], sdz[8], sdx[8], sdn[8];
+  float gj[8], bj[8], sdz[8], sdx[8], sdn[8], sw3[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     gj[i] = ln ? __ldg(g + l + 32 * i) : 1.f;
     bj[i] = ln ? __ldg(be + l + 32 * i) : 0.f;
-    sdz[i] = sdx[i] = sdn[i] = 0.f;
+    sdz[i] = sdx[i] = sdn[i] = sw3[i] = 0.f;
   }
   const int r0 = blockIdx.x * WB_ROWS + w * (WB_ROWS / 8);
   for (int rr = 0; rr < WB_ROWS / 8; ++rr) {
@@ -309,15 +313,19 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
       dh[i] = 0.f;
       x[i] = __ldg(xh + (size_t)row * HID + l + 32 * i);
     }
+    float d0 = 0.f;
     for (int o = 0; o < n_out; ++o) {
       const float d = __ldg(dz3 + (size_t)row * MAX_OUT + o);
+      if (o == 0) d0 = d;
 #pragma unroll
       for (int i = 0; i < 8; ++i) dh[i] = fmaf(d, w3s[o * HID + l + 32 * i], dh[i]);
     }
     float dn[8], dx[8], s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const bool on = ln ? (fmaf(x[i], gj[i], bj[i]) > 0.f) : (x[i] > 0.f);
+      const float pre = ln ? fmaf(x[i], gj[i], bj[i]) : x[i];  // the forward pre-ReLU value, recomputed bit-exactly
+      const bool on = pre > 0.f;
+      sw3[i] = fmaf(d0, on ? pre : 0.f, sw3[i]);
       dn[i] = on ? dh[i] : 0.f;
       dx[i] = dn[i] * gj[i];
       s1 += dx[i];
@@ -355,6 +363,16 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
 #pragma unroll
     for (int ww = 0; ww < 8; ++ww) s += red[(ww * 3 + v) * HID + t];
     part[((size_t)blockIdx.x * 3 + v) * HID + t] = s;
+  }
+  if (dw3_part) {  // (uniform) one more cross-warp reduction through the same buffer
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[w * HID + l + 32 * i] = sw3[i];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += red[ww * HID + t];
+    dw3_part[(size_t)blockIdx.x * 3 * HID + t] = s;
   }
 }
 
@@ -598,9 +616,10 @@ cudaError_t launch_wide_q_head(const WideQArgs& q, const Stk& k, cudaStream_t st
   return cudaGetLastError();
 }
 cudaError_t launch_wide_ln_bwd(const float* dz3, int n_out, const float* w3, const float* xh, const float* stat, const float* g,
-                               const float* be, int ln, int M, float* dz, float* part, const Stk& k, cudaStream_t st) {
+                               const float* be, int ln, int M, float* dz, float* part, float* dw3_part, const Stk& k,
+                               cudaStream_t st) {
   wide_ln_bwd_kernel<<<dim3((M + WB_ROWS - 1) / WB_ROWS, k.n), 256, (size_t)(n_out + 24) * HID * 4, st>>>(
-      dz3, n_out, w3, xh, reinterpret_cast<const float2*>(stat), g, be, ln, M, dz, part, k.ps);
+      dz3, n_out, w3, xh, reinterpret_cast<const float2*>(stat), g, be, ln, M, dz, part, dw3_part, k.ps);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,

@@ -70,16 +70,17 @@ class _Owner:
         return L.Seg(begin, end, lr, int(adam), int(polyak), counter, 1.0, int(clip))
 
 
-def _tc_wgrads(lib, stk, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, dz3, bump, st):
-    """dW1t = X0^T dZ1, dW2t = H1^T dZ2 (+ the w2n transposed shadow), dW3 = dZ3^T H2 of one network, on the tensor cores
-    (tc_wgrad.cu) into the arena's gradient region at G."""
+def _tc_wgrads(lib, stk, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, dz3, bump, st, w3_done=False):
+    """dW1t = X0^T dZ1, dW2t = H1^T dZ2, dW3 = dZ3^T H2 of one network, on the tensor cores (tc_wgrad.cu) into the arena's
+    gradient region at G. w3_done: the scalar head's gradient came out of wide_ln_bwd already (critics)."""
     o = net.off
     f = lambda off: G + 4 * off
     sc = scratch.data_ptr()
     L.check(lib.b2rl_tc_wgrad(x0_ptr, ldx, ldx, net.in_dim, dz1, M, f(o["w1t"]), None, sc, x3, None, stk, st), "tc_wgrad w1")
     # (no transposed copy into the w2n shadow's gradient: the Adam launch derives the shadow from w2t, adam.cu)
-    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), None, sc, x3, None, stk, st), "tc_wgrad w2")
-    L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, stk, st), "tc_wgrad w3")
+    L.check(lib.b2rl_tc_wgrad(h1, 256, 256, 256, dz2, M, f(o["w2t"]), None, sc, x3, bump if w3_done else None, stk, st), "tc_wgrad w2")
+    if not w3_done:
+        L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, stk, st), "tc_wgrad w3")
 
 
 def _wgrad_scratch(own: "_Owner", M):
@@ -109,6 +110,7 @@ class WideCritic:
         self.st1, self.st2 = torch.zeros(2, NM, 2, **f32), torch.zeros(2, NM, 2, **f32)
         self.P128, self.P8 = (M + 127) // 128, (M + 7) // 8   # per agent
         self.part1, self.part2 = torch.zeros(2, n * self.P128, 3, 256, **f32), torch.zeros(2, n * self.P128, 3, 256, **f32)
+        self.part3 = torch.zeros(2, n * self.P128, 3, 256, **f32)  # slot 0: per-CTA partials of the critics' head gradient
         self.sq = torch.zeros(2, n * self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
         self.ws = own.workspace(M)
         # lo parts (3xTF32) of the online and target regions, same offsets: one [2][region] mirror per agent, created (and
@@ -202,11 +204,14 @@ class WideCritic:
         for k in range(2):
             net, o = lay.critic[k], lay.critic[k].off
             first(rows.data_ptr(), rs, O + A, net, RP, self._ws(0, k), self.xh1[k].data_ptr(), self.st1[k].data_ptr())
-            hidden(self._ws(0, k), net, RP, self._ws(1, k), self.xh2[k].data_ptr(), self.st2[k].data_ptr(), 3 + k,
+            # (h2 itself never goes to memory: the head rides in the epilogue and its weight gradient is rebuilt from x-hat
+            # inside wide_ln_bwd; only x-hat and the statistics are kept for the backward pass)
+            hidden(self._ws(0, k), net, RP, none, self.xh2[k].data_ptr(), self.st2[k].data_ptr(), 3 + k,
                    head=q_head(net, RP, k, 1))
             L.check(lib.b2rl_wide_ln_bwd(self._dz3(k), 1, self._p(RP, o["w3"]), self.xh2[k].data_ptr(), self.st2[k].data_ptr(),
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
-                                         self._ws(3, k), self.part2[k].data_ptr(), stk, st), "wide_ln_bwd")
+                                         self._ws(3, k), self.part2[k].data_ptr(), self.part3[k].data_ptr(), stk, st), "wide_ln_bwd")
+            L.check(lib.b2rl_wide_colsum(self.part3[k].data_ptr(), self.P128, G, o["w3"], 0, 0, 0, stk, st), "wide_colsum (dW3)")
             w2t = self._p(RP, o["w2t"])
             L.check(lib.b2rl_tc_linear_bwd(self._ws(3, k), M, w2t, lo_of(5 + k, w2t), self.xh1[k].data_ptr(), self.st1[k].data_ptr(),
                                            self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
@@ -221,7 +226,8 @@ class WideCritic:
         # ---- weight gradients (wgrad.cu reads rows / H1 / H2 / DZ1 / DZ2 / DZ3 of the workspace), then Adam
         for k in range(2):
             _tc_wgrads(lib, stk, M, int(self.x3), self.gscratch, G, lay.critic[k], rows.data_ptr(), rs, self._ws(0, k), self._ws(1, k),
-                       self._ws(2, k), self._ws(3, k), self._dz3(k), ag.counters.data_ptr() + 8 * L.CTR_Q if k == 1 else None, st)
+                       self._ws(2, k), self._ws(3, k), self._dz3(k), ag.counters.data_ptr() + 8 * L.CTR_Q if k == 1 else None, st,
+                       w3_done=True)
         if adam:
             ag.launch_adam([ag.seg(lay.critic[0].begin, lay.critic[1].end, float(ag.hps.qnets_lr), True, polyak, L.CTR_Q)]
                            + list(extra_segs))
@@ -317,7 +323,7 @@ class WideActor:
             o = net.off
             L.check(lib.b2rl_wide_ln_bwd(dz3_ptr, n_out, self._p(RP, o["w3"]), xh2, st2,
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
-                                         dz2_out, part[0].data_ptr(), stk, st), "wide_ln_bwd")
+                                         dz2_out, part[0].data_ptr(), None, stk, st), "wide_ln_bwd")
             w2t = self._p(RP, o["w2t"])
             L.check(lib.b2rl_tc_linear_bwd(dz2_out, M, w2t, lo_of(slot, w2t), xh1, st1,
                                            self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
