@@ -268,9 +268,13 @@ typedef struct b2rl_stack {
 int b2rl_tc_linear(const float* X, int64_t ldx, int32_t M, const float* W, const float* W_lo, const float* bias, const float* g,
                    const float* be, int32_t layer_norm, int32_t relu, float* H, float* XH, float* stat, const b2rl_stack_t* stack,
                    void* stream);
-/* W_lo (here and in b2rl_tc_linear_bwd): NULL => plain TF32 products (~1e-3); else the "lo part" of W from
- * b2rl_tc_split_lo => 3xTF32: x = hi + lo, a.b ~ hi.hi + lo.hi + hi.lo as three MMAs into the same TMEM accumulator
- * — fp32-level accuracy (~1e-6) on the tensor cores (the activations' lo parts are made in shared memory). */
+/* W_lo (here, in b2rl_tc_linear_q and in b2rl_tc_linear_bwd): NULL => plain TF32 products (~1e-3); else 3xTF32: x = hi +
+ * lo, a.b ~ hi.hi + lo.hi + hi.lo as three MMAs into the same TMEM accumulator — fp32-level accuracy (~1e-6) on the
+ * tensor cores (the activations' lo parts are made in shared memory). The weights' lo parts come from W_lo, the mirror
+ * b2rl_tc_split_lo / the optimizer launch (b2rl_adam_args_t.lo) keep — or, with W_lo == W, are made in shared memory as
+ * well from each slab TMA delivers: no mirror to read or to keep current, the right trade when a weight slab serves one
+ * tile pair only (stacked agents: per-agent weights). The same three products either way (their order in the
+ * accumulation differs, so results agree to fp32 rounding, not bitwise). */
 int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, const b2rl_stack_t* stack, void* stream);
 
 /* ---- the wide (layer-by-layer, tensor-core) path for large batches: csrc/wide.cu, csrc/tc_linear.cu ------------------

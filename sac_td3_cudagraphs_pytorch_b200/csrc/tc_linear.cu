@@ -36,6 +36,10 @@ constexpr int TCM = 128, TCN = 256, TCK = 32, TC_THREADS = 256;
 //         fp32, re-truncated to TF32: 2^-21 of x); a.b ~ hi.hi + lo.hi + hi.lo, three MMAs into the same accumulator —
 //         fp32-level accuracy (~1e-6) from the tensor cores. The weights' lo parts are precomputed (tc_split_lo), the
 //         activations' are made in shared memory by the (otherwise idle) epilogue warps; 2-stage ring of 96 KB.
+// PREC 2: 3xTF32 with the WEIGHTS' lo parts made in shared memory as well (by the same two warps, from the slab TMA has
+//         just delivered) instead of being read from a precomputed mirror: for stacked agents every weight slab serves one
+//         tile pair only, so a mirror costs as many HBM bytes as the weights themselves (268 MB per launch at 1 024 agents,
+//         plus the optimizer's writes to keep it current) while the split costs ~2 us of two idle warps per 15 us tile.
 template <int PREC>
 struct __align__(1024) TcSmemT {
   static constexpr int STAGES = PREC ? 2 : 4;
@@ -175,7 +179,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   extern __shared__ unsigned char tc_raw[];  // (the swizzle atoms need 1024-byte alignment: align by hand)
   using Smem = TcSmemT<PREC>;
   constexpr int TC_STAGES = Smem::STAGES;
-  constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN * (PREC ? 2 : 1)) * TCK * sizeof(float);
+  constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN * (PREC == 1 ? 2 : 1)) * TCK * sizeof(float);
   Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (M + TCM - 1) / TCM;  // per agent (M = rows per agent)
@@ -222,6 +226,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_load_3d(S.a[s], &mapA, kb * TCK, m0, ag, &S.full[s]);
           tma_load_3d_mc(S.b[s] + half * TCK, &mapB, kb * TCK, half, ag, &S.full[s], 3);
           if constexpr (PREC == 1) tma_load_3d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, ag, &S.full[s], 3);
+          (void)mapBlo;
         }
       }
     }
@@ -244,11 +249,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
             if constexpr (PREC == 1) umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
           }
-          if constexpr (PREC == 1) {  // the two products whose operands TMA delivered run while the lo split is made
+          if constexpr (PREC != 0) {  // the product(s) whose operands TMA delivered run while the lo split is made
             mbar_wait_(&S.lo_ready[s], (it / TC_STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int k = 0; k < TCK / 8; ++k) umma_tf32(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
+            for (int k = 0; k < TCK / 8; ++k) {
+              umma_tf32(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
+              if constexpr (PREC == 2) umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+            }
           }
           umma_commit_mc(&S.empty[s], 3);  // (implies tcgen05.fence::before_thread_sync) frees the slot in both CTAs
         }
@@ -256,7 +264,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (warp >= 6) {  // ===== (3xTF32) the activations' lo parts, slab by slab as the ring fills
-    if constexpr (PREC == 1) {
+    if constexpr (PREC != 0) {
       const int lt = threadIdx.x - 192;  // 0..63
       for (int it = 0; it < my_tiles * KB; ++it) {
         const int s = it % TC_STAGES;
@@ -264,14 +272,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const float4* src = reinterpret_cast<const float4*>(S.a[s]);
         float4* dst = reinterpret_cast<float4*>(S.alo[s]);
 #pragma unroll 4
-        for (int i = 0; i < TCM * TCK / 4 / 64; ++i) {  // element-wise, so the swizzled layout carries over
-          const float4 x = src[lt + 64 * i];
-          float4 lo;
-          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          dst[lt + 64 * i] = lo;
+        for (int i = 0; i < TCM * TCK / 4 / 64; ++i)  // element-wise, so the swizzled layout carries over
+          dst[lt + 64 * i] = tf32_lo4(src[lt + 64 * i]);
+        if constexpr (PREC == 2) {  // the weight slab too (both halves: TMA multicast delivered the whole slab here)
+          const float4* bs = reinterpret_cast<const float4*>(S.b[s]);
+          float4* bd = reinterpret_cast<float4*>(S.blo[s]);
+#pragma unroll 4
+          for (int i = 0; i < TCN * TCK / 4 / 64; ++i) bd[lt + 64 * i] = tf32_lo4(bs[lt + 64 * i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
@@ -542,12 +549,15 @@ cudaError_t init_tc() {
   if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 0>, sizeof(TcSmemT<0>));
   if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 1>, sizeof(TcSmemT<1>));
   if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 1>, sizeof(TcSmemT<1>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 2>, sizeof(TcSmemT<2>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 2>, sizeof(TcSmemT<2>));
   cudaFuncAttributes fa;
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, tc_split_lo_kernel);
   return e;
 }
 
-// Wlo: the precomputed lo part of W (tc_split_lo) => 3xTF32; NULL => plain TF32
+// Wlo: the precomputed lo part of W (tc_split_lo) => 3xTF32; == W => 3xTF32 with the weights' lo parts made in the kernel;
+// NULL => plain TF32
 cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W, const float* Wlo, const float* bias,
                              const float* g, const float* be, int ln, int relu, float* H, float* XH, float* stat,
                              const b2rl_wide_q_t* head, const Stk& k, cudaStream_t st) {
@@ -559,6 +569,9 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
+  if (Wlo == W)
+    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, bias, g, be, ln, relu, H, XH,
+                    st2, none, q, k);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
     return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
@@ -578,6 +591,9 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
   const float* none = nullptr;
   const b2rl_wide_q_t q = {};
+  if (w2t_lo == w2t)
+    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1,
+                    part, q, k);
   if (w2t_lo) {
     if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
     return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, none, g1, be1, ln, 0, DZ1, xh, st1,

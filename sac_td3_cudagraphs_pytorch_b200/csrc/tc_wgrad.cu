@@ -27,7 +27,7 @@ struct __align__(1024) GSmemT {
   float b[STAGES][GN * GK];
   float alo[PREC ? STAGES : 1][PREC ? GM * GK : 4];
   float blo[PREC ? STAGES : 1][PREC ? GN * GK : 4];
-  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full;
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
@@ -73,34 +73,50 @@ __device__ __forceinline__ void g_split_lo(const float* src, float* dst, int n_f
   }
 }
 
-// grid (m tiles, splits, agents): CTA (mt, sp, ag) accumulates rows [sp * rows_per_split, ...) of agent ag's batch for
-// output rows [128 mt, 128 mt + 128) and writes its slice to part[ag][sp][MA_pad][256].
+// Work items (m tile, split, agent): item (mt, sp, ag) accumulates rows [sp * rows_per_split, ...) of agent ag's batch for
+// output rows [128 mt, 128 mt + 128) and writes its slice to part[ag][sp][MA_pad][256] (or, with one split, straight to the
+// gradient tensor). PERSISTENT: one CTA per SM walks items blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs on
+// across items and the accumulator is double-buffered in TMEM (2 x 256 columns), so the prologue (barrier init, TMEM
+// allocation, descriptor fetch) is paid once per SM and the epilogue of one item overlaps the loads and MMAs of the next —
+// a stacked population is 1 024-2 048 items of only 8 slabs each (the one-CTA-per-item version spent 60 % of its time
+// outside the main loop: 103 us to read 268 MB). Warps: 0 TMA producer, 1 MMA issuer, 2-5 epilogue (thread <-> TMEM lane
+// <-> output row m), 6-7 the operands' lo parts (3xTF32).
+constexpr int G_THREADS_P = 256;
 template <int PREC>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS_P, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Bn, int rows_per_split,
                 int MA_pad, int MA, float* __restrict__ part, float* __restrict__ Cd, float* __restrict__ Ctd,
-                unsigned long long* bump, long long ps, long long cs) {
+                unsigned long long* bump, long long ps, long long cs, int n_mt, int n_sp, int n_ag) {
   extern __shared__ unsigned char g_raw[];
   using Smem = GSmemT<PREC>;
   constexpr int ST = Smem::STAGES;
   Smem& S = *reinterpret_cast<Smem*>(g_raw + ((1024u - (gs32(g_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GM, sp = blockIdx.y, ag = blockIdx.z;
-  part += (size_t)ag * gridDim.y * MA_pad * GN;
-  const int kb0 = sp * rows_per_split, kb1 = min(Bn, kb0 + rows_per_split);
-  const int KB = (max(kb1 - kb0, 0) + GK - 1) / GK;
+  const int n_items = n_mt * n_sp * n_ag;
+  // item -> (mt, sp, ag, first batch row, slabs)
+  auto item_of = [&](int i, int& mt, int& sp, int& ag, int& kb0, int& KB) {
+    mt = i % n_mt;
+    sp = (i / n_mt) % n_sp;
+    ag = i / (n_mt * n_sp);
+    kb0 = sp * rows_per_split;
+    const int kb1 = min(Bn, kb0 + rows_per_split);
+    KB = (max(kb1 - kb0, 0) + GK - 1) / GK;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ST; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(1) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.empty[s])), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.lo_ready[s])), "r"(128) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.lo_ready[s])), "r"(64) : "memory");
     }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_full)), "r"(1) : "memory");
+    for (int b = 0; b < 2; ++b) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_full[b])), "r"(1) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_empty[b])), "r"(128) : "memory");
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gs32(&S.tmem_base)), "n"(GN) : "memory");
+  if (warp == 1) {  // two accumulator tiles of 256 fp32 columns x 128 lanes (all of TMEM: one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gs32(&S.tmem_base)), "n"(2 * GN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -109,97 +125,142 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer: 4 + 8 boxes of 32 columns x 32 batch rows per stage
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % ST;
-        if (kb >= ST) g_mbar_wait(&S.empty[s], ((kb / ST) - 1) & 1);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(G_A_BYTES + G_B_BYTES) : "memory");
-        const int row = kb0 + kb * GK;  // (rows beyond the batch are zero-filled by TMA: they add nothing)
+    if (lane == 0) {  // ===== TMA producer: 4 + 8 boxes of 32 columns x 32 batch rows per stage; the ring runs on across items
+      int it = 0;
+      for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+        int mt, sp, ag, kb0, KB;
+        item_of(i, mt, sp, ag, kb0, KB);
+        const int m0 = mt * GM;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % ST;
+          if (it >= ST) g_mbar_wait(&S.empty[s], ((it / ST) - 1) & 1);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(G_A_BYTES + G_B_BYTES) : "memory");
+          const int row = kb0 + kb * GK;  // (rows beyond the batch are zero-filled by TMA: they add nothing)
 #pragma unroll
-        for (int c = 0; c < GM / 32; ++c) g_tma_3d(S.a[s] + c * 1024, &mapA, m0 + 32 * c, row, ag, &S.full[s]);
+          for (int c = 0; c < GM / 32; ++c) g_tma_3d(S.a[s] + c * 1024, &mapA, m0 + 32 * c, row, ag, &S.full[s]);
 #pragma unroll
-        for (int c = 0; c < GN / 32; ++c) g_tma_3d(S.b[s] + c * 1024, &mapB, 32 * c, row, ag, &S.full[s]);
+          for (int c = 0; c < GN / 32; ++c) g_tma_3d(S.b[s] + c * 1024, &mapB, 32 * c, row, ag, &S.full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % ST;
-        g_mbar_wait(&S.full[s], (kb / ST) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < GK / 8; ++k)  // 8 batch rows (two atoms, 1 KB) of every chunk per instruction
-          g_umma(tmem, g_desc(S.a[s], k * 1024), g_desc(S.b[s], k * 1024), (kb | k) != 0);
-        if constexpr (PREC == 1) {  // (the hi.hi product runs while the lo parts are made)
-          g_mbar_wait(&S.lo_ready[s], (kb / ST) & 1);
+      int it = 0, nb = 0;  // nb: non-empty items so far (they alternate between the two accumulator tiles)
+      for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+        int mt, sp, ag, kb0, KB;
+        item_of(i, mt, sp, ag, kb0, KB);
+        if (KB == 0) continue;
+        const int buf = nb & 1;
+        const uint32_t acc = tmem + buf * GN;
+        if (nb >= 2) {  // the epilogue must have drained this tile (item nb - 2)
+          g_mbar_wait(&S.acc_empty[buf], ((nb >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % ST;
+          g_mbar_wait(&S.full[s], (it / ST) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-          for (int k = 0; k < GK / 8; ++k) {
-            g_umma(tmem, g_desc(S.alo[s], k * 1024), g_desc(S.b[s], k * 1024), 1);
-            g_umma(tmem, g_desc(S.a[s], k * 1024), g_desc(S.blo[s], k * 1024), 1);
+          for (int k = 0; k < GK / 8; ++k)  // 8 batch rows (two atoms, 1 KB) of every chunk per instruction
+            g_umma(acc, g_desc(S.a[s], k * 1024), g_desc(S.b[s], k * 1024), (kb | k) != 0);
+          if constexpr (PREC == 1) {  // (the hi.hi product runs while the lo parts are made)
+            g_mbar_wait(&S.lo_ready[s], (it / ST) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < GK / 8; ++k) {
+              g_umma(acc, g_desc(S.alo[s], k * 1024), g_desc(S.b[s], k * 1024), 1);
+              g_umma(acc, g_desc(S.a[s], k * 1024), g_desc(S.blo[s], k * 1024), 1);
+            }
           }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gs32(&S.empty[s])) : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gs32(&S.empty[s])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gs32(&S.acc_full[buf])) : "memory");
+        ++nb;
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gs32(&S.acc_full)) : "memory");
     }
-  } else {  // ===== epilogue warps: lo parts while the ring runs (PREC 1), then TMEM -> this split's slice
-    const int et = threadIdx.x - 64, lg = warp & 3;
+  } else if (warp >= 6) {  // ===== (3xTF32) both operands' lo parts, slab by slab as the ring fills
     if constexpr (PREC == 1) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % ST;
-        g_mbar_wait(&S.full[s], (kb / ST) & 1);
-        g_split_lo(S.a[s], S.alo[s], GM * GK / 4, et);
-        g_split_lo(S.b[s], S.blo[s], GN * GK / 4, et);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.lo_ready[s])) : "memory");
-      }
-    }
-    // Cd != NULL (one split: nothing to add up): the tile goes straight to the gradient tensor C [MA][256] of this agent
-    // (thread <-> row m: 128 contiguous bytes per chunk) and to its transpose Ct [256][MA] (lanes <-> consecutive m:
-    // coalesced), and CTA (0, 0, agent) advances the agent's update counter — no reduce launch, no scratch round trip.
-    const int mrow = m0 + 32 * lg + lane;
-    float* dst = Cd ? Cd + (size_t)ag * ps + (size_t)mrow * GN : part + ((size_t)sp * MA_pad + mrow) * GN;
-    float* dstT = (Cd && Ctd) ? Ctd + (size_t)ag * ps + mrow : nullptr;
-    if (Cd && bump && blockIdx.x == 0 && et == 0) bump[(size_t)ag * cs] += 1ull;
-    const bool live = mrow < MA;  // only rows that exist are written (dW1: 14 of 128, a critic's dW3: 1)
-    if (m0 + 32 * lg >= MA) {
-      // none of this warp's 32 rows exists: nothing to read back or write
-    } else if (KB > 0) {
-      g_mbar_wait(&S.acc_full, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tl = tmem + ((uint32_t)(32 * lg) << 16);
-      for (int c = 0; c < GN / 32; ++c) {
-        uint32_t r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(tl + c * 32));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-        if (live) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) d4[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
-          if (dstT) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dstT[(size_t)(c * 32 + i) * MA] = __uint_as_float(r[i]);
-          }
+      const int lt = threadIdx.x - 192;  // 0..63
+      int it = 0;
+      for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+        int mt, sp, ag, kb0, KB;
+        item_of(i, mt, sp, ag, kb0, KB);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % ST;
+          g_mbar_wait(&S.full[s], (it / ST) & 1);
+          const float4* a4 = reinterpret_cast<const float4*>(S.a[s]);
+          float4* al4 = reinterpret_cast<float4*>(S.alo[s]);
+#pragma unroll 4
+          for (int q = 0; q < GM * GK / 4 / 64; ++q) al4[lt + 64 * q] = tf32_lo4(a4[lt + 64 * q]);
+          const float4* b4 = reinterpret_cast<const float4*>(S.b[s]);
+          float4* bl4 = reinterpret_cast<float4*>(S.blo[s]);
+#pragma unroll 4
+          for (int q = 0; q < GN * GK / 4 / 64; ++q) bl4[lt + 64 * q] = tf32_lo4(b4[lt + 64 * q]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.lo_ready[s])) : "memory");
         }
       }
-    } else if (live) {  // an empty slice (more splits than slabs): zeros
-      for (int c = 0; c < GN / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (dstT)
-        for (int n = 0; n < GN; ++n) dstT[(size_t)n * MA] = 0.f;
+    }
+  } else {  // ===== epilogue warps 2-5: TMEM -> this item's slice (or the gradient tensor itself)
+    const int et = threadIdx.x - 64, lg = warp & 3;
+    int nb = 0;
+    for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+      int mt, sp, ag, kb0, KB;
+      item_of(i, mt, sp, ag, kb0, KB);
+      const int m0 = mt * GM;
+      // Cd != NULL (one split: nothing to add up): the tile goes straight to the gradient tensor C [MA][256] of this agent
+      // (thread <-> row m: 128 contiguous bytes per chunk) and to its transpose Ct [256][MA] (lanes <-> consecutive m:
+      // coalesced), and the item (mt 0, agent) advances the agent's update counter — no reduce launch, no scratch round trip.
+      const int mrow = m0 + 32 * lg + lane;
+      float* dst = Cd ? Cd + (size_t)ag * ps + (size_t)mrow * GN
+                      : part + (((size_t)ag * n_sp + sp) * MA_pad + mrow) * GN;
+      float* dstT = (Cd && Ctd) ? Ctd + (size_t)ag * ps + mrow : nullptr;
+      if (Cd && bump && mt == 0 && et == 0) bump[(size_t)ag * cs] += 1ull;
+      const bool live = mrow < MA;  // only rows that exist are written (dW1: 14 of 128, a critic's dW3: 1)
+      if (KB > 0) {
+        const int buf = nb & 1;
+        // (every epilogue warp waits, also one none of whose rows exists: the four warps then stay within one item of each
+        // other and of the MMA issuer, which the arrival counts of acc_empty rely on)
+        g_mbar_wait(&S.acc_full[buf], (nb >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (m0 + 32 * lg < MA) {  // (else nothing to read back or write)
+          const uint32_t tl = tmem + buf * GN + ((uint32_t)(32 * lg) << 16);
+          for (int c = 0; c < GN / 32; ++c) {
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(tl + c * 32));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+            if (live) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) d4[q] = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+              if (dstT) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) dstT[(size_t)(c * 32 + q) * MA] = __uint_as_float(r[q]);
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // hand the tile back to the MMA issuer
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.acc_empty[buf])) : "memory");
+        ++nb;
+      } else if (live) {  // an empty slice (more splits than slabs): zeros
+        for (int c = 0; c < GN / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dstT)
+          for (int n = 0; n < GN; ++n) dstT[(size_t)n * MA] = 0.f;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(GN) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * GN) : "memory");
 }
 
 // bump, if given, is incremented once (the update counter that wgrad.cu's extra CTA advances).
@@ -301,8 +362,14 @@ cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, con
   const bool direct = stacked && S == 1;  // one split per agent: the epilogue writes C / Ct itself (and bumps the counter)
   float* cd = direct ? C : nullptr;
   float* ctd = direct ? Ct : nullptr;
-  if (x3) tc_wgrad_kernel<1><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs);
-  else tc_wgrad_kernel<0><<<dim3(mt, S, k.n), G_THREADS, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs);
+  static int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int n_items = mt * S * k.n, grid = n_items < sms ? n_items : sms;  // persistent: one CTA per SM
+  if (x3) tc_wgrad_kernel<1><<<grid, G_THREADS_P, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs, mt, S, k.n);
+  else tc_wgrad_kernel<0><<<grid, G_THREADS_P, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs, mt, S, k.n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || direct) return e;
   tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8, k.n), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump, k.ps, k.cs);

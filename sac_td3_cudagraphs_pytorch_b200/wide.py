@@ -113,9 +113,12 @@ class WideCritic:
         self.part3 = torch.zeros(2, n * self.P128, 3, 256, **f32)  # slot 0: per-CTA partials of the critics' head gradient
         self.sq = torch.zeros(2, n * self.P8, 2, **f32)  # per-CTA {sum sq err, sum dQ} of wide_q_head
         self.ws = own.workspace(M)
-        # lo parts (3xTF32) of the online and target regions, same offsets: one [2][region] mirror per agent, created (and
-        # filled) here, kept current from now on by the owner's Adam / Polyak launches — no split pass per step
-        self.wlo = own.lo_mirror() if self.x3 else None
+        # lo parts (3xTF32) of the weights. One learner: a [2][region] mirror of the online and target regions at the
+        # parameters' own offsets, created (and filled) here, kept current from now on by the owner's Adam / Polyak launches —
+        # no split pass per step. Stacked agents: no mirror at all — every weight slab serves one tile pair, so the kernel
+        # splits it in shared memory (W_lo == W, include/b2rl.h) and 268 MB of reads per launch and the optimizer's mirror
+        # writes (2.2 of 9.4 MB per agent and critic step) disappear.
+        self.wlo = own.lo_mirror() if (self.x3 and not own.stacked) else None
         self.stk = own.stack(lo_stride=2 * own.layout.region)
         self.gscratch = _wgrad_scratch(own, M)
 
@@ -155,7 +158,9 @@ class WideCritic:
         act = lay.actor
 
         def lo_of(slot, w_ptr):
-            return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
+            if not self.x3:
+                return none
+            return w_ptr if self.wlo is None else self.wlo.data_ptr() + (w_ptr - base)
 
         def hidden(x_ptr, net, region, H, XH, stat, slot, head=None):
             o = net.off
@@ -269,7 +274,7 @@ class WideActor:
         self.part = torch.zeros(2, n * self.P128, 3, 256, **f32)
         self.part_s, self.part_du = torch.zeros(n * self.P256, 2, **f32), torch.zeros(n * self.P256, L.MAX_OUT, **f32)
         self.ws = own.workspace(M)
-        self.wlo = own.lo_mirror() if self.x3 else None  # (shared with WideCritic; see there)
+        self.wlo = own.lo_mirror() if (self.x3 and not own.stacked) else None  # (shared with WideCritic; see there)
         self.stk = own.stack(lo_stride=2 * own.layout.region)
         self.gscratch = _wgrad_scratch(own, M)
 
@@ -299,7 +304,9 @@ class WideActor:
         base = self._p(RP, 0)
 
         def lo_of(slot, w_ptr):
-            return self.wlo.data_ptr() + (w_ptr - base) if self.x3 else none
+            if not self.x3:
+                return none
+            return w_ptr if self.wlo is None else self.wlo.data_ptr() + (w_ptr - base)
 
         def hidden(x_ptr, net, H, XH, stat, slot):
             o = net.off
@@ -402,7 +409,9 @@ class WideActor:
                                     self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
                                     self.t1.data_ptr(), none, none, stk, st), "wide_first")
         w = self._p(RP, o["w2n"])
-        wl = self.wlo.data_ptr() + (w - self._p(RP, 0)) if self.x3 else none  # (current: the actor's Adam launch wrote it)
+        wl = none  # 3xTF32: the mirror the actor's Adam launch has just refreshed, or (stacked) the in-kernel split
+        if self.x3:
+            wl = w if self.wlo is None else self.wlo.data_ptr() + (w - self._p(RP, 0))
         L.check(lib.b2rl_tc_linear(self.t1.data_ptr(), 256, M, w, wl, self._p(RP, o["b2"]), self._p(RP, o["g2"]) if ln else none,
                                    self._p(RP, o["be2"]) if ln else none, ln, 1, self.t2.data_ptr(), none, none, stk, st), "tc_linear")
         p = L.WidePolicy()
