@@ -1,23 +1,24 @@
 // tc_wgrad.cu — weight gradients for LARGE batches on the tensor cores:  D[m][n] = sum_b A[b][m] * Bm[b][n]
 // (dW1t = X0^T dZ1, dW2t = H1^T dZ2, dW3 = dZ3^T H2: the contraction over the batch that `loss.backward()` does for the
 // parameters, agents/agent.py:235,283). wgrad.cu's FFMA tiles each walk the whole batch and take 1 ms at B = 65 536;
-// here the batch is split over CTAs (split-K), each CTA accumulates a 128 x 256 tile in TMEM over its slice, and a second
-// kernel adds the slices in a fixed order (deterministic) and writes the transposed copy the w2n shadow needs.
+// here the batch is split over work items (split-K), each accumulated as a 128 x 256 tile in TMEM over its slice, and a
+// second kernel adds the slices in a fixed order (deterministic). Stacked agents with one split per agent skip the second
+// kernel: the TMEM epilogue writes the gradient tensor itself.
 //
 // Both operands are MN-major (the batch index is the contraction and the slow one in memory). For 32-bit MN-major
 // operands tcgen05 accepts ONE shared-memory layout, SWIZZLE_128B_BASE32B (measured: with the plain 128-byte swizzle the
 // MMA returns zeros): 128-byte rows of 32 consecutive m, 32-byte units XORed with (row & 3), atoms of 4 batch rows —
 // in 16-byte units ((8,n),(4,k)):((1,LBO),(8,SBO)) (cute/atom/mma_traits_sm100.hpp). TMA writes exactly that with
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B and boxes of 32 columns x 32 batch rows: atoms 512 B apart (SBO), 32-column chunks
-// 4 KB apart (LBO). One tcgen05.mma kind::tf32 (K = 8) consumes two atoms (1 KB) of every chunk. PREC 1 = 3xTF32 as in tc_linear.cu (both operands are activations here: both lo parts are made in
-// shared memory by the epilogue warps).
+// 4 KB apart (LBO). One tcgen05.mma kind::tf32 (K = 8) consumes two atoms (1 KB) of every chunk. PREC 1 = 3xTF32 as in
+// tc_linear.cu (both operands are activations here: both lo parts are made in shared memory by two split warps).
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace b2rl {
 
-constexpr int GM = 128, GN = 256, GK = 32, G_THREADS = 192;
+constexpr int GM = 128, GN = 256, GK = 32;
 constexpr int G_A_BYTES = GM * GK * 4, G_B_BYTES = GN * GK * 4;  // 16 KB, 32 KB per stage
 
 template <int PREC>
@@ -59,20 +60,6 @@ __device__ __forceinline__ void g_umma(uint32_t tmem_d, uint64_t da, uint64_t db
       G_IDESC), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void g_split_lo(const float* src, float* dst, int n_float4, int et) {
-  const float4* s4 = reinterpret_cast<const float4*>(src);
-  float4* d4 = reinterpret_cast<float4*>(dst);
-  for (int i = et; i < n_float4; i += 128) {
-    const float4 x = s4[i];
-    float4 lo;
-    lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-    lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-    lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-    lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-    d4[i] = lo;
-  }
-}
-
 // Work items (m tile, split, agent): item (mt, sp, ag) accumulates rows [sp * rows_per_split, ...) of agent ag's batch for
 // output rows [128 mt, 128 mt + 128) and writes its slice to part[ag][sp][MA_pad][256] (or, with one split, straight to the
 // gradient tensor). PERSISTENT: one CTA per SM walks items blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs on

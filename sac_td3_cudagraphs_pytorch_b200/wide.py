@@ -1,13 +1,16 @@
-"""The wide (layer-by-layer, tensor-core) critic update for LARGE batches (BASELINE.json config 5).
+"""The wide (layer-by-layer, tensor-core) update for LARGE batches (BASELINE.json config 5) and for STACKED agents
+(config 4).
 
-``Agent.update_qnets`` (agents/agent.py:183-242) restated as a sequence of batch-parallel kernels
-(csrc/wide.cu) around the tcgen05 hidden layers (csrc/tc_linear.cu): the row-group kernels that win at
-batch 256 stream every layer's weights from L2 once per 8 rows and stay at ~10 TFLOP/s however large the
-batch is; here weights are read once per 128 rows (TMA) and the 256x256 products run on the tensor cores
-as TF32. Everything outside the products (LayerNorm, heads, TD target, losses, optimizer) is fp32 and the
-Philox noise is keyed exactly as in the row path, so both paths draw the same samples; results agree to
-TF32 accuracy (~1e-3, the north star's "looser stated bound" for tensor-core modes; tests/test_gpu_wide.py).
-Operates on an ``Agent``'s arena, counters, workspace and optimizer: it is a drop-in for the critic step.
+``Agent.update_qnets`` / ``update_actor`` (agents/agent.py:183-318) restated as a sequence of batch-parallel kernels
+(csrc/wide.cu) around the tcgen05 hidden layers (csrc/tc_linear.cu, csrc/tc_wgrad.cu): the row-group kernels that win
+at batch 256 stream every layer's weights from L2 once per 8 rows and stay at ~10 TFLOP/s however large the batch is;
+here weights are read once per 128 rows (TMA) and the 256x256 products — forward, dX and weight gradients — run on the
+tensor cores. Precision "3xtf32" (default) splits every operand into a TF32 hi and lo part and issues three MMAs per
+product: fp32-level accuracy (gradients within 2e-5 of the oracle, tests/test_gpu_wide.py); "tf32" is the plain,
+~1e-3-per-product mode (the north star's "looser stated bound"). Everything outside the products (LayerNorm, heads, TD
+target, losses, optimizer) is fp32 and the Philox noise is keyed exactly as in the row path, so both paths draw the same
+samples. The owner is an ``Agent`` (one learner) or a ``population.Population`` (n learners stacked along the rows of the
+same launches: include/b2rl.h, b2rl_stack_t).
 """
 from __future__ import annotations
 
