@@ -87,7 +87,12 @@ def _dp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_gradient_bucket_all_reduce_and_shadow_rebuild(tmp_path):
+def test_gradient_bucket_all_reduce(tmp_path):
+    """One all-reduce per optimizer step over the contiguous gradient span of the trained nets (W = 2, gloo). The w2n
+    shadows' gradient slots are NOT part of the contract any more: the Adam launch steps w2t from its reduced gradient and
+    writes the result to both layouts (csrc/adam.cu "shadow pairs"; checked on the GPU by tests/dp_worker.py: replicas
+    bit-identical, shadows == primaries transposed), so a slot that lies inside the span is summed along unused and the
+    last net's is left alone."""
     from sac_td3_cudagraphs_pytorch_b200.arena import make_layout
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -100,6 +105,5 @@ def test_gradient_bucket_all_reduce_and_shadow_rebuild(tmp_path):
     want = locals_[0] + locals_[1]
     for net in (*lay.critic, lay.actor):
         assert torch.equal(got[net.begin:net.core_end], want[net.begin:net.core_end])      # summed over ranks
-        w2t = got[net.off["w2t"]:net.off["w2t"] + 65536].view(256, 256)
-        w2n = got[net.off["w2n"]:net.off["w2n"] + 65536].view(256, 256)
-        assert torch.equal(w2n, w2t.t())                                                     # shadow == primary^T
+    last = lay.actor  # (its shadow slot lies beyond the reduced span: untouched local values)
+    assert torch.equal(got[last.off["w2n"]:last.off["w2n"] + 65536], locals_[0][last.off["w2n"]:last.off["w2n"] + 65536])
