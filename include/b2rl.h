@@ -285,6 +285,14 @@ int b2rl_tc_split_lo(const float* W, float* W_lo, int32_t n, const b2rl_stack_t*
 int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
                     const float* be, int32_t layer_norm, float* H, float* XH, float* stat, const b2rl_stack_t* stack, void* stream);
 
+/* The same first layer on the tensor cores (tc_linear.cu, MODE 1): the rows' inputs are the K-major operand (columns beyond
+ * K zero-filled by TMA), w1t — forward layout, i.e. MN-major — the other; LayerNorm / ReLU / outputs in the TMEM epilogue as
+ * in b2rl_tc_linear. x3 != 0: 3xTF32 (both lo parts made in shared memory), else plain TF32. Needs X 16-byte aligned and
+ * ldx a multiple of 4 floats (TMA); b2rl_wide_first is the fallback for other layouts. */
+int b2rl_tc_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
+                  const float* be, int32_t layer_norm, float* H, float* XH, float* stat, int32_t x3, const b2rl_stack_t* stack,
+                  void* stream);
+
 /* Backward dX product of the hidden layer on the tensor cores with the LayerNorm / ReLU backward of layer 1 in the
  * epilogue: DZ1 = LNbwd(ReLU'(DZ2 . W2)); w2t = forward-layout copy of fc_block_2.fc.weight; part [ceil(M/128)][3][256]
  * receives per-CTA column sums {sum dz, sum dn*xhat, sum dn}. */

@@ -108,6 +108,8 @@ SYMBOLS = {
     "b2rl_tc_split_lo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, _STK, C.c_void_p]),
     "b2rl_wide_first": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_tc_first": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, _STK, C.c_void_p]),
     "b2rl_tc_linear_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_wide_policy_head": (C.c_int, [C.POINTER(WidePolicy), _STK, C.c_void_p]),

@@ -57,6 +57,8 @@ cudaError_t launch_wide_critic_scalars(const float*, const float*, int, const fl
 cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*, int,
                              int, float*, float*, float*, const b2rl_wide_q_t*, const Stk&, cudaStream_t);
 cudaError_t launch_tc_split_lo(const float*, float*, int, const Stk&, cudaStream_t);
+cudaError_t launch_tc_first(const float*, int64_t, int, int, const float*, const float*, const float*, const float*, int, float*, float*,
+                            float*, int, const Stk&, cudaStream_t);
 }  // namespace b2rl
 
 namespace b2rl {
@@ -270,6 +272,17 @@ int b2rl_wide_first(const float* X, int64_t ldx, int32_t M, int32_t K, const flo
   if (int rc = check_stack(stack, "wide_first")) return rc;
   if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "wide_first: LayerNorm needs weight and bias");
   return check_launch(b2rl::launch_wide_first(X, ldx, M, K, w1t, b, g, be, layer_norm, H, XH, stat, make_stk(stack), (cudaStream_t)stream), "wide_first");
+}
+int b2rl_tc_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float* w1t, const float* b, const float* g,
+                  const float* be, int32_t layer_norm, float* H, float* XH, float* stat, int32_t x3, const b2rl_stack_t* stack,
+                  void* stream) {
+  if (!X || !w1t || !b || !H || M < 1 || K < 1 || K > 1024 || ldx < K) return fail(B2RL_E_INVALID, "tc_first: bad arguments");
+  if (layer_norm && (!g || !be)) return fail(B2RL_E_INVALID, "tc_first: LayerNorm needs weight and bias");
+  if (!aligned16(X) || (ldx & 3) || !aligned16(w1t) || !aligned16(H) || (XH && !aligned16(XH)))
+    return fail(B2RL_E_INVALID, "tc_first: X / w1t / H must be 16-byte aligned and ldx a multiple of 4 floats (use b2rl_wide_first otherwise)");
+  if (int rc = check_stack(stack, "tc_first")) return rc;
+  return check_launch(b2rl::launch_tc_first(X, ldx, M, K, w1t, b, g, be, layer_norm, H, XH, stat, x3, make_stk(stack), (cudaStream_t)stream),
+                      "tc_first");
 }
 int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
                        const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, const b2rl_stack_t* stack,

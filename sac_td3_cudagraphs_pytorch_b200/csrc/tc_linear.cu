@@ -83,11 +83,19 @@ __device__ __forceinline__ uint64_t umma_desc(const void* smem, int byte_off) {
 // cute::UMMA::InstrDescriptor: c_format F32 = 1 [4,6), a/b format TF32 = 2 [7,10) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)(TCM >> 4) << 24);
 
+template <bool B_MN = false>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  constexpr uint32_t idesc = TC_IDESC | (B_MN ? (1u << 16) : 0u);  // bit 16: b_major = MN
   asm volatile(
       "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate)
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// MN-major B operand, SWIZZLE_128B_BASE32B (layout type 1): 32-column chunks 4 KB apart (LBO), 4-row atoms 512 B apart (SBO);
+// one K = 8 instruction consumes two atoms (1 KB) of every chunk (tc_wgrad.cu)
+__device__ __forceinline__ uint64_t umma_desc_mn(const void* smem, int byte_off) {
+  const uint64_t addr = (uint64_t)((s32(smem) + (uint32_t)byte_off) & 0x3FFFFu) >> 4;
+  return addr | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 // multicast forms (2-CTA cluster): the load lands at the same shared-memory offset of every CTA in `mask` and counts its
 // bytes on the mbarrier at the same offset there; the commit arrives on the mbarrier of every CTA in `mask`
@@ -166,13 +174,18 @@ __device__ __forceinline__ float tile_colsum(const float* t, int lane) {  // sum
 }
 
 // MODE 0: forward  H = [ReLU](LayerNorm(A . B^T + bias)), optional x-hat / statistics outputs.
+// MODE 1: the FIRST layer (agents/nets.py:66-72), same epilogue: A = the rows' inputs X [M][K] (any K: ceil(K/32) slabs,
+//         columns beyond K zero-filled by TMA), B = w1t [K][256] in the arena's forward layout, i.e. an MN-MAJOR operand:
+//         staged by TMA in the SWIZZLE_128B_BASE32B layout tc_wgrad.cu uses (boxes of 32 columns x 32 k) and described to
+//         the tensor core with b_major = MN. The FFMA first layer (wide.cu) is issue/latency-bound at 152 us per 262 144
+//         rows; on the tensor cores the layer costs its epilogue.
 // MODE 2: backward dX: D = A . B^T with A = dz2 [M][256], B = w2t; epilogue = the ReLU mask and LayerNorm backward of
 //         layer 1 (x-hat and rstd read per row), H <- dz1, and this CTA's column sums {sum dz, sum dn*xhat, sum dn}
 //         -> part[cta][3][256] (bias / LayerNorm-affine gradients; deterministic: transposed through shared memory).
 template <int MODE, int PREC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapBlo, int M,
+                 const __grid_constant__ CUtensorMap mapBlo, int M, int kb_first,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part,
                  const __grid_constant__ b2rl_wide_q_t Q, const Stk K) {
@@ -211,7 +224,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   cluster_sync_all();  // the peer's barriers are initialised before anything of ours can land on them
   const uint32_t tmem = S.tmem_base;
-  constexpr int KB = HID / TCK;  // 8 k-slabs
+  const int KB = MODE == 1 ? kb_first : HID / TCK;  // k-slabs: 8 for the hidden layers, ceil(K / 32) for a first layer
+  constexpr bool BMN = MODE == 1;                   // the first layer's weights are MN-major (forward layout)
+  auto bdesc = [&](const float* base, int k) { return BMN ? umma_desc_mn(base, k * 1024) : umma_desc(base, k * 32); };
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: the ring runs on across tiles
@@ -224,6 +239,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (it >= TC_STAGES) mbar_wait_(&S.empty[s], ((it / TC_STAGES) - 1) & 1);  // free in BOTH CTAs
           mbar_expect_(&S.full[s], TC_STAGE_BYTES);
           tma_load_3d(S.a[s], &mapA, kb * TCK, m0, ag, &S.full[s]);
+          if constexpr (BMN) {  // this CTA's four 32-column chunks of the [32 k][256] slab, multicast to both CTAs
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              tma_load_3d_mc(S.b[s] + (4 * (int)crank + c) * 1024, &mapB, 32 * (4 * (int)crank + c), kb * TCK, ag, &S.full[s], 3);
+          } else
           tma_load_3d_mc(S.b[s] + half * TCK, &mapB, kb * TCK, half, ag, &S.full[s], 3);
           if constexpr (PREC == 1) tma_load_3d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, ag, &S.full[s], 3);
           (void)mapBlo;
@@ -246,16 +266,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int k = 0; k < TCK / 8; ++k) {  // UMMA K = 8 tf32 = 32 bytes: advance inside the 128-byte swizzle row
-            umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
-            if constexpr (PREC == 1) umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+            umma_tf32<BMN>(acc, umma_desc(S.a[s], k * 32), bdesc(S.b[s], k), (kb | k) != 0);
+            if constexpr (PREC == 1) umma_tf32<BMN>(acc, umma_desc(S.a[s], k * 32), bdesc(S.blo[s], k), 1);
           }
           if constexpr (PREC != 0) {  // the product(s) whose operands TMA delivered run while the lo split is made
             mbar_wait_(&S.lo_ready[s], (it / TC_STAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int k = 0; k < TCK / 8; ++k) {
-              umma_tf32(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
-              if constexpr (PREC == 2) umma_tf32(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+              umma_tf32<BMN>(acc, umma_desc(S.alo[s], k * 32), bdesc(S.b[s], k), 1);
+              if constexpr (PREC == 2) umma_tf32<BMN>(acc, umma_desc(S.a[s], k * 32), bdesc(S.blo[s], k), 1);
             }
           }
           umma_commit_mc(&S.empty[s], 3);  // (implies tcgen05.fence::before_thread_sync) frees the slot in both CTAs
@@ -287,28 +307,50 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
     const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
     float* T = S.tile[ew];
-    const float *cb = S.cvec[0], *cg = S.cvec[1], *cbe = S.cvec[2], *cw3 = S.cvec[3];
-    const bool head = MODE == 0 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
+    const bool head = MODE != 2 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
+    // Per-column vectors {bias, gamma, beta, w3} of the tile's agent, in shared memory (broadcast reads). One learner: loaded
+    // once. Stacked agents: every tile pair belongs to another agent, and loading its vectors at the top of the tile put a
+    // dependent global round trip and two barriers on every tile (ncu: 18 % long-scoreboard + 15-20 % barrier stalls of a
+    // first-layer launch) — so there are two sets, and the NEXT agent's set is fetched with cp.async while this tile is
+    // worked on. Set 1 lives where the other mode's data would be: in wpart (forward: unused) or in the bias / w3 slots of
+    // set 0 (backward: only gamma and beta are needed).
+    auto vptr = [&](int set, int q) -> float* {  // vector q of set `set`
+      if constexpr (MODE == 2) return S.cvec[set ? (q == 1 ? 0 : 3) : q];
+      return (set ? &S.wpart[0][0][0] : &S.cvec[0][0]) + q * HID;
+    };
+    auto fetch_vectors = [&](int ag, int set) {  // 64 cp.async of 16 bytes per vector; constants where a vector is absent
+      const size_t po = (size_t)ag * K.ps;
+      for (int i = et; i < 4 * (HID / 4); i += 128) {
+        const int q = i / (HID / 4), u = i - q * (HID / 4);
+        if (MODE == 2 && (q == 0 || q == 3)) continue;
+        const float* src = q == 0 ? bias : q == 1 ? g : q == 2 ? be : Q.w3;
+        float* dst = vptr(set, q) + 4 * u;
+        if (src) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s32(dst)), "l"(src + po + 4 * u) : "memory");
+        } else {
+          const float c = q == 1 ? 1.f : 0.f;
+          *reinterpret_cast<float4*>(dst) = make_float4(c, c, c, c);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     float v[32];
-    int cur_agent = -1;
+    int cset = 0;
+    if (my_tiles > 0) fetch_vectors(agent_of(0), 0);
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int tile = tile_of(ti), buf = ti & 1, ag = agent_of(ti);
-      if (ag != cur_agent) {  // per-column vectors of this agent: into shared memory once (broadcast reads); all four
-        if (cur_agent >= 0) asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps are done with the previous agent's
-        cur_agent = ag;
-        const size_t po = (size_t)ag * K.ps;
-        for (int i = et; i < 4 * HID; i += 128) {
-          const int q = i / HID, j = i - q * HID;
-          const float* src = q == 0 ? bias : q == 1 ? g : q == 2 ? be : Q.w3;
-          S.cvec[q][j] = src ? __ldg(src + po + j) : (q == 1 ? 1.f : 0.f);
-        }
+      const bool next_differs = ti + 1 < my_tiles && agent_of(ti + 1) != ag;
+      if (ti == 0 || agent_of(ti - 1) != ag) {  // this agent's set has landed, and everyone is done with the other set
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      if (next_differs) fetch_vectors(agent_of(ti + 1), cset ^ 1);
+      const float *cb = vptr(cset, 0), *cg = vptr(cset, 1), *cbe = vptr(cset, 2), *cw3 = vptr(cset, 3);
       const size_t arow = (size_t)ag * M;           // first row of this agent in the stacked arrays
       const int row0 = tile * TCM + 32 * lg, row = row0 + lane;  // inside the agent's batch
       const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
       const uint32_t tl = tmem + buf * TCN + ((uint32_t)(32 * lg) << 16);
-      if constexpr (MODE == 0) {
+      if constexpr (MODE != 2) {
         mbar_wait_(&S.acc_full[buf], (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float mean = 0.f, rstd = 1.f;
@@ -477,6 +519,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // (wpart is rewritten by the next tile)
       }
+      if (next_differs) cset ^= 1;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -525,6 +568,20 @@ static bool make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t co
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// MN-major operand [n_agents][rows = k][cols] fp32 (the arena's forward-layout w1t): boxes of 32 columns x 32 rows x 1 agent
+// in the SWIZZLE_128B_ATOM_32B pattern (tc_wgrad.cu); rows beyond `rows` are zero-filled
+static bool make_map_mn(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int n_agents, int64_t agent_stride) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  if (n_agents <= 1) agent_stride = rows * ld;
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(n_agents < 1 ? 1 : n_agents)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)agent_stride * sizeof(float)};
+  const cuuint32_t box[3] = {32, (cuuint32_t)TCK, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // lo part of a weight matrix for the 3xTF32 mode: lo = w - tf32_truncate(w)
 __global__ void tc_split_lo_kernel(const float* __restrict__ w, float* __restrict__ lo, int n, long long ps, long long ls) {
   w += (size_t)blockIdx.y * ps, lo += (size_t)blockIdx.y * ls;  // stacked agents: blockIdx.y = agent
@@ -551,6 +608,8 @@ cudaError_t init_tc() {
   if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 1>, sizeof(TcSmemT<1>));
   if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 2>, sizeof(TcSmemT<2>));
   if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 2>, sizeof(TcSmemT<2>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<1, 0>, sizeof(TcSmemT<0>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<1, 2>, sizeof(TcSmemT<2>));
   cudaFuncAttributes fa;
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, tc_split_lo_kernel);
   return e;
@@ -570,14 +629,32 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo == W)
-    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   }
-  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, bias, g, be, ln, relu, H, XH, st2,
+  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH, st2,
+                  none, q, k);
+}
+// First layer on the tensor cores: X [M][K] (row pitch ldx), w1t [K][256] forward layout; x3: 3xTF32 with both lo parts made
+// in the kernel, else plain TF32.
+cudaError_t launch_tc_first(const float* X, int64_t ldx, int M, int K, const float* w1t, const float* bias, const float* g,
+                            const float* be, int ln, float* H, float* XH, float* stat, int x3, const Stk& k, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, X, M, K, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map_mn(&mb, w1t, K, HID, HID, k.n, k.ps))
+    return cudaErrorInvalidValue;
+  const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
+  float2* st2 = reinterpret_cast<float2*>(stat);
+  float* none = nullptr;
+  const b2rl_wide_q_t q = {};
+  const int kb = (K + TCK - 1) / TCK;
+  if (x3)
+    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH,
+                    st2, none, q, k);
+  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH, st2,
                   none, q, k);
 }
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
@@ -592,14 +669,14 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   const float* none = nullptr;
   const b2rl_wide_q_t q = {};
   if (w2t_lo == w2t)
-    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   if (w2t_lo) {
     if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   }
-  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
 }
 
 }  // namespace b2rl

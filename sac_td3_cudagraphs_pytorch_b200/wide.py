@@ -73,6 +73,16 @@ class _Owner:
         return L.Seg(begin, end, lr, int(adam), int(polyak), counter, 1.0, int(clip))
 
 
+def _first_layer(lib, x_ptr, ldx, M, K, w1t, b, g, be, ln, H, XH, stat, x3, stk, st):
+    """First layer of a network (agents/nets.py:66-72): on the tensor cores (tc_linear.cu MODE 1) when TMA can address the
+    rows' inputs (16-byte aligned, pitch a multiple of 4 floats), else the FFMA kernel of wide.cu."""
+    import os
+    if x_ptr % 16 == 0 and ldx % 4 == 0 and os.environ.get("B2RL_WIDE_FIRST", "tc") == "tc":
+        L.check(lib.b2rl_tc_first(x_ptr, ldx, M, K, w1t, b, g, be, ln, H, XH, stat, x3, stk, st), "tc_first")
+    else:
+        L.check(lib.b2rl_wide_first(x_ptr, ldx, M, K, w1t, b, g, be, ln, H, XH, stat, stk, st), "wide_first")
+
+
 def _tc_wgrads(lib, stk, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, dz3, bump, st, w3_done=False):
     """dW1t = X0^T dZ1, dW2t = H1^T dZ2, dW3 = dZ3^T H2 of one network, on the tensor cores (tc_wgrad.cu) into the arena's
     gradient region at G. w3_done: the scalar head's gradient came out of wide_ln_bwd already (critics)."""
@@ -151,9 +161,9 @@ class WideCritic:
 
         def first(x_ptr, ldx, K, net, region, H, XH, stat):
             o = net.off
-            L.check(lib.b2rl_wide_first(x_ptr, ldx, M, K, self._p(region, o["w1t"]), self._p(region, o["b1"]),
-                                        self._p(region, o["g1"]) if ln else none, self._p(region, o["be1"]) if ln else none, ln,
-                                        H, XH, stat, stk, st), "wide_first")
+            _first_layer(lib, x_ptr, ldx, M, K, self._p(region, o["w1t"]), self._p(region, o["b1"]),
+                         self._p(region, o["g1"]) if ln else none, self._p(region, o["be1"]) if ln else none, ln,
+                         H, XH, stat, int(self.x3), stk, st)
 
         # every weight keeps its arena offset in the lo mirror (3xTF32), which the optimizer launches keep current
         base = self._p(RP, 0)
@@ -300,9 +310,9 @@ class WideActor:
 
         def first(x_ptr, ldx, K, net, H, XH, stat):
             o = net.off
-            L.check(lib.b2rl_wide_first(x_ptr, ldx, M, K, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
-                                        self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                        H, XH, stat, stk, st), "wide_first")
+            _first_layer(lib, x_ptr, ldx, M, K, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
+                         self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
+                         H, XH, stat, int(self.x3), stk, st)
 
         base = self._p(RP, 0)
 
@@ -408,9 +418,9 @@ class WideActor:
         act, o, RP = lay.actor, lay.actor.off, L.REGION_P
         none = None
         stk = C.byref(self.stk) if self.stk is not None else None
-        L.check(lib.b2rl_wide_first(rows.data_ptr(), rs, M, O, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
-                                    self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                    self.t1.data_ptr(), none, none, stk, st), "wide_first")
+        _first_layer(lib, rows.data_ptr(), rs, M, O, self._p(RP, o["w1t"]), self._p(RP, o["b1"]),
+                     self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
+                     self.t1.data_ptr(), none, none, int(self.x3), stk, st)
         w = self._p(RP, o["w2n"])
         wl = none  # 3xTF32: the mirror the actor's Adam launch has just refreshed, or (stacked) the in-kernel split
         if self.x3:

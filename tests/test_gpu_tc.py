@@ -163,3 +163,53 @@ def test_tc_wgrad_stacked_agents_match_torch(n_agents, Bn, MA, lda, x3):
                               int(x3), None, C.byref(stk1), st), "tc_wgrad")
     torch.cuda.synchronize()
     assert torch.equal(G1[0, :MA * 256], G[a, :MA * 256])
+
+
+@pytest.mark.parametrize("x3", [False, True])
+@pytest.mark.parametrize("n_agents,M,K,ldx", [(1, 256, 14, 28), (3, 200, 14, 28), (1, 1000, 11, 16), (2, 256, 393, 396), (1, 128, 32, 32),
+                                              (4, 72, 5, 8)])
+def test_tc_first_layer_matches_torch(n_agents, M, K, ldx, x3):
+    """The first layer on the tensor cores (MODE 1): X [M][K] K-major, w1t [K][256] MN-major (the arena's forward layout),
+    K not a multiple of 32 (tails zero-filled by TMA on both operands), stacked agents with their own weights, vs float64
+    and vs the FFMA kernel b2rl_wide_first."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(7 * n_agents + M + K)
+    ps = ((K * 256 + 3 * 256 + 3) // 4) * 4 + 64
+    P = torch.zeros(n_agents, ps, device="cuda")
+    P[:, :K * 256] = torch.randn(n_agents, K * 256, device="cuda", generator=g) / (K ** 0.5)
+    ob, og, obe = K * 256, K * 256 + 256, K * 256 + 512
+    P[:, ob:ob + 256] = torch.randn(n_agents, 256, device="cuda", generator=g) * 0.1
+    P[:, og:og + 256] = 1.0 + 0.1 * torch.randn(n_agents, 256, device="cuda", generator=g)
+    P[:, obe:obe + 256] = 0.1 * torch.randn(n_agents, 256, device="cuda", generator=g)
+    X = torch.randn(n_agents * M, ldx, device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    stk = C.byref(L.Stack(n_agents, 0, ps, 0, 0, 0, 0)) if n_agents > 1 else None
+    base = P.data_ptr()
+    outs = []
+    for fn in ("tc", "ffma"):
+        H = torch.full((n_agents * M, 256), float("nan"), device="cuda")
+        XH = torch.full((n_agents * M, 256), float("nan"), device="cuda")
+        stat = torch.zeros(n_agents * M, 2, device="cuda")
+        if fn == "tc":
+            L.check(lib.b2rl_tc_first(X.data_ptr(), ldx, M, K, base, base + 4 * ob, base + 4 * og, base + 4 * obe, 1, H.data_ptr(),
+                                      XH.data_ptr(), stat.data_ptr(), int(x3), stk, st), "tc_first")
+        else:
+            L.check(lib.b2rl_wide_first(X.data_ptr(), ldx, M, K, base, base + 4 * ob, base + 4 * og, base + 4 * obe, 1, H.data_ptr(),
+                                        XH.data_ptr(), stat.data_ptr(), stk, st), "wide_first")
+        torch.cuda.synchronize()
+        outs.append((H, XH, stat))
+    tol = 4e-6 if x3 else 3e-3
+    for a in range(n_agents):
+        W = P[a, :K * 256].view(K, 256).double()
+        z = X[a * M:(a + 1) * M, :K].double() @ W + P[a, ob:ob + 256].double()
+        mu, var = z.mean(1, keepdim=True), z.var(1, unbiased=False, keepdim=True)
+        xh = (z - mu) / torch.sqrt(var + 1e-5)
+        want = torch.relu(xh * P[a, og:og + 256].double() + P[a, obe:obe + 256].double())
+        for (H, XH, stat), t in zip(outs, (tol, 2e-6)):
+            sl = slice(a * M, (a + 1) * M)
+            assert torch.isfinite(H[sl]).all()
+            assert float((H[sl].double() - want).abs().max()) / float(want.abs().max()) <= t
+            assert float((XH[sl].double() - xh).abs().max()) / float(xh.abs().max()) <= t
+            assert float((stat[sl, 0].double() - mu[:, 0]).abs().max()) <= 4 * t * max(1.0, float(mu.abs().max()))
