@@ -3,6 +3,7 @@ loaded (or built with nvcc when absent) importing the update path raises."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HID = 256
@@ -146,7 +147,7 @@ SYMBOLS = {
     "b2rl_ffma_probe": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_void_p]),
 }
 
-LIB_PATH = Path(__file__).resolve().parent / "libb2rl.so"
+LIB_PATH = Path(os.environ.get("B2RL_LIB") or Path(__file__).resolve().parent / "libb2rl.so")
 _lib = None
 
 

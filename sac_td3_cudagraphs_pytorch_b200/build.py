@@ -17,8 +17,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
-LIB = PKG / "libb2rl.so"
-STAMP = PKG / "csrc" / ".build_stamp"
+LIB = Path(os.environ.get("B2RL_LIB") or PKG / "libb2rl.so")  # B2RL_LIB: an instrumented build beside the product one
+STAMP = PKG / "csrc" / (".build_stamp" if LIB.name == "libb2rl.so" else f".build_stamp_{LIB.stem}")
 
 SOURCES = ["api.cu", "replay.cu", "critic.cu", "actor.cu", "wgrad.cu", "adam.cu", "tc_linear.cu", "wide.cu", "tc_wgrad.cu"]
 NVCC_FLAGS = [
