@@ -40,14 +40,26 @@ constexpr int TCM = 128, TCN = 256, TCK = 32, TC_THREADS = 256;
 //         just delivered) instead of being read from a precomputed mirror: for stacked agents every weight slab serves one
 //         tile pair only, so a mirror costs as many HBM bytes as the weights themselves (268 MB per launch at 1 024 agents,
 //         plus the optimizer's writes to keep it current) while the split costs ~2 us of two idle warps per 15 us tile.
-template <int PREC>
+// PAIR (the 3xTF32 hidden layers, forward and backward): the two CTAs of the cluster run ONE tensor-core instruction
+// together — tcgen05.mma.cta_group::2, M = 256: CTA r supplies its own 128 rows of A and rows [128r, 128r + 128) of the
+// weight slab (its half of N), and receives its own 128 x 256 accumulator tile in its own TMEM. Each CTA then holds (and,
+// for stacked agents, splits) only HALF of every weight slab: a stage is 64 KB instead of 96, so the 192 KB ring has three
+// stages, and each SM's tensor core reads 8 KB of operands per instruction from its shared memory instead of 12 (three
+// products per k-step make the operand reads of the MMAs the largest shared-memory client of the kernel).
+template <int MODE, int PREC>
+struct TcCfg {
+  static constexpr bool PAIR = MODE != 1 && PREC != 0;
+  static constexpr int BN = PAIR ? TCN / 2 : TCN;            // weight rows per CTA and stage
+  static constexpr int STAGES = PAIR ? 3 : (PREC ? 2 : 4);
+};
+template <int MODE, int PREC>
 struct __align__(1024) TcSmemT {
-  static constexpr int STAGES = PREC ? 2 : 4;
+  static constexpr int STAGES = TcCfg<MODE, PREC>::STAGES, BN = TcCfg<MODE, PREC>::BN;
   float a[STAGES][TCM * TCK];  // 16 KB per stage, 128-byte rows, swizzle-128B
-  float b[STAGES][TCN * TCK];  // 32 KB per stage
+  float b[STAGES][BN * TCK];   // 32 KB per stage (PAIR: 16 KB)
   float alo[PREC ? STAGES : 1][PREC ? TCM * TCK : 4];
-  float blo[PREC ? STAGES : 1][PREC ? TCN * TCK : 4];
-  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full[2], acc_empty[2];
+  float blo[PREC ? STAGES : 1][PREC ? BN * TCK : 4];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
   // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
   // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials
@@ -110,6 +122,32 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
                "h"(mask)
                : "memory");
+}
+// ---- cta_group::2 forms: issued by one thread of the cluster's rank-0 CTA on behalf of both SMs
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TCN >> 3) << 17) | ((uint32_t)((2 * TCM) >> 4) << 24);
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` of BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the mbarrier at the same offset as `bar` in the cluster's rank-0 CTA. Plain (CTA-scope release) forms on both
+// sides, as for every other cross-CTA mbarrier of these kernels: what the arrivals order is shared-memory traffic the
+// issuing threads have already fenced towards the async proxy (split warps) or TMEM reads completed with
+// tcgen05.wait::ld (epilogue). The .release.cluster / .acquire.cluster forms compile to MEMBAR.ALL.GPU + ERRBAR per
+// arrival — which also waits for the epilogue's global stores — and CCTL.IVALL per wait: measured 68 instead of 55 us
+// per 65 536-row launch (ncu SASS view).
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(s32(bar)));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -190,9 +228,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part,
                  const __grid_constant__ b2rl_wide_q_t Q, const Stk K) {
   extern __shared__ unsigned char tc_raw[];  // (the swizzle atoms need 1024-byte alignment: align by hand)
-  using Smem = TcSmemT<PREC>;
+  using Smem = TcSmemT<MODE, PREC>;
   constexpr int TC_STAGES = Smem::STAGES;
-  constexpr uint32_t TC_STAGE_BYTES = (TCM + TCN * (PREC == 1 ? 2 : 1)) * TCK * sizeof(float);
+  constexpr bool PAIR = TcCfg<MODE, PREC>::PAIR;
+  // bytes TMA delivers into one stage of THIS CTA (multicast path: the whole weight slab, half of it sent by the peer)
+  constexpr uint32_t TC_STAGE_BYTES = (TCM + Smem::BN * (PREC == 1 ? 2 : 1)) * TCK * sizeof(float);
   Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (M + TCM - 1) / TCM;  // per agent (M = rows per agent)
@@ -211,13 +251,25 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   auto tile_of = [&](int i) { return 2 * ((ci + i * n_clusters) % ppa) + (int)crank; };  // tile inside the agent's batch
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init_(&S.full[s], 1); mbar_init_(&S.empty[s], 2); mbar_init_(&S.lo_ready[s], 64); }  // empty: both CTAs' MMA commits
-    for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], 128); }
+    // multicast path: `empty` collects both CTAs' MMA commits. PAIR: one commit reaches both CTAs; the issuing CTA's
+    // lo_ready / acc_empty collect the split warps / epilogue threads of BOTH CTAs.
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init_(&S.full[s], 1);
+      mbar_init_(&S.empty[s], PAIR ? 1 : 2);
+      mbar_init_(&S.lo_ready[s], PAIR ? 128 : 64);
+      mbar_init_(&S.peer_full[s], 1);  // (PAIR, rank 0) the peer CTA's slab has landed: relayed by the peer's idle MMA warp
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], PAIR ? 256 : 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two accumulator tiles of 256 fp32 columns x 128 lanes (all 512 columns: one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&S.tmem_base)), "n"(2 * TCN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {  // (the same warp of both CTAs, the same destination offset)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&S.tmem_base)), "n"(2 * TCN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&S.tmem_base)), "n"(2 * TCN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -239,19 +291,58 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           if (it >= TC_STAGES) mbar_wait_(&S.empty[s], ((it / TC_STAGES) - 1) & 1);  // free in BOTH CTAs
           mbar_expect_(&S.full[s], TC_STAGE_BYTES);
           tma_load_3d(S.a[s], &mapA, kb * TCK, m0, ag, &S.full[s]);
-          if constexpr (BMN) {  // this CTA's four 32-column chunks of the [32 k][256] slab, multicast to both CTAs
+          if constexpr (PAIR) {  // this CTA's half of the weight slab, into its own shared memory only
+            tma_load_3d(S.b[s], &mapB, kb * TCK, half, ag, &S.full[s]);
+            if constexpr (PREC == 1) tma_load_3d(S.blo[s], &mapBlo, kb * TCK, half, ag, &S.full[s]);
+          } else if constexpr (BMN) {  // this CTA's four 32-column chunks of the [32 k][256] slab, multicast to both CTAs
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               tma_load_3d_mc(S.b[s] + (4 * (int)crank + c) * 1024, &mapB, 32 * (4 * (int)crank + c), kb * TCK, ag, &S.full[s], 3);
           } else
           tma_load_3d_mc(S.b[s] + half * TCK, &mapB, kb * TCK, half, ag, &S.full[s], 3);
-          if constexpr (PREC == 1) tma_load_3d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, ag, &S.full[s], 3);
+          if constexpr (PREC == 1 && !PAIR) tma_load_3d_mc(S.blo[s] + half * TCK, &mapBlo, kb * TCK, half, ag, &S.full[s], 3);
           (void)mapBlo;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer
+    if (PAIR && lane == 0 && crank == 0) {  // ===== MMA issuer of the pair: every instruction drives both SMs
+      int it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i & 1;
+        const uint32_t acc = tmem + buf * TCN;
+        if (i >= 2) {  // BOTH epilogues must have drained this buffer (tile i - 2)
+          mbar_wait_(&S.acc_empty[buf], ((i >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          mbar_wait_(&S.full[s], (it / TC_STAGES) & 1);               // this CTA's slab has landed ...
+          mbar_wait_(&S.peer_full[s], (it / TC_STAGES) & 1);  // ... and the peer's
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < TCK / 8; ++k) {  // the product(s) whose operands TMA delivered run while the lo split is made
+            umma_tf32_pair(acc, umma_desc(S.a[s], k * 32), umma_desc(S.b[s], k * 32), (kb | k) != 0);
+            if constexpr (PREC == 1) umma_tf32_pair(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+          }
+          mbar_wait_(&S.lo_ready[s], (it / TC_STAGES) & 1);  // both CTAs' split warps are done with this slab
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < TCK / 8; ++k) {
+            umma_tf32_pair(acc, umma_desc(S.alo[s], k * 32), umma_desc(S.b[s], k * 32), 1);
+            if constexpr (PREC == 2) umma_tf32_pair(acc, umma_desc(S.a[s], k * 32), umma_desc(S.blo[s], k * 32), 1);
+          }
+          umma_commit_pair(&S.empty[s]);  // frees the slot in both CTAs
+        }
+        umma_commit_pair(&S.acc_full[buf]);
+      }
+    } else if (PAIR && lane == 0) {  // rank 1: tell the issuer when this CTA's slabs have landed
+      for (int it = 0; it < my_tiles * KB; ++it) {
+        const int s = it % TC_STAGES;
+        mbar_wait_(&S.full[s], (it / TC_STAGES) & 1);
+        mbar_arrive_rank0(&S.peer_full[s]);
+      }
+    } else if (!PAIR && lane == 0) {  // ===== MMA issuer
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int buf = i & 1;
@@ -294,14 +385,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 4
         for (int i = 0; i < TCM * TCK / 4 / 64; ++i)  // element-wise, so the swizzled layout carries over
           dst[lt + 64 * i] = tf32_lo4(src[lt + 64 * i]);
-        if constexpr (PREC == 2) {  // the weight slab too (both halves: TMA multicast delivered the whole slab here)
+        if constexpr (PREC == 2) {  // the weight slab too (multicast path: both halves landed here; PAIR: this CTA's half)
           const float4* bs = reinterpret_cast<const float4*>(S.b[s]);
           float4* bd = reinterpret_cast<float4*>(S.blo[s]);
 #pragma unroll 4
-          for (int i = 0; i < TCN * TCK / 4 / 64; ++i) bd[lt + 64 * i] = tf32_lo4(bs[lt + 64 * i]);
+          for (int i = 0; i < Smem::BN * TCK / 4 / 64; ++i) bd[lt + 64 * i] = tf32_lo4(bs[lt + 64 * i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA's reads
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
+        if constexpr (PAIR) mbar_arrive_rank0(&S.lo_ready[s]);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
       }
     }
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
@@ -379,7 +471,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tmem_ld32(tl + c * 32, v);
           if (c == TCN / 32 - 1) {  // last TMEM read of this tile: hand the buffer back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
+            if constexpr (PAIR) mbar_arrive_rank0(&S.acc_empty[buf]);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
           }
           float h[32];
 #pragma unroll
@@ -479,7 +572,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tmem_ld32(tl + c * 32, v);
           if (c == TCN / 32 - 1) {  // last TMEM read of this tile
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
+            if constexpr (PAIR) mbar_arrive_rank0(&S.acc_empty[buf]);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
           }
           float dz[32];
 #pragma unroll
@@ -525,7 +619,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   cluster_sync_all();  // (the peer's last commits arrive on this CTA's barriers: do not exit under them)
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TCN) : "memory");
+  if (warp == 1) {
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TCN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * TCN) : "memory");
+  }
 }
 
 static int tc_grid(int M, int n_agents) {  // persistent: one CTA per SM (or per tile when there are fewer)
@@ -602,14 +699,14 @@ static cudaError_t tc_opt_in(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes + 1024);
 }
 cudaError_t init_tc() {
-  cudaError_t e = tc_opt_in(tc_linear_kernel<0, 0>, sizeof(TcSmemT<0>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 0>, sizeof(TcSmemT<0>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 1>, sizeof(TcSmemT<1>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 1>, sizeof(TcSmemT<1>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 2>, sizeof(TcSmemT<2>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 2>, sizeof(TcSmemT<2>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<1, 0>, sizeof(TcSmemT<0>));
-  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<1, 2>, sizeof(TcSmemT<2>));
+  cudaError_t e = tc_opt_in(tc_linear_kernel<0, 0>, sizeof(TcSmemT<0, 0>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 0>, sizeof(TcSmemT<2, 0>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 1>, sizeof(TcSmemT<0, 1>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 1>, sizeof(TcSmemT<2, 1>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<0, 2>, sizeof(TcSmemT<0, 2>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<2, 2>, sizeof(TcSmemT<2, 2>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<1, 0>, sizeof(TcSmemT<1, 0>));
+  if (e == cudaSuccess) e = tc_opt_in(tc_linear_kernel<1, 2>, sizeof(TcSmemT<1, 2>));
   cudaFuncAttributes fa;
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, tc_split_lo_kernel);
   return e;
@@ -629,14 +726,14 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo == W)
-    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   }
-  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH, st2,
+  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0, 0>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH, st2,
                   none, q, k);
 }
 // First layer on the tensor cores: X [M][K] (row pitch ldx), w1t [K][256] forward layout; x3: 3xTF32 with both lo parts made
@@ -652,9 +749,9 @@ cudaError_t launch_tc_first(const float* X, int64_t ldx, int M, int K, const flo
   const b2rl_wide_q_t q = {};
   const int kb = (K + TCK - 1) / TCK;
   if (x3)
-    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH,
+    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<1, 2>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH,
                     st2, none, q, k);
-  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH, st2,
+  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<1, 0>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH, st2,
                   none, q, k);
 }
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
@@ -669,14 +766,14 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   const float* none = nullptr;
   const b2rl_wide_q_t q = {};
   if (w2t_lo == w2t)
-    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2, 2>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   if (w2t_lo) {
     if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<1>) + 1024, st, ma, mb, ml, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<2, 1>) + 1024, st, ma, mb, ml, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   }
-  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<0>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<2, 0>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
 }
 
 }  // namespace b2rl
