@@ -50,20 +50,23 @@ template <int MODE, int PREC>
 struct TcCfg {
   static constexpr bool PAIR = MODE != 1 && PREC != 0;
   static constexpr int BN = PAIR ? TCN / 2 : TCN;            // weight rows per CTA and stage
-  static constexpr int STAGES = PAIR ? 3 : (PREC ? 2 : 4);
+  // (the backward kernel is bound by its epilogue: it gives a stage's worth of shared memory to the x-hat rings)
+  static constexpr int STAGES = PAIR ? (MODE == 2 ? 2 : 3) : (PREC ? 2 : (MODE == 2 ? 3 : 4));
+  static constexpr int NXB = MODE == 2 ? 4 : 1;  // staging tiles per epilogue warp
 };
 template <int MODE, int PREC>
 struct __align__(1024) TcSmemT {
-  static constexpr int STAGES = TcCfg<MODE, PREC>::STAGES, BN = TcCfg<MODE, PREC>::BN;
+  static constexpr int STAGES = TcCfg<MODE, PREC>::STAGES, BN = TcCfg<MODE, PREC>::BN, NXB = TcCfg<MODE, PREC>::NXB;
   float a[STAGES][TCM * TCK];  // 16 KB per stage, 128-byte rows, swizzle-128B
   float b[STAGES][BN * TCK];   // 32 KB per stage (PAIR: 16 KB)
   float alo[PREC ? STAGES : 1][PREC ? TCM * TCK : 4];
   float blo[PREC ? STAGES : 1][PREC ? BN * TCK : 4];
-  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2], xfull[4][NXB];
   uint32_t tmem_base;
   // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
-  // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials
-  alignas(128) float tile[4][32 * 32];
+  // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials. MODE 2: four tiles per warp — the ring TMA
+  // fills with the x-hat chunks the LayerNorm backward reads (and the staging tile of the chunk being worked on)
+  alignas(1024) float tile[4][NXB][32 * 32];
   alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
   float wpart[4][3][HID];
 };
@@ -223,7 +226,7 @@ __device__ __forceinline__ float tile_colsum(const float* t, int lane) {  // sum
 template <int MODE, int PREC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapBlo, int M, int kb_first,
+                 const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapX, int M, int kb_first,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part,
                  const __grid_constant__ b2rl_wide_q_t Q, const Stk K) {
@@ -260,6 +263,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init_(&S.peer_full[s], 1);  // (PAIR, rank 0) the peer CTA's slab has landed: relayed by the peer's idle MMA warp
     }
     for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], PAIR ? 256 : 128); }
+    for (int e = 0; e < 4; ++e)
+      for (int j = 0; j < Smem::NXB; ++j) mbar_init_(&S.xfull[e][j], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: two accumulator tiles of 256 fp32 columns x 128 lanes (all 512 columns: one CTA per SM)
@@ -398,7 +403,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
     const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
-    float* T = S.tile[ew];
+    float* T = S.tile[ew][0];
     const bool head = MODE != 2 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
     // Per-column vectors {bias, gamma, beta, w3} of the tile's agent, in shared memory (broadcast reads). One learner: loaded
     // once. Stacked agents: every tile pair belongs to another agent, and loading its vectors at the top of the tile put a
@@ -536,21 +541,35 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
       } else {  // ===== backward epilogue: XH = x-hat of layer 1 (input), stat = its (mean, rstd), H <- dz1
+        // x-hat reaches the warp through its own ring of NXB 32x32 tiles filled by TMA (boxes of 32 rows x 32 columns in
+        // the 128-byte swizzle = exactly the staging-tile layout): lane 0 requests the chunk of visit v + NXB as soon as the
+        // warp is done with the tile of visit v, so NXB - 1 chunks are always in flight — across the two passes and across
+        // tiles (x-hat does not depend on this kernel's products). The first version fetched each chunk with the epilogue
+        // threads' own loads one chunk ahead (all the registers allow): 16 KB in flight per SM, a third of the launch's
+        // long-scoreboard stalls on the store that staged it (ncu), 24 us of epilogue per tile against 11 us of MMAs.
         const bool live = row < M;
-        const float* X0 = XH + (arow + row0) * TCN;  // this warp's 32 rows of x-hat: fetched coalesced, one chunk ahead
-        float4 pf[8];
+        constexpr int NXB = Smem::NXB;
+        const int vpt = ln ? 2 * (TCN / 32) : TCN / 32;  // chunk visits per tile: two passes with LayerNorm, else one
+        auto xissue = [&](int vj) {  // lane 0 only
+          if (vj < my_tiles * vpt) {
+            const int tj = vj / vpt, c = (vj - tj * vpt) & 7, b = vj % NXB;
+            mbar_expect_(&S.xfull[ew][b], 32 * 32 * sizeof(float));
+            tma_load_3d(S.tile[ew][b], &mapX, c * 32, tile_of(tj) * TCM + 32 * lg, agent_of(tj), &S.xfull[ew][b]);
+          }
+        };
+        if (ti == 0 && lane == 0)
+          for (int j = 0; j < NXB; ++j) xissue(j);
+        int vi = ti * vpt;
         float x[32];
-        rows_fetch(X0, lane, rows_valid, pf);
         mbar_wait_(&S.acc_full[buf], (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float s1 = 0.f, s2 = 0.f;
         if (ln) {
-          for (int c = 0; c < TCN / 32; ++c) {
-            rows_put(T, lane, pf);
+          for (int c = 0; c < TCN / 32; ++c, ++vi) {
+            mbar_wait_(&S.xfull[ew][vi % NXB], (vi / NXB) & 1);
+            tile_get(S.tile[ew][vi % NXB], lane, x);
             __syncwarp();
-            tile_get(T, lane, x);
-            __syncwarp();
-            rows_fetch(X0 + ((c + 1) & 7) * 32, lane, rows_valid, pf);  // (the last one fetches chunk 0 for the second pass)
+            if (lane == 0) xissue(vi + NXB);
             tmem_ld32(tl + c * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -563,12 +582,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
         const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[arow + row].y : 1.f;
-        for (int c = 0; c < TCN / 32; ++c) {
-          rows_put(T, lane, pf);
-          __syncwarp();
+        for (int c = 0; c < TCN / 32; ++c, ++vi) {
+          T = S.tile[ew][vi % NXB];  // the chunk's tile doubles as the staging tile once x-hat is in registers
+          mbar_wait_(&S.xfull[ew][vi % NXB], (vi / NXB) & 1);
           tile_get(T, lane, x);
           __syncwarp();
-          if (c + 1 < TCN / 32) rows_fetch(X0 + (c + 1) * 32, lane, rows_valid, pf);
           tmem_ld32(tl + c * 32, v);
           if (c == TCN / 32 - 1) {  // last TMEM read of this tile
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -604,7 +622,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tile_put(T, lane, v);
           __syncwarp();
           S.wpart[ew][2][c * 32 + lane] = tile_colsum(T, lane);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's generic accesses before TMA's next write
           __syncwarp();
+          if (lane == 0) xissue(vi + NXB);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
         for (int i = et; i < 3 * HID && tile < n_tiles; i += 128) {
@@ -726,14 +746,14 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo == W)
-    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, ma, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, ma, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   }
-  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0, 0>) + 1024, st, ma, mb, mb, M, 0, bias, g, be, ln, relu, H, XH, st2,
+  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0, 0>) + 1024, st, ma, mb, mb, ma, M, 0, bias, g, be, ln, relu, H, XH, st2,
                   none, q, k);
 }
 // First layer on the tensor cores: X [M][K] (row pitch ldx), w1t [K][256] forward layout; x3: 3xTF32 with both lo parts made
@@ -749,16 +769,17 @@ cudaError_t launch_tc_first(const float* X, int64_t ldx, int M, int K, const flo
   const b2rl_wide_q_t q = {};
   const int kb = (K + TCK - 1) / TCK;
   if (x3)
-    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<1, 2>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH,
+    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<1, 2>) + 1024, st, ma, mb, mb, ma, M, kb, bias, g, be, ln, 1, H, XH,
                     st2, none, q, k);
-  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<1, 0>) + 1024, st, ma, mb, mb, M, kb, bias, g, be, ln, 1, H, XH, st2,
+  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<1, 0>) + 1024, st, ma, mb, mb, ma, M, kb, bias, g, be, ln, 1, H, XH, st2,
                   none, q, k);
 }
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
                                  const float* stat1, const float* g1, const float* be1, int ln, float* DZ1, float* part,
                                  const Stk& k, cudaStream_t st) {
-  CUtensorMap ma, mb, ml;
-  if (!make_map(&ma, DZ2, M, HID, HID, TCM, k.n, (int64_t)M * HID) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2, k.n, k.ps))
+  CUtensorMap ma, mb, ml, mx;  // mx: x-hat in boxes of 32 rows x 32 columns (the epilogue warps' rings)
+  if (!make_map(&ma, DZ2, M, HID, HID, TCM, k.n, (int64_t)M * HID) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2, k.n, k.ps) ||
+      !make_map(&mx, xh1, M, HID, HID, 32, k.n, (int64_t)M * HID))
     return cudaErrorInvalidValue;
   const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
   float* xh = const_cast<float*>(xh1);
@@ -766,14 +787,14 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   const float* none = nullptr;
   const b2rl_wide_q_t q = {};
   if (w2t_lo == w2t)
-    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2, 2>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2, 2>) + 1024, st, ma, mb, mb, mx, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   if (w2t_lo) {
     if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<2, 1>) + 1024, st, ma, mb, ml, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<2, 1>) + 1024, st, ma, mb, ml, mx, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   }
-  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<2, 0>) + 1024, st, ma, mb, mb, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<2, 0>) + 1024, st, ma, mb, mb, mx, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
 }
 
 }  // namespace b2rl
