@@ -51,24 +51,31 @@ struct TcCfg {
   static constexpr bool PAIR = MODE != 1 && PREC != 0;
   static constexpr int BN = PAIR ? TCN / 2 : TCN;            // weight rows per CTA and stage
   // (the backward kernel is bound by its epilogue: it gives a stage's worth of shared memory to the x-hat rings)
-  static constexpr int STAGES = PAIR ? (MODE == 2 ? 2 : 3) : (PREC ? 2 : (MODE == 2 ? 3 : 4));
-  static constexpr int NXB = MODE == 2 ? 4 : 1;  // staging tiles per epilogue warp
+  static constexpr int STAGES = MODE == 2 ? 2 : (PAIR ? 3 : (PREC ? 2 : 4));
+  // Epilogue warps: one per 32 accumulator rows (TMEM lanes 32 * (warp % 4) ..); the backward kernel, whose epilogue is
+  // instruction-bound (~10 k warp instructions per tile on a lone warp per scheduler: 20 us against 7 us of MMAs), runs two
+  // per 32 rows, each on one half of the columns.
+  static constexpr int EPW = MODE == 2 ? 8 : 4;
+  static constexpr int THREADS = 128 + 32 * EPW;  // warp 0 TMA, 1 MMA, 2-3 lo split, 4.. epilogue
+  static constexpr int NXB = MODE == 2 ? 2 : 1;   // staging tiles per epilogue warp
 };
 template <int MODE, int PREC>
 struct __align__(1024) TcSmemT {
   static constexpr int STAGES = TcCfg<MODE, PREC>::STAGES, BN = TcCfg<MODE, PREC>::BN, NXB = TcCfg<MODE, PREC>::NXB;
+  static constexpr int EPW = TcCfg<MODE, PREC>::EPW;
   float a[STAGES][TCM * TCK];  // 16 KB per stage, 128-byte rows, swizzle-128B
   float b[STAGES][BN * TCK];   // 32 KB per stage (PAIR: 16 KB)
   float alo[PREC ? STAGES : 1][PREC ? TCM * TCK : 4];
   float blo[PREC ? STAGES : 1][PREC ? BN * TCK : 4];
-  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2], xfull[4][NXB];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2], xfull[EPW][NXB];
   uint32_t tmem_base;
   // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
   // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials. MODE 2: four tiles per warp — the ring TMA
   // fills with the x-hat chunks the LayerNorm backward reads (and the staging tile of the chunk being worked on)
-  alignas(1024) float tile[4][NXB][32 * 32];
+  alignas(MODE == 2 ? 1024 : 128) float tile[EPW][NXB][32 * 32];
   alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
   float wpart[4][3][HID];
+  float2 xch[MODE == 2 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,7 +231,7 @@ __device__ __forceinline__ float tile_colsum(const float* t, int lane) {  // sum
 //         layer 1 (x-hat and rstd read per row), H <- dz1, and this CTA's column sums {sum dz, sum dn*xhat, sum dn}
 //         -> part[cta][3][256] (bias / LayerNorm-affine gradients; deterministic: transposed through shared memory).
 template <int MODE, int PREC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((TcCfg<MODE, PREC>::THREADS), 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapX, int M, int kb_first,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
@@ -234,6 +241,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   using Smem = TcSmemT<MODE, PREC>;
   constexpr int TC_STAGES = Smem::STAGES;
   constexpr bool PAIR = TcCfg<MODE, PREC>::PAIR;
+  constexpr int EPW = Smem::EPW, EPT = 32 * EPW;  // epilogue warps / threads
   // bytes TMA delivers into one stage of THIS CTA (multicast path: the whole weight slab, half of it sent by the peer)
   constexpr uint32_t TC_STAGE_BYTES = (TCM + Smem::BN * (PREC == 1 ? 2 : 1)) * TCK * sizeof(float);
   Smem& S = *reinterpret_cast<Smem*>(tc_raw + ((1024u - (s32(tc_raw) & 1023u)) & 1023u));
@@ -262,8 +270,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init_(&S.lo_ready[s], PAIR ? 128 : 64);
       mbar_init_(&S.peer_full[s], 1);  // (PAIR, rank 0) the peer CTA's slab has landed: relayed by the peer's idle MMA warp
     }
-    for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], PAIR ? 256 : 128); }
-    for (int e = 0; e < 4; ++e)
+    for (int b = 0; b < 2; ++b) { mbar_init_(&S.acc_full[b], 1); mbar_init_(&S.acc_empty[b], PAIR ? 2 * EPT : EPT); }
+    for (int e = 0; e < EPW; ++e)
       for (int j = 0; j < Smem::NXB; ++j) mbar_init_(&S.xfull[e][j], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -285,6 +293,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   constexpr bool BMN = MODE == 1;                   // the first layer's weights are MN-major (forward layout)
   auto bdesc = [&](const float* base, int k) { return BMN ? umma_desc_mn(base, k * 1024) : umma_desc(base, k * 32); };
 
+  // 384-thread form: the first warpgroup (TMA, MMA, lo split) hands registers to the two epilogue warpgroups
+  // (each warpgroup's setmaxnreg opens a branch that does not rejoin the other before the teardown)
+  if (warp < 4) {
+  if constexpr (EPW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: the ring runs on across tiles
       int it = 0;
@@ -379,9 +391,9 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         umma_commit(&S.acc_full[buf]);
       }
     }
-  } else if (warp >= 6) {  // ===== (3xTF32) the activations' lo parts, slab by slab as the ring fills
+  } else {  // ===== (3xTF32) the activations' lo parts, slab by slab as the ring fills
     if constexpr (PREC != 0) {
-      const int lt = threadIdx.x - 192;  // 0..63
+      const int lt = threadIdx.x - 64;  // 0..63
       for (int it = 0; it < my_tiles * KB; ++it) {
         const int s = it % TC_STAGES;
         mbar_wait_(&S.full[s], (it / TC_STAGES) & 1);
@@ -401,8 +413,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.lo_ready[s])) : "memory");
       }
     }
+  }
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
-    const int lg = warp & 3, ew = warp - 2, et = threadIdx.x - 64;
+    if constexpr (EPW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
+    const int lg = warp & 3, ew = warp - 4, et = threadIdx.x - 128;
     float* T = S.tile[ew][0];
     const bool head = MODE != 2 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
     // Per-column vectors {bias, gamma, beta, w3} of the tile's agent, in shared memory (broadcast reads). One learner: loaded
@@ -417,7 +431,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     };
     auto fetch_vectors = [&](int ag, int set) {  // 64 cp.async of 16 bytes per vector; constants where a vector is absent
       const size_t po = (size_t)ag * K.ps;
-      for (int i = et; i < 4 * (HID / 4); i += 128) {
+      for (int i = et; i < 4 * (HID / 4); i += EPT) {
         const int q = i / (HID / 4), u = i - q * (HID / 4);
         if (MODE == 2 && (q == 0 || q == 3)) continue;
         const float* src = q == 0 ? bias : q == 1 ? g : q == 2 ? be : Q.w3;
@@ -439,7 +453,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool next_differs = ti + 1 < my_tiles && agent_of(ti + 1) != ag;
       if (ti == 0 || agent_of(ti - 1) != ag) {  // this agent's set has landed, and everyone is done with the other set
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");
       }
       if (next_differs) fetch_vectors(agent_of(ti + 1), cset ^ 1);
       const float *cb = vptr(cset, 0), *cg = vptr(cset, 1), *cbe = vptr(cset, 2), *cw3 = vptr(cset, 3);
@@ -547,12 +561,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // tiles (x-hat does not depend on this kernel's products). The first version fetched each chunk with the epilogue
         // threads' own loads one chunk ahead (all the registers allow): 16 KB in flight per SM, a third of the launch's
         // long-scoreboard stalls on the store that staged it (ncu), 24 us of epilogue per tile against 11 us of MMAs.
+        // Two warps per 32 rows: warp (eh, lg) owns column chunks 4 * eh .. 4 * eh + 3; the row sums of the LayerNorm backward
+        // are the two halves' partial sums added in a fixed order (half 0 + half 1), swapped through shared memory.
         const bool live = row < M;
-        constexpr int NXB = Smem::NXB;
-        const int vpt = ln ? 2 * (TCN / 32) : TCN / 32;  // chunk visits per tile: two passes with LayerNorm, else one
+        constexpr int NXB = Smem::NXB, CPW = TCN / 32 / 2;  // column chunks per warp
+        const int eh = ew >> 2, c0 = CPW * eh;
+        const int vpt = ln ? 2 * CPW : CPW;  // chunk visits per tile: two passes with LayerNorm, else one
         auto xissue = [&](int vj) {  // lane 0 only
           if (vj < my_tiles * vpt) {
-            const int tj = vj / vpt, c = (vj - tj * vpt) & 7, b = vj % NXB;
+            const int tj = vj / vpt, c = c0 + ((vj - tj * vpt) & (CPW - 1)), b = vj % NXB;
             mbar_expect_(&S.xfull[ew][b], 32 * 32 * sizeof(float));
             tma_load_3d(S.tile[ew][b], &mapX, c * 32, tile_of(tj) * TCM + 32 * lg, agent_of(tj), &S.xfull[ew][b]);
           }
@@ -565,7 +582,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float s1 = 0.f, s2 = 0.f;
         if (ln) {
-          for (int c = 0; c < TCN / 32; ++c, ++vi) {
+          for (int c = c0; c < c0 + CPW; ++c, ++vi) {
             mbar_wait_(&S.xfull[ew][vi % NXB], (vi / NXB) & 1);
             tile_get(S.tile[ew][vi % NXB], lane, x);
             __syncwarp();
@@ -580,15 +597,21 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               s2 = fmaf(dx, x[i], s2);
             }
           }
+          float2* xs = S.xch + (ti % 3) * 2 * TCM;  // [half][row of the tile]; a slot is reused two pair barriers later
+          xs[eh * TCM + 32 * lg + lane] = make_float2(s1, s2);
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
+          const float2 o = xs[(eh ^ 1) * TCM + 32 * lg + lane];
+          s1 = eh ? o.x + s1 : s1 + o.x;
+          s2 = eh ? o.y + s2 : s2 + o.y;
         }
         const float m1 = s1 * (1.0f / TCN), m2 = s2 * (1.0f / TCN), rstd = (ln && live) ? stat[arow + row].y : 1.f;
-        for (int c = 0; c < TCN / 32; ++c, ++vi) {
+        for (int c = c0; c < c0 + CPW; ++c, ++vi) {
           T = S.tile[ew][vi % NXB];  // the chunk's tile doubles as the staging tile once x-hat is in registers
           mbar_wait_(&S.xfull[ew][vi % NXB], (vi / NXB) & 1);
           tile_get(T, lane, x);
           __syncwarp();
           tmem_ld32(tl + c * 32, v);
-          if (c == TCN / 32 - 1) {  // last TMEM read of this tile
+          if (c == c0 + CPW - 1) {  // last TMEM read of this tile
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if constexpr (PAIR) mbar_arrive_rank0(&S.acc_empty[buf]);
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
@@ -613,25 +636,25 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tile_put(T, lane, dz);
           __syncwarp();
           tile_store(T, lane, H + (arow + row0) * TCN + c * 32, rows_valid);
-          S.wpart[ew][0][c * 32 + lane] = tile_colsum(T, lane);
+          S.wpart[lg][0][c * 32 + lane] = tile_colsum(T, lane);
           __syncwarp();
           tile_put(T, lane, x);
           __syncwarp();
-          S.wpart[ew][1][c * 32 + lane] = tile_colsum(T, lane);
+          S.wpart[lg][1][c * 32 + lane] = tile_colsum(T, lane);
           __syncwarp();
           tile_put(T, lane, v);
           __syncwarp();
-          S.wpart[ew][2][c * 32 + lane] = tile_colsum(T, lane);
+          S.wpart[lg][2][c * 32 + lane] = tile_colsum(T, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's generic accesses before TMA's next write
           __syncwarp();
           if (lane == 0) xissue(vi + NXB);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-        for (int i = et; i < 3 * HID && tile < n_tiles; i += 128) {
+        asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");  // all epilogue warps
+        for (int i = et; i < 3 * HID && tile < n_tiles; i += EPT) {
           const int q = i / HID, j = i - q * HID;
           part[(((size_t)ag * n_tiles + tile) * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // (wpart is rewritten by the next tile)
+        asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");  // (wpart is rewritten by the next tile)
       }
       if (next_differs) cset ^= 1;
     }
@@ -742,7 +765,7 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   CUtensorMap ma, mb, ml;  // (the weight maps have boxes of HALF a slab: each CTA of a cluster loads one and multicasts it)
   if (!make_map(&ma, X, M, HID, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map(&mb, W, HID, HID, HID, TCN / 2, k.n, k.ps))
     return cudaErrorInvalidValue;
-  const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
+  const dim3 grid(tc_grid(M, k.n)), block(TcCfg<0, 0>::THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo == W)
@@ -763,7 +786,7 @@ cudaError_t launch_tc_first(const float* X, int64_t ldx, int M, int K, const flo
   CUtensorMap ma, mb;
   if (!make_map(&ma, X, M, K, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map_mn(&mb, w1t, K, HID, HID, k.n, k.ps))
     return cudaErrorInvalidValue;
-  const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
+  const dim3 grid(tc_grid(M, k.n)), block(TcCfg<0, 0>::THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   const b2rl_wide_q_t q = {};
@@ -781,7 +804,7 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   if (!make_map(&ma, DZ2, M, HID, HID, TCM, k.n, (int64_t)M * HID) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2, k.n, k.ps) ||
       !make_map(&mx, xh1, M, HID, HID, 32, k.n, (int64_t)M * HID))
     return cudaErrorInvalidValue;
-  const dim3 grid(tc_grid(M, k.n)), block(TC_THREADS);
+  const dim3 grid(tc_grid(M, k.n)), block(TcCfg<2, 0>::THREADS);
   float* xh = const_cast<float*>(xh1);
   float2* st1 = reinterpret_cast<float2*>(const_cast<float*>(stat1));
   const float* none = nullptr;
