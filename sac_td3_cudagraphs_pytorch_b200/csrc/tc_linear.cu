@@ -51,11 +51,12 @@ struct TcCfg {
   static constexpr bool PAIR = MODE != 1 && PREC != 0;
   static constexpr int BN = PAIR ? TCN / 2 : TCN;            // weight rows per CTA and stage
   // (the backward kernel is bound by its epilogue: it gives a stage's worth of shared memory to the x-hat rings)
-  static constexpr int STAGES = MODE == 2 ? 2 : (PAIR ? 3 : (PREC ? 2 : 4));
+  // (the first layer is one or two k-slabs per tile and all epilogue: a short ring, two epilogue warps per 32 rows)
+  static constexpr int STAGES = MODE == 2 ? 2 : MODE == 1 ? (PREC ? 1 : 2) : (PAIR ? 3 : (PREC ? 2 : 4));
   // Epilogue warps: one per 32 accumulator rows (TMEM lanes 32 * (warp % 4) ..); the backward kernel, whose epilogue is
   // instruction-bound (~10 k warp instructions per tile on a lone warp per scheduler: 20 us against 7 us of MMAs), runs two
   // per 32 rows, each on one half of the columns.
-  static constexpr int EPW = MODE == 2 ? 8 : 4;
+  static constexpr int EPW = MODE == 0 ? 4 : 8;
   static constexpr int THREADS = 128 + 32 * EPW;  // warp 0 TMA, 1 MMA, 2-3 lo split, 4.. epilogue
   static constexpr int NXB = MODE == 2 ? 2 : 1;   // staging tiles per epilogue warp
 };
@@ -75,7 +76,7 @@ struct __align__(1024) TcSmemT {
   alignas(MODE == 2 ? 1024 : 128) float tile[EPW][NXB][32 * 32];
   alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
   float wpart[4][3][HID];
-  float2 xch[MODE == 2 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
+  float2 xch[MODE != 0 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -296,7 +297,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   // 384-thread form: the first warpgroup (TMA, MMA, lo split) hands registers to the two epilogue warpgroups
   // (each warpgroup's setmaxnreg opens a branch that does not rejoin the other before the teardown)
   if (warp < 4) {
-  if constexpr (EPW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
+  if constexpr (MODE == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;" ::: "memory");
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: the ring runs on across tiles
       int it = 0;
@@ -415,7 +416,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   }
   } else {  // ===== epilogue: warp w may touch TMEM lanes 32*(w % 4) .. +31
-    if constexpr (EPW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
+    if constexpr (MODE == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
     const int lg = warp & 3, ew = warp - 4, et = threadIdx.x - 128;
     float* T = S.tile[ew][0];
     const bool head = MODE != 2 && Q.w3 != nullptr;  // the critic's scalar head rides in this epilogue (wide.cu::wide_q_head)
@@ -462,19 +463,33 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
       const uint32_t tl = tmem + buf * TCN + ((uint32_t)(32 * lg) << 16);
       if constexpr (MODE != 2) {
+        // EPW == 8 (first layer): warp (eh, lg) owns column chunks 4 eh .. 4 eh + 3 of rows 32 lg ..; the LayerNorm sums are
+        // the two halves' partial sums added in a fixed order (half 0 + half 1), swapped through shared memory
+        constexpr int CPW = (TCN / 32) / (EPW / 4);
+        const int eh = ew >> 2, c0 = CPW * eh;
+        auto pair_sum = [&](float p, int slot) -> float {
+          if constexpr (EPW == 8) {
+            float* xs = reinterpret_cast<float*>(S.xch) + slot * 2 * TCM;  // (a slot is reused two pair barriers later)
+            xs[eh * TCM + 32 * lg + lane] = p;
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
+            const float o = xs[(eh ^ 1) * TCM + 32 * lg + lane];
+            return eh ? o + p : p + o;
+          }
+          return p;
+        };
         mbar_wait_(&S.acc_full[buf], (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float mean = 0.f, rstd = 1.f;
         if (ln) {
           float s1 = 0.f;
-          for (int c = 0; c < TCN / 32; ++c) {
+          for (int c = c0; c < c0 + CPW; ++c) {
             tmem_ld32(tl + c * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) s1 += v[i] + cb[c * 32 + i];
           }
-          mean = s1 * (1.0f / TCN);
+          mean = pair_sum(s1, (2 * ti) % 3) * (1.0f / TCN);
           float s2 = 0.f;
-          for (int c = 0; c < TCN / 32; ++c) {
+          for (int c = c0; c < c0 + CPW; ++c) {
             tmem_ld32(tl + c * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -482,13 +497,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               s2 = fmaf(d, d, s2);
             }
           }
-          rstd = 1.0f / sqrtf(s2 * (1.0f / TCN) + LN_EPS);
-          if (stat && row < M) stat[arow + row] = make_float2(mean, rstd);
+          rstd = 1.0f / sqrtf(pair_sum(s2, (2 * ti + 1) % 3) * (1.0f / TCN) + LN_EPS);
+          if (stat && row < M && eh == 0) stat[arow + row] = make_float2(mean, rstd);
         }
         float qacc = 0.f;
-        for (int c = 0; c < TCN / 32; ++c) {
+        for (int c = c0; c < c0 + CPW; ++c) {
           tmem_ld32(tl + c * 32, v);
-          if (c == TCN / 32 - 1) {  // last TMEM read of this tile: hand the buffer back to the MMA issuer
+          if (c == c0 + CPW - 1) {  // last TMEM read of this tile: hand the buffer back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if constexpr (PAIR) mbar_arrive_rank0(&S.acc_empty[buf]);
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&S.acc_empty[buf])) : "memory");
@@ -521,7 +536,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             __syncwarp();
           }
         }
-        if (head) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
+        if (head && EPW == 4) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
           float sq = 0.f, dqv = 0.f;
           const size_t grow = arow + row;
           if (row < M) {
@@ -786,7 +801,7 @@ cudaError_t launch_tc_first(const float* X, int64_t ldx, int M, int K, const flo
   CUtensorMap ma, mb;
   if (!make_map(&ma, X, M, K, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map_mn(&mb, w1t, K, HID, HID, k.n, k.ps))
     return cudaErrorInvalidValue;
-  const dim3 grid(tc_grid(M, k.n)), block(TcCfg<0, 0>::THREADS);
+  const dim3 grid(tc_grid(M, k.n)), block(TcCfg<1, 0>::THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   const b2rl_wide_q_t q = {};
