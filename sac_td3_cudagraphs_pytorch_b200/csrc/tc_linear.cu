@@ -58,7 +58,7 @@ struct TcCfg {
   // per 32 rows, each on one half of the columns.
   static constexpr int EPW = MODE == 0 ? 4 : 8;
   static constexpr int THREADS = 128 + 32 * EPW;  // warp 0 TMA, 1 MMA, 2-3 lo split, 4.. epilogue
-  static constexpr int NXB = MODE == 2 ? 2 : 1;   // staging tiles per epilogue warp
+  static constexpr int NXB = MODE == 0 ? 1 : 2;   // staging tiles per epilogue warp (MODE 0: no room for a second one)
 };
 template <int MODE, int PREC>
 struct __align__(1024) TcSmemT {
@@ -73,7 +73,7 @@ struct __align__(1024) TcSmemT {
   // epilogue: per-warp 32x32 staging tile (128-byte rows, 16-byte units XOR-swizzled by row & 7), the per-column
   // vectors {bias, gamma, beta}, and (MODE 2) per-warp column-sum partials. MODE 2: four tiles per warp — the ring TMA
   // fills with the x-hat chunks the LayerNorm backward reads (and the staging tile of the chunk being worked on)
-  alignas(MODE == 2 ? 1024 : 128) float tile[EPW][NXB][32 * 32];
+  alignas(1024) float tile[EPW][NXB][32 * 32];  // (TMA reads and writes them: the 128-byte swizzle follows absolute address bits)
   alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
   float wpart[4][3][HID];
   float2 xch[MODE != 0 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
@@ -96,6 +96,18 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s32(dst)),
                "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar))
                : "memory");
+}
+// TMA store of one staging tile (32 rows x 32 columns, the box of the output's map); rows beyond the agent's batch are
+// clipped by the map. Bulk-group completion: wait_group.read N = all but the N most recent groups have READ their source.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(s32(src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 // K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor fields:
 // start address [0,14), stride byte offset [32,46), version = 1 [46,48), layout SWIZZLE_128B = 2 [61,64))
@@ -204,17 +216,6 @@ __device__ __forceinline__ void tile_store(float* t, int lane, float* G, int row
     if (r < rows_valid) *reinterpret_cast<float4*>(G + (size_t)r * TCN + q * 4) = *tile_q(t, r, q);
   }
 }
-__device__ __forceinline__ void rows_fetch(const float* G, int lane, int rows_valid, float4 (&p)[8]) {  // global -> registers
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3), q = lane & 7;
-    p[it] = r < rows_valid ? __ldg(reinterpret_cast<const float4*>(G + (size_t)r * TCN + q * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-__device__ __forceinline__ void rows_put(float* t, int lane, const float4 (&p)[8]) {
-#pragma unroll
-  for (int it = 0; it < 8; ++it) *tile_q(t, it * 4 + (lane >> 3), lane & 7) = p[it];
-}
 __device__ __forceinline__ float tile_colsum(const float* t, int lane) {  // sum over the 32 rows of column `lane`
   float cs = 0.f;
 #pragma unroll
@@ -234,7 +235,8 @@ __device__ __forceinline__ float tile_colsum(const float* t, int lane) {  // sum
 template <int MODE, int PREC>
 __global__ void __launch_bounds__((TcCfg<MODE, PREC>::THREADS), 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapX, int M, int kb_first,
+                 const __grid_constant__ CUtensorMap mapBlo, const __grid_constant__ CUtensorMap mapX,
+                 const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapXH, int M, int kb_first,
                  const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ be, int ln, int relu,
                  float* __restrict__ H, float* __restrict__ XH, float2* __restrict__ stat, float* __restrict__ part,
                  const __grid_constant__ b2rl_wide_q_t Q, const Stk K) {
@@ -447,7 +449,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     float v[32];
-    int cset = 0;
+    int cset = 0, sti = 0;  // sti: this warp's TMA stores so far (the staging tiles rotate)
+    (void)sti;
     if (my_tiles > 0) fetch_vectors(agent_of(0), 0);
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int tile = tile_of(ti), buf = ti & 1, ag = agent_of(ti);
@@ -460,7 +463,6 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const float *cb = vptr(cset, 0), *cg = vptr(cset, 1), *cbe = vptr(cset, 2), *cw3 = vptr(cset, 3);
       const size_t arow = (size_t)ag * M;           // first row of this agent in the stacked arrays
       const int row0 = tile * TCM + 32 * lg, row = row0 + lane;  // inside the agent's batch
-      const int rows_valid = M - row0;  // (<= 0: nothing of this warp's quarter is live)
       const uint32_t tl = tmem + buf * TCN + ((uint32_t)(32 * lg) << 16);
       if constexpr (MODE != 2) {
         // EPW == 8 (first layer): warp (eh, lg) owns column chunks 4 eh .. 4 eh + 3 of rows 32 lg ..; the LayerNorm sums are
@@ -523,17 +525,45 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             h[i] = relu ? fmaxf(x, 0.f) : x;
             if (head) qacc = fmaf(h[i], cw3[j], qacc);
           }
+          // Outputs leave through TMA stores of the staging tile (one instruction of one lane instead of 8 LDS.128 + 8
+          // STG.128 per lane: the staging was the epilogue's MIO bottleneck, ncu short-scoreboard / mio stalls) where the
+          // warp has two tiles to alternate; with one (MODE 0: the ring takes the rest) a store's read latency would sit
+          // between every two tiles written (measured 53 vs 46 us), so there the warp copies the tile out itself.
+          if constexpr (Smem::NXB < 2) {
+            const int rows_valid = M - row0;
+            if (H) {
+              tile_put(T, lane, h);
+              __syncwarp();
+              tile_store(T, lane, H + (arow + row0) * TCN + c * 32, rows_valid);
+              __syncwarp();
+            }
+            if (XH) {
+              tile_put(T, lane, v);
+              __syncwarp();
+              tile_store(T, lane, XH + (arow + row0) * TCN + c * 32, rows_valid);
+              __syncwarp();
+            }
+          } else {
           if (H) {  // (a target critic with the fused head never needs its h2 in memory)
-            tile_put(T, lane, h);
+            float* Ts = S.tile[ew][sti % Smem::NXB];
+            if (lane == 0) tma_store_wait_read<Smem::NXB - 1>();  // the store that last read this tile is done with it
             __syncwarp();
-            tile_store(T, lane, H + (arow + row0) * TCN + c * 32, rows_valid);
+            tile_put(Ts, lane, h);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
+            if (lane == 0) tma_store_3d(&mapH, Ts, c * 32, row0, ag);
+            ++sti;
           }
           if (XH) {
-            tile_put(T, lane, v);
+            float* Ts = S.tile[ew][sti % Smem::NXB];
+            if (lane == 0) tma_store_wait_read<Smem::NXB - 1>();
             __syncwarp();
-            tile_store(T, lane, XH + (arow + row0) * TCN + c * 32, rows_valid);
+            tile_put(Ts, lane, v);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
+            if (lane == 0) tma_store_3d(&mapXH, Ts, c * 32, row0, ag);
+            ++sti;
+          }
           }
         }
         if (head && EPW == 4) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
@@ -649,9 +679,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           // dz: to global (coalesced through the tile) and its column sums; then the two LayerNorm-affine sums.
           // Column sums over this warp's 32 rows: lane <-> column of the tile (deterministic, fixed order).
           tile_put(T, lane, dz);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          tile_store(T, lane, H + (arow + row0) * TCN + c * 32, rows_valid);
+          if (lane == 0) tma_store_3d(&mapH, T, c * 32, row0, ag);  // dz1 -> global, while the column sums read the tile
           S.wpart[lg][0][c * 32 + lane] = tile_colsum(T, lane);
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           tile_put(T, lane, x);
           __syncwarp();
@@ -673,6 +705,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       if (next_differs) cset ^= 1;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's stores have left shared memory
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -780,18 +813,21 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   CUtensorMap ma, mb, ml;  // (the weight maps have boxes of HALF a slab: each CTA of a cluster loads one and multicasts it)
   if (!make_map(&ma, X, M, HID, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map(&mb, W, HID, HID, HID, TCN / 2, k.n, k.ps))
     return cudaErrorInvalidValue;
+  CUtensorMap mh = ma, mxh = ma;  // outputs: boxes of 32 rows x 32 columns (TMA stores of the epilogue's staging tiles)
+  if ((H && !make_map(&mh, H, M, HID, HID, 32, k.n, (int64_t)M * HID)) || (XH && !make_map(&mxh, XH, M, HID, HID, 32, k.n, (int64_t)M * HID)))
+    return cudaErrorInvalidValue;
   const dim3 grid(tc_grid(M, k.n)), block(TcCfg<0, 0>::THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo == W)
-    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, ma, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, ma, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   }
-  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0, 0>) + 1024, st, ma, mb, mb, ma, M, 0, bias, g, be, ln, relu, H, XH, st2,
+  return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0, 0>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH, st2,
                   none, q, k);
 }
 // First layer on the tensor cores: X [M][K] (row pitch ldx), w1t [K][256] forward layout; x3: 3xTF32 with both lo parts made
@@ -801,23 +837,26 @@ cudaError_t launch_tc_first(const float* X, int64_t ldx, int M, int K, const flo
   CUtensorMap ma, mb;
   if (!make_map(&ma, X, M, K, ldx, TCM, k.n, (int64_t)M * ldx) || !make_map_mn(&mb, w1t, K, HID, HID, k.n, k.ps))
     return cudaErrorInvalidValue;
+  CUtensorMap mh = ma, mxh = ma;
+  if ((H && !make_map(&mh, H, M, HID, HID, 32, k.n, (int64_t)M * HID)) || (XH && !make_map(&mxh, XH, M, HID, HID, 32, k.n, (int64_t)M * HID)))
+    return cudaErrorInvalidValue;
   const dim3 grid(tc_grid(M, k.n)), block(TcCfg<1, 0>::THREADS);
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   const b2rl_wide_q_t q = {};
   const int kb = (K + TCK - 1) / TCK;
   if (x3)
-    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<1, 2>) + 1024, st, ma, mb, mb, ma, M, kb, bias, g, be, ln, 1, H, XH,
+    return launch_k(tc_linear_kernel<1, 2>, grid, block, -2, sizeof(TcSmemT<1, 2>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, kb, bias, g, be, ln, 1, H, XH,
                     st2, none, q, k);
-  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<1, 0>) + 1024, st, ma, mb, mb, ma, M, kb, bias, g, be, ln, 1, H, XH, st2,
+  return launch_k(tc_linear_kernel<1, 0>, grid, block, -2, sizeof(TcSmemT<1, 0>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, kb, bias, g, be, ln, 1, H, XH, st2,
                   none, q, k);
 }
 cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, const float* w2t_lo, const float* xh1,
                                  const float* stat1, const float* g1, const float* be1, int ln, float* DZ1, float* part,
                                  const Stk& k, cudaStream_t st) {
-  CUtensorMap ma, mb, ml, mx;  // mx: x-hat in boxes of 32 rows x 32 columns (the epilogue warps' rings)
+  CUtensorMap ma, mb, ml, mx, mh;  // mx: x-hat in boxes of 32 rows x 32 columns (the epilogue warps' rings)
   if (!make_map(&ma, DZ2, M, HID, HID, TCM, k.n, (int64_t)M * HID) || !make_map(&mb, w2t, HID, HID, HID, TCN / 2, k.n, k.ps) ||
-      !make_map(&mx, xh1, M, HID, HID, 32, k.n, (int64_t)M * HID))
+      !make_map(&mx, xh1, M, HID, HID, 32, k.n, (int64_t)M * HID) || !make_map(&mh, DZ1, M, HID, HID, 32, k.n, (int64_t)M * HID))
     return cudaErrorInvalidValue;
   const dim3 grid(tc_grid(M, k.n)), block(TcCfg<2, 0>::THREADS);
   float* xh = const_cast<float*>(xh1);
@@ -825,14 +864,14 @@ cudaError_t launch_tc_linear_bwd(const float* DZ2, int M, const float* w2t, cons
   const float* none = nullptr;
   const b2rl_wide_q_t q = {};
   if (w2t_lo == w2t)
-    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2, 2>) + 1024, st, ma, mb, mb, mx, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 2>, grid, block, -2, sizeof(TcSmemT<2, 2>) + 1024, st, ma, mb, mb, mx, mh, mh, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   if (w2t_lo) {
     if (!make_map(&ml, w2t_lo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<2, 1>) + 1024, st, ma, mb, ml, mx, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
+    return launch_k(tc_linear_kernel<2, 1>, grid, block, -2, sizeof(TcSmemT<2, 1>) + 1024, st, ma, mb, ml, mx, mh, mh, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1,
                     part, q, k);
   }
-  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<2, 0>) + 1024, st, ma, mb, mb, mx, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
+  return launch_k(tc_linear_kernel<2, 0>, grid, block, -2, sizeof(TcSmemT<2, 0>) + 1024, st, ma, mb, mb, mx, mh, mh, M, 0, none, g1, be1, ln, 0, DZ1, xh, st1, part, q, k);
 }
 
 }  // namespace b2rl
