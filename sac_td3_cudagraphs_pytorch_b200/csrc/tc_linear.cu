@@ -52,13 +52,15 @@ struct TcCfg {
   static constexpr int BN = PAIR ? TCN / 2 : TCN;            // weight rows per CTA and stage
   // (the backward kernel is bound by its epilogue: it gives a stage's worth of shared memory to the x-hat rings)
   // (the first layer is one or two k-slabs per tile and all epilogue: a short ring, two epilogue warps per 32 rows)
-  static constexpr int STAGES = MODE == 2 ? 2 : MODE == 1 ? (PREC ? 1 : 2) : (PAIR ? 3 : (PREC ? 2 : 4));
+  static constexpr int STAGES = MODE == 2 ? 2 : MODE == 1 ? (PREC ? 1 : 2) : 3;
   // Epilogue warps: one per 32 accumulator rows (TMEM lanes 32 * (warp % 4) ..); the backward kernel, whose epilogue is
   // instruction-bound (~10 k warp instructions per tile on a lone warp per scheduler: 20 us against 7 us of MMAs), runs two
   // per 32 rows, each on one half of the columns.
-  static constexpr int EPW = MODE == 0 ? 4 : 8;
+  // The 3xTF32 hidden layer keeps one warp per 32 rows: its three 64 KB stages leave room for four staging tiles only,
+  // and with a two-stage ring the MMA pipeline, not the epilogue, sets its pace (measured: 59.8 vs 54.3 us per 65 536 rows).
+  static constexpr int EPW = (MODE == 0 && PREC != 0) ? 4 : 8;
   static constexpr int THREADS = 128 + 32 * EPW;  // warp 0 TMA, 1 MMA, 2-3 lo split, 4.. epilogue
-  static constexpr int NXB = MODE == 0 ? 1 : 2;   // staging tiles per epilogue warp (MODE 0: no room for a second one)
+  static constexpr int NXB = EPW == 8 ? 2 : 1;     // staging tiles per epilogue warp
 };
 template <int MODE, int PREC>
 struct __align__(1024) TcSmemT {
@@ -75,8 +77,8 @@ struct __align__(1024) TcSmemT {
   // fills with the x-hat chunks the LayerNorm backward reads (and the staging tile of the chunk being worked on)
   alignas(1024) float tile[EPW][NXB][32 * 32];  // (TMA reads and writes them: the 128-byte swizzle follows absolute address bits)
   alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
-  float wpart[4][3][HID];
-  float2 xch[MODE != 0 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
+  float wpart[MODE == 2 ? 4 : 2][3][HID];  // (forward: only the second vector set lives here, 4 KB)
+  float2 xch[EPW == 8 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -449,8 +451,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     float v[32];
-    int cset = 0, sti = 0;  // sti: this warp's TMA stores so far (the staging tiles rotate)
-    (void)sti;
+    int cset = 0, sti = 0, xc = 0;  // sti: this warp's TMA stores so far (the staging tiles rotate); xc: pair exchanges
+    (void)sti, (void)xc;
     if (my_tiles > 0) fetch_vectors(agent_of(0), 0);
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int tile = tile_of(ti), buf = ti & 1, ag = agent_of(ti);
@@ -469,9 +471,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // the two halves' partial sums added in a fixed order (half 0 + half 1), swapped through shared memory
         constexpr int CPW = (TCN / 32) / (EPW / 4);
         const int eh = ew >> 2, c0 = CPW * eh;
-        auto pair_sum = [&](float p, int slot) -> float {
+        auto pair_sum = [&](float p) -> float {
           if constexpr (EPW == 8) {
-            float* xs = reinterpret_cast<float*>(S.xch) + slot * 2 * TCM;  // (a slot is reused two pair barriers later)
+            float* xs = reinterpret_cast<float*>(S.xch) + (xc % 3) * 2 * TCM;  // (a slot is reused two pair barriers later)
+            ++xc;
             xs[eh * TCM + 32 * lg + lane] = p;
             asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
             const float o = xs[(eh ^ 1) * TCM + 32 * lg + lane];
@@ -489,7 +492,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 32; ++i) s1 += v[i] + cb[c * 32 + i];
           }
-          mean = pair_sum(s1, (2 * ti) % 3) * (1.0f / TCN);
+          mean = pair_sum(s1) * (1.0f / TCN);
           float s2 = 0.f;
           for (int c = c0; c < c0 + CPW; ++c) {
             tmem_ld32(tl + c * 32, v);
@@ -499,7 +502,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               s2 = fmaf(d, d, s2);
             }
           }
-          rstd = 1.0f / sqrtf(pair_sum(s2, (2 * ti + 1) % 3) * (1.0f / TCN) + LN_EPS);
+          rstd = 1.0f / sqrtf(pair_sum(s2) * (1.0f / TCN) + LN_EPS);
           if (stat && row < M && eh == 0) stat[arow + row] = make_float2(mean, rstd);
         }
         float qacc = 0.f;
@@ -566,7 +569,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           }
         }
-        if (head && EPW == 4) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
+        if (head) qacc = pair_sum(qacc);  // the two column halves' parts of w3 . h2
+        if (head && eh == 0) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
           float sq = 0.f, dqv = 0.f;
           const size_t grow = arow + row;
           if (row < M) {
@@ -820,11 +824,11 @@ cudaError_t launch_tc_linear(const float* X, int64_t ldx, int M, const float* W,
   float2* st2 = reinterpret_cast<float2*>(stat);
   float* none = nullptr;
   if (Wlo == W)
-    return launch_k(tc_linear_kernel<0, 2>, grid, block, -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 2>, grid, dim3(TcCfg<0, 2>::THREADS), -2, sizeof(TcSmemT<0, 2>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   if (Wlo) {
     if (!make_map(&ml, Wlo, HID, HID, HID, TCN / 2, k.n, k.ls)) return cudaErrorInvalidValue;
-    return launch_k(tc_linear_kernel<0, 1>, grid, block, -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH,
+    return launch_k(tc_linear_kernel<0, 1>, grid, dim3(TcCfg<0, 1>::THREADS), -2, sizeof(TcSmemT<0, 1>) + 1024, st, ma, mb, ml, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH,
                     st2, none, q, k);
   }
   return launch_k(tc_linear_kernel<0, 0>, grid, block, -2, sizeof(TcSmemT<0, 0>) + 1024, st, ma, mb, mb, ma, mh, mxh, M, 0, bias, g, be, ln, relu, H, XH, st2,
