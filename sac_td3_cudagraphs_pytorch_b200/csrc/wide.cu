@@ -378,23 +378,34 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
 
 // ---- final reductions ----------------------------------------------------------------------------------------------------
 // G[off[v] + j] = sum_p part[p][v][j], v < 3 (v >= 1 only when layer_norm). Grid (8 column chunks, 3 vectors); thread
-// (c = t & 31, s = t >> 5) sums partials s, s + 8, ... of column 32 * chunk + c; fixed-order combine over s.
-__global__ void __launch_bounds__(256)
+// (c = t & 31, s = t >> 5) sums partials s, s + 32, ... of column 32 * chunk + c; fixed-order combine over s. 1 024 threads:
+// the kernel is a chain of L2 round trips (512 partials per column at batch 65 536), so the slices are spread over 32 warps
+// and each takes its partials eight loads at a time.
+__global__ void __launch_bounds__(1024)
 wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
                    long long ps) {
   part += (size_t)blockIdx.z * P * 3 * HID;  // stacked agents: blockIdx.z = agent
   G += (size_t)blockIdx.z * ps;
-  __shared__ float red[8][32];
+  __shared__ float red[32][32];
   const int v = blockIdx.y, t = threadIdx.x, c = t & 31, sl = t >> 5, j = blockIdx.x * 32 + c;
   if (v > 0 && !ln) return;
   float s = 0.f;
-  for (int p = sl; p < P; p += 8) s += part[((size_t)p * 3 + v) * HID + j];
+  const int nsl = (int)blockDim.x >> 5;  // 32 warps for long lists (P >= 64), 8 otherwise: a function of P only
+  for (int p0 = sl; p0 < P; p0 += 8 * nsl) {  // eight loads in flight, added in the order of the plain loop
+    float u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = p0 + nsl * i;
+      u[i] = p < P ? __ldg(part + ((size_t)p * 3 + v) * HID + j) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += u[i];
+  }
   red[sl][c] = s;
   __syncthreads();
   if (sl == 0) {
     float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a += red[i][c];
+    for (int i = 0; i < nsl; ++i) a += red[i][c];
     G[(v == 0 ? off_b : v == 1 ? off_g : off_be) + j] = a;
   }
 }
@@ -624,7 +635,7 @@ cudaError_t launch_wide_ln_bwd(const float* dz3, int n_out, const float* w3, con
 }
 cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
                                const Stk& k, cudaStream_t st) {
-  wide_colsum_kernel<<<dim3(HID / 32, 3, k.n), 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln, k.ps);
+  wide_colsum_kernel<<<dim3(HID / 32, 3, k.n), P >= 64 ? 1024 : 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln, k.ps);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float*, const float*, int M, float* G,
