@@ -295,7 +295,8 @@ int b2rl_tc_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float
 
 /* Backward dX product of the hidden layer on the tensor cores with the LayerNorm / ReLU backward of layer 1 in the
  * epilogue: DZ1 = LNbwd(ReLU'(DZ2 . W2)); w2t = forward-layout copy of fc_block_2.fc.weight; part [ceil(M/128)][3][256]
- * receives per-CTA column sums {sum dz, sum dn*xhat, sum dn}. */
+ * receives per-CTA column sums {sum dz, sum dn*xhat, sum dn}, or is NULL when only DZ1 is wanted (the actor step's pass
+ * through the critics, agents/agent.py:272-283: no critic parameter gradient is used there). */
 int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
                        const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, const b2rl_stack_t* stack,
                        void* stream);
@@ -348,7 +349,7 @@ int b2rl_tc_linear_q(const float* X, int64_t ldx, int32_t M, const float* W, con
                      const b2rl_stack_t* stack, void* stream);
 
 /* Head backward + ReLU mask + LayerNorm backward of layer 2: dz = LNbwd(ReLU'(dz3[:, :n_out] . w3)); part
- * [ceil(M/128)][3][256] per-CTA column sums. dw3_part (NULL, or [ceil(M/128)][3][256] with n_out == 1): per-CTA partials
+ * [ceil(M/128)][3][256] per-CTA column sums (NULL: dz only). dw3_part (NULL, or [ceil(M/128)][3][256] with n_out == 1): per-CTA partials
  * (slot 0) of the scalar head's weight gradient dW3[j] = sum_b dz3[b] * h2[b][j], h2 recomputed from x-hat — finish with
  * b2rl_wide_colsum(dw3_part, P, G, off_w3, 0, 0, 0, ...): the critics then need no b2rl_tc_wgrad launch for w3. */
 int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const float* xh, const float* stat, const float* g,

@@ -287,7 +287,7 @@ int b2rl_tc_first(const float* X, int64_t ldx, int32_t M, int32_t K, const float
 int b2rl_tc_linear_bwd(const float* DZ2, int32_t M, const float* w2t, const float* w2t_lo, const float* xh1, const float* stat1,
                        const float* g1, const float* be1, int32_t layer_norm, float* DZ1, float* part, const b2rl_stack_t* stack,
                        void* stream) {
-  if (!DZ2 || !w2t || !xh1 || !DZ1 || !part || M < 1) return fail(B2RL_E_INVALID, "tc_linear_bwd: bad arguments");
+  if (!DZ2 || !w2t || !xh1 || !DZ1 || M < 1) return fail(B2RL_E_INVALID, "tc_linear_bwd: bad arguments");
   if (int rc = check_stack(stack, "tc_linear_bwd")) return rc;
   if (layer_norm && (!g1 || !be1 || !stat1)) return fail(B2RL_E_INVALID, "tc_linear_bwd: LayerNorm needs weight, bias and statistics");
   if (!aligned16(DZ2) || !aligned16(w2t) || !aligned16(DZ1)) return fail(B2RL_E_INVALID, "tc_linear_bwd: 16-byte aligned tensors");
@@ -313,7 +313,8 @@ int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const flo
                      const b2rl_stack_t* stack, void* stream) {
   if (int rc = check_stack(stack, "wide_ln_bwd")) return rc;
   if (dw3_part && n_out != 1) return fail(B2RL_E_INVALID, "wide_ln_bwd: dw3_part is for scalar heads (n_out == 1)");
-  if (!dz3 || !w3 || !xh || !dz || !part || M < 1 || n_out < 1 || n_out > B2RL_MAX_OUT) return fail(B2RL_E_INVALID, "wide_ln_bwd: bad arguments");
+  if (!dz3 || !w3 || !xh || !dz || M < 1 || n_out < 1 || n_out > B2RL_MAX_OUT) return fail(B2RL_E_INVALID, "wide_ln_bwd: bad arguments");
+  if (dw3_part && !part) return fail(B2RL_E_INVALID, "wide_ln_bwd: dw3_part without part");
   if (layer_norm && (!g || !be || !stat)) return fail(B2RL_E_INVALID, "wide_ln_bwd: LayerNorm needs weight, bias and statistics");
   return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, dw3_part, make_stk(stack), (cudaStream_t)stream), "wide_ln_bwd");
 }

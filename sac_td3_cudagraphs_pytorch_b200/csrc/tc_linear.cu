@@ -686,26 +686,32 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) tma_store_3d(&mapH, T, c * 32, row0, ag);  // dz1 -> global, while the column sums read the tile
-          S.wpart[lg][0][c * 32 + lane] = tile_colsum(T, lane);
-          if (lane == 0) tma_store_wait_read<0>();
-          __syncwarp();
-          tile_put(T, lane, x);
-          __syncwarp();
-          S.wpart[lg][1][c * 32 + lane] = tile_colsum(T, lane);
-          __syncwarp();
-          tile_put(T, lane, v);
-          __syncwarp();
-          S.wpart[lg][2][c * 32 + lane] = tile_colsum(T, lane);
+          if (part) {  // (uniform; NULL: dz1 only — the actor step's pass through the critics needs no parameter gradients)
+            S.wpart[lg][0][c * 32 + lane] = tile_colsum(T, lane);
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            tile_put(T, lane, x);
+            __syncwarp();
+            S.wpart[lg][1][c * 32 + lane] = tile_colsum(T, lane);
+            __syncwarp();
+            tile_put(T, lane, v);
+            __syncwarp();
+            S.wpart[lg][2][c * 32 + lane] = tile_colsum(T, lane);
+          } else if (lane == 0) {
+            tma_store_wait_read<0>();
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's generic accesses before TMA's next write
           __syncwarp();
           if (lane == 0) xissue(vi + NXB);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");  // all epilogue warps
-        for (int i = et; i < 3 * HID && tile < n_tiles; i += EPT) {
-          const int q = i / HID, j = i - q * HID;
-          part[(((size_t)ag * n_tiles + tile) * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
+        if (part) {
+          asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");  // all epilogue warps
+          for (int i = et; i < 3 * HID && tile < n_tiles; i += EPT) {
+            const int q = i / HID, j = i - q * HID;
+            part[(((size_t)ag * n_tiles + tile) * 3 + q) * HID + j] = (S.wpart[0][q][j] + S.wpart[1][q][j]) + (S.wpart[2][q][j] + S.wpart[3][q][j]);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");  // (wpart is rewritten by the next tile)
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(EPT) : "memory");  // (wpart is rewritten by the next tile)
       }
       if (next_differs) cset ^= 1;
     }

@@ -286,7 +286,7 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
   {  // stacked agents: blockIdx.y = agent
     const size_t ag = blockIdx.y;
     dz3 += ag * M * MAX_OUT, xh += ag * M * HID, dz += ag * M * HID, w3 += ag * ps;
-    part += ag * gridDim.x * 3 * HID;
+    if (part) part += ag * gridDim.x * 3 * HID;
     if (dw3_part) dw3_part += ag * gridDim.x * 3 * HID;
     if (ln) stat += ag * M, g += ag * ps, be += ag * ps;
   }
@@ -361,18 +361,20 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
       sdn[i] += dn[i];
     }
   }
+  if (part) {  // (uniform; NULL: the pass is after dz only — the actor step's way through the critics)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    red[(w * 3 + 0) * HID + l + 32 * i] = sdz[i];
-    red[(w * 3 + 1) * HID + l + 32 * i] = sdx[i];
-    red[(w * 3 + 2) * HID + l + 32 * i] = sdn[i];
-  }
-  __syncthreads();
-  for (int v = 0; v < 3; ++v) {
-    float s = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      red[(w * 3 + 0) * HID + l + 32 * i] = sdz[i];
+      red[(w * 3 + 1) * HID + l + 32 * i] = sdx[i];
+      red[(w * 3 + 2) * HID + l + 32 * i] = sdn[i];
+    }
+    __syncthreads();
+    for (int v = 0; v < 3; ++v) {
+      float s = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) s += red[(ww * 3 + v) * HID + t];
-    part[((size_t)blockIdx.x * 3 + v) * HID + t] = s;
+      for (int ww = 0; ww < 8; ++ww) s += red[(ww * 3 + v) * HID + t];
+      part[((size_t)blockIdx.x * 3 + v) * HID + t] = s;
+    }
   }
   if (dw3_part) {  // (uniform) one more cross-warp reduction through the same buffer
     __syncthreads();

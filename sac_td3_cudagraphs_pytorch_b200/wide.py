@@ -343,11 +343,11 @@ class WideActor:
             o = net.off
             L.check(lib.b2rl_wide_ln_bwd(dz3_ptr, n_out, self._p(RP, o["w3"]), xh2, st2,
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
-                                         dz2_out, part[0].data_ptr(), None, stk, st), "wide_ln_bwd")
+                                         dz2_out, part[0].data_ptr() if part is not None else None, None, stk, st), "wide_ln_bwd")
             w2t = self._p(RP, o["w2t"])
             L.check(lib.b2rl_tc_linear_bwd(dz2_out, M, w2t, lo_of(slot, w2t), xh1, st1,
                                            self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
-                                           dz1_out, part[1].data_ptr(), stk, st), "tc_linear_bwd")
+                                           dz1_out, part[1].data_ptr() if part is not None else None, stk, st), "tc_linear_bwd")
 
         # ---- actor forward on obs, sample (agent.py:251 / :254-255): H1 / H2 go to workspace slot 0 for wgrad
         first(rows.data_ptr(), rs, O, act, self._ws(0, 0), self.xa1.data_ptr(), self.sa1.data_ptr())
@@ -374,7 +374,7 @@ class WideActor:
         for k in range(self.nq):
             net = lay.critic[k]
             bwd_layers(self.dzq[k].data_ptr(), 1, net, self.xq2[k].data_ptr(), self.sq2[k].data_ptr(), self.xq1[k].data_ptr(),
-                       self.sq1[k].data_ptr(), self.t1.data_ptr(), self.t2.data_ptr(), self.part, 3 + k)
+                       self.sq1[k].data_ptr(), self.t1.data_ptr(), self.t2.data_ptr(), None, 3 + k)  # (dX only: no column sums)
             L.check(lib.b2rl_wide_dqda(self.t2.data_ptr(), self._p(RP, net.off["w1t"]) + 4 * O * 256, A, M,
                                        self.dqda[k].data_ptr(), stk, st), "wide_dqda")
         # ---- backward through the action head and the actor
