@@ -213,3 +213,117 @@ def test_tc_first_layer_matches_torch(n_agents, M, K, ldx, x3):
             assert float((H[sl].double() - want).abs().max()) / float(want.abs().max()) <= t
             assert float((XH[sl].double() - xh).abs().max()) / float(xh.abs().max()) <= t
             assert float((stat[sl, 0].double() - mu[:, 0]).abs().max()) <= 4 * t * max(1.0, float(mu.abs().max()))
+
+
+def _bwd_reference(DZ2, W2t, XH, rstd, gam, bet, ln):
+    """float64 restatement of the dX product + ReLU mask + LayerNorm backward of layer 1 (agents/nets.py:66-82 differentiated):
+    returns dz1 and the three column sums {sum dz, sum dn * x-hat, sum dn}."""
+    dh = DZ2.double() @ W2t.double().T  # w2t [in][out]: dh[b][i] = sum_o dz2[b][o] * W2[o][i]
+    x = XH.double()
+    if ln:
+        on = (x * gam.double() + bet.double()) > 0
+        dn = torch.where(on, dh, torch.zeros_like(dh))
+        dx = dn * gam.double()
+        m1, m2 = dx.mean(1, keepdim=True), (dx * x).mean(1, keepdim=True)
+        dz = rstd.double()[:, None] * (dx - m1 - x * m2)
+    else:
+        dn = torch.where(x > 0, dh, torch.zeros_like(dh))
+        dz = dn
+    return dz, torch.stack([dz.sum(0), (dn * x).sum(0), dn.sum(0)])
+
+
+@pytest.mark.parametrize("x3", [False, True, "in-kernel"])  # in-kernel: W_lo == W, the weights' lo parts made in shared memory
+@pytest.mark.parametrize("n_agents,M,ln", [(1, 1000, True), (1, 4096, True), (3, 200, True), (1, 300, False), (2, 72, True)])
+def test_tc_linear_bwd_matches_torch(n_agents, M, ln, x3):
+    """b2rl_tc_linear_bwd against float64: dz1 and the per-tile column sums (ragged and stacked batches), and part = NULL
+    (dX only, the actor step's pass through the critics) gives the same dz1 bit for bit."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(7 * n_agents + M)
+    ps = 65536 + 1024  # [w2t | gamma | beta | pad] per agent
+    P = torch.zeros(n_agents, ps, device="cuda")
+    P[:, :65536] = torch.randn(n_agents, 65536, device="cuda", generator=g) / 16.0
+    P[:, 65536:65792] = 1.0 + 0.1 * torch.randn(n_agents, 256, device="cuda", generator=g)
+    P[:, 65792:66048] = 0.1 * torch.randn(n_agents, 256, device="cuda", generator=g)
+    Plo = torch.zeros_like(P)
+    R = n_agents * M
+    DZ2 = torch.randn(R, 256, device="cuda", generator=g)
+    XH = torch.randn(R, 256, device="cuda", generator=g)
+    stat = torch.stack([torch.zeros(R, device="cuda"), 0.5 + torch.rand(R, device="cuda", generator=g)], 1).contiguous()
+    n_tiles = (M + 127) // 128
+    st = torch.cuda.current_stream().cuda_stream
+    stk = L.Stack(n_agents, 0, ps, ps, 0, 0, 0)
+    sp = C.byref(stk) if n_agents > 1 else None
+    base = P.data_ptr()
+    if x3 is True:
+        L.check(lib.b2rl_tc_split_lo(base, Plo.data_ptr(), 65536, C.byref(stk), st), "split")
+    lo_ptr = None if not x3 else (base if x3 == "in-kernel" else Plo.data_ptr())
+    out = []
+    for with_part in (True, False):
+        DZ1 = torch.full((R, 256), float("nan"), device="cuda")
+        part = torch.full((n_agents, n_tiles, 3, 256), float("nan"), device="cuda")
+        L.check(lib.b2rl_tc_linear_bwd(DZ2.data_ptr(), M, base, lo_ptr, XH.data_ptr(), stat.data_ptr(),
+                                       (base + 4 * 65536) if ln else None, (base + 4 * 65792) if ln else None, int(ln),
+                                       DZ1.data_ptr(), part.data_ptr() if with_part else None, sp, st), "tc_linear_bwd")
+        torch.cuda.synchronize()
+        out.append((DZ1, part))
+    (DZ1, part), (DZ1n, _) = out
+    assert torch.isfinite(DZ1).all() and torch.equal(DZ1, DZ1n)
+    tol = 6e-6 if x3 else 4e-3
+    for a in range(n_agents):
+        rows = slice(a * M, (a + 1) * M)
+        dz, cs = _bwd_reference(DZ2[rows], P[a, :65536].view(256, 256), XH[rows], stat[rows, 1], P[a, 65536:65792],
+                                P[a, 65792:66048], ln)
+        e = float((DZ1[rows].double() - dz).abs().max()) / float(dz.abs().max())
+        got = part[a].double().sum(0)
+        nq = 3 if ln else 1  # (without LayerNorm only the bias gradient is defined)
+        ec = float((got[:nq] - cs[:nq]).abs().max()) / float(cs[:nq].abs().max())
+        print(f"\nagents={n_agents} M={M} ln={ln} 3xTF32={x3} agent {a}: dz1 {e:.2e}, column sums {ec:.2e}")
+        assert e <= tol and ec <= tol
+
+
+@pytest.mark.parametrize("M,n_out", [(1000, 1), (300, 6), (4096, 1)])
+def test_wide_ln_bwd_matches_torch(M, n_out):
+    """b2rl_wide_ln_bwd (head backward + ReLU mask + LayerNorm backward of layer 2) against float64, its column sums, the
+    scalar head's weight gradient (dw3_part, n_out == 1), and part = NULL == the same dz."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(M + n_out)
+    MO = L.MAX_OUT
+    dz3 = torch.zeros(M, MO, device="cuda")
+    dz3[:, :n_out] = torch.randn(M, n_out, device="cuda", generator=g)
+    w3 = torch.randn(n_out, 256, device="cuda", generator=g) / 16.0
+    XH = torch.randn(M, 256, device="cuda", generator=g)
+    stat = torch.stack([torch.zeros(M, device="cuda"), 0.5 + torch.rand(M, device="cuda", generator=g)], 1).contiguous()
+    gam = 1.0 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    bet = 0.1 * torch.randn(256, device="cuda", generator=g)
+    P = (M + 127) // 128
+    st = torch.cuda.current_stream().cuda_stream
+    res = []
+    for with_part in (True, False):
+        dz = torch.full((M, 256), float("nan"), device="cuda")
+        part = torch.full((P, 3, 256), float("nan"), device="cuda")
+        dw3 = torch.full((P, 3, 256), float("nan"), device="cuda")
+        L.check(lib.b2rl_wide_ln_bwd(dz3.data_ptr(), n_out, w3.data_ptr(), XH.data_ptr(), stat.data_ptr(), gam.data_ptr(),
+                                     bet.data_ptr(), 1, M, dz.data_ptr(), part.data_ptr() if with_part else None,
+                                     dw3.data_ptr() if (with_part and n_out == 1) else None, None, st), "wide_ln_bwd")
+        torch.cuda.synchronize()
+        res.append((dz, part, dw3))
+    (dz, part, dw3), (dzn, _, _) = res
+    assert torch.isfinite(dz).all() and torch.equal(dz, dzn)
+    x = XH.double()
+    dh = dz3[:, :n_out].double() @ w3.double()
+    pre = x * gam.double() + bet.double()
+    dn = torch.where(pre > 0, dh, torch.zeros_like(dh))
+    dx = dn * gam.double()
+    want = stat[:, 1].double()[:, None] * (dx - dx.mean(1, keepdim=True) - x * (dx * x).mean(1, keepdim=True))
+    cs = torch.stack([want.sum(0), (dn * x).sum(0), dn.sum(0)])
+    e = float((dz.double() - want).abs().max()) / float(want.abs().max())
+    ec = float((part.double().sum(0) - cs).abs().max()) / float(cs.abs().max())
+    print(f"\nM={M} n_out={n_out}: dz {e:.2e}, column sums {ec:.2e}")
+    assert e <= 2e-6 and ec <= 2e-6
+    if n_out == 1:
+        w = (dz3[:, :1].double() * torch.relu(pre)).sum(0)
+        assert float((dw3[:, 0].double().sum(0) - w).abs().max()) / float(w.abs().max()) <= 2e-6
