@@ -21,14 +21,19 @@ namespace b2rl {
 constexpr int GM = 128, GN = 256, GK = 32;
 constexpr int G_A_BYTES = GM * GK * 4, G_B_BYTES = GN * GK * 4;  // 16 KB, 32 KB per stage
 
-template <int PREC>
+// PAIR (3xTF32, gradients of 129..256 rows: dW2): the two m tiles of a split are the two CTAs of a cluster running ONE
+// tcgen05.mma.cta_group::2 (M = 256) per k-step and product — CTA r supplies its 128 columns of A and columns
+// [128 r, 128 r + 128) of B, as in tc_linear.cu's pair form. The single-SM form made each m tile's CTA load (and split) the
+// WHOLE B slab: 201 MB of operands for a 65 536-row dW2 instead of 134, 96 KB per stage instead of 64.
+template <int PREC, bool PAIR>
 struct __align__(1024) GSmemT {
-  static constexpr int STAGES = PREC ? 2 : 4;
+  static constexpr int STAGES = PREC ? (PAIR ? 3 : 2) : 4;
+  static constexpr int BN = PAIR ? GN / 2 : GN;  // B columns this CTA holds
   float a[STAGES][GM * GK];
-  float b[STAGES][GN * GK];
+  float b[STAGES][BN * GK];
   float alo[PREC ? STAGES : 1][PREC ? GM * GK : 4];
-  float blo[PREC ? STAGES : 1][PREC ? GN * GK : 4];
-  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], acc_full[2], acc_empty[2];
+  float blo[PREC ? STAGES : 1][PREC ? BN * GK : 4];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[STAGES], peer_full[STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
@@ -60,6 +65,30 @@ __device__ __forceinline__ void g_umma(uint32_t tmem_d, uint64_t da, uint64_t db
       G_IDESC), "r"(accumulate)
       : "memory");
 }
+// the pair forms (tc_linear.cu): one thread of cluster rank 0 drives both SMs; commits arrive in both CTAs
+__device__ __forceinline__ void g_umma_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(GN >> 3) << 17) |
+                             ((uint32_t)((2 * GM) >> 4) << 24);
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void g_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(gs32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void g_arrive_rank0(uint64_t* bar) {  // the mbarrier at the same offset in cluster rank 0
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(gs32(bar)));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void g_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // Work items (m tile, split, agent): item (mt, sp, ag) accumulates rows [sp * rows_per_split, ...) of agent ag's batch for
 // output rows [128 mt, 128 mt + 128) and writes its slice to part[ag][sp][MA_pad][256] (or, with one split, straight to the
 // gradient tensor). PERSISTENT: one CTA per SM walks items blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs on
@@ -69,22 +98,33 @@ __device__ __forceinline__ void g_umma(uint32_t tmem_d, uint64_t da, uint64_t db
 // outside the main loop: 103 us to read 268 MB). Warps: 0 TMA producer, 1 MMA issuer, 2-5 epilogue (thread <-> TMEM lane
 // <-> output row m), 6-7 the operands' lo parts (3xTF32).
 constexpr int G_THREADS_P = 256;
-template <int PREC>
+template <int PREC, bool PAIR>
 __global__ void __launch_bounds__(G_THREADS_P, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int Bn, int rows_per_split,
                 int MA_pad, int MA, float* __restrict__ part, float* __restrict__ Cd, float* __restrict__ Ctd,
                 unsigned long long* bump, long long ps, long long cs, int n_mt, int n_sp, int n_ag) {
   extern __shared__ unsigned char g_raw[];
-  using Smem = GSmemT<PREC>;
+  using Smem = GSmemT<PREC, PAIR>;
   constexpr int ST = Smem::STAGES;
+  constexpr uint32_t STAGE_BYTES = G_A_BYTES + Smem::BN * GK * 4;
   Smem& S = *reinterpret_cast<Smem*>(g_raw + ((1024u - (gs32(g_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = n_mt * n_sp * n_ag;
+  uint32_t crank = 0;
+  if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  // PAIR: an item is (split, agent) and the cluster's CTA r takes m tile r; the walkers below are per cluster then
+  const int n_items = PAIR ? n_sp * n_ag : n_mt * n_sp * n_ag;
+  const int w0 = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x, wstep = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
   // item -> (mt, sp, ag, first batch row, slabs)
   auto item_of = [&](int i, int& mt, int& sp, int& ag, int& kb0, int& KB) {
-    mt = i % n_mt;
-    sp = (i / n_mt) % n_sp;
-    ag = i / (n_mt * n_sp);
+    if constexpr (PAIR) {
+      mt = (int)crank;
+      sp = i % n_sp;
+      ag = i / n_sp;
+    } else {
+      mt = i % n_mt;
+      sp = (i / n_mt) % n_sp;
+      ag = i / (n_mt * n_sp);
+    }
     kb0 = sp * rows_per_split;
     const int kb1 = min(Bn, kb0 + rows_per_split);
     KB = (max(kb1 - kb0, 0) + GK - 1) / GK;
@@ -94,46 +134,94 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     for (int s = 0; s < ST; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(1) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.empty[s])), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.lo_ready[s])), "r"(64) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.lo_ready[s])), "r"(PAIR ? 128 : 64) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.peer_full[s])), "r"(1) : "memory");
     }
     for (int b = 0; b < 2; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_full[b])), "r"(1) : "memory");
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_empty[b])), "r"(128) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs32(&S.acc_empty[b])), "r"(PAIR ? 256 : 128) : "memory");
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // two accumulator tiles of 256 fp32 columns x 128 lanes (all of TMEM: one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gs32(&S.tmem_base)), "n"(2 * GN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gs32(&S.tmem_base)), "n"(2 * GN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gs32(&S.tmem_base)), "n"(2 * GN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if constexpr (PAIR) g_cluster_sync();  // the peer's barriers are initialised before anything of ours can land on them
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer: 4 + 8 boxes of 32 columns x 32 batch rows per stage; the ring runs on across items
       int it = 0;
-      for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+      for (int i = w0; i < n_items; i += wstep) {
         int mt, sp, ag, kb0, KB;
         item_of(i, mt, sp, ag, kb0, KB);
-        const int m0 = mt * GM;
+        const int m0 = mt * GM, n0 = PAIR ? (int)crank * (GN / 2) : 0;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % ST;
           if (it >= ST) g_mbar_wait(&S.empty[s], ((it / ST) - 1) & 1);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(G_A_BYTES + G_B_BYTES) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs32(&S.full[s])), "r"(STAGE_BYTES) : "memory");
           const int row = kb0 + kb * GK;  // (rows beyond the batch are zero-filled by TMA: they add nothing)
 #pragma unroll
           for (int c = 0; c < GM / 32; ++c) g_tma_3d(S.a[s] + c * 1024, &mapA, m0 + 32 * c, row, ag, &S.full[s]);
 #pragma unroll
-          for (int c = 0; c < GN / 32; ++c) g_tma_3d(S.b[s] + c * 1024, &mapB, 32 * c, row, ag, &S.full[s]);
+          for (int c = 0; c < Smem::BN / 32; ++c) g_tma_3d(S.b[s] + c * 1024, &mapB, n0 + 32 * c, row, ag, &S.full[s]);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer
+    if (PAIR && lane == 0 && crank == 1) {  // rank 1: tell the issuer when this CTA's slabs have landed
+      int it = 0;
+      for (int i = w0; i < n_items; i += wstep) {
+        int mt, sp, ag, kb0, KB;
+        item_of(i, mt, sp, ag, kb0, KB);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          g_mbar_wait(&S.full[it % ST], (it / ST) & 1);
+          g_arrive_rank0(&S.peer_full[it % ST]);
+        }
+      }
+    } else if (PAIR && lane == 0) {  // ===== MMA issuer of the pair: every instruction drives both SMs
+      int it = 0, nb = 0;
+      for (int i = w0; i < n_items; i += wstep) {
+        int mt, sp, ag, kb0, KB;
+        item_of(i, mt, sp, ag, kb0, KB);
+        if (KB == 0) continue;
+        const int buf = nb & 1;
+        const uint32_t acc = tmem + buf * GN;
+        if (nb >= 2) {  // BOTH epilogues must have drained this tile (item nb - 2)
+          g_mbar_wait(&S.acc_empty[buf], ((nb >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % ST;
+          g_mbar_wait(&S.full[s], (it / ST) & 1);
+          g_mbar_wait(&S.peer_full[s], (it / ST) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < GK / 8; ++k) g_umma_pair(acc, g_desc(S.a[s], k * 1024), g_desc(S.b[s], k * 1024), (kb | k) != 0);
+          g_mbar_wait(&S.lo_ready[s], (it / ST) & 1);  // both CTAs' split warps are done with this slab
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < GK / 8; ++k) {
+            g_umma_pair(acc, g_desc(S.alo[s], k * 1024), g_desc(S.b[s], k * 1024), 1);
+            g_umma_pair(acc, g_desc(S.a[s], k * 1024), g_desc(S.blo[s], k * 1024), 1);
+          }
+          g_commit_pair(&S.empty[s]);
+        }
+        g_commit_pair(&S.acc_full[buf]);
+        ++nb;
+      }
+    } else if (!PAIR && lane == 0) {  // ===== MMA issuer
       int it = 0, nb = 0;  // nb: non-empty items so far (they alternate between the two accumulator tiles)
-      for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+      for (int i = w0; i < n_items; i += wstep) {
         int mt, sp, ag, kb0, KB;
         item_of(i, mt, sp, ag, kb0, KB);
         if (KB == 0) continue;
@@ -169,7 +257,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if constexpr (PREC == 1) {
       const int lt = threadIdx.x - 192;  // 0..63
       int it = 0;
-      for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+      for (int i = w0; i < n_items; i += wstep) {
         int mt, sp, ag, kb0, KB;
         item_of(i, mt, sp, ag, kb0, KB);
         for (int kb = 0; kb < KB; ++kb, ++it) {
@@ -182,16 +270,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const float4* b4 = reinterpret_cast<const float4*>(S.b[s]);
           float4* bl4 = reinterpret_cast<float4*>(S.blo[s]);
 #pragma unroll 4
-          for (int q = 0; q < GN * GK / 4 / 64; ++q) bl4[lt + 64 * q] = tf32_lo4(b4[lt + 64 * q]);
+          for (int q = 0; q < Smem::BN * GK / 4 / 64; ++q) bl4[lt + 64 * q] = tf32_lo4(b4[lt + 64 * q]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.lo_ready[s])) : "memory");
+          if constexpr (PAIR) g_arrive_rank0(&S.lo_ready[s]);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.lo_ready[s])) : "memory");
         }
       }
     }
   } else {  // ===== epilogue warps 2-5: TMEM -> this item's slice (or the gradient tensor itself)
     const int et = threadIdx.x - 64, lg = warp & 3;
     int nb = 0;
-    for (int i = blockIdx.x; i < n_items; i += gridDim.x) {
+    for (int i = w0; i < n_items; i += wstep) {
       int mt, sp, ag, kb0, KB;
       item_of(i, mt, sp, ag, kb0, KB);
       const int m0 = mt * GM;
@@ -236,7 +325,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // hand the tile back to the MMA issuer
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.acc_empty[buf])) : "memory");
+        if constexpr (PAIR) g_arrive_rank0(&S.acc_empty[buf]);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs32(&S.acc_empty[buf])) : "memory");
         ++nb;
       } else if (live) {  // an empty slice (more splits than slabs): zeros
         for (int c = 0; c < GN / 4; ++c) reinterpret_cast<float4*>(dst)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,7 +337,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * GN) : "memory");
+  if constexpr (PAIR) g_cluster_sync();  // (the peer's last commits arrive on this CTA's barriers: do not exit under them)
+  if (warp == 1) {
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * GN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * GN) : "memory");
+  }
 }
 
 // bump, if given, is incremented once (the update counter that wgrad.cu's extra CTA advances).
@@ -330,9 +424,11 @@ static bool g_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols,
 }
 
 cudaError_t init_tc_wgrad() {
-  cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<0>) + 1024);
+  cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<0, false>) + 1024);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<1>) + 1024);
+    e = cudaFuncSetAttribute(tc_wgrad_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<1, false>) + 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tc_wgrad_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmemT<1, true>) + 1024);
   cudaFuncAttributes fa;
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, tc_wgrad_reduce_kernel);
   return e;
@@ -365,9 +461,16 @@ cudaError_t launch_tc_wgrad(const float* A, int64_t lda, int a_cols, int MA, con
     return n;
   }();
   const int n_items = mt * S * k.n, grid = n_items < sms ? n_items : sms;  // persistent: one CTA per SM
-  if (x3) tc_wgrad_kernel<1><<<grid, G_THREADS_P, sizeof(GSmemT<1>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs, mt, S, k.n);
-  else tc_wgrad_kernel<0><<<grid, G_THREADS_P, sizeof(GSmemT<0>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs, mt, S, k.n);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (x3 && mt == 2) {  // 3xTF32, 129..256 rows: the two m tiles of a split as one cluster on 2-SM MMAs
+    const int pairs = S * k.n, clusters = pairs < sms / 2 ? pairs : sms / 2;
+    e = launch_k(tc_wgrad_kernel<1, true>, dim3(2 * clusters), dim3(G_THREADS_P), -2, sizeof(GSmemT<1, true>) + 1024, st, ma, mb, Bn, rps,
+                 MA_pad, MA, scratch, cd, ctd, bump, (long long)k.ps, (long long)k.cs, mt, S, k.n);
+  } else {
+    if (x3) tc_wgrad_kernel<1, false><<<grid, G_THREADS_P, sizeof(GSmemT<1, false>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs, mt, S, k.n);
+    else tc_wgrad_kernel<0, false><<<grid, G_THREADS_P, sizeof(GSmemT<0, false>) + 1024, st>>>(ma, mb, Bn, rps, MA_pad, MA, scratch, cd, ctd, bump, k.ps, k.cs, mt, S, k.n);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess || direct) return e;
   tc_wgrad_reduce_kernel<<<dim3(GN / 32, (MA + 7) / 8, k.n), 256, 0, st>>>(scratch, S, MA, MA_pad, C, Ct, bump, k.ps, k.cs);
   return cudaGetLastError();
