@@ -170,12 +170,39 @@ __global__ void __launch_bounds__(256) wide_policy_head_kernel(const __grid_cons
     const float* src = P.rows + grow * P.row_stride + P.src_off;
     float* xr = P.xn + grow * P.ldn;
     for (int k = l; k < P.O; k += 32) xr[k] = __ldg(src + k);
-    for (int o = 0; o < P.out_dim; ++o) {
-      float s = 0.f;
+    if (P.out_dim <= 8) {
+      // Heads of up to 8 outputs (every task but Humanoid's SAC head): the dot products are reduced TOGETHER — a butterfly
+      // that halves the number of live sums at each of its first three steps (9 shuffles instead of 5 per output; the same
+      // pairs are added in the same order as warp_sum does). The per-output loop made the kernel issue-bound (ncu: 61 %
+      // issue utilisation at 46 us per 65 536 rows, ~220 warp instructions per row).
+      float s[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
-      s = warp_sum(s);
-      if (l == 0) us[rr * P.out_dim + o] = s + __ldg(b3g + o);
+      for (int o = 0; o < 8; ++o) {
+        s[o] = 0.f;
+        if (o < P.out_dim) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[o] = fmaf(w3s[o * HID + l + 32 * i], h[i], s[o]);
+        }
+      }
+      const bool b4 = l & 16, b3 = l & 8, b2 = l & 4;  // the output this lane ends up with: 4 b4 + 2 b3 + b2
+      float a4[4], a2[2], a1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a4[j] = (b4 ? s[4 + j] : s[j]) + __shfl_xor_sync(0xffffffffu, b4 ? s[j] : s[4 + j], 16);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) a2[j] = (b3 ? a4[2 + j] : a4[j]) + __shfl_xor_sync(0xffffffffu, b3 ? a4[j] : a4[2 + j], 8);
+      a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      const int o = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+      if ((l & 3) == 0 && o < P.out_dim) us[rr * P.out_dim + o] = a1 + __ldg(b3g + o);
+    } else {
+      for (int o = 0; o < P.out_dim; ++o) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(w3s[o * HID + l + 32 * i], h[i], s);
+        s = warp_sum(s);
+        if (l == 0) us[rr * P.out_dim + o] = s + __ldg(b3g + o);
+      }
     }
   }
   __syncthreads();
