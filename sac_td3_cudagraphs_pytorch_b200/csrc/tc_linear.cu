@@ -77,8 +77,8 @@ struct __align__(1024) TcSmemT {
   // fills with the x-hat chunks the LayerNorm backward reads (and the staging tile of the chunk being worked on)
   alignas(1024) float tile[EPW][NXB][32 * 32];  // (TMA reads and writes them: the 128-byte swizzle follows absolute address bits)
   alignas(16) float cvec[4][HID];  // bias, gamma, beta, and (fused critic head) w3
-  float wpart[MODE == 2 ? 4 : 2][3][HID];  // (forward: only the second vector set lives here, 4 KB)
-  float2 xch[EPW == 8 ? 3 * 2 * TCM : 1];  // (MODE 2) [slot][half][row]: the column halves' row sums, swapped by the paired warps
+  float wpart[MODE == 2 ? 4 : 1][MODE == 2 ? 3 : 4][HID];  // (forward: only the second vector set lives here, 4 KB)
+  float4 xch[EPW == 8 ? 2 * 2 * TCM : 1];  // [slot][half][row]: what the two column halves of a row swap (paired epilogue warps)
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -471,38 +471,52 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         // the two halves' partial sums added in a fixed order (half 0 + half 1), swapped through shared memory
         constexpr int CPW = (TCN / 32) / (EPW / 4);
         const int eh = ew >> 2, c0 = CPW * eh;
-        auto pair_sum = [&](float p) -> float {
-          if constexpr (EPW == 8) {
-            float* xs = reinterpret_cast<float*>(S.xch) + (xc % 3) * 2 * TCM;  // (a slot is reused two pair barriers later)
-            ++xc;
-            xs[eh * TCM + 32 * lg + lane] = p;
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
-            const float o = xs[(eh ^ 1) * TCM + 32 * lg + lane];
-            return eh ? o + p : p + o;
-          }
-          return p;
+        // what the two halves of a row exchange (one 64-thread named barrier; a slot is reused two exchanges later)
+        auto pair_swap = [&](float4 mine) -> float4 {
+          float4* xs = S.xch + (xc & 1) * 2 * TCM;
+          ++xc;
+          xs[eh * TCM + 32 * lg + lane] = mine;
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
+          return xs[(eh ^ 1) * TCM + 32 * lg + lane];
         };
         mbar_wait_(&S.acc_full[buf], (ti >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float mean = 0.f, rstd = 1.f;
         if (ln) {
-          float s1 = 0.f;
-          for (int c = c0; c < c0 + CPW; ++c) {
-            tmem_ld32(tl + c * 32, v);
+          // LayerNorm statistics in ONE pass over the accumulator (the two-pass form read all of it twice before the output
+          // pass): sums of d = z - shift and d^2 with shift = the mean of the row's first 32 columns (of this warp's half),
+          // so |mean - shift| is a fraction of the row's standard deviation and the variance formula below cancels nothing
+          // of significance (its terms are sigma^2 (1 + O(1/32)) and O(sigma^2 / 32)).
+          tmem_ld32(tl + c0 * 32, v);
+          float sh = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s1 += v[i] + cb[c * 32 + i];
-          }
-          mean = pair_sum(s1) * (1.0f / TCN);
-          float s2 = 0.f;
+          for (int i = 0; i < 32; ++i) sh += v[i] + cb[c0 * 32 + i];
+          sh *= (1.0f / 32);
+          float s1 = 0.f, s2 = 0.f;
           for (int c = c0; c < c0 + CPW; ++c) {
-            tmem_ld32(tl + c * 32, v);
+            if (c != c0) tmem_ld32(tl + c * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float d = v[i] + cb[c * 32 + i] - mean;
+              const float d = v[i] + cb[c * 32 + i] - sh;
+              s1 += d;
               s2 = fmaf(d, d, s2);
             }
           }
-          rstd = 1.0f / sqrtf(pair_sum(s2) * (1.0f / TCN) + LN_EPS);
+          float var;
+          if constexpr (EPW == 8) {  // combine the halves in the order (half 0, half 1): both warps get the same bits
+            const float4 o = pair_swap(make_float4(sh, s1, s2, 0.f));
+            const float sh0 = eh ? o.x : sh, a0 = eh ? o.y : s1, q0 = eh ? o.z : s2;
+            const float sh1 = eh ? sh : o.x, a1 = eh ? s1 : o.y, q1 = eh ? s2 : o.z;
+            constexpr float NH = TCN / 2;
+            mean = (fmaf(NH, sh0, a0) + fmaf(NH, sh1, a1)) * (1.0f / TCN);
+            const float e0 = mean - sh0, e1 = mean - sh1;
+            var = ((q0 - 2.f * e0 * a0 + NH * e0 * e0) + (q1 - 2.f * e1 * a1 + NH * e1 * e1)) * (1.0f / TCN);
+          } else {
+            const float m = s1 * (1.0f / TCN);
+            mean = sh + m;
+            var = fmaf(-m, m, s2 * (1.0f / TCN));
+          }
+          rstd = 1.0f / sqrtf(fmaxf(var, 0.f) + LN_EPS);
           if (stat && row < M && eh == 0) stat[arow + row] = make_float2(mean, rstd);
         }
         float qacc = 0.f;
@@ -569,7 +583,12 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           }
         }
-        if (head) qacc = pair_sum(qacc);  // the two column halves' parts of w3 . h2
+        if constexpr (EPW == 8) {  // the two column halves' parts of w3 . h2, added in the order (half 0, half 1)
+          if (head) {
+            const float o = pair_swap(make_float4(qacc, 0.f, 0.f, 0.f)).x;
+            qacc = eh ? o + qacc : qacc + o;
+          }
+        }
         if (head && eh == 0) {  // q = w3 . h2 + b3 per row (thread); online critics: TD target, dLoss/dQ, squared error (agent.py:212-233)
           float sq = 0.f, dqv = 0.f;
           const size_t grow = arow + row;
@@ -646,10 +665,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               s2 = fmaf(dx, x[i], s2);
             }
           }
-          float2* xs = S.xch + (ti % 3) * 2 * TCM;  // [half][row of the tile]; a slot is reused two pair barriers later
-          xs[eh * TCM + 32 * lg + lane] = make_float2(s1, s2);
+          float4* xs = S.xch + (ti & 1) * 2 * TCM;  // [half][row of the tile]; a slot is reused two pair barriers later
+          xs[eh * TCM + 32 * lg + lane] = make_float4(s1, s2, 0.f, 0.f);
           asm volatile("bar.sync %0, 64;" ::"r"(2 + lg) : "memory");
-          const float2 o = xs[(eh ^ 1) * TCM + 32 * lg + lane];
+          const float4 o = xs[(eh ^ 1) * TCM + 32 * lg + lane];
           s1 = eh ? o.x + s1 : s1 + o.x;
           s2 = eh ? o.y + s2 : s2 + o.y;
         }
