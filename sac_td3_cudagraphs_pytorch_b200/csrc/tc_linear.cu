@@ -4,22 +4,25 @@
 // config 5, batch 65 536; stacked populations), where the row-group kernels of mlp_cluster.cuh stream every layer's
 // weights from L2 once per 8 rows and top out at ~10 TFLOP/s.
 //
-// Persistent CTAs (one per SM) over 128-row tiles, warp-specialised (256 threads); two TMEM accumulator buffers, so the
+// Persistent CTAs (one per SM, clusters of 2) over 128-row tiles, warp-specialised; two TMEM accumulator buffers, so the
 // epilogue of one tile overlaps the loads and MMAs of the next:
-//   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of the A tile (128 x 32 fp32) and of HALF the weight k-slab
-//            (128 x 32 fp32), the latter multicast to both CTAs of the 2-CTA cluster (every tile needs the same
-//            weights: the multicast halves their L2->SM traffic, 256 KB (512 KB in 3xTF32) of the 384 (640) KB a tile
-//            reads), into a 4-stage shared-memory ring, 128-byte swizzle, completion on mbarriers; a ring slot is
-//            reused when BOTH CTAs' MMAs have released it (multicast tcgen05.commit);
-//   warp 1   TMEM allocation (2 x 256 columns) and the MMA issuer: one elected thread issues
-//            tcgen05.mma.cta_group::1.kind::tf32  M=128 N=256 K=8, four per k-slab, accumulating in TMEM;
-//            tcgen05.commit releases each ring slot back to the producer and finally signals the epilogue;
-//   warps 2-5 epilogue: thread <-> TMEM lane <-> one output ROW, so bias, the LayerNorm statistics (two passes over
-//            the row, no shuffles), affine and ReLU are thread-local. Per-column vectors sit in shared memory (as
-//            global loads they were 1280 exposed L1 round trips per warp and tile: ncu, long scoreboard); rows go
-//            to / come from global memory through a swizzled 32x32 per-warp tile so every warp instruction moves
-//            four full 128-byte row segments (thread-per-row stores touched 32 lines each).
-//   warps 6-7 (3xTF32 only) split each arriving activation slab into its lo part for the second MMA.
+//   warp 0   TMA producer: cp.async.bulk.tensor loads of the A tile (128 x 32 fp32) and of this CTA's HALF of the weight
+//            k-slab (128 x 32 fp32) into a shared-memory ring, 128-byte swizzle, completion on mbarriers. 3xTF32 hidden
+//            layers (PAIR): the half stays in this CTA and the two CTAs run 2-SM MMAs; otherwise it is multicast to both
+//            CTAs of the cluster (every tile needs the same weights) and a ring slot is reused when BOTH CTAs' MMAs have
+//            released it (multicast tcgen05.commit);
+//   warp 1   TMEM allocation (2 x 256 columns) and the MMA issuer: one elected thread issues tcgen05.mma kind::tf32
+//            (cta_group::1 M=128, or cta_group::2 M=256 from cluster rank 0 on behalf of both SMs; rank 1's warp 1 then
+//            relays "my slab has landed"), N=256 K=8, accumulating in TMEM; tcgen05.commit releases each ring slot back to
+//            the producer and finally signals the epilogue;
+//   warps 2-3 (3xTF32 only) split each arriving activation slab (stacked agents: and weight slab) into its lo part;
+//   warps 4.. epilogue, 4 or 8 warps (TcCfg::EPW): thread <-> TMEM lane <-> one output ROW, so bias, the LayerNorm statistics
+//            (one shifted pass over the row, no shuffles), affine and ReLU are thread-local; with 8 warps two warps share 32
+//            rows, each taking half of the columns and swapping its row sums through shared memory. Per-column vectors sit
+//            in shared memory (as global loads they were 1280 exposed L1 round trips per warp and tile: ncu, long
+//            scoreboard); rows go to / come from global memory through swizzled 32x32 per-warp tiles that TMA fills
+//            (x-hat for the backward epilogue) and TMA stores drain (outputs), or that the warp copies out itself where
+//            it has one tile only.
 // Operands are fp32 in memory and are read by the tensor core as TF32 (10-bit mantissa, truncated): products carry
 // ~1e-3 relative error — the "looser stated bound" of the north star for tensor-core modes; the accumulation, the
 // LayerNorm and everything downstream are fp32. Both operands are K-major: X rows and the natural-layout weight
@@ -30,12 +33,12 @@
 
 namespace b2rl {
 
-constexpr int TCM = 128, TCN = 256, TCK = 32, TC_THREADS = 256;
-// PREC 0: TF32 products (operands truncated to 10 mantissa bits by the tensor core), 4-stage ring.
+constexpr int TCM = 128, TCN = 256, TCK = 32;
+// PREC 0: TF32 products (operands truncated to 10 mantissa bits by the tensor core); ring depths: TcCfg below.
 // PREC 1: "3xTF32": x = hi + lo with hi = the TF32 truncation the tensor core applies anyway and lo = x - hi (exact in
 //         fp32, re-truncated to TF32: 2^-21 of x); a.b ~ hi.hi + lo.hi + hi.lo, three MMAs into the same accumulator —
 //         fp32-level accuracy (~1e-6) from the tensor cores. The weights' lo parts are precomputed (tc_split_lo), the
-//         activations' are made in shared memory by the (otherwise idle) epilogue warps; 2-stage ring of 96 KB.
+//         activations' are made in shared memory by two split warps.
 // PREC 2: 3xTF32 with the WEIGHTS' lo parts made in shared memory as well (by the same two warps, from the slab TMA has
 //         just delivered) instead of being read from a precomputed mirror: for stacked agents every weight slab serves one
 //         tile pair only, so a mirror costs as many HBM bytes as the weights themselves (268 MB per launch at 1 024 agents,

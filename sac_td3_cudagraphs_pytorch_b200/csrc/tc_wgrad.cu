@@ -96,7 +96,8 @@ __device__ __forceinline__ void g_cluster_sync() {
 // allocation, descriptor fetch) is paid once per SM and the epilogue of one item overlaps the loads and MMAs of the next —
 // a stacked population is 1 024-2 048 items of only 8 slabs each (the one-CTA-per-item version spent 60 % of its time
 // outside the main loop: 103 us to read 268 MB). Warps: 0 TMA producer, 1 MMA issuer, 2-5 epilogue (thread <-> TMEM lane
-// <-> output row m), 6-7 the operands' lo parts (3xTF32).
+// <-> output row m), 6-7 the operands' lo parts (3xTF32). PAIR: see GSmemT — the walkers then run per cluster and rank 0's
+// elected thread issues for both SMs.
 constexpr int G_THREADS_P = 256;
 template <int PREC, bool PAIR>
 __global__ void __launch_bounds__(G_THREADS_P, 1)
