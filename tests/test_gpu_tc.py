@@ -327,3 +327,46 @@ def test_wide_ln_bwd_matches_torch(M, n_out):
     if n_out == 1:
         w = (dz3[:, :1].double() * torch.relu(pre)).sum(0)
         assert float((dw3[:, 0].double().sum(0) - w).abs().max()) / float(w.abs().max()) <= 2e-6
+
+
+def test_tc_kernels_are_reproducible_at_full_grid():
+    """The 2-SM pipelines at a machine-filling size (65 536 rows: 148 CTAs, four tiles each, every ring slot and both TMEM
+    buffers reused; cross-CTA mbarrier arrivals, TMA-fed and TMA-stored epilogues): 12 launches each of the 3xTF32 forward,
+    backward and weight-gradient kernels from the same inputs must give the same bits — a race in the hand-rolled
+    synchronisation would show up as a result that depends on timing."""
+    from sac_td3_cudagraphs_pytorch_b200 import _lib as L
+    lib = L.load()
+    L.init_device(torch.device("cuda"))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M = 65536
+    X = torch.randn(M, 256, device="cuda", generator=g)
+    DZ = torch.randn(M, 256, device="cuda", generator=g)
+    W = torch.randn(256, 256, device="cuda", generator=g) / 16.0
+    Wlo = torch.empty_like(W)
+    b = 0.1 * torch.randn(256, device="cuda", generator=g)
+    gam = 1.0 + 0.1 * torch.randn(256, device="cuda", generator=g)
+    bet = 0.1 * torch.randn(256, device="cuda", generator=g)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b2rl_tc_split_lo(W.data_ptr(), Wlo.data_ptr(), W.numel(), None, st), "split")
+    nt = (M + 127) // 128
+    scratch = torch.empty(lib.b2rl_tc_wgrad_scratch_floats(256, M, 0), device="cuda")
+    first = None
+    for it in range(12):
+        H, XH = torch.empty(M, 256, device="cuda"), torch.empty(M, 256, device="cuda")
+        stat = torch.empty(M, 2, device="cuda")
+        L.check(lib.b2rl_tc_linear(X.data_ptr(), 256, M, W.data_ptr(), Wlo.data_ptr(), b.data_ptr(), gam.data_ptr(), bet.data_ptr(),
+                                   1, 1, H.data_ptr(), XH.data_ptr(), stat.data_ptr(), None, st), "tc_linear")
+        DZ1, part = torch.empty(M, 256, device="cuda"), torch.empty(nt, 3, 256, device="cuda")
+        L.check(lib.b2rl_tc_linear_bwd(DZ.data_ptr(), M, W.data_ptr(), Wlo.data_ptr(), XH.data_ptr(), stat.data_ptr(), gam.data_ptr(),
+                                       bet.data_ptr(), 1, DZ1.data_ptr(), part.data_ptr(), None, st), "tc_linear_bwd")
+        G, Gt = torch.empty(256, 256, device="cuda"), torch.empty(256, 256, device="cuda")
+        L.check(lib.b2rl_tc_wgrad(H.data_ptr(), 256, 256, 256, DZ1.data_ptr(), M, G.data_ptr(), Gt.data_ptr(), scratch.data_ptr(), 1,
+                                  None, None, st), "tc_wgrad")
+        torch.cuda.synchronize()
+        cur = (H, XH, stat, DZ1, part, G, Gt)
+        if first is None:
+            first = cur
+            assert all(torch.isfinite(t).all() for t in cur)
+        else:
+            for a, c, what in zip(first, cur, ("H", "x-hat", "stat", "dz1", "column sums", "dW", "dW^T")):
+                assert torch.equal(a, c), f"launch {it}: {what} differs from the first launch"
