@@ -34,6 +34,10 @@ CASES = {
     # (meta.reference_fp32_vs_fp64_oracle is ~1e-2); parity on it is judged against float64
     "sac_saturated": dict(base=SAC, ob=24, ac=8, lo=[-1.0] * 8, hi=[1.0] * 8, B=64, N=256, iters=3, seed=7000,
                           head_scale=4.0, over=dict(batch_size=64)),
+    # Ant shapes (27 / 8): the actor's first layer (27 inputs) is staged in shared memory while the critics' (35 inputs) is
+    # streamed from global memory — both first-layer forms inside one kernel instantiation; TD3 with the default options
+    "td3_ant_mixed_first": dict(base=TD3, ob=27, ac=8, lo=[-1.0] * 8, hi=[1.0] * 8, B=64, N=256, iters=4, seed=9000,
+                                over=dict(batch_size=64)),
     # SAC with clipping and a slower target cadence
     "sac_clip_targfreq2": dict(base=SAC, ob=17, ac=6, lo=[-1.0] * 6, hi=[1.0] * 6, B=64, N=256, iters=6, seed=6000,
                                over=dict(clip_norm=0.5, crit_targ_update_freq=2, batch_size=64)),
