@@ -36,7 +36,7 @@ TOLS = {"3xtf32": (1e-5, 2e-5), "tf32": (5e-3, 1.5e-1)}
 
 
 @pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
-@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq"])
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq", "td3_ant_mixed_first"])
 def test_wide_critic_step_matches_oracle(name, precision):
     from sac_td3_cudagraphs_pytorch_b200.replay import pack_rows
     from sac_td3_cudagraphs_pytorch_b200.wide import WideCritic
@@ -107,7 +107,7 @@ def kink_safe_actor(inp, batch, eps, margin=2e-5):
 
 
 @pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
-@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq"])
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq", "td3_ant_mixed_first"])
 def test_wide_actor_step_matches_oracle(name, precision):
     from sac_td3_cudagraphs_pytorch_b200.replay import pack_rows
     from sac_td3_cudagraphs_pytorch_b200.wide import WideActor
@@ -171,7 +171,7 @@ def test_dp_learner_graph_replay_equals_eager(name, wide):
     assert agents[0].actor_updates_so_far == agents[1].actor_updates_so_far
 
 
-@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq"])
+@pytest.mark.parametrize("name", ["sac_hopper", "td3_hopper", "sac_humanoid", "sac_noln_fixedalpha_bcq", "td3_ant_mixed_first"])
 def test_wide_critic_step_bound_on_the_whole_batch(name):
     """The same comparison WITHOUT the kink filter (every row of the fixture batch): forward quantities — Q, TD target,
     loss — keep the 1e-5 bound (a unit that flips sits within ~1e-6 of zero, so its activation moves by that much);
