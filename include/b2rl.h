@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B2RL_VERSION 110 /* 0.1.1 */
+#define B2RL_VERSION 111 /* 0.1.1 */
 #define B2RL_HID 256     /* hidden width; agents/agent.py:56,101 hard-codes (256, 256) */
 #define B2RL_ROWS 8      /* batch rows per CTA group of the fused kernels; a batch need not be a multiple (the tail is masked) */
 #define B2RL_MAX_OUT 64  /* max head width (2*A for SAC) */
@@ -356,6 +356,18 @@ int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const flo
                      const float* be, int32_t layer_norm, int32_t M, float* dz, float* part, float* dw3_part,
                      const b2rl_stack_t* stack, void* stream);
 /* Column-sum partials -> gradients of bias / ln.weight / ln.bias at float offsets off_* of the gradient region G. */
+typedef struct b2rl_colsum_job {
+  const float* part;              /* [P][3][256] per-CTA partial column sums (agent g: P * 768 floats further) */
+  int64_t off_b, off_g, off_be;   /* float offsets in the gradient region: column sums 0 / 1 / 2 (1, 2: layer_norm only) */
+  int32_t layer_norm;
+  int32_t reserved;
+} b2rl_colsum_job_t;
+#define B2RL_MAX_COLSUM_JOBS 8
+/* The same for up to 8 partial-sum arrays of equal P in ONE launch (`jobs` is read on the host at call time): a step's
+ * column sums have different producers but one consumer, the optimizer launch, so they can all be taken at the end of the
+ * step. Per job bitwise equal to b2rl_wide_colsum. */
+int b2rl_wide_colsum_multi(const b2rl_colsum_job_t* jobs, int32_t n_jobs, int32_t P, float* G, const b2rl_stack_t* stack,
+                           void* stream);
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
                      const b2rl_stack_t* stack, void* stream);
 /* qf_loss -> out[B2RL_OUT_QF_LOSS] and the head-bias gradients of the twin critics, from wide_q_head's per-CTA partials

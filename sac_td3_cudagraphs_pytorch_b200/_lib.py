@@ -79,6 +79,12 @@ class WideQ(C.Structure):
                 ("bcq_mix", C.c_int32), ("gamma", C.c_float), ("reserved", C.c_uint32)]
 
 
+class ColsumJob(C.Structure):
+    """b2rl_colsum_job_t"""
+    _fields_ = [("part", C.c_void_p), ("off_b", C.c_int64), ("off_g", C.c_int64), ("off_be", C.c_int64),
+                ("layer_norm", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Stack(C.Structure):
     """b2rl_stack_t: agents stacked along the row dimension of the wide path (NULL = one learner)."""
     _fields_ = [("n_agents", C.c_int32), ("agent_base", C.c_int32), ("param_stride", C.c_int64), ("lo_stride", C.c_int64),
@@ -117,6 +123,7 @@ SYMBOLS = {
     "b2rl_wide_q_head": (C.c_int, [C.POINTER(WideQ), _STK, C.c_void_p]),
     "b2rl_wide_ln_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, _STK, C.c_void_p]),
+    "b2rl_wide_colsum_multi": (C.c_int, [C.POINTER(ColsumJob), C.c_int32, C.c_int32, C.c_void_p, _STK, C.c_void_p]),
     "b2rl_wide_colsum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _STK, C.c_void_p]),
     "b2rl_wide_critic_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                           C.c_int64, C.c_int64, C.c_void_p, _STK, C.c_void_p]),
@@ -169,8 +176,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype, fn.argtypes = res, args
-    if lib.b2rl_version() != 110:
-        raise B2rlError(f"libb2rl version {lib.b2rl_version()} does not match the binding (110)")
+    if lib.b2rl_version() != 111:
+        raise B2rlError(f"libb2rl version {lib.b2rl_version()} does not match the binding (111)")
     _lib = lib
     return lib
 

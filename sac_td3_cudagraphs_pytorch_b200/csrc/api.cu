@@ -52,6 +52,7 @@ cudaError_t launch_wide_actor_scalars(const float*, const float*, int, int, int,
                                       const Stk&, cudaStream_t);
 cudaError_t launch_wide_alpha_grad(const float*, int, float, float*, const Stk&, cudaStream_t);
 cudaError_t launch_wide_colsum(const float*, int, float*, int64_t, int64_t, int64_t, int, const Stk&, cudaStream_t);
+cudaError_t launch_wide_colsum_multi(const ColsumJobs&, int, float*, const Stk&, cudaStream_t);
 cudaError_t launch_wide_critic_scalars(const float*, const float*, int, const float*, const float*, int, float*, int64_t, int64_t,
                                        float*, const Stk&, cudaStream_t);
 cudaError_t launch_tc_linear(const float*, int64_t, int, const float*, const float*, const float*, const float*, const float*, int,
@@ -317,6 +318,19 @@ int b2rl_wide_ln_bwd(const float* dz3, int32_t n_out, const float* w3, const flo
   if (dw3_part && !part) return fail(B2RL_E_INVALID, "wide_ln_bwd: dw3_part without part");
   if (layer_norm && (!g || !be || !stat)) return fail(B2RL_E_INVALID, "wide_ln_bwd: LayerNorm needs weight, bias and statistics");
   return check_launch(b2rl::launch_wide_ln_bwd(dz3, n_out, w3, xh, stat, g, be, layer_norm, M, dz, part, dw3_part, make_stk(stack), (cudaStream_t)stream), "wide_ln_bwd");
+}
+int b2rl_wide_colsum_multi(const b2rl_colsum_job_t* jobs, int32_t n_jobs, int32_t P, float* G, const b2rl_stack_t* stack,
+                           void* stream) {
+  if (int rc = check_stack(stack, "wide_colsum_multi")) return rc;
+  if (!jobs || !G || P < 1 || n_jobs < 1 || n_jobs > B2RL_MAX_COLSUM_JOBS) return fail(B2RL_E_INVALID, "wide_colsum_multi: bad arguments");
+  b2rl::ColsumJobs J = {};
+  for (int i = 0; i < n_jobs; ++i) {
+    if (!jobs[i].part) return fail(B2RL_E_INVALID, "wide_colsum_multi: a job without partial sums");
+    J.part[i] = jobs[i].part, J.off[i][0] = jobs[i].off_b, J.off[i][1] = jobs[i].off_g, J.off[i][2] = jobs[i].off_be;
+    J.ln[i] = jobs[i].layer_norm;
+  }
+  J.n = n_jobs;
+  return check_launch(b2rl::launch_wide_colsum_multi(J, P, G, make_stk(stack), (cudaStream_t)stream), "wide_colsum_multi");
 }
 int b2rl_wide_colsum(const float* part, int32_t P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int32_t layer_norm,
                      const b2rl_stack_t* stack, void* stream) {

@@ -123,6 +123,14 @@ inline Stk make_stk(const b2rl_stack_t* s) {
   return k;
 }
 
+// the job table of wide.cu::wide_colsum_kernel (b2rl_wide_colsum_multi), passed by value
+struct ColsumJobs {
+  const float* part[8];
+  long long off[8][3];
+  int ln[8];
+  int n;
+};
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // streaming 128-bit load/store that do not allocate in L1 (replay rows are touched once)

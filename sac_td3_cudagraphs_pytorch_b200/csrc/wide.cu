@@ -420,13 +420,16 @@ wide_ln_bwd_kernel(const float* __restrict__ dz3, int n_out, const float* __rest
 // (c = t & 31, s = t >> 5) sums partials s, s + 32, ... of column 32 * chunk + c; fixed-order combine over s. 1 024 threads:
 // the kernel is a chain of L2 round trips (512 partials per column at batch 65 536), so the slices are spread over 32 warps
 // and each takes its partials eight loads at a time.
+// Up to 8 jobs (partial-sum arrays of equal P) per launch: blockIdx.y = 3 * job + vector.
 __global__ void __launch_bounds__(1024)
-wide_colsum_kernel(const float* __restrict__ part, int P, float* __restrict__ G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
-                   long long ps) {
-  part += (size_t)blockIdx.z * P * 3 * HID;  // stacked agents: blockIdx.z = agent
+wide_colsum_kernel(const __grid_constant__ ColsumJobs J, int P, float* __restrict__ G, long long ps) {
+  const int job = blockIdx.y / 3, v = blockIdx.y - 3 * job;
+  const float* __restrict__ part = J.part[job] + (size_t)blockIdx.z * P * 3 * HID;  // stacked agents: blockIdx.z = agent
+  const int64_t off_b = J.off[job][0], off_g = J.off[job][1], off_be = J.off[job][2];
+  const int ln = J.ln[job];
   G += (size_t)blockIdx.z * ps;
   __shared__ float red[32][32];
-  const int v = blockIdx.y, t = threadIdx.x, c = t & 31, sl = t >> 5, j = blockIdx.x * 32 + c;
+  const int t = threadIdx.x, c = t & 31, sl = t >> 5, j = blockIdx.x * 32 + c;
   if (v > 0 && !ln) return;
   float s = 0.f;
   const int nsl = (int)blockDim.x >> 5;  // 32 warps for long lists (P >= 64), 8 otherwise: a function of P only
@@ -672,10 +675,15 @@ cudaError_t launch_wide_ln_bwd(const float* dz3, int n_out, const float* w3, con
       dz3, n_out, w3, xh, reinterpret_cast<const float2*>(stat), g, be, ln, M, dz, part, dw3_part, k.ps);
   return cudaGetLastError();
 }
+cudaError_t launch_wide_colsum_multi(const ColsumJobs& J, int P, float* G, const Stk& k, cudaStream_t st) {
+  wide_colsum_kernel<<<dim3(HID / 32, 3 * J.n, k.n), P >= 64 ? 1024 : 256, 0, st>>>(J, P, G, k.ps);
+  return cudaGetLastError();
+}
 cudaError_t launch_wide_colsum(const float* part, int P, float* G, int64_t off_b, int64_t off_g, int64_t off_be, int ln,
                                const Stk& k, cudaStream_t st) {
-  wide_colsum_kernel<<<dim3(HID / 32, 3, k.n), P >= 64 ? 1024 : 256, 0, st>>>(part, P, G, off_b, off_g, off_be, ln, k.ps);
-  return cudaGetLastError();
+  ColsumJobs J = {};
+  J.part[0] = part, J.off[0][0] = off_b, J.off[0][1] = off_g, J.off[0][2] = off_be, J.ln[0] = ln, J.n = 1;
+  return launch_wide_colsum_multi(J, P, G, k, st);
 }
 cudaError_t launch_wide_critic_scalars(const float* sq0, const float* sq1, int P, const float*, const float*, int M, float* G,
                                        int64_t off0, int64_t off1, float* out, const Stk& k, cudaStream_t st) {

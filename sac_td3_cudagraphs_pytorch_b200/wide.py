@@ -96,6 +96,15 @@ def _tc_wgrads(lib, stk, M, x3, scratch, G, net, x0_ptr, ldx, h1, h2, dz1, dz2, 
         L.check(lib.b2rl_tc_wgrad(dz3, L.MAX_OUT, L.MAX_OUT, net.out_dim, h2, M, f(o["w3"]), None, sc, x3, bump, stk, st), "tc_wgrad w3")
 
 
+def _colsums(lib, jobs, P, G, stk, st):
+    """All column-sum reductions of a step in one launch (b2rl_wide_colsum_multi): jobs = [(part_ptr, off_b, off_g, off_be, ln)].
+    Their producers differ (wide_ln_bwd, tc_linear_bwd), their only consumer is the optimizer launch."""
+    arr = (L.ColsumJob * len(jobs))()
+    for a, (part, ob, og, obe, ln) in zip(arr, jobs):
+        a.part, a.off_b, a.off_g, a.off_be, a.layer_norm = part, ob, og, obe, int(ln)
+    L.check(lib.b2rl_wide_colsum_multi(arr, len(jobs), P, G, stk, st), "wide_colsum_multi")
+
+
 def _wgrad_scratch(own: "_Owner", M):
     dims = {1, 256} | {n.in_dim for n in [own.layout.actor, *own.layout.critic]}
     n = own.n if own.stacked else 0
@@ -219,6 +228,7 @@ class WideCritic:
             hidden(self.t1.data_ptr(), net, RT, none, none, none, 1 + k, head=q_head(net, RT, k, 0))  # (h2 stays on chip)
         # ---- twin online Q, TD target, loss, backward (agent.py:212-235)
         G = self._p(RG, 0)
+        jobs = []
         for k in range(2):
             net, o = lay.critic[k], lay.critic[k].off
             first(rows.data_ptr(), rs, O + A, net, RP, self._ws(0, k), self.xh1[k].data_ptr(), self.st1[k].data_ptr())
@@ -229,15 +239,14 @@ class WideCritic:
             L.check(lib.b2rl_wide_ln_bwd(self._dz3(k), 1, self._p(RP, o["w3"]), self.xh2[k].data_ptr(), self.st2[k].data_ptr(),
                                          self._p(RP, o["g2"]) if ln else none, self._p(RP, o["be2"]) if ln else none, ln, M,
                                          self._ws(3, k), self.part2[k].data_ptr(), self.part3[k].data_ptr(), stk, st), "wide_ln_bwd")
-            L.check(lib.b2rl_wide_colsum(self.part3[k].data_ptr(), self.P128, G, o["w3"], 0, 0, 0, stk, st), "wide_colsum (dW3)")
+            jobs.append((self.part3[k].data_ptr(), o["w3"], 0, 0, 0))  # dW3
             w2t = self._p(RP, o["w2t"])
             L.check(lib.b2rl_tc_linear_bwd(self._ws(3, k), M, w2t, lo_of(5 + k, w2t), self.xh1[k].data_ptr(), self.st1[k].data_ptr(),
                                            self._p(RP, o["g1"]) if ln else none, self._p(RP, o["be1"]) if ln else none, ln,
                                            self._ws(2, k), self.part1[k].data_ptr(), stk, st), "tc_linear_bwd")
-            L.check(lib.b2rl_wide_colsum(self.part2[k].data_ptr(), self.P128, G, o["b2"], o["g2"] if ln else 0, o["be2"] if ln else 0,
-                                         ln, stk, st), "wide_colsum")
-            L.check(lib.b2rl_wide_colsum(self.part1[k].data_ptr(), self.P128, G, o["b1"], o["g1"] if ln else 0, o["be1"] if ln else 0,
-                                         ln, stk, st), "wide_colsum")
+            jobs.append((self.part2[k].data_ptr(), o["b2"], o["g2"] if ln else 0, o["be2"] if ln else 0, ln))
+            jobs.append((self.part1[k].data_ptr(), o["b1"], o["g1"] if ln else 0, o["be1"] if ln else 0, ln))
+        _colsums(lib, jobs, self.P128, G, stk, st)
         L.check(lib.b2rl_wide_critic_scalars(self.sq[0].data_ptr(), self.sq[1].data_ptr(), self.P8, self._dz3(0), self._dz3(1), M, G,
                                              lay.critic[0].off["b3"], lay.critic[1].off["b3"], ag.out.data_ptr(), stk, st),
                 "wide_critic_scalars")
@@ -385,10 +394,8 @@ class WideActor:
                 "wide_actor_head_bwd")
         bwd_layers(self._dz3(0), act.out_dim, act, self.xa2.data_ptr(), self.sa2.data_ptr(), self.xa1.data_ptr(),
                    self.sa1.data_ptr(), self._ws(3, 0), self._ws(2, 0), self.part, 5)
-        L.check(lib.b2rl_wide_colsum(self.part[0].data_ptr(), self.P128, G, ao["b2"], ao["g2"] if ln else 0,
-                                     ao["be2"] if ln else 0, ln, stk, st), "wide_colsum")
-        L.check(lib.b2rl_wide_colsum(self.part[1].data_ptr(), self.P128, G, ao["b1"], ao["g1"] if ln else 0,
-                                     ao["be1"] if ln else 0, ln, stk, st), "wide_colsum")
+        _colsums(lib, [(self.part[0].data_ptr(), ao["b2"], ao["g2"] if ln else 0, ao["be2"] if ln else 0, ln),
+                       (self.part[1].data_ptr(), ao["b1"], ao["g1"] if ln else 0, ao["be1"] if ln else 0, ln)], self.P128, G, stk, st)
         L.check(lib.b2rl_wide_actor_scalars(self.part_s.data_ptr(), self.part_du.data_ptr(), self.P256, M, act.out_dim,
                                             int(ag.td3), None if ag.td3 else la, G, ao["b3"], ag.out.data_ptr(), stk, st),
                 "wide_actor_scalars")

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b2rl.h but not exported"
         assert n in L.SYMBOLS, f"{n} has no ctypes prototype"
-    assert lib.b2rl_version() == 110
+    assert lib.b2rl_version() == 111
 
 
 def test_prototypes_have_the_declared_number_of_arguments():
@@ -43,10 +43,11 @@ def test_prototypes_have_the_declared_number_of_arguments():
 
 
 def test_struct_layouts_match_the_c_compiler():
-    src = '#include <stdio.h>\n#include "b2rl.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "b2rl.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(b2rl_net_t),sizeof(b2rl_rowfmt_t),sizeof(b2rl_hyper_t),sizeof(b2rl_update_args_t),' \
           'sizeof(b2rl_seg_t),sizeof(b2rl_adam_args_t),__builtin_offsetof(b2rl_update_args_t, workspace),' \
-          'sizeof(b2rl_stack_t),sizeof(b2rl_wide_policy_t),sizeof(b2rl_wide_q_t),__builtin_offsetof(b2rl_stack_t, out_stride));return 0;}'
+          'sizeof(b2rl_stack_t),sizeof(b2rl_wide_policy_t),sizeof(b2rl_wide_q_t),__builtin_offsetof(b2rl_stack_t, out_stride),' \
+          'sizeof(b2rl_colsum_job_t));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         c = Path(d) / "s.c"
         c.write_text(src)
@@ -54,7 +55,7 @@ def test_struct_layouts_match_the_c_compiler():
         out = subprocess.check_output([str(Path(d) / "s")]).split()
     got = [C.sizeof(L.Net), C.sizeof(L.RowFmt), C.sizeof(L.Hyper), C.sizeof(L.UpdateArgs), C.sizeof(L.Seg),
            C.sizeof(L.AdamArgs), L.UpdateArgs.workspace.offset, C.sizeof(L.Stack), C.sizeof(L.WidePolicy), C.sizeof(L.WideQ),
-           L.Stack.out_stride.offset]
+           L.Stack.out_stride.offset, C.sizeof(L.ColsumJob)]
     assert [int(x) for x in out] == got
 
 
