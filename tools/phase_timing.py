@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""In-kernel phase timing of critic_fused (CTA 0, thread 0; clock64). Needs a timing build:
-   B2RL_EXTRA_NVCC_FLAGS=-DB2RL_TIMING python -m sac_td3_cudagraphs_pytorch_b200.build --force"""
+"""In-kernel phase timing of critic_fused (CTA 0, thread 0; clock64). Needs a timing build, kept beside the product library:
+   export B2RL_LIB=$PWD/sac_td3_cudagraphs_pytorch_b200/libb2rl_timing.so
+   B2RL_EXTRA_NVCC_FLAGS=-DB2RL_TIMING python -m sac_td3_cudagraphs_pytorch_b200.build      # writes $B2RL_LIB
+   python tools/phase_timing.py td3 | sac [O A]                                              # loads $B2RL_LIB
+(profiles/r2_phase_timing_*.txt)"""
 import ctypes as C, sys
 from pathlib import Path
 import numpy as np, torch
