@@ -520,7 +520,10 @@ wide_actor_loss_kernel(const float* __restrict__ q0, const float* __restrict__ q
   }
 }
 
-// dQ/da[row][a] = sum_j dz1[row][j] * w1t[O + a][j]  (first-layer dX, action columns only); warp per row
+// dQ/da[row][a] = sum_j dz1[row][j] * w1t[O + a][j]  (first-layer dX, action columns only); warp per row, 64 rows per CTA
+// (the action rows of w1t are staged once per 64 rows — with 8 rows per CTA they were a third of the bytes the kernel read —
+// and a warp requests its next row before it reduces the current one)
+constexpr int WD_ROWS = 64;
 __global__ void __launch_bounds__(256)
 wide_dqda_kernel(const float* __restrict__ dz1, const float* __restrict__ w1a /* w1t + O * 256: [A][256] */, int A, int M,
                  float* __restrict__ dqda, long long ps) {
@@ -529,17 +532,28 @@ wide_dqda_kernel(const float* __restrict__ dz1, const float* __restrict__ w1a /*
   const int t = threadIdx.x, w = t >> 5, l = t & 31;
   for (int i = t; i < A * HID; i += 256) was[i] = __ldg(w1a + i);
   __syncthreads();
-  const int row = blockIdx.x * 8 + w;
-  if (row >= M) return;
-  float d[8];
+  const int row0 = blockIdx.x * WD_ROWS, nrows = min(WD_ROWS, M - row0);
+  float dn[8];
+  if (w < nrows) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) d[i] = __ldg(dz1 + (size_t)row * HID + l + 32 * i);
-  for (int a = 0; a < A; ++a) {
-    float s = 0.f;
+    for (int i = 0; i < 8; ++i) dn[i] = __ldg(dz1 + (size_t)(row0 + w) * HID + l + 32 * i);
+  }
+  for (int rr = w; rr < nrows; rr += 8) {
+    const int row = row0 + rr;
+    float d[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(d[i], was[a * HID + l + 32 * i], s);
-    s = warp_sum(s);
-    if (l == 0) dqda[(size_t)row * A + a] = s;
+    for (int i = 0; i < 8; ++i) d[i] = dn[i];
+    if (rr + 8 < nrows) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dn[i] = __ldg(dz1 + (size_t)(row + 8) * HID + l + 32 * i);
+    }
+    for (int a = 0; a < A; ++a) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(d[i], was[a * HID + l + 32 * i], s);
+      s = warp_sum(s);
+      if (l == 0) dqda[(size_t)row * A + a] = s;
+    }
   }
 }
 
@@ -625,7 +639,14 @@ wide_alpha_grad_kernel(const float* __restrict__ logp2, int M, float targ_ent, f
   __shared__ float red[256];
   const int t = threadIdx.x;
   float s = 0.f;
-  for (int r = t; r < M; r += 256) s += (-logp2[r] - targ_ent);
+  for (int r0 = t; r0 < M; r0 += 16 * 256) {  // sixteen loads in flight, added in the order of the plain loop
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = r0 + 256 * i < M ? __ldg(logp2 + r0 + 256 * i) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (r0 + 256 * i < M) s += (-v[i] - targ_ent);
+  }
   red[t] = s;
   __syncthreads();
   if (t == 0) {
@@ -697,7 +718,7 @@ cudaError_t launch_wide_actor_loss(const float* q0, const float* q1, const float
   return cudaGetLastError();
 }
 cudaError_t launch_wide_dqda(const float* dz1, const float* w1a, int A, int M, float* dqda, const Stk& k, cudaStream_t st) {
-  wide_dqda_kernel<<<dim3((M + 7) / 8, k.n), 256, (size_t)A * HID * 4, st>>>(dz1, w1a, A, M, dqda, k.ps);
+  wide_dqda_kernel<<<dim3((M + WD_ROWS - 1) / WD_ROWS, k.n), 256, (size_t)A * HID * 4, st>>>(dz1, w1a, A, M, dqda, k.ps);
   return cudaGetLastError();
 }
 cudaError_t launch_wide_actor_head_bwd(const float* dqda0, const float* dqda1, const float* save, const float* min_ac,
